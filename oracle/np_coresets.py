@@ -1,0 +1,163 @@
+"""Oracle: greedy coreset construction (beta-Cores / SparseVI / Hilbert).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates
+bayesiancoresets/coreset/{coreset,bcores,sparsevi,hilbert,projector}.py and
+bayesiancoresets/util/opt.py:36-54 for the individual-point mode with
+learn_beta=False (the only mode the reference drivers run).
+RNG call order (sampler, then np.random.randint for the subsample) is the
+reference's, so seeded runs reproduce its index sequence.
+"""
+import numpy as np
+from . import np_snnls
+
+
+def centred(F):
+    """projector.py:26 / :55: subtract each row's mean over the S samples (in place)."""
+    F -= F.mean(axis=1)[:, np.newaxis]
+    return F
+
+
+def adam_nonneg(x0, grad, itrs, sched, b1=0.9, b2=0.999, eps=1e-8):
+    """util/opt.py:36-54 nn_opt: ADAM with projection onto x >= 0."""
+    x = x0.copy()
+    m1 = np.zeros(x.shape[0])
+    m2 = np.zeros(x.shape[0])
+    for i in range(itrs):
+        g = grad(x)
+        m1 = b1*m1 + (1.-b1)*g
+        m2 = b2*m2 + (1.-b2)*g**2
+        upd = sched(i)*m1/(1.-b1**(i+1))/(eps + np.sqrt(m2/(1.-b2**(i+1))))
+        x -= upd
+        x = np.maximum(x, 0.)
+    return x
+
+
+class GreedyVI(object):
+    """BetaCoreset (potential = beta-likelihood, coreset/bcores.py) and
+    SparseVICoreset (potential = log-likelihood, coreset/sparsevi.py) share this
+    skeleton; `potential(pts, samples)` returns the un-centred (n, S) matrix.
+
+    sampler(S, wts, pts) -> (S, D) is the user's host callback (projector.py:36-37,65-66).
+    """
+
+    def __init__(self, data, sampler, S, potential, n_sub_select=None, n_sub_opt=None,
+                 opt_itrs=100, sched=lambda i: 1./(1.+i)):
+        self.data = data
+        self.sampler = sampler
+        self.S = S
+        self.potential = potential
+        N = data.shape[0]
+        self.n_sub_select = None if n_sub_select is None else min(N, n_sub_select)   # bcores.py:14
+        self.n_sub_opt = None if n_sub_opt is None else min(N, n_sub_opt)            # bcores.py:15
+        self.opt_itrs = opt_itrs
+        self.sched = sched
+        self.wts = np.array([])
+        self.idcs = np.array([], dtype=np.int64)
+        self.pts = np.array([])
+        self.samples = sampler(S, np.array([]), np.array([]))   # projector.py:18,46 (ctor draws once)
+        self.log = []   # oracle extra: per-select diagnostics
+
+    def size(self):
+        return (self.wts > 0).sum()                      # coreset.py:22-23
+
+    def get(self):
+        keep = self.wts > 0                              # coreset.py:25-26
+        return self.wts[keep], self.pts[keep, :], self.idcs[keep]
+
+    def _tangent(self, n_sub, w, p):
+        """bcores.py:37-72 / sparsevi.py:35-70, individual-point branches."""
+        self.samples = self.sampler(self.S, w, p)        # update() first: consumes np.random
+        if n_sub is None:
+            sub = None
+            vecs = centred(self.potential(self.data, self.samples))
+            scale = 1.
+        else:
+            sub = np.random.randint(self.data.shape[0], size=n_sub)     # bcores.py:53
+            vecs = centred(self.potential(self.data[sub], self.samples))
+            scale = self.data.shape[0]/n_sub
+        if self.pts.size > 0:
+            core = centred(self.potential(p, self.samples))
+        else:
+            core = np.zeros((0, vecs.shape[1]))
+        # NB the all-zero-row filter at bcores.py:67-68 / sparsevi.py:63-64 only runs when
+        # select=True, and the individual-point _select (bcores.py:76, sparsevi.py:74) never
+        # passes it: rows whose centred vector is exactly 0 stay in and score 0/0 = NaN.
+        return vecs, scale, sub, core
+
+    def select(self):
+        """bcores.py:75-90 / sparsevi.py:73-92."""
+        vecs, scale, sub, core = self._tangent(self.n_sub_select, self.wts, self.pts)
+        resid = scale*vecs.sum(axis=0) - self.wts.dot(core)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            corrs = vecs.dot(resid) / np.sqrt((vecs**2).sum(axis=1)) / vecs.shape[1]
+            ccorrs = np.fabs(core.dot(resid) / np.sqrt((core**2).sum(axis=1))) / core.shape[1]
+        # np.max / np.argmax propagate NaN (first NaN wins); `nan > x` is False (bcores.py:80)
+        rec = {'best': float(corrs.max()), 'pos': int(np.argmax(corrs)),
+               'core_best': float(ccorrs.max()) if ccorrs.size else None, 'added': False}
+        if ccorrs.size == 0 or corrs.max() > ccorrs.max():
+            f = sub[np.argmax(corrs)] if sub is not None else np.argmax(corrs)
+            rec['f'] = int(f)
+            if f not in self.idcs:
+                self.wts = np.append(self.wts, 0.)
+                self.idcs = np.append(self.idcs, f)
+                self.pts = np.vstack((self.pts.reshape(-1, self.data.shape[1]), self.data[f][np.newaxis, :]))
+                rec['added'] = True
+        self.log.append(rec)
+
+    def optimise(self):
+        """bcores.py:141-150 / sparsevi.py:129-136."""
+        def grad(w):
+            vecs, scale, _, core = self._tangent(self.n_sub_opt, w, self.pts)
+            resid = scale*vecs.sum(axis=0) - w.dot(core)
+            return -core.dot(resid) / core.shape[1]
+        self.wts = adam_nonneg(self.wts, grad, self.opt_itrs, self.sched)
+
+    def build(self, itrs, sz):
+        """coreset.py:33-45 + bcores.py:27-35."""
+        if sz < self.size():
+            raise ValueError('cannot shrink')
+        if self.size()+itrs > sz:
+            raise ValueError('itrs + size > sz')
+        for _ in range(itrs):
+            self.select()
+            self.optimise()
+
+
+class Hilbert(object):
+    """coreset/hilbert.py:7-43: project once, drop zero-norm rows, delegate to a solver."""
+
+    def __init__(self, data, sampler, S, potential, n_sub=None, solver='giga'):
+        self.data = data
+        samples = sampler(S, np.array([]), np.array([]))       # projector ctor draw
+        if n_sub is None:
+            self.sub = None
+            vecs = centred(potential(data, samples))
+        else:
+            n_sub = min(data.shape[0], n_sub)
+            self.sub = np.random.randint(data.shape[0], size=n_sub)
+            vecs = centred(potential(data[self.sub], samples))
+        vecs = vecs[np.sqrt((vecs**2).sum(axis=1)) > 0., :]     # hilbert.py:16
+        self.vecs = vecs
+        self.solver = np_snnls.SOLVERS[solver](vecs.T, vecs.sum(axis=0))
+        self.wts = np.array([])
+        self.idcs = np.array([], dtype=np.int64)
+        self.pts = np.array([])
+
+    def _sync(self):
+        w = self.solver.weights()                               # hilbert.py:30-33
+        self.wts = w[w > 0]
+        self.idcs = self.sub[w > 0] if self.sub is not None else np.where(w > 0)[0]
+        self.pts = self.data[self.idcs]
+
+    def build(self, itrs, sz):
+        if self.solver.size()+itrs > sz:
+            raise ValueError('itrs + size > sz')
+        self.solver.run(itrs)
+        self._sync()
+
+    def optimise(self):
+        self.solver.polish()
+        self._sync()
+
+    def error(self):
+        return self.solver.error()

@@ -1,0 +1,172 @@
+"""Seeded synthetic problems shared by the golden generator, the oracle tests and
+the GPU parity tests.  Pure numpy; imports neither the reference nor the product.
+
+Samplers are *user-side* host callbacks (sampler(S, wts, pts) -> (S, D)) exactly
+as in the reference drivers (examples/zellner_gaussian/main.py:87-92,
+examples/zellner_logreg/main.py:139-144): conjugate posterior / Laplace
+approximation of the weighted coreset posterior, then mu + randn(S, D) L^T on
+the global legacy numpy RNG.
+"""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import np_models as om   # host sampler maths (restated reference functions)
+
+
+# ------------------------------------------------------------------ G1 inputs --
+def model_function_inputs():
+    r = np.random.RandomState(11)
+    N, D, S = 37, 5, 13
+    d = 6
+    A = r.randn(d, d)
+    Sig = A.dot(A.T) + d*np.eye(d)
+    p = dict(
+        Z=r.randn(N, D)*2.0, Th=r.randn(S, D), beta=np.float64(0.3),
+        Xg=r.randn(N, d)*3.0, Thg=r.randn(S, d), Siginv=np.linalg.inv(Sig), logdetSig=np.float64(np.linalg.slogdet(Sig)[1]),
+        Zn=np.hstack((r.randn(N, D), r.randn(N, 1)*2.0)), Thn=r.randn(S, D), sigsq=np.float64(0.7))
+    # large-margin rows exercise the saturating branches (m >= 100, e^m overflow)
+    p['Z'][0] *= 200.0
+    p['Z'][1] *= -200.0
+    p['Z'][2] = 0.0
+    return p
+
+
+# ------------------------------------------------------------------ G2 inputs --
+def snnls_matrix():
+    """SURVEY 8c fingerprint problem (reference tests/test_snnls seed, :8)."""
+    np.random.seed(324)
+    return np.random.randn(1000, 100)
+
+
+def snnls_small_cases():
+    """Data generators of reference tests/test_snnls/test_deterministic.py:18-35."""
+    r = np.random.RandomState(324)
+    cases = []
+    for n, d in ((10, 3), (100, 10), (10, 10)):
+        cases.append(('gauss_%d_%d_' % (n, d), r.randn(n, d)))
+        b = (r.rand(n, d) > 0.5).astype(np.float64)
+        b[b.sum(axis=1) == 0, 0] = 1.
+        cases.append(('bin_%d_%d_' % (n, d), b))
+        g = r.randn(n, d)
+        cases.append(('colinear_%d_%d_' % (n, d), np.vstack((g, g.sum(axis=0)[np.newaxis, :]))))
+        ax = np.zeros((n, d))
+        ax[np.arange(n), r.randint(d, size=n)] = 1. + r.rand(n)
+        cases.append(('axis_%d_%d_' % (n, d), ax))
+    return cases
+
+
+# ------------------------------------------------------------- coreset builds --
+def make_logistic(N, D, seed, zero_rows=()):
+    """SURVEY 8d generator: X ~ N(0, I), theta* = 1/sqrt(D), 10% label flips, Z = y X."""
+    def make():
+        r = np.random.RandomState(seed)
+        X = r.randn(N, D)
+        th = np.ones(D)/np.sqrt(D)
+        y = np.where(r.rand(N) < 1./(1.+np.exp(-X.dot(th))), 1., -1.)
+        y[r.rand(N) < 0.1] *= -1.
+        Z = y[:, np.newaxis]*X
+        for i in zero_rows:
+            Z[i] = 0.
+        mu0 = np.zeros(D)
+
+        def sampler(S, w, pts):
+            if pts.shape[0] == 0:
+                w = np.zeros(1)
+                pts = np.zeros((1, D))
+            mu, L, _ = om.lr_laplace(w, pts, mu0)
+            return mu + np.random.randn(S, mu.shape[0]).dot(L.T)
+        return dict(model='lr', data=Z, sampler=sampler, params={},
+                    ref_betalik=lambda lr, ga, nl: lr.beta_likelihood,
+                    ref_loglik=lambda lr, ga, nl: lr.log_likelihood,
+                    oracle_betalik=lambda beta: (lambda pts, th: om.lr_betalik(pts, th, beta)),
+                    oracle_loglik=lambda: om.lr_loglik)
+    return make
+
+
+def make_gaussian(N, d, seed):
+    """examples/zellner_gaussian/main.py:33-54 scaled down: inliers + three outlier clusters."""
+    def make():
+        r = np.random.RandomState(seed)
+        Sig = 50.*np.eye(d) + 5.*np.ones((d, d))
+        L = np.linalg.cholesky(Sig)
+        X = r.randn(N, d).dot(L.T)
+        Xo = np.concatenate((200. + r.randn(N//50, d).dot(L.T)*np.sqrt(.5),
+                             150. + r.randn(N//50, d).dot(L.T)*np.sqrt(.1),
+                             r.randn(N//10, d).dot(L.T)*np.sqrt(10.)))
+        data = np.concatenate((X, Xo))
+        Siginv = np.linalg.inv(Sig)
+        logdetSig = np.linalg.slogdet(Sig)[1]
+        mu0 = np.zeros(d)
+        Sig0inv = np.eye(d)
+
+        def sampler(S, w, pts):
+            if pts.shape[0] == 0:
+                w = np.zeros(1)
+                pts = np.zeros((1, d))
+            mu, Lp, _ = om.gauss_weighted_post(mu0, Sig0inv, Siginv, pts, w)
+            return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
+        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig),
+                    ref_betalik=lambda lr, ga, nl: (lambda x, th, beta: ga.gaussian_beta_likelihood(x, th, beta, Siginv, logdetSig)),
+                    ref_loglik=lambda lr, ga, nl: (lambda x, th: ga.gaussian_loglikelihood(x, th, Siginv, logdetSig)),
+                    oracle_betalik=lambda beta: (lambda pts, th: om.gauss_betalik(pts, th, beta, Siginv, logdetSig)),
+                    oracle_loglik=lambda: (lambda pts, th: om.gauss_loglik(pts, th, Siginv, logdetSig)))
+    return make
+
+
+def make_neurlin(N, D, seed):
+    """SURVEY 8d C4 scaled down: random-init relu features, y = Phi w* + noise, 10% rows' y ~ N(10, .5^2)."""
+    def make():
+        r = np.random.RandomState(seed)
+        X = r.randn(N, 6)
+        W1 = r.randn(6, 16)/np.sqrt(6.)
+        W2 = r.randn(16, D)/np.sqrt(16.)
+        Phi = np.maximum(np.maximum(X.dot(W1), 0.).dot(W2), 0.)
+        wstar = r.randn(D)
+        sigsq = 0.5
+        y = Phi.dot(wstar) + np.sqrt(sigsq)*r.randn(N)
+        bad = r.rand(N) < 0.1
+        y[bad] = 10. + .5*r.randn(bad.sum())
+        Z = np.hstack((Phi, y[:, np.newaxis]))
+        mu0 = np.zeros(D)
+        Sig0inv = np.eye(D)
+
+        def sampler(S, w, pts):
+            if pts.shape[0] == 0:
+                w = np.zeros(1)
+                pts = np.zeros((1, D+1))
+            mu, Lp, _ = om.nl_weighted_post(mu0, Sig0inv, sigsq, pts, w)
+            return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
+        return dict(model='nl', data=Z, sampler=sampler, params=dict(sigsq=sigsq),
+                    ref_betalik=lambda lr, ga, nl: (lambda z, th, beta: nl.neurlinr_beta_likelihood(z, th, beta, sigsq)),
+                    ref_loglik=lambda lr, ga, nl: (lambda z, th: nl.neurlinr_loglikelihood(z, th, sigsq)),
+                    oracle_betalik=lambda beta: (lambda pts, th: om.nl_betalik(pts, th, beta, sigsq)),
+                    oracle_loglik=lambda: (lambda pts, th: om.nl_loglik(pts, th, sigsq)))
+    return make
+
+
+def _sched(i0):
+    return lambda i: i0/(1.+i)
+
+
+def coreset_cases(heavy=True):
+    c = []
+    base = dict(n_sel=None, n_opt=None, beta=0.1, solver=None)
+    c.append(dict(base, name='lr_beta_small', alg='beta', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
+    c.append(dict(base, name='lr_svi_small', alg='svi', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
+    c.append(dict(base, name='lr_beta_zero_rows', alg='beta', make=make_logistic(1500, 4, 5, zero_rows=(0, 7, 450, 1499)), seed=2, S=64, opt_itrs=10, M=5, sched=_sched(1.)))
+    c.append(dict(base, name='lr_beta_sub', alg='beta', make=make_logistic(3000, 6, 7), seed=4, S=40, opt_itrs=25, M=6, sched=_sched(1.), n_sel=300, n_opt=100))
+    c.append(dict(base, name='gauss_beta_sub', alg='beta', make=make_gaussian(500, 10, 0), seed=5, S=40, opt_itrs=30, M=8, sched=_sched(1.), n_sel=100, n_opt=40, beta=0.01))
+    c.append(dict(base, name='gauss_svi_full', alg='svi', make=make_gaussian(400, 7, 2), seed=6, S=32, opt_itrs=15, M=5, sched=_sched(.1)))
+    c.append(dict(base, name='nl_beta_small', alg='beta', make=make_neurlin(1000, 8, 9), seed=7, S=32, opt_itrs=20, M=5, sched=_sched(.1), beta=0.2))
+    c.append(dict(base, name='nl_svi_small', alg='svi', make=make_neurlin(1000, 8, 9), seed=7, S=32, opt_itrs=20, M=5, sched=_sched(.1)))
+    c.append(dict(base, name='lr_hilbert_giga', alg='hilbert', make=make_logistic(500, 5, 13), seed=8, S=50, opt_itrs=0, M=10, sched=None, solver='GIGA'))
+    c.append(dict(base, name='lr_hilbert_fw_sub', alg='hilbert', make=make_logistic(800, 5, 14), seed=9, S=50, opt_itrs=0, M=10, sched=None, solver='FrankWolfe', n_sel=200))
+    c.append(dict(base, name='gauss_hilbert_omp', alg='hilbert', make=make_gaussian(300, 6, 4), seed=10, S=48, opt_itrs=0, M=8, sched=None, solver='OrthoPursuit'))
+    if heavy:
+        # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
+        c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))
+    return c
