@@ -1,0 +1,127 @@
+"""Device-side plumbing shared by the projectors, coreset classes and solvers.
+
+PyTorch supplies device memory, the current stream and (optionally) a torch.distributed process
+group; the arithmetic is libbetacores.so's.  One `Engine` per (process, device): it owns the
+bc_ctx workspaces and small result buffers.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _native as nv
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise nv.NativeError('no CUDA device: the beta-cores B200 path has no CPU fallback')
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def dist_group():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class Engine(object):
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None):
+        _require_cuda()
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in cls._instances:
+            cls._instances[key] = cls(key)
+        return cls._instances[key]
+
+    def __init__(self, index):
+        self.index = index
+        self.device = torch.device('cuda', index)
+        self._ctx = {}
+        self.sms = None
+
+    def ctx(self, name='main'):
+        """A bc_ctx workspace; `name` separates workspaces used on concurrent streams."""
+        if name not in self._ctx:
+            h = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                nv.call('bc_create', self.index, ctypes.byref(h))
+            self._ctx[name] = h
+            if self.sms is None:
+                self.sms = nv.lib().bc_sm_count(h)
+        return self._ctx[name]
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def upload(self, arr, dtype=torch.float64):
+        a = np.ascontiguousarray(arr)
+        return torch.from_numpy(a).to(self.device, dtype=dtype, non_blocking=False)
+
+
+def padded_ld(ncols):
+    """Device leading dimension of a data matrix: multiple of 4 doubles (32 bytes) so that every
+    row start is 16-byte aligned and the DMMA k-loop never reads past a row's allocation."""
+    return ((ncols + 3) // 4) * 4
+
+
+class DeviceRows(object):
+    """A block of data rows resident in HBM for the whole build (zero-padded to `ld` columns).
+
+    In a torch.distributed job every rank holds a contiguous shard [row0, row0 + n_local) of the
+    N rows; positions reported by the kernels are global row numbers.
+    """
+
+    def __init__(self, engine, host_rows, row0=0, n_total=None):
+        host_rows = np.asarray(host_rows, dtype=np.float64)
+        if host_rows.ndim != 2:
+            host_rows = host_rows.reshape(1, -1) if host_rows.size else host_rows.reshape(0, max(host_rows.shape[-1], 1))
+        self.engine = engine
+        self.n_local, self.ncols = host_rows.shape
+        self.row0 = int(row0)
+        self.n_total = int(n_total) if n_total is not None else self.n_local
+        self.ld = padded_ld(self.ncols)
+        if self.ld == self.ncols:
+            self.t = engine.upload(host_rows)
+        else:
+            self.t = engine.zeros(max(self.n_local, 1), self.ld)
+            if self.n_local:
+                self.t[:self.n_local, :self.ncols].copy_(torch.from_numpy(np.ascontiguousarray(host_rows)))
+        self.rowaux = None          # Gaussian x Siginv x cache
+        self.rowaux_key = None
+
+    @property
+    def sharded(self):
+        return self.n_total != self.n_local
+
+    @property
+    def shape(self):
+        return (self.n_total, self.ncols)
+
+    def __getitem__(self, f):
+        """host copy of GLOBAL row f (the coreset classes read `data[f]` for the selected point); in a
+        sharded job the owning rank broadcasts it."""
+        from ._shard import Comm, owner_of
+        f = int(f)
+        comm = Comm.current()
+        buf = self.engine.empty(self.ld)
+        own = owner_of(f, self.n_total, comm.world) if (comm.world > 1 and self.sharded) else comm.rank
+        if own == comm.rank:
+            buf.copy_(self.t[f-self.row0])
+        if comm.world > 1 and self.sharded:
+            comm.broadcast(buf, own)
+        return buf[:self.ncols].cpu().numpy()

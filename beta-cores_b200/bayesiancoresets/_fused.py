@@ -1,0 +1,103 @@
+"""FusedProjection: one potential + the current posterior samples, bound to a bc_ctx.
+
+Wraps the stage-1/2 entry points of libbetacores.so for the coreset classes:
+    colsum_parts()  -> bc_project_colsum        (column sum of the centred n x S projection, never formed)
+    score()         -> bc_project_score         (residual correlation + arg-max, never formed)
+    materialise()   -> bc_project_materialise   (centred rows written out: coreset points, Hilbert)
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _native as nv
+from ._device import DeviceRows, ptr, stream_ptr
+
+
+class FusedProjection(object):
+    def __init__(self, engine, potential, ncols, ctx_name='main'):
+        if not potential.is_bound():
+            raise TypeError('potential %s has unbound model constants %s' % (potential.__name__, potential.needs))
+        self.eng = engine
+        self.pot = potential
+        self.ncols = ncols
+        self.D = potential.feature_dim(ncols)
+        self.ctx = engine.ctx(ctx_name)
+        self.siginv = engine.upload(potential.bound['Siginv']) if potential.model == 'gaussian' else None
+        self._beta = ()
+        self.S = None
+        self.Sld = None
+        self._theta = None
+
+    # ---- configuration ----
+    def configure(self, beta=None):
+        if self._beta == (beta,):
+            return
+        p = nv.params8(self.pot.params(self.D, beta))
+        nv.call('bc_set_potential', self.ctx, self.pot.model_id, self.pot.kind_id, self.D, p, ptr(self.siginv))
+        self._beta = (beta,)
+        self.S = None          # bc_set_potential invalidates the prepared samples
+
+    def set_samples(self, theta):
+        """theta: host (S, D) ndarray or a device tensor; runs the sample-preparation kernels."""
+        if isinstance(theta, torch.Tensor):
+            t = theta
+        else:
+            theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+            t = self.eng.upload(theta)
+        if t.shape[1] != self.D:
+            raise ValueError('samples have %d columns, potential expects %d' % (t.shape[1], self.D))
+        self._theta = t
+        self.S = int(t.shape[0])
+        self.Sld = nv.lib().bc_colsum_ld(self.S)
+        nv.call('bc_set_samples', self.ctx, ptr(t), self.S, int(t.stride(0)), stream_ptr())
+
+    # ---- helpers ----
+    def _rowaux(self, rows):
+        if self.pot.model != 'gaussian':
+            return None
+        key = id(self.siginv)
+        if rows.rowaux is None or rows.rowaux_key != key:
+            out = self.eng.empty(max(rows.n_local, 1))
+            nv.call('bc_rowquad', self.ctx, ptr(rows.t), rows.n_local, rows.ld, ptr(out), stream_ptr())
+            rows.rowaux, rows.rowaux_key = out, key
+        return rows.rowaux
+
+    def _check(self, rows):
+        if self.S is None:
+            raise nv.NativeError('set_samples() must follow configure()')
+        if rows.ncols != self.ncols:
+            raise ValueError('data rows have %d columns, projector was built for %d' % (rows.ncols, self.ncols))
+
+    # ---- passes ----
+    def colsum_parts(self, rows, sub=None, out=None):
+        """(2*Sld,) tensor: hi plane, lo plane; element S = sum of row means.  `sub`: optional
+        int64 device tensor of local row numbers (gather; duplicates allowed)."""
+        self._check(rows)
+        if out is None:
+            out = self.eng.empty(2 * self.Sld)
+        n = rows.n_local if sub is None else int(sub.numel())
+        nv.call('bc_project_colsum', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(self._rowaux(rows)), ptr(out), stream_ptr())
+        return out
+
+    def combine(self, parts, nparts, out=None):
+        if out is None:
+            out = self.eng.empty(self.S)
+        nv.call('bc_colsum_combine', self.ctx, ptr(parts), nparts, self.S, ptr(out), stream_ptr())
+        return out
+
+    def score(self, rows, sub, resid, idx_offset, out_best, scores=None):
+        """out_best (>=2 doubles): best score, int64 bits of (position + idx_offset)."""
+        self._check(rows)
+        n = rows.n_local if sub is None else int(sub.numel())
+        nv.call('bc_project_score', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(self._rowaux(rows)), ptr(resid),
+                int(idx_offset), ptr(out_best), ptr(scores), stream_ptr())
+
+    def materialise(self, rows, sub=None, want_norms=False, want_colsum=False, raw=False):
+        self._check(rows)
+        n = rows.n_local if sub is None else int(sub.numel())
+        V = self.eng.empty(max(n, 1), self.S)
+        norms = self.eng.empty(max(n, 1)) if want_norms else None
+        dd = self.eng.empty(2 * self.Sld) if want_colsum else None
+        nv.call('bc_project_materialise', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(self._rowaux(rows)), ptr(V), self.S,
+                ptr(norms), ptr(dd), 1 if raw else 0, stream_ptr())
+        return V[:n], (norms[:n] if want_norms else None), dd

@@ -1,0 +1,93 @@
+"""ctypes binding of libbetacores.so (the C ABI declared in include/betacores.h).
+
+There is NO CPU path: importing this module without the compiled CUDA library, or calling it
+without a CUDA device, raises.  PyTorch is used only for device memory, streams and
+torch.distributed; every arithmetic step of the hot path is one of the kernels behind these calls.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libbetacores.so')
+
+c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+# name -> argument types (all return int); mirrors include/betacores.h one to one
+SIGNATURES = {
+    'bc_create': [c_int, ctypes.POINTER(c_vp)],
+    'bc_destroy': [c_vp],
+    'bc_set_potential': [c_vp, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp],
+    'bc_set_samples': [c_vp, c_vp, c_int, c_int, c_vp],
+    'bc_rowquad': [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
+    'bc_project_colsum': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
+    'bc_project_score': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    'bc_project_materialise': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp],
+    'bc_colsum_combine': [c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    'bc_core_resid': [c_vp, c_vp, c_dbl, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp],
+    'bc_core_maxcorr': [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_int, c_vp, c_vp],
+    'bc_core_grad': [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp],
+    'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
+    'bc_dense_rownorms': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp],
+    'bc_dense_center': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp],
+    'bc_dense_colsum': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp],
+    'bc_dense_score': [c_vp, c_int, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    'bc_dense_combine': [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
+    'bc_dense_gather': [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_vp],
+    'bc_transpose': [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp],
+    'bc_vec_step': [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp],
+    'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
+}
+PLAIN = {'bc_version': ([], c_int), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+         'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
+
+MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2
+KIND_LOGLIK, KIND_BETALIK, KIND_BETAGRAD = 0, 1, 2
+SCORE_FW, SCORE_GIGA, SCORE_CORR, SCORE_OMP = 0, 1, 2, 3
+VEC_GIGA_DIR, VEC_GIGA_STEP, VEC_RESID, VEC_FW_STEP = 0, 1, 2, 3
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Fails loudly if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError('libbetacores.so not found at %s -- build it with `python beta-cores_b200/build.py` '
+                              '(there is no CPU fallback)' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        for name, (args, res) in PLAIN.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        L = lib()
+        msg = L.bc_error_string(rc).decode()
+        if rc == -5:
+            msg += ' [cudaError %d]' % L.bc_last_cuda_error()
+        raise NativeError('%s failed: %s' % (what, msg))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def params8(values):
+    arr = (c_dbl * 8)()
+    for i, v in enumerate(values):
+        arr[i] = float(v)
+    return arr

@@ -1,0 +1,292 @@
+"""Greedy variational coreset construction on the device: the loop BetaCoreset and SparseVICoreset
+share (bayesiancoresets/coreset/bcores.py:27-150, sparsevi.py:26-136; individual-point mode).
+
+Per `build` iteration:
+  _select   : sampler -> Theta (host callback) ; pass A over the data rows = column sum of the centred
+              projection (bc_project_colsum) ; coreset rows materialised (M x S) ; residual ; pass B over the
+              data rows = per-row correlation + arg-max (bc_project_score) ; gate against the coreset rows.
+  _optimize : opt_itrs x [sampler -> Theta ; pass A ; coreset rows ; residual ; gradient ; ADAM step on device ;
+              weights back to the host for the next sampler call].
+The (n, S) matrix of the data rows is never formed when the projector's likelihood is a bound
+DevicePotential ("fused" tangent).  Opaque Python callbacks take the "dense" tangent: the callback's host
+matrix is uploaded and the same reductions run on it with the materialised-matrix kernels.
+
+Rows may be sharded over torch.distributed ranks (DeviceRows.row0 / n_total): per step the ranks exchange one
+2 x (S+1) double-double part, per selection one (score, position) pair (_shard.py).
+"""
+import ctypes
+import numpy as np
+import torch
+
+from .. import _native as nv
+from .._device import Engine, DeviceRows, ptr, stream_ptr, padded_ld
+from .._shard import Comm, local_subsample, merge_best, owner_of
+from ..util.opt import nn_opt, partial_nn_opt
+from .coreset import Coreset
+
+
+def _as_f64_2d(a):
+    return np.atleast_2d(np.asarray(a, dtype=np.float64))
+
+
+class _Tangent(object):
+    """Common device-side algebra once a column sum / coreset-row matrix is available."""
+
+    def __init__(self, owner):
+        self.o = owner
+        self.eng = Engine.get()
+        self.ctx = self.eng.ctx()
+        self.comm = Comm.current()
+        self.resid = None
+        self.out4 = self.eng.zeros(4)
+
+    # residual = scaling * colsum - w . Vc      (bcores.py:77 / :145); element S = its sum
+    def residual(self, colsum, scaling, Vc, w_dev):
+        S = colsum.shape[0]
+        if self.resid is None or self.resid.shape[0] != S+1:
+            self.resid = self.eng.empty(S+1)
+        M = 0 if Vc is None else Vc.shape[0]
+        nv.call('bc_core_resid', self.ctx, ptr(colsum), float(scaling), ptr(Vc), M, S, S if Vc is None else int(Vc.stride(0)),
+                ptr(w_dev), ptr(self.resid), stream_ptr())
+        return self.resid
+
+    def grad(self, Vc, resid, out):
+        nv.call('bc_core_grad', self.ctx, ptr(Vc), Vc.shape[0], Vc.shape[1], int(Vc.stride(0)), ptr(resid), ptr(out), stream_ptr())
+        return out
+
+    def core_max(self, Vc, resid, skip, out):
+        nv.call('bc_core_maxcorr', self.ctx, ptr(Vc), Vc.shape[0], Vc.shape[1], int(Vc.stride(0)), ptr(resid), int(skip), ptr(out),
+                stream_ptr())
+
+
+class _FusedTangent(_Tangent):
+    """likelihood = bound DevicePotential: everything stays on the device, nothing of size n x S exists."""
+
+    def __init__(self, owner, fused, rows):
+        super().__init__(owner)
+        self.fp = fused
+        self.rows = rows
+        self.parts = None
+        self.colsum_buf = None
+        self._theta_buf = None
+
+    def begin(self, w, p, beta):
+        prj = self.o.ll_projector
+        prj.update(w, p)                                   # host sampler: consumes np.random exactly like the reference
+        th = np.ascontiguousarray(np.atleast_2d(np.asarray(prj.samples, dtype=np.float64)))
+        if self._theta_buf is None or tuple(self._theta_buf.shape) != th.shape:
+            self._theta_buf = self.eng.empty(*th.shape)
+        self._theta_buf.copy_(torch.from_numpy(th))
+        self.comm.broadcast(self._theta_buf, 0)            # bit-identical samples on every rank
+        self.fp.configure(beta)
+        self.fp.set_samples(self._theta_buf)
+        self.S = self.fp.S
+
+    def _sub_local(self, sub_idcs):
+        if sub_idcs is None:
+            return None, None
+        pos, loc = local_subsample(sub_idcs, self.rows.row0, self.rows.n_local)
+        return pos, self.eng.upload(loc, dtype=torch.int64)
+
+    def colsum(self, sub_idcs):
+        """column sum of the centred projection of the (sub-sampled) data rows, all ranks combined"""
+        Sld = self.fp.Sld
+        if self.parts is None or self.parts.shape[0] != 2*Sld:
+            self.parts = self.eng.empty(2*Sld)
+            self.colsum_buf = self.eng.empty(self.S)
+        self._pos, self._loc = self._sub_local(sub_idcs)
+        self.fp.colsum_parts(self.rows, self._loc, out=self.parts)
+        allparts = self.comm.allgather(self.parts)
+        return self.fp.combine(allparts, self.comm.world, out=self.colsum_buf)
+
+    def core_rows(self, pts_rows):
+        V, _, _ = self.fp.materialise(pts_rows)
+        return V
+
+    def best_row(self, sub_idcs, resid):
+        """(score, position) of np.argmax(corrs) over the rows of the last colsum() call"""
+        n_here = self.rows.n_local if sub_idcs is None else int(self._loc.numel())
+        out = self.out4
+        if n_here > 0:
+            self.fp.score(self.rows, self._loc, resid, self.rows.row0 if sub_idcs is None else 0, out)
+            v = out[:2].cpu().numpy()
+            score = float(v[0])
+            p = int(v[1:2].view(np.int64)[0])
+            if sub_idcs is not None:
+                p = int(self._pos[p])                      # position in the global subsample list
+        else:
+            score, p = 0.0, -1
+        if self.comm.world == 1:
+            return score, p
+        mine = torch.tensor([score, float(p)], dtype=torch.float64, device=self.eng.device)
+        allc = self.comm.allgather(mine).cpu().numpy()
+        return merge_best((allc[r, 0], int(allc[r, 1])) for r in range(allc.shape[0]))
+
+
+class _DenseTangent(_Tangent):
+    """opaque Python likelihood callbacks: the projector's centred (n, S) host matrix is uploaded and reduced
+    with the materialised-matrix kernels (no sharding: the callback sees whole host arrays)."""
+
+    def __init__(self, owner, project):
+        super().__init__(owner)
+        self.project = project          # (pts) -> centred (n, S) host array, through the projector
+        if self.comm.world > 1:
+            raise NotImplementedError('row sharding needs a DevicePotential likelihood (opaque callbacks see host arrays)')
+
+    def begin(self, w, p, beta):
+        self.o.ll_projector.update(w, p)
+        self.beta = beta
+
+    def colsum(self, sub_idcs):
+        data = self.o.data
+        vecs = self.project(data if sub_idcs is None else data[sub_idcs])
+        self.V = self.eng.upload(_as_f64_2d(vecs))
+        n, S = self.V.shape
+        self.S = S
+        dd = self.eng.empty(2*(S+1))
+        nv.call('bc_dense_colsum', self.ctx, ptr(self.V), n, S, int(self.V.stride(0)), ptr(dd), stream_ptr())
+        out = self.eng.empty(S)
+        nv.call('bc_colsum_combine', self.ctx, ptr(dd), 1, S, ptr(out), stream_ptr())
+        return out
+
+    def core_rows(self, pts_host):
+        return self.eng.upload(_as_f64_2d(self.project(pts_host)))
+
+    def best_row(self, sub_idcs, resid):
+        n, S = self.V.shape
+        nv.call('bc_dense_score', self.ctx, nv.SCORE_CORR, ptr(self.V), n, S, int(self.V.stride(0)), None, ptr(resid), None, 0,
+                ptr(self.out4), None, stream_ptr())
+        v = self.out4[:2].cpu().numpy()
+        return float(v[0]), int(v[1:2].view(np.int64)[0])
+
+
+class GreedyVICoreset(Coreset):
+    """shared implementation; subclasses set `_uses_beta` and the projector method names"""
+    _uses_beta = False
+
+    def _init_greedy(self, data, ll_projector, n_subsample_select, n_subsample_opt, opt_itrs, step_sched, groups, initialized, kw):
+        self.ll_projector = ll_projector
+        if isinstance(data, DeviceRows):
+            self.rows = data
+            self.data = data                     # rows fetched on demand (data[f] -> DeviceRows.__getitem__)
+            n_total, ncols = data.n_total, data.ncols
+        else:
+            self.rows = None
+            self.data = data
+            n_total, ncols = data.shape[0], data.shape[1]
+        self._n_total, self._ncols = n_total, ncols
+        self.n_subsample_select = None if n_subsample_select is None else min(n_total, n_subsample_select)
+        self.n_subsample_opt = None if n_subsample_opt is None else min(n_total, n_subsample_opt)
+        self.step_sched = step_sched
+        self.opt_itrs = opt_itrs
+        self.groups = groups
+        self.selected_groups = []
+        if groups is not None:
+            raise NotImplementedError('group-wise selection is not on the accelerated path yet (SURVEY 8f.1)')
+        Coreset.__init__(self, **kw)
+        self.initialized = int(initialized)*len(self.wts)
+        self._tangent = None
+
+    # ---- tangent-space back-end ----
+    def _host_project(self, pts):
+        raise NotImplementedError
+
+    def _beta(self):
+        return None
+
+    def _get_tangent(self):
+        if self._tangent is None:
+            fused = self.ll_projector.fused(self._ncols) if hasattr(self.ll_projector, 'fused') else None
+            if fused is not None:
+                eng = Engine.get()
+                if self.rows is None:
+                    comm = Comm.current()
+                    if comm.world > 1:
+                        from .._shard import partition_rows
+                        r0, nl = partition_rows(self._n_total, comm.world, comm.rank)
+                        self.rows = DeviceRows(eng, self.data[r0:r0+nl], row0=r0, n_total=self._n_total)
+                    else:
+                        self.rows = DeviceRows(eng, self.data)
+                self._tangent = _FusedTangent(self, fused, self.rows)
+            else:
+                if self.rows is not None and not isinstance(self.data, np.ndarray):
+                    raise TypeError('DeviceRows data need a DevicePotential likelihood')
+                self._tangent = _DenseTangent(self, self._host_project)
+        return self._tangent
+
+    def _core_operand(self, t):
+        """coreset points in the form the tangent's core_rows() takes"""
+        if isinstance(t, _FusedTangent):
+            return DeviceRows(t.eng, self.pts.reshape(-1, self._ncols))
+        return self.pts
+
+    def _build(self, itrs, sz):
+        if self.size()+itrs > sz:
+            raise ValueError('%s._build(): # itrs + current size cannot exceed total desired size sz. # itr = %s cur sz: %s '
+                             'desired sz: %s' % (self.alg_name, itrs, self.size(), sz))
+        for i in range(itrs):
+            self._select()
+            self._optimize()
+
+    # bcores.py:75-90 / sparsevi.py:73-92
+    def _select(self):
+        t = self._get_tangent()
+        M = self.wts.shape[0]
+        t.begin(self.wts, self.pts, self._beta())
+        if self.n_subsample_select is None:
+            sub_idcs, scaling = None, 1.
+        else:
+            sub_idcs = np.random.randint(self._n_total, size=self.n_subsample_select)      # bcores.py:53
+            scaling = self._n_total/self.n_subsample_select
+        colsum = t.colsum(sub_idcs)
+        if self.pts.size > 0:
+            Vc = t.core_rows(self._core_operand(t))
+            w_dev = t.eng.upload(self.wts)
+            resid = t.residual(colsum, scaling, Vc, w_dev)
+            t.core_max(Vc, resid, 0, t.out4[2:3])
+        else:
+            Vc = None
+            resid = t.residual(colsum, scaling, None, None)
+        best, pos = t.best_row(sub_idcs, resid)
+        if Vc is not None:
+            core_best = float(t.out4[2:3].cpu().numpy()[0])
+            take = best > core_best                          # NaN on either side -> False, like `corrs.max() > corecorrs.max()`
+        else:
+            take = True
+        self._last_select = dict(best=best, pos=pos, take=bool(take))
+        if take and pos >= 0:
+            f = int(sub_idcs[pos]) if sub_idcs is not None else int(pos)
+            if f not in self.idcs:
+                row = np.asarray(self.data[f], dtype=np.float64).reshape(1, -1)
+                self.wts = np.append(self.wts, 0.)
+                self.idcs = np.append(self.idcs, np.int64(f)).astype(np.int64)
+                self.pts = np.vstack((self.pts.reshape(-1, self._ncols), row))
+
+    # bcores.py:141-150 / sparsevi.py:129-136
+    def _optimize(self):
+        t = self._get_tangent()
+        M = self.wts.shape[0]
+        if M == 0:
+            # the reference still calls the sampler (and draws the subsample) opt_itrs times
+            for i in range(self.opt_itrs):
+                self.ll_projector.update(self.wts, self.pts)
+                if self.n_subsample_opt is not None:
+                    np.random.randint(self._n_total, size=self.n_subsample_opt)
+            return
+        core = self._core_operand(t)
+        g = t.eng.empty(M)
+        beta = self._beta()
+        scaling = 1. if self.n_subsample_opt is None else self._n_total/self.n_subsample_opt
+
+        def grd(w_host, w_dev):
+            t.begin(w_host, self.pts, beta)
+            sub_idcs = None if self.n_subsample_opt is None else np.random.randint(self._n_total, size=self.n_subsample_opt)
+            colsum = t.colsum(sub_idcs)
+            Vc = t.core_rows(core)
+            resid = t.residual(colsum, scaling, Vc, w_dev)
+            return t.grad(Vc, resid, g)
+        grd.wants_device_iterate = True
+        self.wts = nn_opt(self.wts, grd, opt_itrs=self.opt_itrs, step_sched=self.step_sched)
+
+    def error(self):
+        return 0.       # the reference has no KL estimate either (bcores.py:152-153)

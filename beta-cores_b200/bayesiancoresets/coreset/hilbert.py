@@ -1,0 +1,78 @@
+"""HilbertCoreset: project once, then sparse non-negative least squares in the S-dimensional tangent space
+(drop-in for bayesiancoresets/coreset/hilbert.py:7-43).
+
+With a bound DevicePotential log-likelihood the (n, S) matrix is written by the materialise kernel straight
+into HBM, datapoint-major, together with its row norms and column sum, and the solver is attached to it
+without a host round trip.  Opaque callbacks go through project() (host matrix) like the reference.
+"""
+import numpy as np
+import torch
+
+from .. import _native as nv
+from .._device import Engine, DeviceRows, ptr, stream_ptr
+from ..snnls.giga import GIGA
+from ..snnls.snnls import SparseNNLS
+from .coreset import Coreset
+
+
+class HilbertCoreset(Coreset):
+    def __init__(self, data, ll_projector, n_subsample=None, snnls=GIGA, **kw):
+        if n_subsample is None:
+            sub_idcs = None
+        else:
+            n_subsample = min(data.shape[0], n_subsample)
+            sub_idcs = np.random.randint(data.shape[0], size=n_subsample)          # hilbert.py:14
+        fused = ll_projector.fused(data.shape[1]) if hasattr(ll_projector, 'fused') else None
+        device_solver = isinstance(snnls, type) and issubclass(snnls, SparseNNLS)
+        if fused is not None and device_solver:
+            eng = Engine.get()
+            rows = DeviceRows(eng, data if sub_idcs is None else data[sub_idcs])
+            fused.configure(None)
+            fused.set_samples(ll_projector.samples)
+            V, norms, _ = fused.materialise(rows, want_norms=True)
+            nh = norms.cpu().numpy()
+            keep = nh > 0.                                                           # hilbert.py:16
+            if not keep.all():
+                idx = eng.upload(np.nonzero(keep)[0].astype(np.int64), dtype=torch.int64)
+                Vk = eng.empty(max(int(keep.sum()), 1), V.shape[1])
+                nv.call('bc_dense_gather', eng.ctx(), ptr(V), int(V.stride(0)), V.shape[1], ptr(idx), int(keep.sum()), ptr(Vk),
+                        V.shape[1], stream_ptr())
+                V = Vk[:int(keep.sum())]
+                norms = eng.upload(nh[keep])
+            S = V.shape[1]
+            dd = eng.empty(2*(S+1))
+            b = eng.empty(S)
+            nv.call('bc_dense_colsum', eng.ctx(), ptr(V), V.shape[0], S, int(V.stride(0)), ptr(dd), stream_ptr())
+            nv.call('bc_colsum_combine', eng.ctx(), ptr(dd), 1, S, ptr(b), stream_ptr())
+            self.snnls = snnls.from_device(V, norms, b.cpu().numpy())               # hilbert.py:17: snnls(vecs.T, vecs.sum(0))
+        else:
+            vecs = ll_projector.project(data if sub_idcs is None else data[sub_idcs])
+            vecs = vecs[np.sqrt((vecs**2).sum(axis=1)) > 0., :]
+            self.snnls = snnls(vecs.T, vecs.sum(axis=0))
+        self.sub_idcs = sub_idcs
+        self.data = data
+        super().__init__(**kw)
+
+    def reset(self):
+        self.snnls.reset()
+        super().reset()
+
+    def _sync_from_solver(self):
+        w = self.snnls.weights()
+        self.wts = w[w > 0]
+        self.idcs = self.sub_idcs[w > 0] if self.sub_idcs is not None else np.where(w > 0)[0]
+        self.pts = self.data[self.idcs]
+
+    def _build(self, itrs, sz):
+        if self.snnls.size()+itrs > sz:
+            raise ValueError('%s._build(): # itrs + current size cannot exceed total desired size sz. # itr = %s cur sz: %s '
+                             'desired sz: %s' % (self.alg_name, itrs, self.snnls.size(), sz))
+        self.snnls.build(itrs)
+        self._sync_from_solver()
+
+    def _optimize(self):
+        self.snnls.optimize()
+        self._sync_from_solver()
+
+    def error(self):
+        return self.snnls.error()

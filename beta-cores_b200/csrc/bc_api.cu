@@ -1,0 +1,384 @@
+// beta-cores B200: extern "C" entry points (see include/betacores.h for the contract).
+#include <new>
+#include "../../include/betacores.h"
+#include "bc_kernels.h"
+
+using namespace bc;
+
+static thread_local int g_last_cuda = 0;
+
+struct bc_ctx {
+  int device = 0, sms = 0;
+  // potential
+  bool potential_set = false;
+  int model = 0, kind = 0, Dk = 0, Dc = 0, Dpad = 0, ss = 0, tile_cfg = 0, BM = 0, BN = 0;
+  size_t smem = 0;
+  ModelParams mp{};
+  const double* d_siginv = nullptr;
+  // samples
+  bool samples_set = false;
+  int S = 0;
+  double* B = nullptr;  // S x Dpad
+  double* colaux = nullptr;
+  double* bbar = nullptr;
+  size_t capB = 0, capS = 0, capD = 0;
+  // per-CTA partials
+  double* part_colsum = nullptr;
+  size_t cap_part = 0;
+  double* part_misc = nullptr;
+  double* dense_part = nullptr;
+  size_t cap_dense = 0;
+};
+
+static int cuda_fail(cudaError_t e) {
+  g_last_cuda = (int)e;
+  return BC_ERR_CUDA;
+}
+#define BC_CUDA(x)                                \
+  do {                                            \
+    cudaError_t e__ = (x);                        \
+    if (e__ != cudaSuccess) return cuda_fail(e__); \
+  } while (0)
+
+static int grow(double** p, size_t* cap, size_t need) {
+  if (need <= *cap) return BC_OK;
+  if (*p) BC_CUDA(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  BC_CUDA(cudaMalloc((void**)p, need * sizeof(double)));
+  *cap = need;
+  return BC_OK;
+}
+
+extern "C" {
+
+int bc_version(void) { return 100; }
+
+const char* bc_error_string(int code) {
+  switch (code) {
+    case BC_OK: return "ok";
+    case BC_ERR_ARG: return "bad argument";
+    case BC_ERR_ALIGN: return "alignment requirement violated (16-byte base pointer, even leading dimension)";
+    case BC_ERR_UNSUPPORTED: return "shape not supported by the kernels (feature dimension too large for one shared-memory tile)";
+    case BC_ERR_STATE: return "call order: bc_set_potential / bc_set_samples first";
+    case BC_ERR_CUDA: return "CUDA runtime error (see bc_last_cuda_error)";
+    default: return "unknown error";
+  }
+}
+
+int bc_last_cuda_error(void) { return g_last_cuda; }
+
+int bc_create(int device, bc_ctx** out) {
+  if (!out) return BC_ERR_ARG;
+  BC_CUDA(cudaSetDevice(device));
+  bc_ctx* c = new (std::nothrow) bc_ctx();
+  if (!c) return BC_ERR_ARG;
+  c->device = device;
+  cudaDeviceProp prop;
+  BC_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sms = prop.multiProcessorCount;
+  BC_CUDA(cudaMalloc((void**)&c->part_misc, (size_t)4 * 1024 * sizeof(double)));
+  *out = c;
+  return BC_OK;
+}
+
+int bc_destroy(bc_ctx* c) {
+  if (!c) return BC_OK;
+  cudaFree(c->B);
+  cudaFree(c->colaux);
+  cudaFree(c->bbar);
+  cudaFree(c->part_colsum);
+  cudaFree(c->part_misc);
+  cudaFree(c->dense_part);
+  delete c;
+  return BC_OK;
+}
+
+int bc_sm_count(const bc_ctx* c) { return c ? c->sms : 0; }
+int bc_colsum_ld(int S) { return S + 1; }
+
+int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_params, const double* d_siginv) {
+  if (!c || D <= 0 || !h_params) return BC_ERR_ARG;
+  if (model < 0 || model > 2 || kind < 0 || kind > 2) return BC_ERR_ARG;
+  if (kind == BC_KIND_BETAGRAD && model != BC_MODEL_GAUSSIAN) return BC_ERR_UNSUPPORTED;
+  if (model == BC_MODEL_GAUSSIAN && !d_siginv) return BC_ERR_ARG;
+  const int extra = (model == BC_MODEL_NEURLIN) ? 1 : 0;   // y rides along as column D
+  const int Dc = ((D + extra + 1) / 2) * 2;                 // bulk-copy width (16-byte multiple)
+  const int Dpad = ((Dc + 3) / 4) * 4;                      // contraction length (DMMA k = 4)
+  int BM, BN, ss;
+  size_t smem;
+  const int cfg = project_tile_config(Dpad, &BM, &BN, &ss, &smem);
+  if (cfg < 0) return BC_ERR_UNSUPPORTED;
+  c->model = model;
+  c->kind = kind;
+  c->Dk = D;
+  c->Dc = Dc;
+  c->Dpad = Dpad;
+  c->ss = ss;
+  c->tile_cfg = cfg;
+  c->BM = BM;
+  c->BN = BN;
+  c->smem = smem;
+  for (int i = 0; i < 8; ++i) c->mp.p[i] = h_params[i];
+  c->d_siginv = d_siginv;
+  c->potential_set = true;
+  c->samples_set = false;
+  return BC_OK;
+}
+
+int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* stream) {
+  if (!c || !d_theta || S <= 0 || ldt < c->Dk) return BC_ERR_ARG;
+  if (!c->potential_set) return BC_ERR_STATE;
+  int rc;
+  if ((rc = grow(&c->B, &c->capB, (size_t)S * c->Dpad))) return rc;
+  if ((rc = grow(&c->colaux, &c->capS, (size_t)S))) return rc;
+  if ((rc = grow(&c->bbar, &c->capD, (size_t)c->Dpad + 1))) return rc;
+  if ((rc = grow(&c->part_colsum, &c->cap_part, (size_t)c->sms * 2 * bc_colsum_ld(S)))) return rc;
+  c->S = S;
+  BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->B, c->Dpad, c->colaux, c->bbar,
+                                 (cudaStream_t)stream));
+  c->samples_set = true;
+  return BC_OK;
+}
+
+int bc_rowquad(bc_ctx* c, const double* d_X, int64_t n, int64_t ldx, double* d_out, void* stream) {
+  if (!c || !d_X || !d_out || n < 0) return BC_ERR_ARG;
+  if (!c->potential_set || c->model != BC_MODEL_GAUSSIAN) return BC_ERR_STATE;
+  BC_CUDA(launch_rowquad(d_X, n, c->Dk, ldx, c->d_siginv, d_out, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+static int project_common(bc_ctx* c, int mode, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n,
+                          const double* d_rowaux, ProjArgs& P, int* grid) {
+  if (!c || !d_X || n < 0) return BC_ERR_ARG;
+  if (!c->potential_set || !c->samples_set) return BC_ERR_STATE;
+  if ((reinterpret_cast<uintptr_t>(d_X) & 15) || (ldx & 1) || ldx < c->Dc) return BC_ERR_ALIGN;
+  if (c->model == BC_MODEL_GAUSSIAN && !d_rowaux) return BC_ERR_ARG;
+  P.A = d_X;
+  P.lda = ldx;
+  P.rows = reinterpret_cast<const long long*>(d_rows);
+  P.n = n;
+  P.idx_offset = 0;
+  P.B = c->B;
+  P.ldb = c->Dpad;
+  P.S = c->S;
+  P.Dk = c->Dk;
+  P.Dc = c->Dc;
+  P.Dpad = c->Dpad;
+  P.ss = c->ss;
+  P.colaux = (c->model == BC_MODEL_GAUSSIAN) ? c->colaux : nullptr;
+  P.rowaux = (c->model == BC_MODEL_GAUSSIAN) ? d_rowaux : nullptr;
+  P.bbar = c->bbar;
+  P.mp = c->mp;
+  P.part_colsum = c->part_colsum;
+  P.part_misc = c->part_misc;
+  P.Sld = bc_colsum_ld(c->S);
+  P.resid = nullptr;
+  P.scores = nullptr;
+  P.V = nullptr;
+  P.ldv = 0;
+  P.norms = nullptr;
+  P.raw = 0;
+  const int64_t tiles = (n + c->BM - 1) / c->BM;
+  *grid = (int)(tiles < c->sms ? tiles : c->sms);
+  (void)mode;
+  return BC_OK;
+}
+
+int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                      double* d_out_dd, void* stream) {
+  ProjArgs P;
+  int grid, rc;
+  if (!d_out_dd) return BC_ERR_ARG;
+  if ((rc = project_common(c, MODE_COLSUM, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
+    return BC_OK;
+  }
+  BC_CUDA(launch_project(P, c->model, c->kind, MODE_COLSUM, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
+  return BC_OK;
+}
+
+int bc_project_score(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                     const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream) {
+  ProjArgs P;
+  int grid, rc;
+  if (!d_resid || !d_best || n <= 0) return BC_ERR_ARG;
+  if ((rc = project_common(c, MODE_SCORE, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  P.resid = d_resid;
+  P.scores = d_scores;
+  P.idx_offset = idx_offset;
+  cudaStream_t st = (cudaStream_t)stream;
+  BC_CUDA(launch_project(P, c->model, c->kind, MODE_SCORE, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
+  return BC_OK;
+}
+
+int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                           double* d_V, int64_t ldv, double* d_norms, double* d_out_dd, int raw, void* stream) {
+  ProjArgs P;
+  int grid, rc;
+  if (!d_V) return BC_ERR_ARG;
+  if ((rc = project_common(c, MODE_MATERIALISE, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  if (ldv < c->S) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    if (d_out_dd) BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
+    return BC_OK;
+  }
+  P.V = d_V;
+  P.ldv = ldv;
+  P.norms = raw ? nullptr : d_norms;
+  P.raw = raw ? 1 : 0;
+  BC_CUDA(launch_project(P, c->model, c->kind, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
+  if (d_out_dd)
+    BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_MATERIALISE, st));
+  return BC_OK;
+}
+
+int bc_colsum_combine(bc_ctx* c, const double* d_parts, int nparts, int S, double* d_out, void* stream) {
+  if (!c || !d_parts || !d_out || nparts <= 0 || S <= 0) return BC_ERR_ARG;
+  BC_CUDA(launch_colsum_combine(d_parts, nparts, S, bc_colsum_ld(S), d_out, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_core_resid(bc_ctx* c, const double* d_colsum, double scaling, const double* d_Vc, int M, int S, int64_t ldv,
+                  const double* d_w, double* d_resid, void* stream) {
+  if (!c || !d_colsum || !d_resid || M < 0 || S <= 0 || (M > 0 && (!d_Vc || !d_w))) return BC_ERR_ARG;
+  BC_CUDA(launch_core_resid(d_colsum, scaling, d_Vc, M, S, ldv, d_w, d_resid, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_core_maxcorr(bc_ctx* c, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, int skip, double* d_out,
+                    void* stream) {
+  if (!c || !d_Vc || !d_resid || !d_out || M <= 0 || S <= 0) return BC_ERR_ARG;
+  BC_CUDA(launch_core_maxcorr(d_Vc, M, S, ldv, d_resid, skip, d_out, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_core_grad(bc_ctx* c, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, double* d_grad, void* stream) {
+  if (!c || !d_Vc || !d_resid || !d_grad || M <= 0 || S <= 0) return BC_ERR_ARG;
+  BC_CUDA(launch_core_grad(d_Vc, M, S, ldv, d_resid, d_grad, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_adam_step(bc_ctx* c, const double* d_g, double* d_x, double* d_m1, double* d_m2, int n, double lr, double b1, double b2,
+                 double c1, double c2, double eps, const unsigned char* d_nn_mask, void* stream) {
+  if (!c || !d_g || !d_x || !d_m1 || !d_m2 || n < 0) return BC_ERR_ARG;
+  BC_CUDA(launch_adam(d_g, d_x, d_m1, d_m2, n, lr, b1, b2, c1, c2, eps, d_nn_mask, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_dense_rownorms(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream) {
+  if (!c || !d_V || !d_norms || n < 0 || S <= 0) return BC_ERR_ARG;
+  BC_CUDA(launch_dense_rowstats(d_V, n, S, ldv, nullptr, 0, d_norms, nullptr, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+static int dense_ws(bc_ctx* c, int S) {
+  const size_t need = (size_t)c->sms * 8 * (size_t)(S > 4 ? S : 4);
+  return grow(&c->dense_part, &c->cap_dense, need);
+}
+
+int bc_dense_center(bc_ctx* c, double* d_V, int64_t n, int S, int64_t ldv, void* stream) {
+  if (!c || !d_V || n < 0 || S <= 0) return BC_ERR_ARG;
+  BC_CUDA(launch_dense_center(d_V, n, S, ldv, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_dense_colsum(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_out_dd, void* stream) {
+  if (!c || !d_V || !d_out_dd || n < 0 || S <= 0) return BC_ERR_ARG;
+  int rc;
+  if ((rc = dense_ws(c, S))) return rc;
+  BC_CUDA(launch_dense_colsum(d_V, n, S, ldv, c->dense_part, c->sms * 8, d_out_dd, bc_colsum_ld(S), (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_dense_score(bc_ctx* c, int mode, const double* d_V, int64_t n, int S, int64_t ldv, const double* d_norms,
+                   const double* d_u, const unsigned char* d_active, int64_t idx_offset, double* d_out, double* d_scores,
+                   void* stream) {
+  if (!c || !d_V || !d_u || !d_out || n <= 0 || S <= 0 || mode < 0 || mode > 3) return BC_ERR_ARG;
+  if (mode != BC_SCORE_CORR && !d_norms) return BC_ERR_ARG;
+  if (mode == BC_SCORE_OMP && !d_active) return BC_ERR_ARG;
+  if ((size_t)S * 2 * sizeof(double) > 200 * 1024) return BC_ERR_UNSUPPORTED;
+  int rc;
+  if ((rc = dense_ws(c, S))) return rc;
+  BC_CUDA(launch_dense_score(d_V, n, S, ldv, d_norms, d_u, mode, d_active, idx_offset, c->dense_part, c->sms * 8, d_out, d_scores,
+                             (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_dense_combine(bc_ctx* c, const double* d_V, int64_t ldv, int S, const int64_t* d_idx, const double* d_w, int m,
+                     double* d_out, void* stream) {
+  if (!c || !d_V || !d_out || S <= 0 || m < 0 || (m > 0 && (!d_idx || !d_w))) return BC_ERR_ARG;
+  BC_CUDA(launch_dense_combine(d_V, ldv, S, reinterpret_cast<const long long*>(d_idx), d_w, m, d_out, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_dense_gather(bc_ctx* c, const double* d_V, int64_t ldv, int S, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo,
+                    void* stream) {
+  if (!c || !d_V || !d_out || S <= 0 || m < 0 || (m > 0 && !d_idx)) return BC_ERR_ARG;
+  BC_CUDA(launch_dense_gather(d_V, ldv, S, reinterpret_cast<const long long*>(d_idx), m, d_out, ldo, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_transpose(bc_ctx* c, const double* d_A, int64_t rows, int64_t cols, int64_t lda, double* d_out, int64_t ldo, void* stream) {
+  if (!c || !d_A || !d_out || rows < 0 || cols < 0) return BC_ERR_ARG;
+  BC_CUDA(launch_transpose(d_A, rows, cols, lda, d_out, ldo, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_vec_step(bc_ctx* c, int op, const double* d_xw, const double* d_xf, const double* d_b, int S, double aux, double* d_u,
+                double* d_out, void* stream) {
+  if (!c || !d_xw || !d_b || !d_out || S <= 0 || op < 0 || op > 3) return BC_ERR_ARG;
+  if ((op == BC_VEC_GIGA_STEP || op == BC_VEC_FW_STEP) && !d_xf) return BC_ERR_ARG;
+  if (op == BC_VEC_GIGA_DIR && !d_u) return BC_ERR_ARG;
+  BC_CUDA(launch_vec_step(op, d_xw, d_xf, d_b, S, aux, d_u, d_out, (cudaStream_t)stream));
+  return BC_OK;
+}
+
+int bc_host_project(int device, int model, int kind, int D, const double* h_params, const double* h_siginv, const double* h_X,
+                    int64_t n, int64_t ldx_h, const double* h_theta, int S, double* h_V, int centred) {
+  if (!h_X || !h_theta || !h_V || n < 0 || S <= 0 || D <= 0) return BC_ERR_ARG;
+  bc_ctx* c = nullptr;
+  int rc = bc_create(device, &c);
+  if (rc) return rc;
+  const int extra = (model == BC_MODEL_NEURLIN) ? 1 : 0;
+  if (ldx_h < D + extra) {
+    bc_destroy(c);
+    return BC_ERR_ARG;
+  }
+  const int64_t ldx = ((D + extra + 3) / 4) * 4;  // padded device layout
+  double *dX = nullptr, *dT = nullptr, *dV = nullptr, *dSig = nullptr, *dRa = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto fail = [&](int code) {
+    cudaFree(dX); cudaFree(dT); cudaFree(dV); cudaFree(dSig); cudaFree(dRa);
+    bc_destroy(c);
+    return code;
+  };
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  if ((e = cudaMalloc((void**)&dX, nn * ldx * 8)) != cudaSuccess) return fail(cuda_fail(e));
+  if ((e = cudaMalloc((void**)&dT, (size_t)S * D * 8)) != cudaSuccess) return fail(cuda_fail(e));
+  if ((e = cudaMalloc((void**)&dV, nn * S * 8)) != cudaSuccess) return fail(cuda_fail(e));
+  if ((e = cudaMemset(dX, 0, nn * ldx * 8)) != cudaSuccess) return fail(cuda_fail(e));
+  if (n > 0 && (e = cudaMemcpy2D(dX, ldx * 8, h_X, ldx_h * 8, (size_t)(D + extra) * 8, n, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail(cuda_fail(e));
+  if ((e = cudaMemcpy(dT, h_theta, (size_t)S * D * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e));
+  if (model == BC_MODEL_GAUSSIAN) {
+    if (!h_siginv) return fail(BC_ERR_ARG);
+    if ((e = cudaMalloc((void**)&dSig, (size_t)D * D * 8)) != cudaSuccess) return fail(cuda_fail(e));
+    if ((e = cudaMemcpy(dSig, h_siginv, (size_t)D * D * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e));
+    if ((e = cudaMalloc((void**)&dRa, nn * 8)) != cudaSuccess) return fail(cuda_fail(e));
+  }
+  if ((rc = bc_set_potential(c, model, kind, D, h_params, dSig))) return fail(rc);
+  if ((rc = bc_set_samples(c, dT, S, D, nullptr))) return fail(rc);
+  if (model == BC_MODEL_GAUSSIAN && (rc = bc_rowquad(c, dX, n, ldx, dRa, nullptr))) return fail(rc);
+  if ((rc = bc_project_materialise(c, dX, ldx, nullptr, n, dRa, dV, S, nullptr, nullptr, centred ? 0 : 1, nullptr))) return fail(rc);
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(cuda_fail(e));
+  if (n > 0 && (e = cudaMemcpy(h_V, dV, (size_t)n * S * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(cuda_fail(e));
+  return fail(BC_OK);
+}
+
+}  // extern "C"

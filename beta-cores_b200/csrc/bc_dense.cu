@@ -1,0 +1,413 @@
+// beta-cores B200: stage 2 on a MATERIALISED n x S matrix V (row n = datapoint n's centred
+// projection, contiguous) -- the layout HilbertCoreset hands to the snnls solvers
+// (bayesiancoresets/coreset/hilbert.py:17: A = vecs.T) -- plus the S-length vector steps of
+// GIGA / Frank-Wolfe / OrthoPursuit (bayesiancoresets/snnls/{giga,frankwolfe,orthopursuit}.py).
+// The n x S passes are HBM-bound: one warp per row, 16-byte coalesced loads, the S-vector(s) in
+// shared memory, warp-shuffle + block arg-max, two-phase grid reduction (no float atomics).
+#include "bc_kernels.h"
+
+namespace bc {
+
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ double block_sum_d(double x, double* red) {
+  x = warp_sum(x);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    double y = (l < nw) ? red[l] : 0.0;
+    y = warp_sum(y);
+    if (l == 0) red[32] = y;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// per-warp row reduction: up to three accumulators (v.u0, v.u1, v.v)
+template <int NU, bool NORM>
+__device__ __forceinline__ void row_dots(const double* __restrict__ v, int S, const double* __restrict__ u_s, int lane, bool vec_ok,
+                                         double& d0, double& d1, double& n2) {
+  d0 = d1 = n2 = 0.0;
+  if (vec_ok) {
+    for (int c = lane * 2; c < S; c += 64) {  // S even and row 16-byte aligned
+      const double2 x = ld_stream2(v + c);
+      d0 = fma(x.x, u_s[c], d0);
+      d0 = fma(x.y, u_s[c + 1], d0);
+      if (NU > 1) {
+        d1 = fma(x.x, u_s[S + c], d1);
+        d1 = fma(x.y, u_s[S + c + 1], d1);
+      }
+      if (NORM) {
+        n2 = fma(x.x, x.x, n2);
+        n2 = fma(x.y, x.y, n2);
+      }
+    }
+  } else {
+    for (int c = lane; c < S; c += 32) {
+      const double x = v[c];
+      d0 = fma(x, u_s[c], d0);
+      if (NU > 1) d1 = fma(x, u_s[S + c], d1);
+      if (NORM) n2 = fma(x, x, n2);
+    }
+  }
+  d0 = warp_sum(d0);
+  if (NU > 1) d1 = warp_sum(d1);
+  if (NORM) n2 = warp_sum(n2);
+}
+
+// ------------------------------------------------------------- row norms ----
+// norms[r] = sqrt(sum_s V[r][s]^2)        giga.py:10, frankwolfe.py:10, hilbert.py:16
+__global__ void k_dense_rownorms(const double* __restrict__ V, long long n, int S, long long ldv, double* __restrict__ norms) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool vec_ok = (S % 2 == 0) && (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n; r += (long long)gridDim.x * nw) {
+    const double* v = V + r * ldv;
+    double n2 = 0.0;
+    if (vec_ok) {
+      for (int c = lane * 2; c < S; c += 64) {
+        const double2 x = ld_stream2(v + c);
+        n2 = fma(x.x, x.x, n2);
+        n2 = fma(x.y, x.y, n2);
+      }
+    } else {
+      for (int c = lane; c < S; c += 32) n2 = fma(v[c], v[c], n2);
+    }
+    n2 = warp_sum(n2);
+    if (lane == 0) norms[r] = sqrt(n2);
+  }
+}
+
+cudaError_t launch_dense_rowstats(const double* V, long long n, int S, long long ldv, const double*, int, double* norms, double*,
+                                  cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_dense_rownorms<<<(int)blocks, 256, 0, st>>>(V, n, S, ldv, norms);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------ column sums ---
+// part[b][s] = sum over block b's rows; then dd-combine over blocks in fixed order.
+__global__ void k_dense_colsum_part(const double* __restrict__ V, long long n, int S, long long ldv, double* __restrict__ part) {
+  const long long rows_per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per;
+  long long r1 = r0 + rows_per;
+  if (r1 > n) r1 = n;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long long r = r0;
+    for (; r + 3 < r1; r += 4) {
+      a0 += V[r * ldv + s];
+      a1 += V[(r + 1) * ldv + s];
+      a2 += V[(r + 2) * ldv + s];
+      a3 += V[(r + 3) * ldv + s];
+    }
+    for (; r < r1; ++r) a0 += V[r * ldv + s];
+    part[(size_t)blockIdx.x * S + s] = (a0 + a1) + (a2 + a3);
+  }
+}
+__global__ void k_dense_colsum_fin(const double* __restrict__ part, int nparts, int S, int Sld, double* __restrict__ out_dd) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > S) return;
+  dd a = {0.0, 0.0};
+  if (s < S)
+    for (int p = 0; p < nparts; ++p) a = dd_add_d(a, part[(size_t)p * S + s]);
+  out_dd[s] = a.hi;  // element S (sum of row means) is 0: V is already centred
+  out_dd[Sld + s] = a.lo;
+}
+
+cudaError_t launch_dense_colsum(const double* V, long long n, int S, long long ldv, double* part, int nparts, double* out_dd,
+                                int Sld, cudaStream_t st) {
+  if (n < nparts) nparts = n > 0 ? (int)n : 1;
+  k_dense_colsum_part<<<nparts, 256, 0, st>>>(V, n, S, ldv, part);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_dense_colsum_fin<<<(S + 1 + 127) / 128, 128, 0, st>>>(part, nparts, S, Sld, out_dd);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------- score + arg-max ----
+// mode 0 (FW)  : score = (V_r . u0) / norm_r                                   frankwolfe.py:15-17
+// mode 1 (GIGA): s0 = V_r.u0/norm_r, s1 = V_r.u1/norm_r;
+//                ok = s1 > -1+1e-14 and 1-s1^2 > 0; score = s0 / (ok ? sqrt(1-s1^2) : inf)   giga.py:31-38
+// mode 2 (CORR): score = (V_r . u0) / sqrt(sum V_r^2) / S                      bcores.py:78 (black-box path)
+// mode 3 (OMP) : as FW, plus best of (-score) over rows with active[r] != 0    orthopursuit.py:17-35
+// part: [nblocks][4] = {best v, best i, neg-best v, neg-best i}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dense_score(const double* __restrict__ V, long long n, int S, long long ldv,
+                                                     const double* __restrict__ norms, const double* __restrict__ u,
+                                                     const unsigned char* __restrict__ active, long long idx_offset,
+                                                     double* __restrict__ part, double* __restrict__ scores) {
+  extern __shared__ double u_s[];  // NU * S
+  constexpr int NU = (MODE == 1) ? 2 : 1;
+  __shared__ double bv[8][2];
+  __shared__ long long bi[8][2];
+  for (int i = threadIdx.x; i < NU * S; i += blockDim.x) u_s[i] = u[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool vec_ok = (S % 2 == 0) && (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+  Best best = {0.0, -1}, nbest = {0.0, -1};
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n; r += (long long)gridDim.x * nw) {
+    double d0, d1, n2;
+    row_dots<NU, MODE == 2>(V + r * ldv, S, u_s, lane, vec_ok, d0, d1, n2);
+    double score;
+    if (MODE == 2) {
+      score = d0 / sqrt(n2) / (double)S;
+    } else {
+      const double nr = norms[r];
+      const double s0 = d0 / nr;
+      if (MODE == 1) {
+        const double s1 = d1 / nr;
+        const bool ok = (s1 > -1.0 + 1e-14) && (1.0 - s1 * s1 > 0.0);
+        score = s0 / (ok ? sqrt(1.0 - s1 * s1) : INFINITY);
+      } else {
+        score = s0;
+      }
+    }
+    if (lane == 0) {
+      if (scores) scores[r] = score;
+      Best c = {score, idx_offset + r};
+      best = best_merge(best, c);
+      if (MODE == 3 && active[r]) {
+        Best cn = {-score, idx_offset + r};
+        nbest = best_merge(nbest, cn);
+      }
+    }
+  }
+  if (lane == 0) {
+    bv[warp][0] = best.v; bi[warp][0] = best.i;
+    bv[warp][1] = nbest.v; bi[warp][1] = nbest.i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) {
+      Best o = {bv[w][0], bi[w][0]}, on = {bv[w][1], bi[w][1]};
+      best = best_merge(best, o);
+      nbest = best_merge(nbest, on);
+    }
+    part[blockIdx.x * 4 + 0] = best.v;
+    part[blockIdx.x * 4 + 1] = __longlong_as_double(best.i);
+    part[blockIdx.x * 4 + 2] = nbest.v;
+    part[blockIdx.x * 4 + 3] = __longlong_as_double(nbest.i);
+  }
+}
+__global__ void k_dense_score_fin(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+  Best b = {0.0, -1}, nb = {0.0, -1};
+  for (int p = 0; p < nparts; ++p) {  // fixed order; nparts is a few hundred
+    Best o = {part[p * 4 + 0], __double_as_longlong(part[p * 4 + 1])};
+    Best on = {part[p * 4 + 2], __double_as_longlong(part[p * 4 + 3])};
+    b = best_merge(b, o);
+    nb = best_merge(nb, on);
+  }
+  out[0] = b.v;
+  out[1] = __longlong_as_double(b.i);
+  out[2] = nb.v;
+  out[3] = __longlong_as_double(nb.i);
+}
+
+cudaError_t launch_dense_score(const double* V, long long n, int S, long long ldv, const double* norms, const double* u, int mode,
+                               const unsigned char* active, long long idx_offset, double* part, int nparts, double* out,
+                               double* scores, cudaStream_t st) {
+  long long want = (n + 7) / 8;
+  if (want < 1) want = 1;
+  if (want < nparts) nparts = (int)want;
+  const size_t smem = (size_t)((mode == 1) ? 2 : 1) * S * sizeof(double);
+  switch (mode) {
+    case 0: k_dense_score<0><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
+    case 1: k_dense_score<1><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
+    case 2: k_dense_score<2><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
+    default: k_dense_score<3><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_dense_score_fin<<<1, 1, 0, st>>>(part, nparts, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------- small row helpers --
+// out[s] = sum_m w[m] V[idx[m]][s]      (= A.dot(w) restricted to the selected columns; giga.py:21)
+__global__ void k_dense_combine(const double* __restrict__ V, long long ldv, int S, const long long* __restrict__ idx,
+                                const double* __restrict__ w, int m, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double acc = 0.0;
+  for (int i = 0; i < m; ++i) acc = fma(w[i], V[idx[i] * ldv + s], acc);
+  out[s] = acc;
+}
+cudaError_t launch_dense_combine(const double* V, long long ldv, int S, const long long* idx, const double* w, int m, double* out,
+                                 cudaStream_t st) {
+  k_dense_combine<<<(S + 127) / 128, 128, 0, st>>>(V, ldv, S, idx, w, m, out);
+  return cudaGetLastError();
+}
+
+// V[r][:] -= mean(V[r][:])      projector.py:26 / :55 for black-box (host callback) potentials
+__global__ void k_dense_center(double* __restrict__ V, long long n, int S, long long ldv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n; r += (long long)gridDim.x * nw) {
+    double* v = V + r * ldv;
+    double a = 0.0;
+    for (int c = lane; c < S; c += 32) a += v[c];
+    a = warp_sum(a) / (double)S;
+    for (int c = lane; c < S; c += 32) v[c] -= a;
+  }
+}
+cudaError_t launch_dense_center(double* V, long long n, int S, long long ldv, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_dense_center<<<(int)blocks, 256, 0, st>>>(V, n, S, ldv);
+  return cudaGetLastError();
+}
+
+__global__ void k_dense_gather(const double* __restrict__ V, long long ldv, int S, const long long* __restrict__ idx, long long m,
+                               double* __restrict__ out, long long ldo) {
+  for (long long r = blockIdx.x; r < m; r += gridDim.x) {
+    const double* src = V + idx[r] * ldv;
+    double* dst = out + r * ldo;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) dst[s] = src[s];
+  }
+}
+cudaError_t launch_dense_gather(const double* V, long long ldv, int S, const long long* idx, long long m, double* out, long long ldo,
+                                cudaStream_t st) {
+  if (m <= 0) return cudaSuccess;
+  long long blocks = m < 148 * 16 ? m : 148 * 16;
+  k_dense_gather<<<(int)blocks, 128, 0, st>>>(V, ldv, S, idx, m, out, ldo);
+  return cudaGetLastError();
+}
+
+// out[c][r] = A[r][c]   (user-supplied (S, N) C-contiguous A -> datapoint-major N x S)
+__global__ void k_transpose(const double* __restrict__ A, long long rows, long long cols, long long lda, double* __restrict__ out,
+                            long long ldo) {
+  __shared__ double tile[32][33];
+  const long long bx = (long long)blockIdx.x * 32, by = (long long)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = by + j, c = bx + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = A[r * lda + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long c = bx + j, r = by + threadIdx.x;
+    if (r < rows && c < cols) out[c * ldo + r] = tile[threadIdx.x][j];
+  }
+}
+cudaError_t launch_transpose(const double* A, long long rows, long long cols, long long lda, double* out, long long ldo,
+                             cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_transpose<<<grid, dim3(32, 8), 0, st>>>(A, rows, cols, lda, out, ldo);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------- S-length solver steps ---
+// One CTA.  out layout (doubles):
+//  op 0 GIGA direction (giga.py:21-30): in xw (raw A w), bn -> u[0:S] = cdir/|cdir|, u[S:2S] = xw/nw;
+//        out[0] = cdirnrm, out[1] = nw
+//  op 1 GIGA step (giga.py:42-62): in xw (raw), xf, bn, bnorm=aux -> out[0]=gA, out[1]=gB, out[2]=alpha, out[3]=beta
+//  op 2 residual (frankwolfe.py:16, orthopursuit.py:18): u = b - xw; out[0] = sqrt(sum (xw-b)^2)  (snnls.py:28-29)
+//  op 3 FW step (frankwolfe.py:30-31): in xw, xf, b, aux = nsum/nf -> out[0]=gammanum, out[1]=gammadenom
+__global__ void k_vec_step(int op, const double* __restrict__ xw, const double* __restrict__ xf, const double* __restrict__ b, int S,
+                           double aux, double* __restrict__ u, double* __restrict__ out) {
+  __shared__ double red[33];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (op == 0) {
+    double a = 0.0;
+    for (int s = tid; s < S; s += nt) a = fma(xw[s], xw[s], a);
+    double nw = sqrt(block_sum_d(a, red));
+    nw = (nw == 0.0) ? 1.0 : nw;
+    double d = 0.0;
+    for (int s = tid; s < S; s += nt) d = fma(b[s], xw[s] / nw, d);
+    d = block_sum_d(d, red);
+    double c2 = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double xn = xw[s] / nw;
+      const double c = b[s] - d * xn;
+      u[s] = c;
+      u[S + s] = xn;
+      c2 = fma(c, c, c2);
+    }
+    const double cn = sqrt(block_sum_d(c2, red));
+    for (int s = tid; s < S; s += nt) u[s] = u[s] / cn;
+    if (tid == 0) {
+      out[0] = cn;
+      out[1] = nw;
+    }
+  } else if (op == 1) {
+    double a = 0.0, f2 = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      a = fma(xw[s], xw[s], a);
+      f2 = fma(xf[s], xf[s], f2);
+    }
+    double nw = sqrt(block_sum_d(a, red));
+    nw = (nw == 0.0) ? 1.0 : nw;
+    const double nf = sqrt(block_sum_d(f2, red));
+    double dbf = 0.0, dbw = 0.0, dwf = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double wn = xw[s] / nw, fn = xf[s] / nf;
+      dbf = fma(b[s], fn, dbf);
+      dbw = fma(b[s], wn, dbw);
+      dwf = fma(wn, fn, dwf);
+    }
+    dbf = block_sum_d(dbf, red);
+    dbw = block_sum_d(dbw, red);
+    dwf = block_sum_d(dwf, red);
+    const double gA = dbf - dbw * dwf;
+    const double gB = dbw - dbf * dwf;
+    const double ca = gB / (gA + gB) / nw;
+    const double cb = gA / (gA + gB) / nf;
+    double x2 = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double x = ca * xw[s] + cb * xf[s];
+      x2 = fma(x, x, x2);
+    }
+    const double nx = sqrt(block_sum_d(x2, red));
+    double xb = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double x = ca * xw[s] + cb * xf[s];
+      xb = fma(x / nx, b[s], xb);
+    }
+    xb = block_sum_d(xb, red);
+    const double scale = aux / nx * xb;  // aux = bnorm
+    if (tid == 0) {
+      out[0] = gA;
+      out[1] = gB;
+      out[2] = ca * scale;
+      out[3] = cb * scale;
+    }
+  } else if (op == 2) {
+    double e2 = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double d = xw[s] - b[s];
+      if (u) u[s] = b[s] - xw[s];
+      e2 = fma(d, d, e2);
+    }
+    e2 = block_sum_d(e2, red);
+    if (tid == 0) out[0] = sqrt(e2);
+  } else {
+    double num = 0.0, den = 0.0;
+    for (int s = tid; s < S; s += nt) {
+      const double dlt = aux * xf[s] - xw[s];
+      num = fma(dlt, b[s] - xw[s], num);
+      den = fma(dlt, dlt, den);
+    }
+    num = block_sum_d(num, red);
+    den = block_sum_d(den, red);
+    if (tid == 0) {
+      out[0] = num;
+      out[1] = den;
+    }
+  }
+}
+
+cudaError_t launch_vec_step(int op, const double* xw, const double* xf, const double* b, int S, double aux, double* u, double* out,
+                            cudaStream_t st) {
+  k_vec_step<<<1, 256, 0, st>>>(op, xw, xf, b, S, aux, u, out);
+  return cudaGetLastError();
+}
+
+}  // namespace bc

@@ -1,0 +1,82 @@
+// beta-cores B200: internal launch interface between the kernel translation units and bc_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "bc_models.cuh"
+
+namespace bc {
+
+constexpr int kComputeWarps = 8;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kThreads = kComputeThreads + 32;  // + one TMA producer warp
+constexpr size_t kMaxSmem = 227 * 1024;
+
+enum : int { MODE_COLSUM = 0, MODE_SCORE = 1, MODE_MATERIALISE = 2 };
+
+struct ProjArgs {
+  // data rows (A operand): row r of the processed list is A + (rows ? rows[r] : r) * lda
+  const double* A;
+  long long lda;
+  const long long* rows;  // optional gather list (device), length n
+  long long n;            // rows to process
+  long long idx_offset;   // added to the reported arg-max position (row-sharded multi-GPU)
+  // prepared samples (B operand): S x ldb, zero beyond Dk, ldb == Dpad
+  const double* B;
+  int ldb;
+  int S, Dk, Dc, Dpad, ss;
+  const double* colaux;  // [S] or null
+  const double* rowaux;  // indexed by absolute row id, or null (neural-linear reads column Dk of the row)
+  const double* bbar;    // [Dpad+1] mean prepared sample (pivot); element Dpad = mean of colaux
+  ModelParams mp;
+  // per-CTA partials
+  double* part_colsum;  // [grid][2][Sld]
+  double* part_misc;    // [grid][4]
+  int Sld;
+  // MODE_SCORE
+  const double* resid;  // [S+1]: residual, then its sum
+  double* scores;       // optional [n]
+  // MODE_MATERIALISE
+  double* V;
+  long long ldv;
+  double* norms;  // optional [n]
+  int raw;        // 1: write the un-centred potential f itself (no pivot, no mean subtraction)
+};
+
+int project_tile_config(int Dpad, int* BM, int* BN, int* ss, size_t* smem);
+cudaError_t launch_project(const ProjArgs& P, int model, int kind, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld, double* out_dd,
+                                    double* out_best, int mode, cudaStream_t st);
+
+// ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----
+cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,
+                                   double* colaux, double* bbar, cudaStream_t st);
+cudaError_t launch_rowquad(const double* X, long long n, int D, long long ldx, const double* siginv, double* out, cudaStream_t st);
+cudaError_t launch_colsum_combine(const double* parts, int nparts, int S, int Sld, double* out, cudaStream_t st);
+cudaError_t launch_core_resid(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, const double* w,
+                              double* resid, cudaStream_t st);
+cudaError_t launch_core_maxcorr(const double* Vc, int M, int S, long long ldv, const double* resid, int skip, double* out,
+                                cudaStream_t st);
+cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, const double* resid, double* grad, cudaStream_t st);
+cudaError_t launch_adam(const double* g, double* x, double* m1, double* m2, int n, double lr, double b1, double b2, double c1,
+                        double c2, double eps, const unsigned char* nn_mask, cudaStream_t st);
+
+// ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----
+cudaError_t launch_dense_rowstats(const double* V, long long n, int S, long long ldv, const double* u, int nu, double* norms,
+                                  double* dots, cudaStream_t st);
+cudaError_t launch_dense_colsum(const double* V, long long n, int S, long long ldv, double* part, int nparts, double* out_dd,
+                                int Sld, cudaStream_t st);
+cudaError_t launch_dense_score(const double* V, long long n, int S, long long ldv, const double* norms, const double* u, int mode,
+                               const unsigned char* active, long long idx_offset, double* part, int nparts, double* out,
+                               double* scores, cudaStream_t st);
+cudaError_t launch_dense_combine(const double* V, long long ldv, int S, const long long* idx, const double* w, int m, double* out,
+                                 cudaStream_t st);
+cudaError_t launch_dense_center(double* V, long long n, int S, long long ldv, cudaStream_t st);
+cudaError_t launch_dense_gather(const double* V, long long ldv, int S, const long long* idx, long long m, double* out, long long ldo,
+                                cudaStream_t st);
+cudaError_t launch_transpose(const double* A, long long rows, long long cols, long long lda, double* out, long long ldo,
+                             cudaStream_t st);
+cudaError_t launch_vec_step(int op, const double* xw, const double* xf, const double* b, int S, double aux, double* u, double* out,
+                            cudaStream_t st);
+
+}  // namespace bc

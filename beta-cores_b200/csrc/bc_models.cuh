@@ -1,0 +1,86 @@
+// beta-cores B200: per-element potentials f(x_n, theta_s), fused into the epilogue of the
+// projection contraction.  Each functor restates one reference function; `c` is the
+// contraction value  sum_k A[n][k] * B[s][k]  for the operands bc_set_samples() prepares.
+#pragma once
+#include "bc_common.cuh"
+
+namespace bc {
+
+enum : int { MODEL_LOGISTIC = 0, MODEL_GAUSSIAN = 1, MODEL_NEURLIN = 2 };
+enum : int { KIND_LOGLIK = 0, KIND_BETALIK = 1, KIND_BETAGRAD = 2 };
+
+struct ModelParams {
+  double p[8];
+};
+
+// reference: examples/common/model_lr.py:72-79 (log_likelihood), :81-86 (beta_likelihood).
+//   A = Z (rows y_n x_n), B = Theta, m = -c.
+//   p[0] = beta, p[1] = (beta+1)/beta
+template <int KIND>
+struct LogisticF {
+  static constexpr bool kRowAux = false, kColAux = false;
+  __device__ __forceinline__ static double eval(double c, double, double, const ModelParams& mp) {
+    const double m = -c;
+    if (KIND == KIND_LOGLIK) {
+      // m < 100: -log1p(e^m); else -m
+      return (m < 100.0) ? -log1p(exp(m)) : -m;
+    } else {
+      // -( k1 (1+e^m)^-b - ( (1+e^m)^(-b-1) + (1+e^-m)^(-b-1) ) ), evaluated overflow-free:
+      // t = e^-|m|, big = 1/(1+t), small = t/(1+t);  big^b = e^(-b log1p t), small^b = e^(-b|m|) big^b.
+      const double beta = mp.p[0], k1 = mp.p[1];
+      const double a = fabs(m);
+      const double t = exp(-a);
+      const double E = exp(-beta * log1p(t));  // big^beta
+      const double G = exp(-beta * a);         // (small/big)^beta
+      const double u = E / (1.0 + t);          // big^(beta+1)
+      const double v = G * t * u;              // small^(beta+1)
+      const double pb = (m >= 0.0) ? G * E : E;  // (1+e^m)^-beta
+      return -(k1 * pb - (u + v));
+    }
+  }
+};
+
+// reference: examples/common/gaussian.py:7-15 (loglik), :34-44 (beta-lik), :46-62 (d/dbeta).
+//   A = X, B = Theta Siginv^T (so c = x Siginv theta), rowaux = x Siginv x, colaux = th Siginv th,
+//   q = rowaux + colaux - 2c.
+//   loglik : p[0] - 0.5 q                       p[0] = -d/2 log 2pi - 1/2 logdetSig
+//   betalik: p[1] exp(p[2] q) - p[3]            p[1] = 1/beta, p[2] = -beta/2, p[3] = (1+beta)^(-d/2-1)
+//   betagrad: p[4](p[1] e - p[3]) - p[5] e - p[6] q e - p[7],  e = exp(p[2] q)
+//            p[4] = logcnst, p[5] = 1/beta^2, p[6] = 1/(2 beta), p[7] = p[3] log(1+beta)
+template <int KIND>
+struct GaussianF {
+  static constexpr bool kRowAux = true, kColAux = true;
+  __device__ __forceinline__ static double eval(double c, double ra, double ca, const ModelParams& mp) {
+    const double q = ra + ca - 2.0 * c;
+    if (KIND == KIND_LOGLIK) {
+      return mp.p[0] - 0.5 * q;
+    } else if (KIND == KIND_BETALIK) {
+      return mp.p[1] * exp(mp.p[2] * q) - mp.p[3];
+    } else {
+      const double e = exp(mp.p[2] * q);
+      const double t1 = mp.p[4] * (mp.p[1] * e - mp.p[3]);
+      return t1 - mp.p[5] * e - mp.p[6] * q * e - mp.p[7];
+    }
+  }
+};
+
+// reference: examples/common/model_neurlinr.py:90-97 (loglik), :102-110 (beta-lik).
+//   A = Phi (first D columns of z), B = Theta, rowaux = y (column D of z), u = c,
+//   r2 = y^2 - 2 u y + u^2.
+//   loglik : p[0] - p[1] r2                     p[0] = -1/2 log(2 pi s2), p[1] = 1/(2 s2)
+//   betalik: p[2] (p[3] exp(p[4] r2) + p[5])    p[2] = (2 pi s2)^(-beta/2), p[3] = -(beta+1)/beta,
+//                                               p[4] = -beta/(2 s2), p[5] = 1/sqrt(1+beta)
+template <int KIND>
+struct NeurlinF {
+  static constexpr bool kRowAux = true, kColAux = false;
+  __device__ __forceinline__ static double eval(double c, double y, double, const ModelParams& mp) {
+    const double r2 = y * y - 2.0 * c * y + c * c;
+    if (KIND == KIND_LOGLIK) {
+      return mp.p[0] - mp.p[1] * r2;
+    } else {
+      return mp.p[2] * (mp.p[3] * exp(mp.p[4] * r2) + mp.p[5]);
+    }
+  }
+};
+
+}  // namespace bc

@@ -1,0 +1,239 @@
+// beta-cores B200: the small kernels around the projection.
+//   * sample preparation (B operand, per-sample aux term, pivot sample)
+//   * Gaussian per-row quadratic form  x Siginv x   (examples/common/gaussian.py:10)
+//   * combination of double-double column-sum parts (one per rank) into the centred column sum
+//   * coreset-side step: residual, correlations of the coreset points, weight gradient
+//     (bayesiancoresets/coreset/bcores.py:77-79, :144-146)
+//   * projected ADAM update (bayesiancoresets/util/opt.py:45-52)
+// All of these touch S- or M-sized data: they are latency-bound, one or a few CTAs each.
+#include "bc_kernels.h"
+
+namespace bc {
+
+// fixed-order block sum; result valid in every thread.  blockDim.x <= 1024, multiple of 32.
+__device__ __forceinline__ double block_sum(double x, double* red /* >= 33 doubles */) {
+  x = warp_sum(x);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();  // protect `red` from a previous call
+  if (l == 0) red[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    double y = (l < nw) ? red[l] : 0.0;
+    y = warp_sum(y);
+    if (l == 0) red[32] = y;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ------------------------------------------------------- sample preparation --
+// one block per sample s.
+__global__ void k_prepare_rows(int model, const double* __restrict__ theta, int S, int D, int ldt,
+                               const double* __restrict__ siginv, double* __restrict__ B, int ldb, double* __restrict__ colaux) {
+  __shared__ double red[33];
+  const int s = blockIdx.x;
+  const double* th = theta + (size_t)s * ldt;
+  double part = 0.0;
+  for (int k = threadIdx.x; k < ldb; k += blockDim.x) {
+    double b = 0.0;
+    if (k < D) {
+      if (model == MODEL_GAUSSIAN) {
+        // B[s][k] = (Siginv theta_s)[k]      gaussian.py:12  x.dot(Siginv.dot(th.T))
+        double acc = 0.0, acc2 = 0.0;
+        for (int j = 0; j < D; ++j) {
+          acc = fma(siginv[(size_t)k * D + j], th[j], acc);
+          acc2 = fma(th[j], siginv[(size_t)j * D + k], acc2);  // (th.dot(Siginv))[k]   gaussian.py:11
+        }
+        b = acc;
+        part = fma(th[k], acc2, part);
+      } else {
+        b = th[k];
+      }
+    }
+    B[(size_t)s * ldb + k] = b;
+  }
+  if (model == MODEL_GAUSSIAN) {
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) colaux[s] = tot;
+  }
+}
+
+// bbar[k] = mean_s B[s][k] for k < ldb; bbar[ldb] = mean_s colaux[s] (0 if no colaux)
+__global__ void k_prepare_mean(const double* __restrict__ B, int S, int ldb, const double* __restrict__ colaux,
+                               double* __restrict__ bbar) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ldb) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc += B[(size_t)s * ldb + k];
+    bbar[k] = acc / (double)S;
+  } else if (k == ldb) {
+    double acc = 0.0;
+    if (colaux)
+      for (int s = 0; s < S; ++s) acc += colaux[s];
+    bbar[ldb] = acc / (double)S;
+  }
+}
+
+cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,
+                                   double* colaux, double* bbar, cudaStream_t st) {
+  k_prepare_rows<<<S, 128, 0, st>>>(model, theta, S, D, ldt, siginv, B, ldb, colaux);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int threads = 128;
+  k_prepare_mean<<<(ldb + 1 + threads - 1) / threads, threads, 0, st>>>(B, S, ldb, model == MODEL_GAUSSIAN ? colaux : nullptr,
+                                                                          bbar);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------- x Siginv x --
+// one warp per row; out[r] = sum_k x[k] * (sum_j x[j] Siginv[j][k])      gaussian.py:10
+__global__ void k_rowquad(const double* __restrict__ X, long long n, int D, long long ldx, const double* __restrict__ siginv,
+                          double* __restrict__ out) {
+  extern __shared__ double xs[];  // [warps][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double* x = xs + (size_t)warp * D;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < n; r += (long long)gridDim.x * nw) {
+    for (int k = lane; k < D; k += 32) x[k] = X[r * ldx + k];
+    __syncwarp();
+    double acc = 0.0;
+    for (int k = lane; k < D; k += 32) {
+      double tk = 0.0;
+      for (int j = 0; j < D; ++j) tk = fma(x[j], __ldg(siginv + (size_t)j * D + k), tk);
+      acc = fma(x[k], tk, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[r] = acc;
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_rowquad(const double* X, long long n, int D, long long ldx, const double* siginv, double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int warps = 8;
+  long long blocks = (n + warps - 1) / warps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_rowquad<<<(int)blocks, warps * 32, (size_t)warps * D * sizeof(double), st>>>(X, n, D, ldx, siginv, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------- dd parts -> colsum --
+// parts: [nparts][2][Sld]; element S of each part = sum of row means.
+// out[s] = (sum_p part_p[s]) - (sum_p part_p[S])   i.e. the column sum of the CENTRED matrix.
+__global__ void k_colsum_combine(const double* __restrict__ parts, int nparts, int S, int Sld, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  dd a = {0.0, 0.0}, m = {0.0, 0.0};
+  for (int p = 0; p < nparts; ++p) {
+    const double* q = parts + (size_t)p * 2 * Sld;
+    dd o = {q[s], q[Sld + s]};
+    a = dd_add(a, o);
+    dd om = {-q[S], -q[Sld + S]};
+    m = dd_add(m, om);
+  }
+  a = dd_add(a, m);
+  out[s] = a.hi;
+}
+
+cudaError_t launch_colsum_combine(const double* parts, int nparts, int S, int Sld, double* out, cudaStream_t st) {
+  k_colsum_combine<<<(S + 127) / 128, 128, 0, st>>>(parts, nparts, S, Sld, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------- coreset-side step --
+// resid[s] = scaling*colsum[s] - sum_m w[m] Vc[m][s];  resid[S] = sum_s resid[s]      bcores.py:77 / :145
+__global__ void k_core_resid(const double* __restrict__ colsum, double scaling, const double* __restrict__ Vc, int M, int S,
+                             long long ldv, const double* __restrict__ w, double* __restrict__ resid) {
+  __shared__ double red[33];
+  double tot = 0.0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    double acc = 0.0;
+    for (int m = 0; m < M; ++m) acc = fma(w[m], Vc[(size_t)m * ldv + s], acc);
+    const double r = scaling * colsum[s] - acc;
+    resid[s] = r;
+    tot += r;
+  }
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) resid[S] = tot;
+}
+
+cudaError_t launch_core_resid(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, const double* w,
+                              double* resid, cudaStream_t st) {
+  k_core_resid<<<1, 1024, 0, st>>>(colsum, scaling, Vc, M, S, ldv, w, resid);
+  return cudaGetLastError();
+}
+
+// out[0] = max_{m >= skip} | Vc_m . r / |Vc_m| | / S   (np.max semantics: NaN propagates)      bcores.py:79
+// grad[m] = -(Vc_m . r) / S                                                               bcores.py:146
+template <bool GRAD>
+__global__ void k_core_rows(const double* __restrict__ Vc, int M, int S, long long ldv, const double* __restrict__ resid, int skip,
+                            double* __restrict__ out) {
+  __shared__ double wmax[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double best = -INFINITY;
+  for (int m = warp + (GRAD ? 0 : skip); m < M; m += nw) {
+    const double* v = Vc + (size_t)m * ldv;
+    double dot = 0.0, n2 = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double x = v[s];
+      dot = fma(x, resid[s], dot);
+      if (!GRAD) n2 = fma(x, x, n2);
+    }
+    dot = warp_sum(dot);
+    if (GRAD) {
+      if (lane == 0) out[m] = -dot / (double)S;
+    } else {
+      n2 = warp_sum(n2);
+      best = nanmax(best, fabs(dot / sqrt(n2)) / (double)S);
+    }
+  }
+  if (!GRAD) {
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b = wmax[0];
+      for (int i = 1; i < nw; ++i) b = nanmax(b, wmax[i]);
+      out[0] = b;
+    }
+  }
+}
+
+cudaError_t launch_core_maxcorr(const double* Vc, int M, int S, long long ldv, const double* resid, int skip, double* out,
+                                cudaStream_t st) {
+  k_core_rows<false><<<1, 1024, 0, st>>>(Vc, M, S, ldv, resid, skip, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, const double* resid, double* grad, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  k_core_rows<true><<<1, 1024, 0, st>>>(Vc, M, S, ldv, resid, 0, grad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------- projected ADAM --
+// util/opt.py:45-52, operation for operation (no FMA contraction: matches numpy's rounding):
+//   m1 = b1*m1 + (1-b1)*g;  m2 = b2*m2 + (1-b2)*g**2
+//   upd = lr*m1/c1/(eps + sqrt(m2/c2));  x -= upd;  x = max(x, 0)   [only where nn_mask, all if null]
+// c1 = 1-b1**(i+1), c2 = 1-b2**(i+1) are computed by the host (python float pow, like the reference).
+__global__ void k_adam(const double* __restrict__ g, double* __restrict__ x, double* __restrict__ m1, double* __restrict__ m2, int n,
+                       double lr, double b1, double b2, double c1, double c2, double eps, const unsigned char* __restrict__ nn_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double gi = g[i];
+  const double a1 = __dadd_rn(__dmul_rn(b1, m1[i]), __dmul_rn(__dsub_rn(1.0, b1), gi));
+  const double a2 = __dadd_rn(__dmul_rn(b2, m2[i]), __dmul_rn(__dsub_rn(1.0, b2), __dmul_rn(gi, gi)));
+  m1[i] = a1;
+  m2[i] = a2;
+  const double upd = __ddiv_rn(__ddiv_rn(__dmul_rn(lr, a1), c1), __dadd_rn(eps, __dsqrt_rn(__ddiv_rn(a2, c2))));
+  double xi = __dsub_rn(x[i], upd);
+  if (!nn_mask || nn_mask[i]) xi = (xi > 0.0 || isnan(xi)) ? xi : 0.0;
+  x[i] = xi;
+}
+
+cudaError_t launch_adam(const double* g, double* x, double* m1, double* m2, int n, double lr, double b1, double b2, double c1,
+                        double c2, double eps, const unsigned char* nn_mask, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_adam<<<(n + 127) / 128, 128, 0, st>>>(g, x, m1, m2, n, lr, b1, b2, c1, c2, eps, nn_mask);
+  return cudaGetLastError();
+}
+
+}  // namespace bc

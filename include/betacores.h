@@ -1,0 +1,128 @@
+/* betacores.h -- C ABI of libbetacores.so, the B200 (sm_100a) implementation of the
+ * beta-Cores coreset-construction hot path.
+ *
+ * The reference (dionman/beta-cores) is pure Python/numpy and has no FFI of its own: its
+ * boundary is the `bayesiancoresets` Python API.  This library sits UNDER a drop-in copy of that
+ * API (beta-cores_b200/bayesiancoresets, loaded with ctypes); every entry point below names the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 (BC_OK) or a negative bc error code; nothing throws;
+ *   - `d_` pointers are DEVICE pointers owned by the caller, `h_` pointers are HOST pointers;
+ *   - all matrices are fp64, row-major; `ld*` are leading dimensions in elements;
+ *   - device work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and is asynchronous; results are valid after the stream is synchronised;
+ *   - a bc_ctx owns a per-device workspace; calls on one ctx must be stream-ordered with each
+ *     other (use one ctx per concurrent stream).  No other global state.
+ *   - data-row operands: base pointer 16-byte aligned, ld even (rows are staged with 16-byte
+ *     bulk copies through the TMA engine).
+ */
+#ifndef BETACORES_H_
+#define BETACORES_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bc_ctx bc_ctx;
+
+enum { BC_OK = 0, BC_ERR_ARG = -1, BC_ERR_ALIGN = -2, BC_ERR_UNSUPPORTED = -3, BC_ERR_STATE = -4, BC_ERR_CUDA = -5 };
+/* models: examples/common/{model_lr,gaussian,model_neurlinr}.py */
+enum { BC_MODEL_LOGISTIC = 0, BC_MODEL_GAUSSIAN = 1, BC_MODEL_NEURLIN = 2 };
+/* potentials: log-likelihood, beta-likelihood, d(beta-likelihood)/d(beta) (Gaussian only) */
+enum { BC_KIND_LOGLIK = 0, BC_KIND_BETALIK = 1, BC_KIND_BETAGRAD = 2 };
+/* bc_dense_score modes */
+enum { BC_SCORE_FW = 0, BC_SCORE_GIGA = 1, BC_SCORE_CORR = 2, BC_SCORE_OMP = 3 };
+/* bc_vec_step ops */
+enum { BC_VEC_GIGA_DIR = 0, BC_VEC_GIGA_STEP = 1, BC_VEC_RESID = 2, BC_VEC_FW_STEP = 3 };
+
+int bc_version(void);
+const char* bc_error_string(int code);
+int bc_last_cuda_error(void);           /* cudaError_t of the most recent BC_ERR_CUDA */
+int bc_create(int device, bc_ctx** ctx);
+int bc_destroy(bc_ctx* ctx);
+int bc_sm_count(const bc_ctx* ctx);
+int bc_colsum_ld(int S);                /* leading dimension of the (hi, lo) planes below: S + 1 */
+
+/* ---- stage 1: potentials and posterior samples ------------------------------------------- */
+/* Select the potential f(x_n, theta_s).  D = contraction length (feature count; the neural-linear
+ * target y is column D of each data row).  h_params: 8 host doubles, see bc_models.cuh / the
+ * Python model modules (they hold beta, sigma^2, normalisers ...).  d_siginv: device D x D
+ * (Gaussian only).  Replaces the likelihood callbacks of
+ * examples/common/model_lr.py:72-86, gaussian.py:7-15,34-62, model_neurlinr.py:90-110. */
+int bc_set_potential(bc_ctx* ctx, int model, int kind, int D, const double* h_params, const double* d_siginv);
+/* Install the S current posterior samples (device, S x ldt): what Projector.update() stores in
+ * self.samples (bayesiancoresets/coreset/projector.py:36-37, :65-66). */
+int bc_set_samples(bc_ctx* ctx, const double* d_theta, int S, int ldt, void* stream);
+/* Gaussian per-row term x Siginv x (gaussian.py:10), computed once per dataset. */
+int bc_rowquad(bc_ctx* ctx, const double* d_X, int64_t n, int64_t ldx, double* d_out, void* stream);
+
+/* Fused projection passes over n data rows (row r = d_X + (d_rows ? d_rows[r] : r) * ldx).
+ * d_rowaux: Gaussian x Siginv x indexed by absolute row id, else NULL.
+ *
+ * colsum : column sum over rows of the row-centred projection, as double-double planes
+ *          d_out_dd[0..S) hi, d_out_dd[ld..ld+S) lo, element S = sum of row means (subtract it:
+ *          bc_colsum_combine).  Replaces `vecs.sum(axis=0)` of project_f()/project() output
+ *          (projector.py:51-55 + bcores.py:77,145 / sparsevi.py:76,132) without materialising it.
+ * score  : corrs = vecs.dot(resid)/sqrt((vecs**2).sum(1))/S and its np.argmax (bcores.py:78,81):
+ *          d_best[0] = best score, d_best[1] = int64 position (bit pattern) + idx_offset;
+ *          NaN ordering as numpy.  d_resid has S+1 entries (residual, then its sum).
+ * materialise: writes the centred rows (what project_f()/project() return) and optionally their
+ *          2-norms (hilbert.py:16) and the column sum planes; raw != 0 writes the un-centred
+ *          potential itself (what the likelihood callbacks return) and no norms. */
+int bc_project_colsum(bc_ctx* ctx, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                      double* d_out_dd, void* stream);
+int bc_project_score(bc_ctx* ctx, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                     const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream);
+int bc_project_materialise(bc_ctx* ctx, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
+                           double* d_V, int64_t ldv, double* d_norms, double* d_out_dd, int raw, void* stream);
+/* out[s] = sum_parts (colsum_s) - sum_parts (sum of row means); parts = [nparts][2][ld] (one per rank). */
+int bc_colsum_combine(bc_ctx* ctx, const double* d_parts, int nparts, int S, double* d_out, void* stream);
+
+/* ---- stage 3: coreset-side step ------------------------------------------------------------ */
+/* resid = scaling*colsum - w . Vc ; resid[S] = sum(resid)          (bcores.py:77, :145) */
+int bc_core_resid(bc_ctx* ctx, const double* d_colsum, double scaling, const double* d_Vc, int M, int S, int64_t ldv,
+                  const double* d_w, double* d_resid, void* stream);
+/* out[0] = max_{m>=skip} |Vc_m.resid/|Vc_m||/S, np.max NaN semantics    (bcores.py:79-80) */
+int bc_core_maxcorr(bc_ctx* ctx, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, int skip, double* d_out,
+                    void* stream);
+/* grad[m] = -(Vc_m . resid)/S                                        (bcores.py:146) */
+int bc_core_grad(bc_ctx* ctx, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, double* d_grad, void* stream);
+/* one projected-ADAM update of x given g (util/opt.py:45-52; c1 = 1-b1**(i+1), c2 = 1-b2**(i+1));
+ * d_nn_mask NULL = clamp every coordinate (nn_opt), else clamp where mask != 0 (partial_nn_opt). */
+int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, double* d_m2, int n, double lr, double b1, double b2,
+                 double c1, double c2, double eps, const unsigned char* d_nn_mask, void* stream);
+
+/* ---- stage 2 on a materialised n x S matrix (snnls solvers, black-box projections) --------- */
+int bc_dense_rownorms(bc_ctx* ctx, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream);
+/* V[r][:] -= mean(V[r][:])  (projector.py:26, :55) for matrices produced by host callbacks */
+int bc_dense_center(bc_ctx* ctx, double* d_V, int64_t n, int S, int64_t ldv, void* stream);
+int bc_dense_colsum(bc_ctx* ctx, const double* d_V, int64_t n, int S, int64_t ldv, double* d_out_dd, void* stream);
+/* d_out[0..4) = {best score, best index bits, best of -score over active rows, its index bits}
+ * (giga.py:20-38, frankwolfe.py:15-17, orthopursuit.py:17-35, bcores.py:78-81). */
+int bc_dense_score(bc_ctx* ctx, int mode, const double* d_V, int64_t n, int S, int64_t ldv, const double* d_norms,
+                   const double* d_u, const unsigned char* d_active, int64_t idx_offset, double* d_out, double* d_scores,
+                   void* stream);
+/* out[s] = sum_m w[m] V[idx[m]][s]   (A.dot(w) over the selected columns; giga.py:21) */
+int bc_dense_combine(bc_ctx* ctx, const double* d_V, int64_t ldv, int S, const int64_t* d_idx, const double* d_w, int m,
+                     double* d_out, void* stream);
+int bc_dense_gather(bc_ctx* ctx, const double* d_V, int64_t ldv, int S, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo,
+                    void* stream);
+int bc_transpose(bc_ctx* ctx, const double* d_A, int64_t rows, int64_t cols, int64_t lda, double* d_out, int64_t ldo, void* stream);
+/* S-length line-search / direction steps of the solvers, one CTA (giga.py:21-30,42-62;
+ * frankwolfe.py:16,30-31; snnls.py:28-29).  See bc_dense.cu for the per-op operand/output layout. */
+int bc_vec_step(bc_ctx* ctx, int op, const double* d_xw, const double* d_xf, const double* d_b, int S, double aux, double* d_u,
+                double* d_out, void* stream);
+
+/* ---- host-buffer convenience (what a foreign-language binding would call first) ------------- */
+/* h_V[n x S] = centred potential matrix = BetaBlackBoxProjector.project_f(pts, beta) /
+ * BlackBoxProjector.project(pts) (projector.py:51-55, :23-26) for HOST inputs; copies in, runs the
+ * materialise pass on `device`, copies out, synchronises.  h_X is n x ldx_h, h_theta is S x D.
+ * centred = 0 returns the un-centred potential (the likelihood callback's own return value). */
+int bc_host_project(int device, int model, int kind, int D, const double* h_params, const double* h_siginv, const double* h_X,
+                    int64_t n, int64_t ldx_h, const double* h_theta, int S, double* h_V, int centred);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BETACORES_H_ */

@@ -1,0 +1,317 @@
+"""GPU parity: the CUDA path (through the C ABI / the drop-in Python API) against the numpy oracle and the
+golden fixtures written by the unmodified reference.
+
+Tolerances: fp64 throughout.  Per-element potentials: rtol 1e-12 (+ tiny atol for values that cancel).
+Index sequences: exact.  Weights / objective values: rtol 1e-6 as the north star states (observed ~1e-10).
+"""
+import ctypes
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import problems
+from oracle import np_models as om, np_snnls as osn, np_coresets as oc
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def bc():
+    import bayesiancoresets as bc
+    return bc
+
+
+@pytest.fixture(scope='module')
+def models():
+    import model_lr, gaussian, model_neurlinr
+    return model_lr, gaussian, model_neurlinr
+
+
+def test_extension_loaded(bc):
+    from bayesiancoresets import _native as nv
+    assert nv.lib().bc_version() >= 100
+    eng = bc.Engine.get()
+    eng.ctx()
+    assert eng.sms >= 100
+
+
+# ------------------------------------------------------------------ potentials vs golden --
+def test_potentials_match_reference_golden(models):
+    lr, ga, nl = models
+    g = np.load(os.path.join(G, 'g1_models.npz'))
+    p = problems.model_function_inputs()
+    beta = float(g['beta'])
+    cases = [
+        (lr.log_likelihood(p['Z'], p['Th']), 'lr_loglik'),
+        (lr.beta_likelihood(p['Z'], p['Th'], beta), 'lr_betalik'),
+        (ga.gaussian_loglikelihood(p['Xg'], p['Thg'], p['Siginv'], p['logdetSig']), 'gauss_loglik'),
+        (ga.gaussian_beta_likelihood(p['Xg'], p['Thg'], beta, p['Siginv'], p['logdetSig']), 'gauss_betalik'),
+        (ga.gaussian_beta_gradient(p['Xg'], p['Thg'], beta, p['Siginv'], p['logdetSig']), 'gauss_betagrad'),
+        (nl.neurlinr_loglikelihood(p['Zn'], p['Thn'], p['sigsq']), 'nl_loglik'),
+        (nl.neurlinr_beta_likelihood(p['Zn'], p['Thn'], beta, p['sigsq']), 'nl_betalik'),
+    ]
+    for got, key in cases:
+        ref = g[key]
+        scale = np.abs(ref).max()
+        np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-13*scale, err_msg=key)
+
+
+def test_project_f_matches_reference_golden(bc, models):
+    lr, _, _ = models
+    g = np.load(os.path.join(G, 'g1_models.npz'))
+    p = problems.model_function_inputs()
+    prj = bc.BetaBlackBoxProjector(lambda S, w, pts: p['Th'], p['Th'].shape[0], lr.beta_likelihood, lr.log_likelihood, None)
+    got = prj.project_f(p['Z'], float(g['beta']))
+    np.testing.assert_allclose(got, g['lr_project_f'], rtol=1e-10, atol=1e-14)
+
+
+# ---------------------------------------------- fused passes vs the oracle's dense algebra --
+def _rand_problem(model, n, D, S, seed):
+    r = np.random.RandomState(seed)
+    if model == 'lr':
+        X = r.randn(n, D)
+        Th = r.randn(S, D)*0.7
+        return X, Th, {}
+    if model == 'gauss':
+        A = r.randn(D, D)
+        Sig = A.dot(A.T) + D*np.eye(D)
+        return r.randn(n, D)*2., r.randn(S, D), dict(Siginv=np.linalg.inv(Sig), logdetSig=np.linalg.slogdet(Sig)[1])
+    X = np.hstack((r.randn(n, D), r.randn(n, 1)*2.))
+    return X, r.randn(S, D)*0.5, dict(sigsq=0.8)
+
+
+def _oracle_matrix(model, kind, X, Th, beta, c):
+    if model == 'lr':
+        return om.lr_betalik(X, Th, beta) if kind == 'betalik' else om.lr_loglik(X, Th)
+    if model == 'gauss':
+        return om.gauss_betalik(X, Th, beta, c['Siginv'], c['logdetSig']) if kind == 'betalik' else om.gauss_loglik(X, Th, c['Siginv'], c['logdetSig'])
+    return om.nl_betalik(X, Th, beta, c['sigsq']) if kind == 'betalik' else om.nl_loglik(X, Th, c['sigsq'])
+
+
+SHAPES = [('lr', 'betalik', 1000, 20, 100), ('lr', 'loglik', 777, 5, 33), ('lr', 'betalik', 3000, 128, 256),
+          ('gauss', 'betalik', 900, 10, 40), ('gauss', 'loglik', 513, 7, 65), ('nl', 'betalik', 1200, 8, 32),
+          ('nl', 'loglik', 640, 64, 128), ('lr', 'betalik', 1, 3, 2), ('lr', 'betalik', 65, 130, 70)]
+
+
+@pytest.mark.parametrize('model,kind,n,D,S', SHAPES)
+def test_fused_colsum_score_materialise(bc, model, kind, n, D, S):
+    import torch
+    from bayesiancoresets._fused import FusedProjection
+    from bayesiancoresets._device import Engine, DeviceRows
+    from bayesiancoresets.potentials import DevicePotential
+    from bayesiancoresets import _native as nv
+    X, Th, consts = _rand_problem(model, n, D, S, seed=n+D+S)
+    beta = 0.25 if kind == 'betalik' else None
+    pot = DevicePotential({'lr': 'logistic', 'gauss': 'gaussian', 'nl': 'neurlin'}[model], kind).bind(**consts)
+    eng = Engine.get()
+    fp = FusedProjection(eng, pot, X.shape[1])
+    fp.configure(beta)
+    fp.set_samples(Th)
+    rows = DeviceRows(eng, X)
+    with np.errstate(all='ignore'):
+        F = _oracle_matrix(model, kind, X, Th, beta, consts)
+    V = oc.centred(F.copy())
+    scale = max(np.abs(V).max(), 1e-300)
+
+    # materialise (centred) + norms + column sum
+    dV, dn, dd = fp.materialise(rows, want_norms=True, want_colsum=True)
+    np.testing.assert_allclose(dV.cpu().numpy(), V, rtol=1e-9, atol=1e-13*max(np.abs(F).max(), 1.))
+    np.testing.assert_allclose(dn.cpu().numpy(), np.sqrt((V**2).sum(axis=1)), rtol=1e-9, atol=1e-12*scale)
+    cs = fp.combine(dd, 1).cpu().numpy()
+    np.testing.assert_allclose(cs, V.sum(axis=0), rtol=1e-9, atol=1e-11*scale*np.sqrt(n))
+    # raw potential
+    dF, _, _ = fp.materialise(rows, raw=True)
+    np.testing.assert_allclose(dF.cpu().numpy(), F, rtol=1e-11, atol=1e-13*np.abs(F).max())
+
+    # fused column sum (nothing materialised)
+    cs2 = fp.combine(fp.colsum_parts(rows), 1).cpu().numpy()
+    np.testing.assert_allclose(cs2, V.sum(axis=0), rtol=1e-9, atol=1e-11*scale*np.sqrt(n))
+
+    # fused score + arg-max against numpy on the oracle matrix
+    r = np.random.RandomState(1).randn(S)
+    resid = eng.upload(np.concatenate((r, [r.sum()])))
+    out = eng.zeros(4)
+    scores = eng.empty(n)
+    fp.score(rows, None, resid, 0, out, scores=scores)
+    with np.errstate(all='ignore'):
+        ref = V.dot(r)/np.sqrt((V**2).sum(axis=1))/S
+    got = scores.cpu().numpy()
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-7, atol=1e-9*np.abs(ref[ok]).max())
+    o = out.cpu().numpy()
+    assert int(o[1:2].view(np.int64)[0]) == int(np.argmax(got))
+    if ok.all():
+        assert int(np.argmax(got)) == int(np.argmax(ref))
+
+    # gathered rows (sub-sample with duplicates)
+    sub = np.random.RandomState(2).randint(n, size=max(n//3, 1))
+    dsub = eng.upload(sub.astype(np.int64), dtype=torch.int64)
+    cs3 = fp.combine(fp.colsum_parts(rows, dsub), 1).cpu().numpy()
+    np.testing.assert_allclose(cs3, V[sub].sum(axis=0), rtol=1e-9, atol=1e-11*scale*np.sqrt(n))
+
+
+def test_score_nan_and_tie_semantics(bc):
+    """zero rows -> 0/0 = NaN: np.argmax returns the first NaN; duplicate rows tie -> lowest position"""
+    import torch
+    from bayesiancoresets._fused import FusedProjection
+    from bayesiancoresets._device import Engine, DeviceRows
+    from bayesiancoresets.potentials import DevicePotential
+    r = np.random.RandomState(0)
+    X = r.randn(500, 6)
+    X[300] = X[17]
+    Th = r.randn(40, 6)
+    eng = Engine.get()
+    fp = FusedProjection(eng, DevicePotential('logistic', 'betalik'), 6)
+    fp.configure(0.1)
+    fp.set_samples(Th)
+    rr = r.randn(40)
+    resid = eng.upload(np.concatenate((rr, [rr.sum()])))
+    out = eng.zeros(4)
+    scores = eng.empty(500)
+    fp.score(DeviceRows(eng, X), None, resid, 0, out, scores=scores)
+    s = scores.cpu().numpy()
+    assert s[300] == s[17]
+    Xz = X.copy()
+    Xz[123] = 0.
+    Xz[77] = 0.
+    fp.score(DeviceRows(eng, Xz), None, resid, 1000, out, scores=scores)
+    o = out.cpu().numpy()
+    assert np.isnan(o[0]) and int(o[1:2].view(np.int64)[0]) == 1077
+    assert np.isnan(scores.cpu().numpy()[[77, 123]]).all()
+
+
+# ------------------------------------------------------------------------------ snnls --
+@pytest.mark.parametrize('name', ['giga', 'fw', 'omp'])
+def test_snnls_fingerprint_matches_reference(bc, name):
+    g = np.load(os.path.join(G, 'g2_snnls.npz'))
+    V = problems.snnls_matrix()
+    cls = {'giga': bc.snnls.GIGA, 'fw': bc.snnls.FrankWolfe, 'omp': bc.snnls.OrthoPursuit}[name]
+    alg = cls(V.T, V.sum(axis=0))
+    fs = []
+    for _ in range(100):
+        f = alg._select(); fs.append(int(f)); alg._reweight(f)
+    np.testing.assert_array_equal(fs, g[name+'_trace'])
+    np.testing.assert_allclose(alg.weights(), g[name+'_w'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(alg.error(), g[name+'_error'], rtol=1e-6, atol=1e-7)
+    # property list of the reference's tests/test_snnls/test_deterministic.py:37-73
+    w = alg.weights()
+    assert (w >= 0).all() and alg.size() == (w > 0).sum() and alg.size() <= 100
+    np.testing.assert_allclose(alg.error(), np.sqrt(((V.T.dot(w)-V.sum(axis=0))**2).sum()), rtol=1e-7, atol=1e-7)
+    alg2 = cls(V.T, V.sum(axis=0)); alg2.build(100)
+    np.testing.assert_allclose(alg2.weights(), g[name+'_build_w'], rtol=1e-6, atol=1e-9)
+    assert bool(alg2.reached_numeric_limit) == bool(g[name+'_build_limit'])
+    alg2.optimize()
+    np.testing.assert_allclose(alg2.weights(), g[name+'_opt_w'], rtol=1e-6, atol=1e-8)
+    alg2.reset()
+    assert alg2.size() == 0 and not alg2.weights().any()
+
+
+def test_snnls_small_cases_and_monotone_error(bc):
+    g = np.load(os.path.join(G, 'g2_snnls.npz'))
+    for tag, A in problems.snnls_small_cases():
+        for name, cls in (('giga', bc.snnls.GIGA), ('fw', bc.snnls.FrankWolfe), ('omp', bc.snnls.OrthoPursuit)):
+            alg = cls(A.T, A.sum(axis=0))
+            prev = np.inf
+            for m in range(A.shape[0]):
+                alg.build(1)
+                e = alg.error()
+                assert e <= prev*(1+1e-6)+1e-6, (tag, name, m, e, prev)
+                prev = e
+            ref_limit = bool(g['small_%s_%s_limit' % (tag, name)])
+            ref_w = g['small_%s_%s_w' % (tag, name)]
+            if not ref_limit and not alg.reached_numeric_limit:
+                np.testing.assert_allclose(alg.weights(), ref_w, rtol=1e-5, atol=1e-7, err_msg=tag+name)
+
+
+# ---------------------------------------------------------------------- coreset builds --
+def _device_potentials(prob, models):
+    lr, ga, nl = models
+    if prob['model'] == 'lr':
+        return lr.beta_likelihood, lr.log_likelihood
+    if prob['model'] == 'gauss':
+        return ga.gaussian_beta_likelihood.bind(**prob['params']), ga.gaussian_loglikelihood.bind(**prob['params'])
+    return nl.neurlinr_beta_likelihood.bind(**prob['params']), nl.neurlinr_loglikelihood.bind(**prob['params'])
+
+
+def _run_product_case(bc, models, case, blackbox=False):
+    prob = case['make']()
+    np.random.seed(case['seed'])
+    bl, ll = _device_potentials(prob, models)
+    if blackbox:      # hide the potentials behind lambdas, as the reference drivers do
+        bl0, ll0 = bl, ll
+        bl = lambda pts, th, beta: bl0(pts, th, beta)
+        ll = lambda pts, th: ll0(pts, th)
+    if case['alg'] == 'beta':
+        prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
+        alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
+                             opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False)
+    elif case['alg'] == 'svi':
+        prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
+        alg = bc.SparseVICoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
+                                 opt_itrs=case['opt_itrs'], step_sched=case['sched'])
+    else:
+        prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
+        alg = bc.HilbertCoreset(prob['data'], prj, n_subsample=case['n_sel'], snnls=getattr(bc.snnls, case['solver']))
+    sizes, sumw = [], []
+    for m in range(1, case['M']+1):
+        alg.build(1, m)
+        r = alg.get()
+        sizes.append(len(r[2])); sumw.append(r[0].sum())
+    return r[0], r[2], np.array(sizes), np.array(sumw)
+
+
+@pytest.mark.parametrize('case', problems.coreset_cases(heavy=True), ids=lambda c: c['name'])
+def test_coreset_builds_match_reference(bc, models, case):
+    g = np.load(os.path.join(G, 'g3_coresets.npz'))
+    w, i, sizes, sumw = _run_product_case(bc, models, case)
+    nm = case['name']
+    np.testing.assert_array_equal(i, g[nm+'_idcs'])
+    np.testing.assert_array_equal(sizes, g[nm+'_sizes'])
+    np.testing.assert_allclose(w, g[nm+'_wts'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(sumw, g[nm+'_sumw'], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['lr_beta_small', 'gauss_beta_sub', 'nl_svi_small'])
+def test_blackbox_callbacks_take_the_dense_path(bc, models, name):
+    """likelihoods hidden behind lambdas (as the reference drivers pass them) give the same coreset"""
+    g = np.load(os.path.join(G, 'g3_coresets.npz'))
+    case = [c for c in problems.coreset_cases(False) if c['name'] == name][0]
+    w, i, sizes, _ = _run_product_case(bc, models, case, blackbox=True)
+    np.testing.assert_array_equal(i, g[name+'_idcs'])
+    np.testing.assert_allclose(w, g[name+'_wts'], rtol=1e-6, atol=1e-9)
+
+
+def test_build_guards(bc, models):
+    lr, _, _ = models
+    prob = problems.make_logistic(300, 4, 1)()
+    np.random.seed(0)
+    prj = bc.BetaBlackBoxProjector(prob['sampler'], 16, lr.beta_likelihood, lr.log_likelihood, None)
+    alg = bc.BetaCoreset(prob['data'], prj, opt_itrs=3, beta=0.1, learn_beta=False)
+    alg.build(2, 2)
+    assert alg.size() <= 2
+    with pytest.raises(ValueError):
+        alg.build(1, 0)                  # cannot shrink
+    with pytest.raises(ValueError):
+        alg.build(5, alg.size()+1)       # itrs + size > sz
+    alg.reset()
+    assert alg.size() == 0
+
+
+# ------------------------------------------------------------------ plain C ABI, host buffers --
+def test_c_abi_host_project(models):
+    from bayesiancoresets import _native as nv
+    p = problems.model_function_inputs()
+    Z, Th = np.ascontiguousarray(p['Z']), np.ascontiguousarray(p['Th'])
+    n, D = Z.shape
+    S = Th.shape[0]
+    out = np.empty((n, S))
+    params = nv.params8([0.3, (0.3+1.)/0.3])
+    rc = nv.lib().bc_host_project(0, nv.MODEL_LOGISTIC, nv.KIND_BETALIK, D, params, None, Z.ctypes.data_as(ctypes.c_void_p), n, D,
+                                  Th.ctypes.data_as(ctypes.c_void_p), S, out.ctypes.data_as(ctypes.c_void_p), 1)
+    assert rc == 0, nv.lib().bc_error_string(rc)
+    g = np.load(os.path.join(G, 'g1_models.npz'))
+    np.testing.assert_allclose(out, g['lr_project_f'], rtol=1e-10, atol=1e-14)
+    # argument errors come back as codes, not crashes
+    assert nv.lib().bc_host_project(0, 0, 1, D, params, None, None, n, D, None, S, None, 1) == -1

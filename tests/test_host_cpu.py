@@ -1,0 +1,171 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/betacores.h declares; host-side logic
+(sharding helpers, arg-max merge semantics, potential constants); world_size-2 gloo exchange of the per-rank
+parts.  No compute call is made (no GPU here): the product has no CPU path and says so."""
+import ctypes
+import os
+import re
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'betacores.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(bc_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    path = ge.build()
+    L = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), 'libbetacores.so does not export %s' % n
+    L.bc_version.restype = ctypes.c_int
+    assert L.bc_version() >= 100
+    L.bc_error_string.restype = ctypes.c_char_p
+    assert b'argument' in L.bc_error_string(-1)
+
+
+def test_ctypes_table_covers_header():
+    from bayesiancoresets import _native as nv
+    bound = set(nv.SIGNATURES) | set(nv.PLAIN)
+    assert bound == set(_declared_symbols())
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import bayesiancoresets as bc
+    from bayesiancoresets import _native as nv
+    import model_lr
+    with pytest.raises(nv.NativeError):
+        model_lr.beta_likelihood(np.zeros((3, 2)), np.zeros((4, 2)), 0.1)
+    with pytest.raises(nv.NativeError):
+        bc.snnls.GIGA(np.ones((3, 5)), np.ones(3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'beta-cores_b200')
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                s = open(os.path.join(d, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', s, flags=re.M), os.path.join(d, f)
+
+
+def test_partition_and_owner():
+    from bayesiancoresets._shard import partition_rows, owner_of, local_subsample
+    for n, w in ((10, 3), (7, 8), (1000003, 8), (16, 4), (5, 1)):
+        spans = [partition_rows(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and sum(s[1] for s in spans) == n
+        for r in range(1, w):
+            assert spans[r][0] == spans[r-1][0]+spans[r-1][1]
+        for row in (0, n-1, n//2, n//3):
+            own = owner_of(row, n, w)
+            assert spans[own][0] <= row < spans[own][0]+spans[own][1]
+    sub = np.array([5, 0, 9, 5, 3, 7])
+    pos, loc = local_subsample(sub, 4, 4)
+    assert list(pos) == [0, 3, 5] and list(loc) == [1, 1, 3]
+
+
+def test_merge_best_is_numpy_argmax():
+    from bayesiancoresets._shard import merge_best, nan_max
+    r = np.random.RandomState(0)
+    for trial in range(200):
+        n = r.randint(1, 30)
+        x = np.round(r.randn(n), 1)
+        if trial % 3 == 0:
+            x[r.randint(n, size=2)] = np.nan
+        cuts = sorted(r.randint(0, n+1, size=3))
+        chunks = [(0, cuts[0]), (cuts[0], cuts[1]), (cuts[1], cuts[2]), (cuts[2], n)]
+        cands = []
+        for a, b in chunks:
+            if b > a:
+                j = int(np.argmax(x[a:b]))
+                cands.append((x[a+j], a+j))
+            else:
+                cands.append((0.0, -1))
+        r.shuffle(cands)
+        v, i = merge_best(cands)
+        assert i == int(np.argmax(x))
+        m = nan_max([c[0] for c in cands if c[1] >= 0])
+        assert (np.isnan(m) and np.isnan(x.max())) or m == x.max()
+
+
+def test_potential_constants_follow_reference_expressions():
+    from bayesiancoresets.potentials import DevicePotential
+    p = DevicePotential('logistic', 'betalik').params(5, 0.3)
+    assert p[0] == 0.3 and p[1] == (0.3+1.)/0.3
+    g = DevicePotential('gaussian', 'betalik').bind(Siginv=np.eye(3), logdetSig=0.7)
+    q = g.params(3, 0.1)
+    assert q[1] == 1./0.1 and q[2] == -.5*0.1 and q[3] == (1+0.1)**(-.5*3.-1)
+    with pytest.raises(TypeError):
+        DevicePotential('gaussian', 'betalik').params(3, None)
+    assert not DevicePotential('neurlin', 'loglik').is_bound()
+    assert DevicePotential('neurlin', 'loglik').bind(sigsq=2.).is_bound()
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'beta-cores_b200'))
+        from bayesiancoresets._shard import Comm, partition_rows, local_subsample, merge_best
+        comm = Comm.current()
+        assert comm.world == world and comm.rank == rank
+        # the data path: every rank reduces its own row block; only S-length parts + one pair are exchanged
+        N, S = 1001, 16
+        V = np.random.RandomState(3).randn(N, S)
+        V[417] = np.nan if False else V[417]
+        resid = np.random.RandomState(4).randn(S)
+        r0, nl = partition_rows(N, world, rank)
+        part = torch.from_numpy(V[r0:r0+nl].sum(axis=0))
+        allp = comm.allgather(part).numpy()
+        colsum = allp.sum(axis=0)
+        sc = V[r0:r0+nl].dot(resid)
+        j = int(np.argmax(sc))
+        mine = torch.tensor([sc[j], float(r0+j)], dtype=torch.float64)
+        allc = comm.allgather(mine).numpy()
+        best = merge_best((allc[r, 0], int(allc[r, 1])) for r in range(world))
+        # subsample ownership
+        sub = np.random.RandomState(5).randint(N, size=200)
+        pos, loc = local_subsample(sub, r0, nl)
+        cnt = comm.allgather(torch.tensor([len(pos)])).numpy().sum()
+        t = torch.zeros(3, dtype=torch.float64)
+        if rank == 1:
+            t += 7.
+        comm.broadcast(t, 1)
+        q.put((rank, colsum, best, int(cnt), t.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_matches_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, S = 1001, 16
+    V = np.random.RandomState(3).randn(N, S)
+    resid = np.random.RandomState(4).randn(S)
+    for rank, colsum, best, cnt, t in res:
+        np.testing.assert_allclose(colsum, V.sum(axis=0), rtol=1e-12, atol=1e-12)
+        assert best[1] == int(np.argmax(V.dot(resid)))
+        assert cnt == 200
+        assert (t == 7.).all()
