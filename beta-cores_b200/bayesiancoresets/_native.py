@@ -37,7 +37,7 @@ SIGNATURES = {
     'bc_vec_step': [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }
-PLAIN = {'bc_version': ([], c_int), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+PLAIN = {'bc_version': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
 MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2

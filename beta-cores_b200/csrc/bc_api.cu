@@ -5,7 +5,10 @@
 
 using namespace bc;
 
+#include <atomic>
 static thread_local int g_last_cuda = 0;
+static std::atomic<long long> g_launches{0};   // kernels launched by this library (bench.py reports it)
+#define BC_LAUNCHED(n) g_launches.fetch_add((n), std::memory_order_relaxed)
 
 struct bc_ctx {
   int device = 0, sms = 0;
@@ -67,6 +70,7 @@ const char* bc_error_string(int code) {
 }
 
 int bc_last_cuda_error(void) { return g_last_cuda; }
+int64_t bc_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int bc_create(int device, bc_ctx** out) {
   if (!out) return BC_ERR_ARG;
@@ -137,6 +141,7 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
   c->S = S;
   BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->B, c->Dpad, c->colaux, c->bbar,
                                  (cudaStream_t)stream));
+  BC_LAUNCHED(2);
   c->samples_set = true;
   return BC_OK;
 }
@@ -145,6 +150,7 @@ int bc_rowquad(bc_ctx* c, const double* d_X, int64_t n, int64_t ldx, double* d_o
   if (!c || !d_X || !d_out || n < 0) return BC_ERR_ARG;
   if (!c->potential_set || c->model != BC_MODEL_GAUSSIAN) return BC_ERR_STATE;
   BC_CUDA(launch_rowquad(d_X, n, c->Dk, ldx, c->d_siginv, d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -198,6 +204,7 @@ int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* 
   }
   BC_CUDA(launch_project(P, c->model, c->kind, MODE_COLSUM, c->tile_cfg, grid, c->smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
+  BC_LAUNCHED(2);
   return BC_OK;
 }
 
@@ -213,6 +220,7 @@ int bc_project_score(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d
   cudaStream_t st = (cudaStream_t)stream;
   BC_CUDA(launch_project(P, c->model, c->kind, MODE_SCORE, c->tile_cfg, grid, c->smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
+  BC_LAUNCHED(2);
   return BC_OK;
 }
 
@@ -233,14 +241,18 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
   P.norms = raw ? nullptr : d_norms;
   P.raw = raw ? 1 : 0;
   BC_CUDA(launch_project(P, c->model, c->kind, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
-  if (d_out_dd)
+  BC_LAUNCHED(1);
+  if (d_out_dd) {
     BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_MATERIALISE, st));
+    BC_LAUNCHED(1);
+  }
   return BC_OK;
 }
 
 int bc_colsum_combine(bc_ctx* c, const double* d_parts, int nparts, int S, double* d_out, void* stream) {
   if (!c || !d_parts || !d_out || nparts <= 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_colsum_combine(d_parts, nparts, S, bc_colsum_ld(S), d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -248,6 +260,7 @@ int bc_core_resid(bc_ctx* c, const double* d_colsum, double scaling, const doubl
                   const double* d_w, double* d_resid, void* stream) {
   if (!c || !d_colsum || !d_resid || M < 0 || S <= 0 || (M > 0 && (!d_Vc || !d_w))) return BC_ERR_ARG;
   BC_CUDA(launch_core_resid(d_colsum, scaling, d_Vc, M, S, ldv, d_w, d_resid, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -255,12 +268,14 @@ int bc_core_maxcorr(bc_ctx* c, const double* d_Vc, int M, int S, int64_t ldv, co
                     void* stream) {
   if (!c || !d_Vc || !d_resid || !d_out || M <= 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_core_maxcorr(d_Vc, M, S, ldv, d_resid, skip, d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
 int bc_core_grad(bc_ctx* c, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, double* d_grad, void* stream) {
   if (!c || !d_Vc || !d_resid || !d_grad || M <= 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_core_grad(d_Vc, M, S, ldv, d_resid, d_grad, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -268,12 +283,14 @@ int bc_adam_step(bc_ctx* c, const double* d_g, double* d_x, double* d_m1, double
                  double c1, double c2, double eps, const unsigned char* d_nn_mask, void* stream) {
   if (!c || !d_g || !d_x || !d_m1 || !d_m2 || n < 0) return BC_ERR_ARG;
   BC_CUDA(launch_adam(d_g, d_x, d_m1, d_m2, n, lr, b1, b2, c1, c2, eps, d_nn_mask, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
 int bc_dense_rownorms(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream) {
   if (!c || !d_V || !d_norms || n < 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_dense_rowstats(d_V, n, S, ldv, nullptr, 0, d_norms, nullptr, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -285,6 +302,7 @@ static int dense_ws(bc_ctx* c, int S) {
 int bc_dense_center(bc_ctx* c, double* d_V, int64_t n, int S, int64_t ldv, void* stream) {
   if (!c || !d_V || n < 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_dense_center(d_V, n, S, ldv, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -293,6 +311,7 @@ int bc_dense_colsum(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv,
   int rc;
   if ((rc = dense_ws(c, S))) return rc;
   BC_CUDA(launch_dense_colsum(d_V, n, S, ldv, c->dense_part, c->sms * 8, d_out_dd, bc_colsum_ld(S), (cudaStream_t)stream));
+  BC_LAUNCHED(2);
   return BC_OK;
 }
 
@@ -307,6 +326,7 @@ int bc_dense_score(bc_ctx* c, int mode, const double* d_V, int64_t n, int S, int
   if ((rc = dense_ws(c, S))) return rc;
   BC_CUDA(launch_dense_score(d_V, n, S, ldv, d_norms, d_u, mode, d_active, idx_offset, c->dense_part, c->sms * 8, d_out, d_scores,
                              (cudaStream_t)stream));
+  BC_LAUNCHED(2);
   return BC_OK;
 }
 
@@ -314,6 +334,7 @@ int bc_dense_combine(bc_ctx* c, const double* d_V, int64_t ldv, int S, const int
                      double* d_out, void* stream) {
   if (!c || !d_V || !d_out || S <= 0 || m < 0 || (m > 0 && (!d_idx || !d_w))) return BC_ERR_ARG;
   BC_CUDA(launch_dense_combine(d_V, ldv, S, reinterpret_cast<const long long*>(d_idx), d_w, m, d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -321,12 +342,14 @@ int bc_dense_gather(bc_ctx* c, const double* d_V, int64_t ldv, int S, const int6
                     void* stream) {
   if (!c || !d_V || !d_out || S <= 0 || m < 0 || (m > 0 && !d_idx)) return BC_ERR_ARG;
   BC_CUDA(launch_dense_gather(d_V, ldv, S, reinterpret_cast<const long long*>(d_idx), m, d_out, ldo, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
 int bc_transpose(bc_ctx* c, const double* d_A, int64_t rows, int64_t cols, int64_t lda, double* d_out, int64_t ldo, void* stream) {
   if (!c || !d_A || !d_out || rows < 0 || cols < 0) return BC_ERR_ARG;
   BC_CUDA(launch_transpose(d_A, rows, cols, lda, d_out, ldo, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 
@@ -336,6 +359,7 @@ int bc_vec_step(bc_ctx* c, int op, const double* d_xw, const double* d_xf, const
   if ((op == BC_VEC_GIGA_STEP || op == BC_VEC_FW_STEP) && !d_xf) return BC_ERR_ARG;
   if (op == BC_VEC_GIGA_DIR && !d_u) return BC_ERR_ARG;
   BC_CUDA(launch_vec_step(op, d_xw, d_xf, d_b, S, aux, d_u, d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 

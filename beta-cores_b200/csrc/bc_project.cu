@@ -209,8 +209,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_project(const ProjArgs P) {
           const bool cv = col < S;
           const int colc = cv ? col : S - 1;
           const double ca = F::kColAux ? __ldg(P.colaux + colc) : 0.0;
-          double f0 = F::eval(acc[j][e], ra0, ca, P.mp) - piv0;
-          double f1 = F::eval(acc[j][2 + e], ra1, ca, P.mp) - piv1;
+          // __dsub_rn: never contracted into an FMA with the potential's last multiply -- a row whose
+          // potential is the same double for every sample must centre to exactly 0 (-> 0/0 = NaN score,
+          // as in the reference, bcores.py:78)
+          double f0 = __dsub_rn(F::eval(acc[j][e], ra0, ca, P.mp), piv0);
+          double f1 = __dsub_rn(F::eval(acc[j][2 + e], ra1, ca, P.mp), piv1);
           f0 = (v0 && cv) ? f0 : 0.0;
           f1 = (v1 && cv) ? f1 : 0.0;
           s1_0 += f0;

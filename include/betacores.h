@@ -39,6 +39,7 @@ enum { BC_VEC_GIGA_DIR = 0, BC_VEC_GIGA_STEP = 1, BC_VEC_RESID = 2, BC_VEC_FW_ST
 int bc_version(void);
 const char* bc_error_string(int code);
 int bc_last_cuda_error(void);           /* cudaError_t of the most recent BC_ERR_CUDA */
+int64_t bc_launch_count(void);          /* kernels this library has launched in this process (instrumentation) */
 int bc_create(int device, bc_ctx** ctx);
 int bc_destroy(bc_ctx* ctx);
 int bc_sm_count(const bc_ctx* ctx);

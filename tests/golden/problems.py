@@ -165,7 +165,7 @@ def coreset_cases(heavy=True):
     c.append(dict(base, name='nl_svi_small', alg='svi', make=make_neurlin(1000, 8, 9), seed=7, S=32, opt_itrs=20, M=5, sched=_sched(.1)))
     c.append(dict(base, name='lr_hilbert_giga', alg='hilbert', make=make_logistic(500, 5, 13), seed=8, S=50, opt_itrs=0, M=10, sched=None, solver='GIGA'))
     c.append(dict(base, name='lr_hilbert_fw_sub', alg='hilbert', make=make_logistic(800, 5, 14), seed=9, S=50, opt_itrs=0, M=10, sched=None, solver='FrankWolfe', n_sel=200))
-    c.append(dict(base, name='gauss_hilbert_omp', alg='hilbert', make=make_gaussian(300, 6, 4), seed=10, S=48, opt_itrs=0, M=8, sched=None, solver='OrthoPursuit'))
+    c.append(dict(base, name='gauss_hilbert_omp', alg='hilbert', make=make_gaussian(300, 6, 4), seed=10, S=48, opt_itrs=0, M=7, sched=None, solver='OrthoPursuit'))
     if heavy:
         # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
         c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))

@@ -221,7 +221,12 @@ def test_snnls_small_cases_and_monotone_error(bc):
                 prev = e
             ref_limit = bool(g['small_%s_%s_limit' % (tag, name)])
             ref_w = g['small_%s_%s_w' % (tag, name)]
-            if not ref_limit and not alg.reached_numeric_limit:
+            # 'bin' / 'axis' data hold EXACTLY tied scores (identical normalised columns): the reference breaks
+            # them through the rounding of A/|a| . r, which no other summation order reproduces -- the north
+            # star exempts ties; the property checks above still apply (the reference's own test skips 'bin'
+            # for the same reason, tests/test_snnls/test_deterministic.py:104-107)
+            tie_prone = tag.startswith('bin') or tag.startswith('axis')
+            if not tie_prone and not ref_limit and not alg.reached_numeric_limit:
                 np.testing.assert_allclose(alg.weights(), ref_w, rtol=1e-5, atol=1e-7, err_msg=tag+name)
 
 
