@@ -104,6 +104,25 @@ class DeviceRows(object):
         self.rowaux = None          # Gaussian x Siginv x cache
         self.rowaux_key = None
 
+    @classmethod
+    def from_device(cls, engine, t, row0=0, n_total=None):
+        """wrap rows that are ALREADY resident in HBM: a contiguous fp64 CUDA tensor (n_local, ld) whose
+        leading dimension satisfies padded_ld (e.g. a shard generated or loaded on the device)"""
+        if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.is_contiguous()):
+            raise TypeError('from_device needs a contiguous 2-d fp64 CUDA tensor')
+        if t.shape[1] != padded_ld(t.shape[1]) or t.data_ptr() % 16:
+            raise ValueError('device rows need a leading dimension that is a multiple of 4 doubles and a 16-byte aligned base')
+        self = cls.__new__(cls)
+        self.engine = engine
+        self.n_local, self.ncols = int(t.shape[0]), int(t.shape[1])
+        self.row0 = int(row0)
+        self.n_total = int(n_total) if n_total is not None else self.n_local
+        self.ld = self.ncols
+        self.t = t
+        self.rowaux = None
+        self.rowaux_key = None
+        return self
+
     @property
     def sharded(self):
         return self.n_total != self.n_local

@@ -13,6 +13,21 @@ from . import _native as nv
 from ._device import DeviceRows, ptr, stream_ptr
 
 
+# Optional instrumentation (bench.py): when a list is installed here, every data-row pass appends
+# (kind, rows, start_event, end_event) recorded on the launching stream around the C-ABI call.
+PASS_TIMERS = None
+
+
+def _timed(kind, n, fn):
+    if PASS_TIMERS is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PASS_TIMERS.append((kind, n, e0, e1))
+
+
 class FusedProjection(object):
     def __init__(self, engine, potential, ncols, ctx_name='main'):
         if not potential.is_bound():
@@ -76,7 +91,9 @@ class FusedProjection(object):
         if out is None:
             out = self.eng.empty(2 * self.Sld)
         n = rows.n_local if sub is None else int(sub.numel())
-        nv.call('bc_project_colsum', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(self._rowaux(rows)), ptr(out), stream_ptr())
+        ra = self._rowaux(rows)
+        _timed('colsum', n, lambda: nv.call('bc_project_colsum', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(ra), ptr(out),
+                                            stream_ptr()))
         return out
 
     def combine(self, parts, nparts, out=None):
@@ -89,8 +106,9 @@ class FusedProjection(object):
         """out_best (>=2 doubles): best score, int64 bits of (position + idx_offset)."""
         self._check(rows)
         n = rows.n_local if sub is None else int(sub.numel())
-        nv.call('bc_project_score', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(self._rowaux(rows)), ptr(resid),
-                int(idx_offset), ptr(out_best), ptr(scores), stream_ptr())
+        ra = self._rowaux(rows)
+        _timed('score', n, lambda: nv.call('bc_project_score', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(ra), ptr(resid),
+                                           int(idx_offset), ptr(out_best), ptr(scores), stream_ptr()))
 
     def materialise(self, rows, sub=None, want_norms=False, want_colsum=False, raw=False):
         self._check(rows)

@@ -73,10 +73,16 @@ class _FusedTangent(_Tangent):
     def begin(self, w, p, beta):
         prj = self.o.ll_projector
         prj.update(w, p)                                   # host sampler: consumes np.random exactly like the reference
-        th = np.ascontiguousarray(np.atleast_2d(np.asarray(prj.samples, dtype=np.float64)))
-        if self._theta_buf is None or tuple(self._theta_buf.shape) != th.shape:
-            self._theta_buf = self.eng.empty(*th.shape)
-        self._theta_buf.copy_(torch.from_numpy(th))
+        if isinstance(prj.samples, torch.Tensor):          # device-side sampler: the samples are already in HBM
+            th = prj.samples.to(device=self.eng.device, dtype=torch.float64)
+            if self._theta_buf is None or tuple(self._theta_buf.shape) != tuple(th.shape):
+                self._theta_buf = self.eng.empty(*th.shape)
+            self._theta_buf.copy_(th)
+        else:
+            th = np.ascontiguousarray(np.atleast_2d(np.asarray(prj.samples, dtype=np.float64)))
+            if self._theta_buf is None or tuple(self._theta_buf.shape) != th.shape:
+                self._theta_buf = self.eng.empty(*th.shape)
+            self._theta_buf.copy_(torch.from_numpy(th))
         self.comm.broadcast(self._theta_buf, 0)            # bit-identical samples on every rank
         self.fp.configure(beta)
         self.fp.set_samples(self._theta_buf)
