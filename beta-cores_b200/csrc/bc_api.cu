@@ -1,4 +1,5 @@
 // beta-cores B200: extern "C" entry points (see include/betacores.h for the contract).
+#include <math.h>
 #include <new>
 #include "../../include/betacores.h"
 #include "bc_kernels.h"
@@ -15,6 +16,7 @@ struct bc_ctx {
   // potential
   bool potential_set = false;
   int model = 0, kind = 0, Dk = 0, Dc = 0, Dpad = 0, ss = 0, tile_cfg = 0, BM = 0, BN = 0;
+  int poly = 0;  // logistic beta-likelihood: degree of the (1+t)^-beta polynomial in use (0 = exp/log1p form)
   size_t smem = 0;
   ModelParams mp{};
   const double* d_siginv = nullptr;
@@ -53,9 +55,45 @@ static int grow(double** p, size_t* cap, size_t need) {
   return BC_OK;
 }
 
+// (1+t)^-beta on t in [0,1] as a polynomial in x = 2t-1: Chebyshev interpolant at 64 nodes, truncated to `deg`,
+// converted to the monomial basis (coefficients decay like 3^-k, so Horner in x is well conditioned); all in
+// long double.  out: deg+1 coefficients, highest degree first.  Returns the truncation bound sum_{j>deg} |c_j|.
+static double fit_pow_poly(double beta, int deg, double* out) {
+  const int n = 64;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  long double fs[n], c[n];
+  for (int k = 0; k < n; ++k) {
+    const long double x = cosl(pi * (k + 0.5L) / n);
+    fs[k] = powl(1.0L + 0.5L * (x + 1.0L), -(long double)beta);
+  }
+  for (int j = 0; j < n; ++j) {
+    long double a = 0.0L;
+    for (int k = 0; k < n; ++k) a += fs[k] * cosl(j * pi * (k + 0.5L) / n);
+    c[j] = 2.0L * a / n;
+  }
+  c[0] *= 0.5L;
+  long double err = 0.0L;
+  for (int j = deg + 1; j < n; ++j) err += fabsl(c[j]);
+  long double Tm[kPowPolyMax + 1] = {0}, Tc[kPowPolyMax + 1] = {0}, Tn[kPowPolyMax + 1], mono[kPowPolyMax + 1] = {0};
+  Tm[0] = 1.0L;  // T_0
+  Tc[1] = 1.0L;  // T_1
+  mono[0] += c[0];
+  if (deg >= 1) mono[1] += c[1];
+  for (int j = 2; j <= deg; ++j) {
+    for (int i = 0; i <= deg; ++i) Tn[i] = (i > 0 ? 2.0L * Tc[i - 1] : 0.0L) - Tm[i];
+    for (int i = 0; i <= deg; ++i) {
+      mono[i] += c[j] * Tn[i];
+      Tm[i] = Tc[i];
+      Tc[i] = Tn[i];
+    }
+  }
+  for (int i = 0; i <= deg; ++i) out[i] = (double)mono[deg - i];
+  return (double)err;
+}
+
 extern "C" {
 
-int bc_version(void) { return 100; }
+int bc_version(void) { return 101; }
 
 const char* bc_error_string(int code) {
   switch (code) {
@@ -70,6 +108,13 @@ const char* bc_error_string(int code) {
 }
 
 int bc_last_cuda_error(void) { return g_last_cuda; }
+
+int bc_fit_pow_poly(double beta, int degree, double* h_coef, double* h_err) {
+  if (!(beta > 0.0) || degree < 1 || degree > kPowPolyMax || !h_coef) return BC_ERR_ARG;
+  const double e = fit_pow_poly(beta, degree, h_coef);
+  if (h_err) *h_err = e;
+  return BC_OK;
+}
 int64_t bc_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int bc_create(int device, bc_ctx** out) {
@@ -124,6 +169,20 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
   c->BN = BN;
   c->smem = smem;
   for (int i = 0; i < 8; ++i) c->mp.p[i] = h_params[i];
+  for (int i = 0; i <= kPowPolyMax; ++i) c->mp.q[i] = 0.0;
+  c->poly = 0;
+  if (model == BC_MODEL_LOGISTIC && kind == BC_KIND_BETALIK) {
+    const double beta = h_params[0];
+    if (!(beta > 0.0)) return BC_ERR_ARG;
+    const int degs[2] = {20, kPowPolyMax};
+    for (int i = 0; i < 2 && c->poly == 0; ++i) {
+      double q[kPowPolyMax + 1];
+      if (fit_pow_poly(beta, degs[i], q) < 2.5e-17) {  // below a quarter ulp of (1+t)^-beta in [2^-beta, 1]
+        for (int k = 0; k <= degs[i]; ++k) c->mp.q[kPowPolyMax - degs[i] + k] = q[k];
+        c->poly = degs[i];
+      }
+    }
+  }
   c->d_siginv = d_siginv;
   c->potential_set = true;
   c->samples_set = false;
@@ -202,7 +261,7 @@ int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* 
     BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
     return BC_OK;
   }
-  BC_CUDA(launch_project(P, c->model, c->kind, MODE_COLSUM, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_COLSUM, c->tile_cfg, grid, c->smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -218,7 +277,7 @@ int bc_project_score(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d
   P.scores = d_scores;
   P.idx_offset = idx_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  BC_CUDA(launch_project(P, c->model, c->kind, MODE_SCORE, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_SCORE, c->tile_cfg, grid, c->smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -240,7 +299,7 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
   P.ldv = ldv;
   P.norms = raw ? nullptr : d_norms;
   P.raw = raw ? 1 : 0;
-  BC_CUDA(launch_project(P, c->model, c->kind, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
   BC_LAUNCHED(1);
   if (d_out_dd) {
     BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_MATERIALISE, st));

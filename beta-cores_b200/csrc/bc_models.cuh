@@ -1,41 +1,59 @@
 // beta-cores B200: per-element potentials f(x_n, theta_s), fused into the epilogue of the
 // projection contraction.  Each functor restates one reference function; `c` is the
 // contraction value  sum_k A[n][k] * B[s][k]  for the operands bc_set_samples() prepares.
+// The transcendental parts use the branch-free restricted-domain functions of bc_fastmath.cuh.
 #pragma once
+#if defined(__CUDACC__)
 #include "bc_common.cuh"
+#endif
+#include "bc_fastmath.cuh"
 
 namespace bc {
 
 enum : int { MODEL_LOGISTIC = 0, MODEL_GAUSSIAN = 1, MODEL_NEURLIN = 2 };
 enum : int { KIND_LOGLIK = 0, KIND_BETALIK = 1, KIND_BETAGRAD = 2 };
 
+constexpr int kPowPolyMax = 24;  // highest degree of the (1+t)^-beta polynomial
 struct ModelParams {
   double p[8];
+  double q[kPowPolyMax + 1];  // logistic beta-likelihood: (1+t)^-beta on t in [0,1] as a polynomial in 2t-1, highest degree
+                              // first, fitted by bc_set_potential for the current beta (bc_api.cu: fit_pow_poly)
 };
 
 // reference: examples/common/model_lr.py:72-79 (log_likelihood), :81-86 (beta_likelihood).
 //   A = Z (rows y_n x_n), B = Theta, m = -c.
 //   p[0] = beta, p[1] = (beta+1)/beta
-template <int KIND>
+// POLY = degree of the (1+t)^-beta polynomial (20 or 24), or 0: evaluate it as exp(-beta log1p t) (any beta).
+//
+// beta-likelihood, overflow-free: a = |m|, t = e^-a in (0,1], big = 1/(1+t), small = t big,
+//   E = big^beta = (1+t)^-beta, G = e^(-beta a) so that small^beta = G E.  Then
+//   (1+e^m)^-beta     = (m >= 0) ? G E : E
+//   (1+e^m)^(-beta-1) + (1+e^-m)^(-beta-1) = big^(beta+1) + small^(beta+1) = E big (1 + G t)
+//   f = -(k1 (1+e^m)^-beta - (...)) = E * ( big (1 + G t) - k1 ((m >= 0) ? G : 1) )
+template <int KIND, int POLY = 20>
 struct LogisticF {
   static constexpr bool kRowAux = false, kColAux = false;
-  __device__ __forceinline__ static double eval(double c, double, double, const ModelParams& mp) {
+  BC_HD static double eval(double c, double, double, const ModelParams& mp) {
     const double m = -c;
+    const double a = fabs(m);
+    const double t = exp_nonpos(-a);
     if (KIND == KIND_LOGLIK) {
-      // m < 100: -log1p(e^m); else -m
-      return (m < 100.0) ? -log1p(exp(m)) : -m;
+      // m < 100: -log1p(e^m); else -m   ==   -(max(m, 0) + log1p(e^-|m|))   (for m >= 100 the log1p term is below ulp(m)/2)
+      const double r = -(fmax(m, 0.0) + log1p_unit(t));
+      return (m != m) ? m : r;
     } else {
-      // -( k1 (1+e^m)^-b - ( (1+e^m)^(-b-1) + (1+e^-m)^(-b-1) ) ), evaluated overflow-free:
-      // t = e^-|m|, big = 1/(1+t), small = t/(1+t);  big^b = e^(-b log1p t), small^b = e^(-b|m|) big^b.
       const double beta = mp.p[0], k1 = mp.p[1];
-      const double a = fabs(m);
-      const double t = exp(-a);
-      const double E = exp(-beta * log1p(t));  // big^beta
-      const double G = exp(-beta * a);         // (small/big)^beta
-      const double u = E / (1.0 + t);          // big^(beta+1)
-      const double v = G * t * u;              // small^(beta+1)
-      const double pb = (m >= 0.0) ? G * E : E;  // (1+e^m)^-beta
-      return -(k1 * pb - (u + v));
+      const double G = exp_nonpos(-beta * a);
+      const double big = rcp_1to2(1.0 + t);
+      double E;
+      if (POLY == 0) {
+        E = exp_nonpos(-beta * log1p_unit(t));
+      } else {
+        E = horner<(POLY > 0 ? POLY : 1)>(mp.q + (kPowPolyMax - POLY), fm_fma(t, 2.0, -1.0));
+      }
+      const double sel = (m >= 0.0) ? k1 * G : k1;
+      const double r = E * fm_fma(big, fm_fma(G, t, 1.0), -sel);
+      return (m != m) ? m : r;
     }
   }
 };
@@ -50,14 +68,14 @@ struct LogisticF {
 template <int KIND>
 struct GaussianF {
   static constexpr bool kRowAux = true, kColAux = true;
-  __device__ __forceinline__ static double eval(double c, double ra, double ca, const ModelParams& mp) {
+  BC_HD static double eval(double c, double ra, double ca, const ModelParams& mp) {
     const double q = ra + ca - 2.0 * c;
     if (KIND == KIND_LOGLIK) {
       return mp.p[0] - 0.5 * q;
     } else if (KIND == KIND_BETALIK) {
-      return mp.p[1] * exp(mp.p[2] * q) - mp.p[3];
+      return mp.p[1] * exp_clamped(mp.p[2] * q) - mp.p[3];
     } else {
-      const double e = exp(mp.p[2] * q);
+      const double e = exp_clamped(mp.p[2] * q);
       const double t1 = mp.p[4] * (mp.p[1] * e - mp.p[3]);
       return t1 - mp.p[5] * e - mp.p[6] * q * e - mp.p[7];
     }
@@ -73,12 +91,12 @@ struct GaussianF {
 template <int KIND>
 struct NeurlinF {
   static constexpr bool kRowAux = true, kColAux = false;
-  __device__ __forceinline__ static double eval(double c, double y, double, const ModelParams& mp) {
+  BC_HD static double eval(double c, double y, double, const ModelParams& mp) {
     const double r2 = y * y - 2.0 * c * y + c * c;
     if (KIND == KIND_LOGLIK) {
       return mp.p[0] - mp.p[1] * r2;
     } else {
-      return mp.p[2] * (mp.p[3] * exp(mp.p[4] * r2) + mp.p[5]);
+      return mp.p[2] * (mp.p[3] * exp_clamped(mp.p[4] * r2) + mp.p[5]);
     }
   }
 };

@@ -14,6 +14,7 @@
 //                                             does not depend on the tile->CTA->GPU assignment)
 //   * per row:    sum f, sum f^2, sum f r   (-> centred norm and correlation -> arg-max)
 // MODE_MATERIALISE additionally writes the centred rows (Hilbert / coreset-point path).
+#include "bc_common.cuh"
 #include "bc_models.cuh"
 #include "bc_kernels.h"
 
@@ -507,11 +508,13 @@ int project_tile_config(int Dpad, int* BM, int* BN, int* ss_out, size_t* smem_ou
   return -1;
 }
 
-cudaError_t launch_project(const ProjArgs& P, int model, int kind, int mode, int tile_cfg, int grid, size_t smem,
+cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem,
                            cudaStream_t st) {
   if (model == MODEL_LOGISTIC) {
-    if (kind == KIND_LOGLIK) return launch_mode<LogisticF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st);
-    return launch_mode<LogisticF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st);
+    if (kind == KIND_LOGLIK) return launch_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, tile_cfg, grid, smem, st);
+    if (poly == 20) return launch_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, tile_cfg, grid, smem, st);
+    if (poly == kPowPolyMax) return launch_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, tile_cfg, grid, smem, st);
+    return launch_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, tile_cfg, grid, smem, st);
   } else if (model == MODEL_GAUSSIAN) {
     if (kind == KIND_LOGLIK) return launch_mode<GaussianF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st);
     if (kind == KIND_BETALIK) return launch_mode<GaussianF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st);

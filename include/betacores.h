@@ -40,6 +40,10 @@ int bc_version(void);
 const char* bc_error_string(int code);
 int bc_last_cuda_error(void);           /* cudaError_t of the most recent BC_ERR_CUDA */
 int64_t bc_launch_count(void);          /* kernels this library has launched in this process (instrumentation) */
+/* Host-only diagnostic: the coefficients (highest degree first, variable 2t-1) bc_set_potential fits for
+ * (1+t)^-beta on t in [0,1] -- the pow() of examples/common/model_lr.py:85 -- and their truncation bound.
+ * degree <= 24.  Used by the CPU tests to check the polynomial against a high-precision reference. */
+int bc_fit_pow_poly(double beta, int degree, double* h_coef, double* h_err);
 int bc_create(int device, bc_ctx** ctx);
 int bc_destroy(bc_ctx* ctx);
 int bc_sm_count(const bc_ctx* ctx);

@@ -1,0 +1,34 @@
+// Host build of the projection epilogue's scalar functions (beta-cores_b200/csrc/bc_fastmath.cuh, bc_models.cuh) so that
+// the CPU test-suite can check the polynomials and the algebraic rewrites against high-precision references.
+// TEST INFRASTRUCTURE: compiled by tests/test_fastmath_cpu.py with g++ into tests/native/_build/; not part of the product.
+#include "../../beta-cores_b200/csrc/bc_models.cuh"
+
+extern "C" {
+double fm_exp(double x) { return bc::exp_clamped(x); }
+double fm_log1p_unit(double t) { return bc::log1p_unit(t); }
+// q: kPowPolyMax+1 coefficients laid out as bc_set_potential stores them (right-aligned)
+double fm_logistic(int kind, int poly, double c, double beta, const double* q) {
+  bc::ModelParams mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = 0.0;
+  mp.p[0] = beta;
+  mp.p[1] = (beta + 1.) / beta;
+  for (int i = 0; i <= bc::kPowPolyMax; ++i) mp.q[i] = q ? q[i] : 0.0;
+  if (kind == bc::KIND_LOGLIK) return bc::LogisticF<bc::KIND_LOGLIK, 0>::eval(c, 0, 0, mp);
+  if (poly == 20) return bc::LogisticF<bc::KIND_BETALIK, 20>::eval(c, 0, 0, mp);
+  if (poly == bc::kPowPolyMax) return bc::LogisticF<bc::KIND_BETALIK, bc::kPowPolyMax>::eval(c, 0, 0, mp);
+  return bc::LogisticF<bc::KIND_BETALIK, 0>::eval(c, 0, 0, mp);
+}
+double fm_gaussian(int kind, double c, double ra, double ca, const double* p8) {
+  bc::ModelParams mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = p8[i];
+  if (kind == bc::KIND_LOGLIK) return bc::GaussianF<bc::KIND_LOGLIK>::eval(c, ra, ca, mp);
+  if (kind == bc::KIND_BETALIK) return bc::GaussianF<bc::KIND_BETALIK>::eval(c, ra, ca, mp);
+  return bc::GaussianF<bc::KIND_BETAGRAD>::eval(c, ra, ca, mp);
+}
+double fm_neurlin(int kind, double c, double y, const double* p8) {
+  bc::ModelParams mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = p8[i];
+  if (kind == bc::KIND_LOGLIK) return bc::NeurlinF<bc::KIND_LOGLIK>::eval(c, y, 0, mp);
+  return bc::NeurlinF<bc::KIND_BETALIK>::eval(c, y, 0, mp);
+}
+}
