@@ -244,6 +244,7 @@ static int project_common(bc_ctx* c, int mode, const double* d_X, int64_t ldx, c
   P.ldv = 0;
   P.norms = nullptr;
   P.raw = 0;
+  P.want_colsum = 0;
   const int64_t tiles = (n + c->BM - 1) / c->BM;
   *grid = (int)(tiles < c->sms ? tiles : c->sms);
   (void)mode;
@@ -299,6 +300,7 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
   P.ldv = ldv;
   P.norms = raw ? nullptr : d_norms;
   P.raw = raw ? 1 : 0;
+  P.want_colsum = d_out_dd ? 1 : 0;
   BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
   BC_LAUNCHED(1);
   if (d_out_dd) {

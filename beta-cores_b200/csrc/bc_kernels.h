@@ -41,6 +41,7 @@ struct ProjArgs {
   long long ldv;
   double* norms;  // optional [n]
   int raw;        // 1: write the un-centred potential f itself (no pivot, no mean subtraction)
+  int want_colsum;  // MODE_MATERIALISE: also accumulate the column sums
 };
 
 int project_tile_config(int Dpad, int* BM, int* BN, int* ss, size_t* smem);
