@@ -22,6 +22,11 @@ SIGNATURES = {
     'bc_project_colsum': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_project_score': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_project_materialise': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp],
+    'bc_q_image_bytes': [c_i64, ctypes.POINTER(c_i64)],
+    'bc_quantise_rows': [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    'bc_project_colsum_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    'bc_project_score_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    'bc_contraction_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp],
     'bc_colsum_combine': [c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     'bc_core_resid': [c_vp, c_vp, c_dbl, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp],
     'bc_core_maxcorr': [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_int, c_vp, c_vp],
@@ -38,7 +43,7 @@ SIGNATURES = {
     'bc_fit_pow_poly': [c_dbl, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }
-PLAIN = {'bc_version': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+PLAIN = {'bc_version': ([], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
 MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2

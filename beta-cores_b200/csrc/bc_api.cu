@@ -3,6 +3,7 @@
 #include <new>
 #include "../../include/betacores.h"
 #include "bc_kernels.h"
+#include "bc_umma.cuh"
 
 using namespace bc;
 
@@ -33,6 +34,12 @@ struct bc_ctx {
   double* part_misc = nullptr;
   double* dense_part = nullptr;
   size_t cap_dense = 0;
+  // tensor-core route: quantised sample image + per-sample scale (valid when q_ready)
+  bool q_ready = false;
+  double* qB = nullptr;  // raw bytes, allocated in doubles
+  size_t cap_qB = 0;
+  double* colscale = nullptr;
+  size_t cap_cs = 0;
 };
 
 static int cuda_fail(cudaError_t e) {
@@ -139,6 +146,8 @@ int bc_destroy(bc_ctx* c) {
   cudaFree(c->part_colsum);
   cudaFree(c->part_misc);
   cudaFree(c->dense_part);
+  cudaFree(c->qB);
+  cudaFree(c->colscale);
   delete c;
   return BC_OK;
 }
@@ -201,6 +210,16 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
   BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->B, c->Dpad, c->colaux, c->bbar,
                                  (cudaStream_t)stream));
   BC_LAUNCHED(2);
+  c->q_ready = false;
+  if (c->Dk <= kQK) {
+    const size_t chunks = (size_t)(S + kQChunk - 1) / kQChunk;
+    if ((rc = grow(&c->qB, &c->cap_qB, chunks * kQChunkBytes / sizeof(double)))) return rc;
+    if ((rc = grow(&c->colscale, &c->cap_cs, chunks * kQChunk))) return rc;
+    BC_CUDA(launch_quantise_samples(c->B, c->Dpad, S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
+                                    (cudaStream_t)stream));
+    BC_LAUNCHED(1);
+    c->q_ready = true;
+  }
   c->samples_set = true;
   return BC_OK;
 }
@@ -307,6 +326,104 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
     BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_MATERIALISE, st));
     BC_LAUNCHED(1);
   }
+  return BC_OK;
+}
+
+// ---- tensor-core route ------------------------------------------------------------------------
+int bc_q_max_features(void) { return kQK; }
+
+int bc_q_image_bytes(int64_t n, int64_t* bytes) {
+  if (n < 0 || !bytes) return BC_ERR_ARG;
+  *bytes = ((n + kQTileRows - 1) / kQTileRows) * (int64_t)kQTileBytes;
+  return BC_OK;
+}
+
+int bc_quantise_rows(bc_ctx* c, const double* d_X, int64_t ldx, int64_t n, int D, int aux_col, void* d_image, double* d_rowscale,
+                     double* d_aux_out, void* stream) {
+  if (!c || !d_X || !d_image || !d_rowscale || n < 0 || D <= 0 || ldx < D) return BC_ERR_ARG;
+  if (D > kQK) return BC_ERR_UNSUPPORTED;
+  if (d_aux_out && (aux_col < 0 || aux_col >= ldx)) return BC_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(d_image) & 15) return BC_ERR_ALIGN;
+  BC_CUDA(launch_quantise_rows(d_X, ldx, n, D, reinterpret_cast<unsigned char*>(d_image), d_rowscale, d_aux_out, aux_col,
+                               (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
+static int q_common(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux, QProjArgs& P,
+                    int* grid) {
+  if (!c || !d_image || !d_rowscale || n < 0) return BC_ERR_ARG;
+  if (!c->potential_set || !c->samples_set) return BC_ERR_STATE;
+  if (!c->q_ready) return BC_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(d_image) & 15) return BC_ERR_ALIGN;
+  if (c->model != BC_MODEL_LOGISTIC && !d_rowaux) return BC_ERR_ARG;
+  P.imgA = reinterpret_cast<const unsigned char*>(d_image);
+  P.rowscale = d_rowscale;
+  P.imgB = reinterpret_cast<const unsigned char*>(c->qB);
+  P.colscale = c->colscale;
+  P.n = n;
+  P.idx_offset = 0;
+  P.S = c->S;
+  P.colaux = (c->model == BC_MODEL_GAUSSIAN) ? c->colaux : nullptr;
+  P.rowaux = (c->model != BC_MODEL_LOGISTIC) ? d_rowaux : nullptr;
+  P.mp = c->mp;
+  P.part_colsum = c->part_colsum;
+  P.part_misc = c->part_misc;
+  P.Sld = bc_colsum_ld(c->S);
+  P.resid = nullptr;
+  P.scores = nullptr;
+  P.V = nullptr;
+  P.ldv = 0;
+  const int64_t tiles = (n + kQTileRows - 1) / kQTileRows;
+  *grid = (int)(tiles < c->sms ? tiles : c->sms);
+  return BC_OK;
+}
+
+int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
+                        double* d_out_dd, void* stream) {
+  QProjArgs P;
+  int grid, rc;
+  if (!d_out_dd) return BC_ERR_ARG;
+  if ((rc = q_common(c, d_image, d_rowscale, n, d_rowaux, P, &grid))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
+    return BC_OK;
+  }
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_COLSUM, grid, st));
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
+  BC_LAUNCHED(2);
+  return BC_OK;
+}
+
+int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
+                       const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream) {
+  QProjArgs P;
+  int grid, rc;
+  if (!d_resid || !d_best || n <= 0) return BC_ERR_ARG;
+  if ((rc = q_common(c, d_image, d_rowscale, n, d_rowaux, P, &grid))) return rc;
+  P.resid = d_resid;
+  P.scores = d_scores;
+  P.idx_offset = idx_offset;
+  cudaStream_t st = (cudaStream_t)stream;
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_SCORE, grid, st));
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
+  BC_LAUNCHED(2);
+  return BC_OK;
+}
+
+int bc_contraction_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, double* d_V, int64_t ldv, void* stream) {
+  QProjArgs P;
+  int grid, rc;
+  static const double dummy = 0.0;
+  if (!d_V || n <= 0) return BC_ERR_ARG;
+  if ((rc = q_common(c, d_image, d_rowscale, n, &dummy, P, &grid))) return rc;
+  if (ldv < c->S) return BC_ERR_ARG;
+  P.rowaux = nullptr;
+  P.V = d_V;
+  P.ldv = ldv;
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_DOT, grid, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
   return BC_OK;
 }
 

@@ -49,6 +49,33 @@ cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld, double* out_dd,
                                     double* out_best, int mode, cudaStream_t st);
 
+
+// ---- bc_project_q.cu: tensor-core (tcgen05 int8 Ozaki) route of the fused projection ----
+enum : int { QMODE_COLSUM = MODE_COLSUM, QMODE_SCORE = MODE_SCORE, QMODE_DOT = 3 };
+struct QProjArgs {
+  const unsigned char* imgA;  // [tiles][7][128][128] swizzled
+  const double* rowscale;     // [n]
+  const unsigned char* imgB;  // [chunks][7][32][128] swizzled
+  const double* colscale;     // [S]
+  long long n;
+  long long idx_offset;
+  int S;
+  const double* colaux;  // [S] or null
+  const double* rowaux;  // [n] or null
+  ModelParams mp;
+  double* part_colsum;  // [grid][2][Sld]
+  double* part_misc;    // [grid][4]
+  int Sld;
+  const double* resid;  // [S+1]
+  double* scores;       // optional [n]
+  double* V;            // QMODE_DOT: the contraction itself, n x ldv
+  long long ldv;
+};
+cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
+                                 double* aux_out, int aux_col, cudaStream_t st);
+cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, cudaStream_t st);
+cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st);
+
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,
                                    double* colaux, double* bbar, cudaStream_t st);

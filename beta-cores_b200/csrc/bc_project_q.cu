@@ -1,0 +1,470 @@
+// beta-cores B200: stage 1 (+2), tensor-core route -- the fused N x S projection with the contraction on tcgen05.
+//
+// Same contract as bc_project.cu (k_project): replaces, without materialising the N x S matrix,
+//   BetaBlackBoxProjector.project_f / BlackBoxProjector.project   (bayesiancoresets/coreset/projector.py:51-55, :23-26)
+//   the column sum / residual correlation of BetaCoreset._select   (bayesiancoresets/coreset/bcores.py:77-81)
+//   the column sum of BetaCoreset._optimize's grd()                (bayesiancoresets/coreset/bcores.py:142-146)
+//
+// The reference contracts in fp64 (numpy dgemm).  tcgen05 has no f64 kind, and the legacy FP64 DMMA shares the FP64 pipe
+// with the potential's polynomials, so here the contraction is done EXACTLY in integers (Ozaki splitting):
+//   z_n = 2^(e_n) sum_i a_i 256^-(i+1),  theta_s = 2^(e_s) sum_j b_j 256^-(j+1),   a_i, b_j int8 digits (7 each, 55 bits)
+//   z_n . theta_s = 2^(e_n + e_s) sum_d 256^-(d+2) D_d,     D_d = sum_{i+j=d} a_i . b_j   (int32, exact)
+// keeping the diagonals d <= 6 (28 of the 49 digit pairs; the dropped ones are below 6*128*2^-58 of |z|max |theta|max).
+// tcgen05.mma.kind::i8 computes D_0..D_6 for a 128-row x 32-sample chunk into 7 x 32 TMEM columns: the MMA for row digit
+// i multiplies against the sample digits 0..6-i STACKED along N (N = 32 (7 - i)), i.e. 7 x 4 instructions per chunk.
+//
+// One persistent CTA per SM, 11 warps:
+//   warps 0-3 / 4-7 : two epilogue groups (even / odd chunks; one TMEM accumulator buffer each).  Thread = data row (TMEM
+//                     lane): tcgen05.ld the 7 diagonals, recombine in int64 (integer pipe), convert exactly, apply the
+//                     model's potential (FP64 pipe), pivot shift, per-row statistics in registers, column partials by a
+//                     transposed warp butterfly -> shared-memory ring.
+//   warp 8          : producer -- cp.async.bulk (TMA engine) of the row tile (112 KB, once per tile) and of the sample
+//                     chunks (28 KB, NSTB-stage ring).  Both images are stored in HBM already in the swizzled layout
+//                     the tensor core reads, so a copy is one contiguous burst.
+//   warp 9          : MMA issuer (one lane) + TMEM allocation.
+//   warp 10         : reducer -- adds the four 32-row column partials of a chunk in fixed order and accumulates them per
+//                     column in double-double (order-insensitive S-vector).
+#include "bc_common.cuh"
+#include "bc_models.cuh"
+#include "bc_kernels.h"
+#include "bc_umma.cuh"
+
+namespace bc {
+
+constexpr int kQStagesB = 3;
+constexpr int kQSlots = 4;
+constexpr int kQThreads = 11 * 32;
+
+struct QSmem {
+  static constexpr size_t a = 0;
+  static constexpr size_t b = a + kQTileBytes;
+  static constexpr size_t ring = b + (size_t)kQStagesB * kQChunkBytes;    // [kQSlots][4 warps][32 cols]
+  static constexpr size_t pivs = ring + (size_t)kQSlots * 4 * kQChunk * 8;  // [2][128]
+  static constexpr size_t stats = pivs + 2 * 128 * 8;                       // [128][3]
+  static constexpr size_t fin = stats + 128 * 3 * 8;                        // [4 warps][2]
+  static constexpr size_t bars = fin + 4 * 2 * 8;
+  static constexpr int nbars = 2 + 2 * kQStagesB + 4 + 2 * kQSlots + 2 + 2;
+  static constexpr size_t tmem = bars + (size_t)nbars * 8;
+  static constexpr size_t total = tmem + 16 + 1024;  // + slack to align the base to 1024 B
+};
+static_assert(QSmem::total <= kMaxSmem, "shared memory budget");
+
+// ------------------------------------------------------------------ quantisers --
+// One warp per row; lane l owns contraction indices 4l .. 4l+3.  R = rows per image tile (128 data rows / 32 samples).
+// Row r of the source is src + (r * ld); indices >= D are zero.  Writes the 7 digit planes of the row into the swizzled
+// image and scale_out[r] = 2^(e - 32) (NaN if the row is not finite: poisons every contraction with it, like the
+// reference's NaN propagation).  Rows in [n, tiles * R) are written as zeros.
+template <int R>
+__global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src, long long ld, long long n, int D,
+                                                   unsigned char* __restrict__ image, double* __restrict__ scale_out,
+                                                   double* __restrict__ aux_out, int aux_col) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows_padded = ((n + R - 1) / R) * R;
+  for (long long r = warp; r < rows_padded; r += nwarps) {
+    double x[4] = {0.0, 0.0, 0.0, 0.0};
+    if (r < n) {
+      const double* p = src + r * ld;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = lane * 4 + i;
+        if (k < D) x[i] = p[k];
+      }
+      if (aux_out && lane == 0) aux_out[r] = p[aux_col];
+    }
+    double amax = fmax(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3])));
+    bool bad = !(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]) && isfinite(x[3]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      const int ob = __shfl_xor_sync(0xffffffffu, (int)bad, o);
+      bad = bad || (ob != 0);
+    }
+    // |x| 2^-e < 1/4  =>  top digit within [-64, 64], the others in [-128, 127]
+    const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
+    uint32_t dig[kQSlices] = {0, 0, 0, 0, 0, 0, 0};
+    if (!bad) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        long long Q = __double2ll_rn(scalbn(x[i], 56 - e));  // |Q| <= 2^54
+#pragma unroll
+        for (int s = kQSlices - 1; s >= 1; --s) {
+          const long long d = (long long)(signed char)(Q & 0xff);
+          dig[s] |= (uint32_t)(d & 0xff) << (8 * i);
+          Q = (Q - d) >> 8;
+        }
+        dig[0] |= (uint32_t)(Q & 0xff) << (8 * i);
+      }
+    }
+    const long long tile = r / R;
+    const uint32_t rr = (uint32_t)(r % R);
+    unsigned char* base = image + (size_t)tile * (kQSlices * R * kQK) + q_swizzle_off(rr, (uint32_t)lane * 4u);
+#pragma unroll
+    for (int s = 0; s < kQSlices; ++s) *reinterpret_cast<uint32_t*>(base + (size_t)s * (R * kQK)) = dig[s];
+    if (r < n && lane == 0) scale_out[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
+  }
+}
+
+cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
+                                 double* aux_out, int aux_col, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long warps = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
+  long long blocks = (warps + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale,
+                                    cudaStream_t st) {
+  const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
+  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, colscale, nullptr, 0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ projection --
+
+
+template <class F, int MODE>
+__global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* As = smem + QSmem::a;
+  unsigned char* Bs = smem + QSmem::b;
+  double* ring = reinterpret_cast<double*>(smem + QSmem::ring);
+  double* pivs = reinterpret_cast<double*>(smem + QSmem::pivs);
+  double* stats = reinterpret_cast<double*>(smem + QSmem::stats);
+  double* fin = reinterpret_cast<double*>(smem + QSmem::fin);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QSmem::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + QSmem::tmem);
+  uint64_t* full_a = bars + 0;
+  uint64_t* empty_a = bars + 1;
+  uint64_t* full_b = bars + 2;                    // [kQStagesB]
+  uint64_t* empty_b = full_b + kQStagesB;         // [kQStagesB]
+  uint64_t* tmem_full = empty_b + kQStagesB;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint64_t* ring_full = tmem_empty + 2;           // [kQSlots]
+  uint64_t* ring_empty = ring_full + kQSlots;     // [kQSlots]
+  uint64_t* piv_full = ring_empty + kQSlots;      // [2]
+  uint64_t* stats_full = piv_full + 2;            // [1]
+  uint64_t* stats_empty = stats_full + 1;         // [1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = P.S;
+  const long long n = P.n;
+  const long long ntiles = (n + kQTileRows - 1) / kQTileRows;
+  const int nchunks = (S + kQChunk - 1) / kQChunk;
+  const bool want_cols = (MODE == QMODE_COLSUM);
+
+  if (tid == 0) {
+    mbar_init(full_a, 1);
+    mbar_init(empty_a, 1);
+    for (int i = 0; i < kQStagesB; ++i) {
+      mbar_init(full_b + i, 1);
+      mbar_init(empty_b + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);
+      mbar_init(piv_full + i, 4);
+    }
+    for (int i = 0; i < kQSlots; ++i) {
+      mbar_init(ring_full + i, 4);
+      mbar_init(ring_empty + i, 1);
+    }
+    mbar_init(stats_full, 4);
+    mbar_init(stats_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ======================= producer: TMA-engine bulk copies =======================
+    if (lane == 0) {
+      uint32_t itb = 0, tcount = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        mbar_wait(empty_a, (tcount & 1) ^ 1);
+        mbar_arrive_expect_tx(full_a, (uint32_t)kQTileBytes);
+        const unsigned char* srcA = P.imgA + (size_t)tile * kQTileBytes;
+#pragma unroll
+        for (int s = 0; s < kQSlices; ++s) bulk_g2s(As + (size_t)s * kQSliceA, srcA + (size_t)s * kQSliceA, kQSliceA, full_a);
+        for (int c = 0; c < nchunks; ++c, ++itb) {
+          const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
+          mbar_wait(empty_b + st, ph ^ 1);
+          mbar_arrive_expect_tx(full_b + st, (uint32_t)kQChunkBytes);
+          bulk_g2s(Bs + (size_t)st * kQChunkBytes, P.imgB + (size_t)c * kQChunkBytes, kQChunkBytes, full_b + st);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      uint32_t idesc[kQSlices];
+#pragma unroll
+      for (int i = 0; i < kQSlices; ++i) idesc[i] = umma_idesc_i8(kQChunk * (kQSlices - i));
+      const uint64_t adesc0 = umma_desc_sw128(smem_u32(As));
+      uint32_t itb = 0, tcount = 0, use0 = 0, use1 = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        mbar_wait(full_a, tcount & 1);
+        for (int c = 0; c < nchunks; ++c, ++itb) {
+          const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
+          const int buf = c & 1;
+          const uint32_t use = buf ? use1 : use0;
+          mbar_wait(tmem_empty + buf, (use & 1) ^ 1);
+          if (buf) ++use1; else ++use0;
+          mbar_wait(full_b + st, ph);
+          tc_fence_after();
+          const uint64_t bdesc0 = umma_desc_sw128(smem_u32(Bs + (size_t)st * kQChunkBytes));
+          const uint32_t d0 = tmem_base + (uint32_t)(buf * kQDiagCols);
+#pragma unroll
+          for (int i = 0; i < kQSlices; ++i) {
+#pragma unroll
+            for (int k = 0; k < kQK / 32; ++k) {
+              // +32 bytes along K inside the swizzle atom = +2 in the (>>4) start-address field
+              umma_i8(d0 + (uint32_t)(i * kQChunk), adesc0 + (uint64_t)(i * (kQSliceA >> 4) + k * 2), bdesc0 + (uint64_t)(k * 2),
+                      idesc[i], (i | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_b + st);
+          umma_commit(tmem_full + buf);
+          if (c == nchunks - 1) umma_commit(empty_a);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ============ reducer: 4 partials per chunk -> double-double column accumulators ============
+    if (want_cols) {
+      double* acc_hi = P.part_colsum + (size_t)blockIdx.x * 2 * P.Sld;
+      double* acc_lo = acc_hi + P.Sld;
+      for (int i = lane; i < 2 * P.Sld; i += 32) __stcg(acc_hi + i, 0.0);
+      __syncwarp();
+      uint32_t itb = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++itb) {
+          const uint32_t slot = itb % kQSlots, ph = (itb / kQSlots) & 1;
+          mbar_wait(ring_full + slot, ph);
+          const double* rs = ring + (size_t)slot * 4 * kQChunk + lane;
+          double v = rs[0];
+          v += rs[kQChunk];
+          v += rs[2 * kQChunk];
+          v += rs[3 * kQChunk];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ring_empty + slot);
+          const int col = c * kQChunk + lane;
+          if (col < S) {
+            dd a;
+            a.hi = __ldcg(acc_hi + col);
+            a.lo = __ldcg(acc_lo + col);
+            a = dd_add_d(a, v);
+            __stcg(acc_hi + col, a.hi);
+            __stcg(acc_lo + col, a.lo);
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue groups ================================
+    const int grp = warp >> 2;   // 0: even chunks (+ pivot, final score), 1: odd chunks
+    const int q = warp & 3;      // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * kQDiagCols);
+    const double dS = (double)S;
+    const double rsum = (MODE == QMODE_SCORE) ? __ldg(P.resid + S) : 0.0;
+    Best best = {0.0, -1};
+    uint32_t use = 0, tcount = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const long long p = tile * kQTileRows + row;
+      const bool rv = p < n;
+      const double rs = rv ? __ldg(P.rowscale + p) : 0.0;
+      const double ra = (F::kRowAux && rv) ? __ldg(P.rowaux + p) : 0.0;
+      double piv = 0.0;
+      double s1 = 0.0, s2 = 0.0, sr = 0.0;
+      if (MODE != QMODE_DOT && grp == 1 && nchunks > 1) {
+        mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
+        piv = pivs[(tcount & 1) * 128 + row];
+      }
+      for (int c = grp; c < nchunks; c += 2) {
+        const uint32_t itb = tcount * (uint32_t)nchunks + (uint32_t)c;
+        mbar_wait(tmem_full + grp, use & 1);
+        ++use;
+        tc_fence_after();
+        const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
+#pragma unroll 1
+        for (int sub = 0; sub < kQChunk / 8; ++sub) {
+          uint32_t dg[kQSlices][8];
+#pragma unroll
+          for (int d = 0; d < kQSlices; ++d) tmem_ld_x8(tlane + (uint32_t)(d * kQChunk + sub * 8), dg[d]);
+          tmem_wait_ld();
+          if (sub == kQChunk / 8 - 1) {
+            // every accumulator column of this buffer is in registers: hand the buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + grp);
+          }
+          double fv[8];
+          const int cb = c * kQChunk + sub * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = cb + e;
+            const bool cv = col < S;
+            const int colc = cv ? col : S - 1;
+            const double h = q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
+                                       (int)dg[6][e]);
+            const double cval = h * (rs * __ldg(P.colscale + colc));
+            if (MODE == QMODE_DOT) {
+              if (rv && cv) P.V[p * P.ldv + col] = cval;
+              fv[e] = 0.0;
+            } else {
+              const double ca = F::kColAux ? __ldg(P.colaux + colc) : 0.0;
+              const double fr = F::eval(cval, ra, ca, P.mp);
+              if (grp == 0 && c == 0 && sub == 0 && e == 0) {
+                // pivot = the potential at the first sample: any per-row constant near the row mean keeps
+                // sum f^2 - S mean^2 well conditioned; group 1 reads it from shared memory
+                piv = fr;
+                pivs[(tcount & 1) * 128 + row] = piv;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(piv_full + (tcount & 1));
+              }
+              // __dsub_rn: never contracted -- a row whose potential is the same double for every sample must centre
+              // to exactly 0 (-> 0/0 = NaN score, as in the reference, bcores.py:78)
+              double f = __dsub_rn(fr, piv);
+              f = (rv && cv) ? f : 0.0;
+              if (MODE == QMODE_SCORE) {
+                const double rr = __ldg(P.resid + colc);
+                s1 += f;
+                s2 = fma(f, f, s2);
+                sr = fma(f, rr, sr);
+              }
+              fv[e] = f;
+            }
+          }
+          if (want_cols) {
+            // transposed butterfly: 32 rows x 8 columns -> lanes with (lane & 3) == 0 own one column total each
+            int off = 0;
+#pragma unroll
+            for (int m = 16, half = 4; m >= 4; m >>= 1, half >>= 1) {
+              const bool up = (lane & m) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (i < half) {
+                  const double send = up ? fv[i] : fv[half + i];
+                  const double keep = up ? fv[half + i] : fv[i];
+                  fv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+              }
+              if (up) off += half;
+            }
+            fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 2);
+            fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 1);
+            if (sub == 0) mbar_wait(ring_empty + slot, rph ^ 1);
+            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + sub * 8 + off] = fv[0];
+          }
+        }
+        if (want_cols) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ring_full + slot);
+        }
+      }
+      if (MODE == QMODE_SCORE) {
+        if (grp == 1) {
+          mbar_wait(stats_empty, (tcount & 1) ^ 1);
+          stats[row * 3 + 0] = s1;
+          stats[row * 3 + 1] = s2;
+          stats[row * 3 + 2] = sr;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stats_full);
+        } else {
+          mbar_wait(stats_full, tcount & 1);
+          s1 += stats[row * 3 + 0];
+          s2 += stats[row * 3 + 1];
+          sr += stats[row * 3 + 2];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stats_empty);
+          // centred quantities: v = g - gbar;  v.r = SR - gbar*sum(r);  |v|^2 = S2 - S*gbar^2
+          const double gb = s1 / dS;
+          double nrm2 = s2 - dS * gb * gb;
+          if (nrm2 < 0.0) nrm2 = 0.0;
+          const double dot = sr - gb * rsum;
+          // bcores.py:78  corrs = vecs.dot(resid) / sqrt((vecs**2).sum(1)) / S
+          const double score = dot / sqrt(nrm2) / dS;
+          if (rv) {
+            if (P.scores) P.scores[p] = score;
+            Best mine = {score, P.idx_offset + p};
+            best = best_merge(best, mine);
+          }
+        }
+      }
+    }
+    if (MODE == QMODE_SCORE && grp == 0) {
+      best = best_warp(best);
+      if (lane == 0) {
+        fin[q * 2 + 0] = best.v;
+        fin[q * 2 + 1] = __longlong_as_double(best.i);
+      }
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        Best b = {fin[0], __double_as_longlong(fin[1])};
+        for (int w = 1; w < 4; ++w) {
+          Best ob = {fin[w * 2 + 0], __double_as_longlong(fin[w * 2 + 1])};
+          b = best_merge(b, ob);
+        }
+        P.part_misc[blockIdx.x * 4 + 2] = b.v;
+        P.part_misc[blockIdx.x * 4 + 3] = __longlong_as_double(b.i);
+      }
+    }
+  }
+
+  // ---- teardown: every tcgen05 operation of this CTA is complete once all roles have left their loops ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ launch --
+template <class F, int MODE>
+static cudaError_t launch_q_one(const QProjArgs& P, int grid, cudaStream_t st) {
+  auto kern = k_project_q<F, MODE>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QSmem::total);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  kern<<<grid, kQThreads, QSmem::total, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <class F>
+static cudaError_t launch_q_mode(const QProjArgs& P, int mode, int grid, cudaStream_t st) {
+  if (mode == QMODE_COLSUM) return launch_q_one<F, QMODE_COLSUM>(P, grid, st);
+  return launch_q_one<F, QMODE_SCORE>(P, grid, st);
+}
+
+cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st) {
+  if (mode == QMODE_DOT) return launch_q_one<LogisticF<KIND_LOGLIK, 0>, QMODE_DOT>(P, grid, st);
+  if (model == MODEL_LOGISTIC) {
+    if (kind == KIND_LOGLIK) return launch_q_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, grid, st);
+    if (poly == 20) return launch_q_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, grid, st);
+    if (poly == kPowPolyMax) return launch_q_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, grid, st);
+    return launch_q_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, grid, st);
+  } else if (model == MODEL_GAUSSIAN) {
+    if (kind == KIND_LOGLIK) return launch_q_mode<GaussianF<KIND_LOGLIK>>(P, mode, grid, st);
+    if (kind == KIND_BETALIK) return launch_q_mode<GaussianF<KIND_BETALIK>>(P, mode, grid, st);
+    return launch_q_mode<GaussianF<KIND_BETAGRAD>>(P, mode, grid, st);
+  } else {
+    if (kind == KIND_LOGLIK) return launch_q_mode<NeurlinF<KIND_LOGLIK>>(P, mode, grid, st);
+    return launch_q_mode<NeurlinF<KIND_BETALIK>>(P, mode, grid, st);
+  }
+}
+
+}  // namespace bc

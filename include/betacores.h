@@ -81,6 +81,26 @@ int bc_project_score(bc_ctx* ctx, const double* d_X, int64_t ldx, const int64_t*
                      const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream);
 int bc_project_materialise(bc_ctx* ctx, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
                            double* d_V, int64_t ldv, double* d_norms, double* d_out_dd, int raw, void* stream);
+/* ---- stage 1 (+2), tensor-core route --------------------------------------------------------
+ * Same results as bc_project_colsum / bc_project_score (same reference lines), with the contraction on the
+ * 5th-generation tensor cores: rows and samples are split error-free into 7 signed base-256 digits and multiplied
+ * exactly in int8 x int8 -> int32 (tcgen05.mma.kind::i8, accumulators in TMEM); see csrc/bc_project_q.cu.
+ * Feature count D <= bc_q_max_features() (128); full row blocks only (no gather list).
+ * The row image is built ONCE per dataset; bc_set_samples() builds the sample image. */
+int bc_q_max_features(void);
+int bc_q_image_bytes(int64_t n, int64_t* bytes);     /* device bytes of the quantised image of n rows */
+/* d_image (16-byte aligned, bc_q_image_bytes(n)), d_rowscale[n]; optional d_aux_out[n] = column aux_col of every row
+ * (the neural-linear target y, model_neurlinr.py:104). */
+int bc_quantise_rows(bc_ctx* ctx, const double* d_X, int64_t ldx, int64_t n, int D, int aux_col, void* d_image, double* d_rowscale,
+                     double* d_aux_out, void* stream);
+/* d_rowaux[n]: Gaussian x Siginv x (bc_rowquad) / neural-linear y (d_aux_out above); NULL for the logistic model. */
+int bc_project_colsum_q(bc_ctx* ctx, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
+                        double* d_out_dd, void* stream);
+int bc_project_score_q(bc_ctx* ctx, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
+                       const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream);
+/* diagnostic: d_V[n x ldv] = the contraction X B^T itself (B = the prepared samples), as the tensor-core route computes it */
+int bc_contraction_q(bc_ctx* ctx, const void* d_image, const double* d_rowscale, int64_t n, double* d_V, int64_t ldv, void* stream);
+
 /* out[s] = sum_parts (colsum_s) - sum_parts (sum of row means); parts = [nparts][2][ld] (one per rank). */
 int bc_colsum_combine(bc_ctx* ctx, const double* d_parts, int nparts, int S, double* d_out, void* stream);
 
