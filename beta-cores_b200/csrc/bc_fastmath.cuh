@@ -50,26 +50,39 @@ BC_HD double fm_add_exponent(double p, int k) {  // p * 2^k for results that sta
 }
 
 // e^x for |x| <= 700 (no range or NaN handling: see the wrappers below).  |error| < 1 ulp.
-BC_HD double exp_core(double x) {
+// W independent arguments advance through the dependent FMA chain in lock step: the source order IS the instruction
+// level parallelism the FP64 pipe needs (one chain per thread leaves it idle for the length of its latency).
+#if defined(__CUDACC__)
+#define BC_UNROLL _Pragma("unroll")
+#else
+#define BC_UNROLL
+#endif
+template <int W>
+BC_HD void exp_core_v(const double (&x)[W], double (&y)[W]) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: the integer nearest to kf lands in the low word
-  double kf = fm_fma(x, 1.4426950408889634, kMagic);
-  const int k = fm_lo(kf);
-  kf -= kMagic;
-  double r = fm_fma(kf, -6.93147180369123816490e-01, x);
-  r = fm_fma(kf, -1.90821492927058770002e-10, r);
-  double p = 2.51149959513019969e-08;
-  p = fm_fma(p, r, 2.76327915826623365e-07);
-  p = fm_fma(p, r, 2.75572245781815778e-06);
-  p = fm_fma(p, r, 2.48014850709743224e-05);
-  p = fm_fma(p, r, 1.98412699096287991e-04);
-  p = fm_fma(p, r, 1.38888889526998121e-03);
-  p = fm_fma(p, r, 8.33333333330933505e-03);
-  p = fm_fma(p, r, 4.16666666664866486e-02);
-  p = fm_fma(p, r, 1.66666666666667018e-01);
-  p = fm_fma(p, r, 5.00000000000001887e-01);
-  p = fm_fma(p, r, 1.0);
-  p = fm_fma(p, r, 1.0);
-  return fm_add_exponent(p, k);
+  const double c[11] = {2.76327915826623365e-07, 2.75572245781815778e-06, 2.48014850709743224e-05, 1.98412699096287991e-04,
+                        1.38888889526998121e-03, 8.33333333330933505e-03, 4.16666666664866486e-02, 1.66666666666667018e-01,
+                        5.00000000000001887e-01, 1.0,                     1.0};
+  double kf[W], r[W], p[W];
+  int k[W];
+  BC_UNROLL for (int i = 0; i < W; ++i) kf[i] = fm_fma(x[i], 1.4426950408889634, kMagic);
+  BC_UNROLL for (int i = 0; i < W; ++i) {
+    k[i] = fm_lo(kf[i]);
+    kf[i] -= kMagic;
+  }
+  BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(kf[i], -6.93147180369123816490e-01, x[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(kf[i], -1.90821492927058770002e-10, r[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = 2.51149959513019969e-08;
+  BC_UNROLL for (int j = 0; j < 11; ++j) {
+    BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], r[i], c[j]);
+  }
+  BC_UNROLL for (int i = 0; i < W; ++i) y[i] = fm_add_exponent(p[i], k[i]);
+}
+BC_HD double exp_core(double x) {
+  const double a[1] = {x};
+  double y[1];
+  exp_core_v<1>(a, y);
+  return y[0];
 }
 // e^x with x clamped to [-700, 700]; NaN propagates.
 BC_HD double exp_clamped(double x) {
@@ -94,6 +107,28 @@ BC_HD double rcp_1to2(double x) {
 #else
   return 1.0 / x;
 #endif
+}
+
+template <int W>
+BC_HD void rcp_1to2_v(const double (&x)[W], double (&r)[W]) {
+#if defined(__CUDACC__)
+  double e[W];
+  BC_UNROLL for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(x[i]));
+  BC_UNROLL for (int i = 0; i < W; ++i) e[i] = fm_fma(-x[i], r[i], 1.0);
+  BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(r[i], e[i], r[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) e[i] = fm_fma(-x[i], r[i], 1.0);
+  BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(r[i], e[i], r[i]);
+#else
+  for (int i = 0; i < W; ++i) r[i] = 1.0 / x[i];
+#endif
+}
+
+template <int N, int W>
+BC_HD void horner_v(const double* c, const double (&x)[W], double (&p)[W]) {
+  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = c[0];
+  BC_UNROLL for (int j = 1; j <= N; ++j) {
+    BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], x[i], c[j]);
+  }
 }
 
 // coefficients highest degree first: c[0] x^N + ... + c[N]

@@ -56,6 +56,54 @@ struct LogisticF {
       return (m != m) ? m : r;
     }
   }
+  // the same arithmetic on W independent elements, stage by stage (instruction-level parallelism for the FP64 pipe);
+  // bit-identical to eval() element by element
+  template <int W>
+  BC_HD static void evalv(const double (&c)[W], double, const double (&)[W], const ModelParams& mp, double (&out)[W]) {
+    double a[W], x[W], t[W];
+    BC_UNROLL for (int i = 0; i < W; ++i) a[i] = fabs(c[i]);
+    BC_UNROLL for (int i = 0; i < W; ++i) x[i] = (-a[i] < -700.0) ? -700.0 : -a[i];
+    exp_core_v<W>(x, t);
+    if (KIND == KIND_LOGLIK) {
+      double u[W], l[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
+      horner_v<22, W>(kLog1pPoly, u, l);
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double m = -c[i];
+        const double r = -(fmax(m, 0.0) + l[i]);
+        out[i] = (m != m) ? m : r;
+      }
+    } else {
+      const double beta = mp.p[0], k1 = mp.p[1];
+      double G[W], big[W], E[W], u[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double y = -beta * a[i];
+        x[i] = (y < -700.0) ? -700.0 : y;
+      }
+      exp_core_v<W>(x, G);
+      BC_UNROLL for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
+      rcp_1to2_v<W>(u, big);
+      if (POLY == 0) {
+        double l[W];
+        BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
+        horner_v<22, W>(kLog1pPoly, u, l);
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          const double y = -beta * l[i];
+          x[i] = (y < -700.0) ? -700.0 : y;
+        }
+        exp_core_v<W>(x, E);
+      } else {
+        BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
+        horner_v<(POLY > 0 ? POLY : 1), W>(mp.q + (kPowPolyMax - POLY), u, E);
+      }
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double m = -c[i];
+        const double sel = (m >= 0.0) ? k1 * G[i] : k1;
+        const double r = E[i] * fm_fma(big[i], fm_fma(G[i], t[i], 1.0), -sel);
+        out[i] = (m != m) ? m : r;
+      }
+    }
+  }
 };
 
 // reference: examples/common/gaussian.py:7-15 (loglik), :34-44 (beta-lik), :46-62 (d/dbeta).
@@ -80,6 +128,32 @@ struct GaussianF {
       return t1 - mp.p[5] * e - mp.p[6] * q * e - mp.p[7];
     }
   }
+  template <int W>
+  BC_HD static void evalv(const double (&c)[W], double ra, const double (&ca)[W], const ModelParams& mp, double (&out)[W]) {
+    double q[W];
+    BC_UNROLL for (int i = 0; i < W; ++i) q[i] = ra + ca[i] - 2.0 * c[i];
+    if (KIND == KIND_LOGLIK) {
+      BC_UNROLL for (int i = 0; i < W; ++i) out[i] = mp.p[0] - 0.5 * q[i];
+    } else {
+      double x[W], e[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double y = mp.p[2] * q[i];
+        const double yc = (y < -700.0) ? -700.0 : y;
+        x[i] = (yc > 700.0) ? 700.0 : yc;
+      }
+      exp_core_v<W>(x, e);
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double y = mp.p[2] * q[i];
+        const double ee = (y != y) ? y : e[i];
+        if (KIND == KIND_BETALIK) {
+          out[i] = mp.p[1] * ee - mp.p[3];
+        } else {
+          const double t1 = mp.p[4] * (mp.p[1] * ee - mp.p[3]);
+          out[i] = t1 - mp.p[5] * ee - mp.p[6] * q[i] * ee - mp.p[7];
+        }
+      }
+    }
+  }
 };
 
 // reference: examples/common/model_neurlinr.py:90-97 (loglik), :102-110 (beta-lik).
@@ -97,6 +171,27 @@ struct NeurlinF {
       return mp.p[0] - mp.p[1] * r2;
     } else {
       return mp.p[2] * (mp.p[3] * exp_clamped(mp.p[4] * r2) + mp.p[5]);
+    }
+  }
+  template <int W>
+  BC_HD static void evalv(const double (&c)[W], double y, const double (&)[W], const ModelParams& mp, double (&out)[W]) {
+    double r2[W];
+    BC_UNROLL for (int i = 0; i < W; ++i) r2[i] = y * y - 2.0 * c[i] * y + c[i] * c[i];
+    if (KIND == KIND_LOGLIK) {
+      BC_UNROLL for (int i = 0; i < W; ++i) out[i] = mp.p[0] - mp.p[1] * r2[i];
+    } else {
+      double x[W], e[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double z = mp.p[4] * r2[i];
+        const double zc = (z < -700.0) ? -700.0 : z;
+        x[i] = (zc > 700.0) ? 700.0 : zc;
+      }
+      exp_core_v<W>(x, e);
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double z = mp.p[4] * r2[i];
+        const double ee = (z != z) ? z : e[i];
+        out[i] = mp.p[2] * (mp.p[3] * ee + mp.p[5]);
+      }
     }
   }
 };

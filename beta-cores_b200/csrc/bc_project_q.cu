@@ -13,17 +13,20 @@
 // tcgen05.mma.kind::i8 computes D_0..D_6 for a 128-row x 32-sample chunk into 7 x 32 TMEM columns: the MMA for row digit
 // i multiplies against the sample digits 0..6-i STACKED along N (N = 32 (7 - i)), i.e. 7 x 4 instructions per chunk.
 //
-// One persistent CTA per SM, 11 warps:
-//   warps 0-3 / 4-7 : two epilogue groups (even / odd chunks; one TMEM accumulator buffer each).  Thread = data row (TMEM
-//                     lane): tcgen05.ld the 7 diagonals, recombine in int64 (integer pipe), convert exactly, apply the
-//                     model's potential (FP64 pipe), pivot shift, per-row statistics in registers, column partials by a
-//                     transposed warp butterfly -> shared-memory ring.
-//   warp 8          : producer -- cp.async.bulk (TMA engine) of the row tile (112 KB, once per tile) and of the sample
-//                     chunks (28 KB, NSTB-stage ring).  Both images are stored in HBM already in the swizzled layout
-//                     the tensor core reads, so a copy is one contiguous burst.
-//   warp 9          : MMA issuer (one lane) + TMEM allocation.
-//   warp 10         : reducer -- adds the four 32-row column partials of a chunk in fixed order and accumulates them per
-//                     column in double-double (order-insensitive S-vector).
+// One persistent CTA per SM, 19 warps:
+//   warps 0-15 : four epilogue groups of four warps (a warp may only read its own TMEM lane quarter).  Groups 0,1 take
+//                the even chunks (accumulator buffer 0), groups 2,3 the odd chunks (buffer 1); within a pair each group
+//                owns 16 of the chunk's 32 sample columns.  Thread = data row (TMEM lane): tcgen05.ld the 7 diagonals,
+//                recombine in int64 (integer pipe), convert exactly, apply the model's potential four columns at a time
+//                (FP64 pipe, four independent dependency chains), pivot shift, per-row statistics in registers, column
+//                partials by a transposed warp butterfly -> shared-memory ring.  Four warps per SM sub-partition is what
+//                keeps the FP64 pipe fed (8-cycle DFMA latency, measured tools/fp64_ipc.cu).
+//   warp 16    : producer -- cp.async.bulk (TMA engine) of the row tile (112 KB, once per tile) and of the sample
+//                chunks (28 KB, 3-stage ring).  Both images are stored in HBM already in the swizzled layout the tensor
+//                core reads, so a copy is one contiguous burst.
+//   warp 17    : MMA issuer (one lane) + TMEM allocation.
+//   warp 18    : reducer -- adds the four 32-row column partials of a chunk in fixed order and accumulates them per
+//                column in double-double (order-insensitive S-vector).
 #include "bc_common.cuh"
 #include "bc_models.cuh"
 #include "bc_kernels.h"
@@ -33,21 +36,41 @@ namespace bc {
 
 constexpr int kQStagesB = 3;
 constexpr int kQSlots = 4;
-constexpr int kQThreads = 11 * 32;
+constexpr int kQGroups = 4;                       // epilogue groups of 4 warps (one warp per TMEM lane quarter)
+constexpr int kQEpiWarps = 4 * kQGroups;          // 16
+constexpr int kQThreads = (kQEpiWarps + 3) * 32;  // + producer, MMA issuer, reducer
+constexpr int kQHalfCols = kQChunk / 2;           // columns of a chunk one group handles
 
 struct QSmem {
   static constexpr size_t a = 0;
   static constexpr size_t b = a + kQTileBytes;
-  static constexpr size_t ring = b + (size_t)kQStagesB * kQChunkBytes;    // [kQSlots][4 warps][32 cols]
+  static constexpr size_t ring = b + (size_t)kQStagesB * kQChunkBytes;    // [kQSlots][4 quarters][32 cols]
   static constexpr size_t pivs = ring + (size_t)kQSlots * 4 * kQChunk * 8;  // [2][128]
-  static constexpr size_t stats = pivs + 2 * 128 * 8;                       // [128][3]
-  static constexpr size_t fin = stats + 128 * 3 * 8;                        // [4 warps][2]
+  static constexpr size_t stats = pivs + 2 * 128 * 8;                       // [3 groups][128][3]
+  static constexpr size_t fin = stats + 3 * 128 * 3 * 8;                    // [4 warps][2]
   static constexpr size_t bars = fin + 4 * 2 * 8;
   static constexpr int nbars = 2 + 2 * kQStagesB + 4 + 2 * kQSlots + 2 + 2;
   static constexpr size_t tmem = bars + (size_t)nbars * 8;
   static constexpr size_t total = tmem + 16 + 1024;  // + slack to align the base to 1024 B
 };
 static_assert(QSmem::total <= kMaxSmem, "shared memory budget");
+
+// mbarrier wait for the service warps (producer / MMA issuer / reducer): they are far off the critical path, and a
+// spinning try_wait loop would steal issue slots from the epilogue warps that share their SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 
 // ------------------------------------------------------------------ quantisers --
 // One warp per row; lane l owns contraction indices 4l .. 4l+3.  R = rows per image tile (128 data rows / 32 samples).
@@ -166,43 +189,43 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 4);
+      mbar_init(tmem_empty + i, 8);
       mbar_init(piv_full + i, 4);
     }
     for (int i = 0; i < kQSlots; ++i) {
-      mbar_init(ring_full + i, 4);
+      mbar_init(ring_full + i, 8);
       mbar_init(ring_empty + i, 1);
     }
-    mbar_init(stats_full, 4);
+    mbar_init(stats_full, 12);
     mbar_init(stats_empty, 4);
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == kQEpiWarps + 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kQEpiWarps) {
     // ======================= producer: TMA-engine bulk copies =======================
     if (lane == 0) {
       uint32_t itb = 0, tcount = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(empty_a, (tcount & 1) ^ 1);
+        mbar_wait_relaxed(empty_a, (tcount & 1) ^ 1);
         mbar_arrive_expect_tx(full_a, (uint32_t)kQTileBytes);
         const unsigned char* srcA = P.imgA + (size_t)tile * kQTileBytes;
 #pragma unroll
         for (int s = 0; s < kQSlices; ++s) bulk_g2s(As + (size_t)s * kQSliceA, srcA + (size_t)s * kQSliceA, kQSliceA, full_a);
         for (int c = 0; c < nchunks; ++c, ++itb) {
           const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
-          mbar_wait(empty_b + st, ph ^ 1);
+          mbar_wait_relaxed(empty_b + st, ph ^ 1);
           mbar_arrive_expect_tx(full_b + st, (uint32_t)kQChunkBytes);
           bulk_g2s(Bs + (size_t)st * kQChunkBytes, P.imgB + (size_t)c * kQChunkBytes, kQChunkBytes, full_b + st);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == kQEpiWarps + 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       uint32_t idesc[kQSlices];
@@ -211,14 +234,14 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
       const uint64_t adesc0 = umma_desc_sw128(smem_u32(As));
       uint32_t itb = 0, tcount = 0, use0 = 0, use1 = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(full_a, tcount & 1);
+        mbar_wait_relaxed(full_a, tcount & 1);
         for (int c = 0; c < nchunks; ++c, ++itb) {
           const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
           const int buf = c & 1;
           const uint32_t use = buf ? use1 : use0;
-          mbar_wait(tmem_empty + buf, (use & 1) ^ 1);
+          mbar_wait_relaxed(tmem_empty + buf, (use & 1) ^ 1);
           if (buf) ++use1; else ++use0;
-          mbar_wait(full_b + st, ph);
+          mbar_wait_relaxed(full_b + st, ph);
           tc_fence_after();
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(Bs + (size_t)st * kQChunkBytes));
           const uint32_t d0 = tmem_base + (uint32_t)(buf * kQDiagCols);
@@ -238,7 +261,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
       }
     }
     __syncwarp();
-  } else if (warp == 10) {
+  } else if (warp == kQEpiWarps + 2) {
     // ============ reducer: 4 partials per chunk -> double-double column accumulators ============
     if (want_cols) {
       double* acc_hi = P.part_colsum + (size_t)blockIdx.x * 2 * P.Sld;
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c, ++itb) {
           const uint32_t slot = itb % kQSlots, ph = (itb / kQSlots) & 1;
-          mbar_wait(ring_full + slot, ph);
+          mbar_wait_relaxed(ring_full + slot, ph);
           const double* rs = ring + (size_t)slot * 4 * kQChunk + lane;
           double v = rs[0];
           v += rs[kQChunk];
@@ -271,10 +294,12 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     }
   } else {
     // ================================ epilogue groups ================================
-    const int grp = warp >> 2;   // 0: even chunks (+ pivot, final score), 1: odd chunks
+    const int grp = warp >> 2;   // 0..3
+    const int buf = grp >> 1;    // accumulator buffer = chunk parity this group serves
+    const int half = grp & 1;    // which 16 of the chunk's 32 columns
     const int q = warp & 3;      // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * kQDiagCols);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kQDiagCols + half * kQHalfCols);
     const double dS = (double)S;
     const double rsum = (MODE == QMODE_SCORE) ? __ldg(P.resid + S) : 0.0;
     Best best = {0.0, -1};
@@ -286,85 +311,100 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
       const double ra = (F::kRowAux && rv) ? __ldg(P.rowaux + p) : 0.0;
       double piv = 0.0;
       double s1 = 0.0, s2 = 0.0, sr = 0.0;
-      if (MODE != QMODE_DOT && grp == 1 && nchunks > 1) {
-        mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
-        piv = pivs[(tcount & 1) * 128 + row];
-      }
-      for (int c = grp; c < nchunks; c += 2) {
+      bool have_piv = (MODE == QMODE_DOT) || grp == 0;
+      for (int c = buf; c < nchunks; c += 2) {
         const uint32_t itb = tcount * (uint32_t)nchunks + (uint32_t)c;
-        mbar_wait(tmem_full + grp, use & 1);
+        mbar_wait(tmem_full + buf, use & 1);
         ++use;
         tc_fence_after();
+        if (!have_piv) {
+          // group 0 publishes the row pivots right after its first four columns of the tile
+          mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
+          piv = pivs[(tcount & 1) * 128 + row];
+          have_piv = true;
+        }
         const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
 #pragma unroll 1
-        for (int sub = 0; sub < kQChunk / 8; ++sub) {
-          uint32_t dg[kQSlices][8];
-#pragma unroll
-          for (int d = 0; d < kQSlices; ++d) tmem_ld_x8(tlane + (uint32_t)(d * kQChunk + sub * 8), dg[d]);
-          tmem_wait_ld();
-          if (sub == kQChunk / 8 - 1) {
-            // every accumulator column of this buffer is in registers: hand the buffer back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + grp);
-          }
+        for (int sub = 0; sub < kQHalfCols / 8; ++sub) {
           double fv[8];
-          const int cb = c * kQChunk + sub * 8;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = cb + e;
-            const bool cv = col < S;
-            const int colc = cv ? col : S - 1;
-            const double h = q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
-                                       (int)dg[6][e]);
-            const double cval = h * (rs * __ldg(P.colscale + colc));
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t dg[kQSlices][4];
+            const int co = sub * 8 + hb * 4;  // column offset inside this group's half
+#pragma unroll
+            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + co), dg[d]);
+            tmem_wait_ld();
+            if (sub == kQHalfCols / 8 - 1 && hb == 1) {
+              // every accumulator column this group owns is in registers: hand the buffer back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tmem_empty + buf);
+            }
+            const int cb = c * kQChunk + half * kQHalfCols + co;
+            double cval[4], ca[4], fr[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = cb + e;
+              const int colc = (col < S) ? col : S - 1;
+              const double h = q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e],
+                                         (int)dg[5][e], (int)dg[6][e]);
+              cval[e] = h * (rs * __ldg(P.colscale + colc));
+              ca[e] = F::kColAux ? __ldg(P.colaux + colc) : 0.0;
+            }
             if (MODE == QMODE_DOT) {
-              if (rv && cv) P.V[p * P.ldv + col] = cval;
-              fv[e] = 0.0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (rv && cb + e < S) P.V[p * P.ldv + cb + e] = cval[e];
+                fv[hb * 4 + e] = 0.0;
+              }
             } else {
-              const double ca = F::kColAux ? __ldg(P.colaux + colc) : 0.0;
-              const double fr = F::eval(cval, ra, ca, P.mp);
-              if (grp == 0 && c == 0 && sub == 0 && e == 0) {
+              F::template evalv<4>(cval, ra, ca, P.mp, fr);
+              if (grp == 0 && c == 0 && sub == 0 && hb == 0) {
                 // pivot = the potential at the first sample: any per-row constant near the row mean keeps
-                // sum f^2 - S mean^2 well conditioned; group 1 reads it from shared memory
-                piv = fr;
+                // sum f^2 - S mean^2 well conditioned; the other groups read it from shared memory
+                piv = fr[0];
                 pivs[(tcount & 1) * 128 + row] = piv;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(piv_full + (tcount & 1));
               }
-              // __dsub_rn: never contracted -- a row whose potential is the same double for every sample must centre
-              // to exactly 0 (-> 0/0 = NaN score, as in the reference, bcores.py:78)
-              double f = __dsub_rn(fr, piv);
-              f = (rv && cv) ? f : 0.0;
-              if (MODE == QMODE_SCORE) {
-                const double rr = __ldg(P.resid + colc);
-                s1 += f;
-                s2 = fma(f, f, s2);
-                sr = fma(f, rr, sr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = cb + e;
+                const bool cv = col < S;
+                // __dsub_rn: never contracted -- a row whose potential is the same double for every sample must centre
+                // to exactly 0 (-> 0/0 = NaN score, as in the reference, bcores.py:78)
+                double f = __dsub_rn(fr[e], piv);
+                f = (rv && cv) ? f : 0.0;
+                if (MODE == QMODE_SCORE) {
+                  const double rr = __ldg(P.resid + (cv ? col : S - 1));
+                  s1 += f;
+                  s2 = fma(f, f, s2);
+                  sr = fma(f, rr, sr);
+                }
+                fv[hb * 4 + e] = f;
               }
-              fv[e] = f;
             }
           }
           if (want_cols) {
             // transposed butterfly: 32 rows x 8 columns -> lanes with (lane & 3) == 0 own one column total each
             int off = 0;
 #pragma unroll
-            for (int m = 16, half = 4; m >= 4; m >>= 1, half >>= 1) {
+            for (int m = 16, hw = 4; m >= 4; m >>= 1, hw >>= 1) {
               const bool up = (lane & m) != 0;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                if (i < half) {
-                  const double send = up ? fv[i] : fv[half + i];
-                  const double keep = up ? fv[half + i] : fv[i];
+                if (i < hw) {
+                  const double send = up ? fv[i] : fv[hw + i];
+                  const double keep = up ? fv[hw + i] : fv[i];
                   fv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
                 }
               }
-              if (up) off += half;
+              if (up) off += hw;
             }
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 2);
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 1);
             if (sub == 0) mbar_wait(ring_empty + slot, rph ^ 1);
-            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + sub * 8 + off] = fv[0];
+            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + sub * 8 + off] = fv[0];
           }
         }
         if (want_cols) {
@@ -373,18 +413,23 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         }
       }
       if (MODE == QMODE_SCORE) {
-        if (grp == 1) {
+        if (grp != 0) {
           mbar_wait(stats_empty, (tcount & 1) ^ 1);
-          stats[row * 3 + 0] = s1;
-          stats[row * 3 + 1] = s2;
-          stats[row * 3 + 2] = sr;
+          double* st = stats + ((size_t)(grp - 1) * 128 + row) * 3;
+          st[0] = s1;
+          st[1] = s2;
+          st[2] = sr;
           __syncwarp();
           if (lane == 0) mbar_arrive(stats_full);
         } else {
           mbar_wait(stats_full, tcount & 1);
-          s1 += stats[row * 3 + 0];
-          s2 += stats[row * 3 + 1];
-          sr += stats[row * 3 + 2];
+#pragma unroll
+          for (int g = 0; g < kQGroups - 1; ++g) {  // fixed order
+            const double* st = stats + ((size_t)g * 128 + row) * 3;
+            s1 += st[0];
+            s2 += st[1];
+            sr += st[2];
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(stats_empty);
           // centred quantities: v = g - gbar;  v.r = SR - gbar*sum(r);  |v|^2 = S2 - S*gbar^2
@@ -424,7 +469,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   // ---- teardown: every tcgen05 operation of this CTA is complete once all roles have left their loops ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kQEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
