@@ -103,6 +103,7 @@ class DeviceRows(object):
                 self.t[:self.n_local, :self.ncols].copy_(torch.from_numpy(np.ascontiguousarray(host_rows)))
         self.rowaux = None          # Gaussian x Siginv x cache
         self.rowaux_key = None
+        self._q = {}
 
     @classmethod
     def from_device(cls, engine, t, row0=0, n_total=None):
@@ -121,7 +122,25 @@ class DeviceRows(object):
         self.t = t
         self.rowaux = None
         self.rowaux_key = None
+        self._q = {}
         return self
+
+    def quantised(self, ctx, D, aux_col=None):
+        """(image, rowscale, aux) for the tensor-core route: the rows split once into 7 int8 digit planes, stored in
+        the tensor core's own swizzled tile layout (bc_quantise_rows); aux = column `aux_col` of every row."""
+        key = (int(D), aux_col)
+        if key not in self._q:
+            from ._native import call, c_i64
+            nb = c_i64()
+            call('bc_q_image_bytes', self.n_local, ctypes.byref(nb))
+            img = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=self.engine.device)
+            rs = self.engine.empty(max(self.n_local, 1))
+            aux = self.engine.empty(max(self.n_local, 1)) if aux_col is not None else None
+            if self.n_local:
+                call('bc_quantise_rows', ctx, ptr(self.t), self.ld, self.n_local, int(D), 0 if aux_col is None else int(aux_col),
+                     ptr(img), ptr(rs), ptr(aux), stream_ptr())
+            self._q[key] = (img, rs, aux)
+        return self._q[key]
 
     @property
     def sharded(self):

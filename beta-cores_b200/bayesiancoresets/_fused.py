@@ -6,6 +6,7 @@ Wraps the stage-1/2 entry points of libbetacores.so for the coreset classes:
     materialise()   -> bc_project_materialise   (centred rows written out: coreset points, Hilbert)
 """
 import ctypes
+import os
 import numpy as np
 import torch
 
@@ -16,6 +17,10 @@ from ._device import DeviceRows, ptr, stream_ptr
 # Optional instrumentation (bench.py): when a list is installed here, every data-row pass appends
 # (kind, rows, start_event, end_event) recorded on the launching stream around the C-ABI call.
 PASS_TIMERS = None
+
+# Contraction route of the full-block passes: 'q' = tcgen05 int8 split (csrc/bc_project_q.cu, feature count <= 128),
+# 'dmma' = FP64 mma.sync (csrc/bc_project.cu, any shape; always used for gathered sub-samples and materialisation).
+ROUTE = os.environ.get('BC_CONTRACTION', 'q')
 
 
 def _timed(kind, n, fn):
@@ -77,6 +82,15 @@ class FusedProjection(object):
             rows.rowaux, rows.rowaux_key = out, key
         return rows.rowaux
 
+    def _q_operands(self, rows, sub):
+        """(image, rowscale, rowaux) when the tensor-core route applies to this pass, else None"""
+        if ROUTE != 'q' or sub is not None or self.D > nv.lib().bc_q_max_features() or rows.n_local == 0:
+            return None
+        aux_col = self.D if self.pot.model == 'neurlin' else None
+        img, rs, aux = rows.quantised(self.ctx, self.D, aux_col)
+        ra = self._rowaux(rows) if self.pot.model == 'gaussian' else aux
+        return img, rs, ra
+
     def _check(self, rows):
         if self.S is None:
             raise nv.NativeError('set_samples() must follow configure()')
@@ -91,6 +105,11 @@ class FusedProjection(object):
         if out is None:
             out = self.eng.empty(2 * self.Sld)
         n = rows.n_local if sub is None else int(sub.numel())
+        q = self._q_operands(rows, sub)
+        if q is not None:
+            _timed('colsum', n, lambda: nv.call('bc_project_colsum_q', self.ctx, ptr(q[0]), ptr(q[1]), n, ptr(q[2]), ptr(out),
+                                                stream_ptr()))
+            return out
         ra = self._rowaux(rows)
         _timed('colsum', n, lambda: nv.call('bc_project_colsum', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(ra), ptr(out),
                                             stream_ptr()))
@@ -106,6 +125,11 @@ class FusedProjection(object):
         """out_best (>=2 doubles): best score, int64 bits of (position + idx_offset)."""
         self._check(rows)
         n = rows.n_local if sub is None else int(sub.numel())
+        q = self._q_operands(rows, sub)
+        if q is not None:
+            _timed('score', n, lambda: nv.call('bc_project_score_q', self.ctx, ptr(q[0]), ptr(q[1]), n, ptr(q[2]), ptr(resid),
+                                               int(idx_offset), ptr(out_best), ptr(scores), stream_ptr()))
+            return
         ra = self._rowaux(rows)
         _timed('score', n, lambda: nv.call('bc_project_score', self.ctx, ptr(rows.t), rows.ld, ptr(sub), n, ptr(ra), ptr(resid),
                                            int(idx_offset), ptr(out_best), ptr(scores), stream_ptr()))

@@ -95,8 +95,18 @@ SHAPES = [('lr', 'betalik', 1000, 20, 100), ('lr', 'loglik', 777, 5, 33), ('lr',
           ('nl', 'loglik', 640, 64, 128), ('lr', 'betalik', 1, 3, 2), ('lr', 'betalik', 65, 130, 70)]
 
 
+@pytest.fixture(params=['q', 'dmma'])
+def route(request):
+    """contraction route of the full-block fused passes: tcgen05 int8 split (default) / FP64 DMMA"""
+    from bayesiancoresets import _fused
+    old = _fused.ROUTE
+    _fused.ROUTE = request.param
+    yield request.param
+    _fused.ROUTE = old
+
+
 @pytest.mark.parametrize('model,kind,n,D,S', SHAPES)
-def test_fused_colsum_score_materialise(bc, model, kind, n, D, S):
+def test_fused_colsum_score_materialise(bc, route, model, kind, n, D, S):
     import torch
     from bayesiancoresets._fused import FusedProjection
     from bayesiancoresets._device import Engine, DeviceRows
@@ -152,7 +162,35 @@ def test_fused_colsum_score_materialise(bc, model, kind, n, D, S):
     np.testing.assert_allclose(cs3, V[sub].sum(axis=0), rtol=1e-9, atol=1e-11*scale*np.sqrt(n))
 
 
-def test_score_nan_and_tie_semantics(bc):
+def test_tensor_core_contraction_is_fp64_exact(bc):
+    """the int8 digit split reproduces the fp64 contraction to the accuracy of dgemm itself (rows / samples of very
+    different magnitudes, ragged sizes, zero rows)"""
+    import ctypes, torch
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    from bayesiancoresets import _native as nv
+    eng = Engine.get()
+    ctx = eng.ctx('qtest')
+    for n, D, S, seed in [(1, 1, 1, 0), (129, 128, 33, 1), (700, 37, 300, 2), (2500, 100, 1000, 3)]:
+        r = np.random.RandomState(seed)
+        X = r.randn(n, D)*np.exp(3.*r.randn(n, 1))
+        if n > 10:
+            X[5] = 0.
+            X[7, :] = 1e-300
+        Th = r.randn(S, D)*np.exp(r.randn(S, 1))
+        rows = DeviceRows(eng, X)
+        T = eng.upload(Th)
+        nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_LOGLIK, D, nv.params8([0]*8), None)
+        nv.call('bc_set_samples', ctx, ptr(T), S, int(T.stride(0)), stream_ptr())
+        img, rs, _ = rows.quantised(ctx, D)
+        V = eng.empty(n, S)
+        nv.call('bc_contraction_q', ctx, ptr(img), ptr(rs), n, ptr(V), S, stream_ptr())
+        ref = (X.astype(np.longdouble) @ Th.T.astype(np.longdouble)).astype(np.float64)
+        bound = np.abs(X).max(axis=1)[:, None]*np.abs(Th).max(axis=1)[None, :]
+        err = np.abs(V.cpu().numpy() - ref)
+        assert (err <= 4e-14*bound + 1e-320).all(), (n, D, S, float((err/np.maximum(bound, 1e-300)).max()))
+
+
+def test_score_nan_and_tie_semantics(bc, route):
     """zero rows -> 0/0 = NaN: np.argmax returns the first NaN; duplicate rows tie -> lowest position"""
     import torch
     from bayesiancoresets._fused import FusedProjection
@@ -268,7 +306,7 @@ def _run_product_case(bc, models, case, blackbox=False):
 
 
 @pytest.mark.parametrize('case', problems.coreset_cases(heavy=True), ids=lambda c: c['name'])
-def test_coreset_builds_match_reference(bc, models, case):
+def test_coreset_builds_match_reference(bc, models, route, case):
     g = np.load(os.path.join(G, 'g3_coresets.npz'))
     w, i, sizes, sumw = _run_product_case(bc, models, case)
     nm = case['name']
