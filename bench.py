@@ -284,12 +284,37 @@ def b200_arm(a):
     except Exception:
         pass
     alg_bytes = 8.*(n_local*D + S*D + S)
+    route = _fused.ROUTE if D <= nv.lib().bc_q_max_features() else 'dmma'
+    bf16_peak = 1644.4
+    try:
+        bf16_peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops']
+    except Exception:
+        pass
+    sm_clock_hz = 1e6*(clk['sm_mhz'] if clk and clk.get('sm_mhz') else 1965.0)
+    if route == 'q':
+        kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
+                 'column sums, fused)')
+        digit_pairs, fp64_inst = 28, 74          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
+        int8_ops = digit_pairs*2.*n_local*S*128
+        extra = {
+            'route': 'q',
+            'int8_tensor': {'ops_per_launch': int8_ops, 'achieved_tops': int8_ops/(col_mean*1e-3)/1e12, 'peak_tops': 2*bf16_peak,
+                            'frac': int8_ops/(col_mean*1e-3)/1e12/(2*bf16_peak),
+                            'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate; no int8 figure measured)'},
+            'fp64_pipe': {'instructions_per_eval': fp64_inst,
+                          'frac_of_issue_peak': n_local*S*fp64_inst/32./(eng.sms*4*0.5*sm_clock_hz*col_mean*1e-3),
+                          'note': 'the potential (two exp, one reciprocal, one degree-20 polynomial per evaluation) runs on the FP64 pipe '
+                                  '(0.5 warp-instructions/cycle/sub-partition, measured tools/fp64_ipc.cu); it, not the tensor pipe, bounds the kernel'}}
+    else:
+        kname = 'k_project<LogisticF<BETALIK>, MODE_COLSUM> (FP64 DMMA contraction + beta-likelihood + centring + column sums, fused)'
+        extra = {'route': 'dmma'}
     roofline = {
-        'kernel': 'k_project<LogisticF<BETALIK>, MODE_COLSUM> (fused contraction + beta-likelihood + centring + column sums)',
+        'kernel': kname,
         'bound': 'tensor', 'achieved': achieved, 'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved/FP64_DMMA_PEAK_TFLOPS,
         'traffic': None,
-        'peak_source': 'FP64 DMMA (mma.sync m16n8k4 f64) peak measured on this pool, profiles/r01_fp64_peaks.jsonl; '
-                       'MEASURED_PEAKS.json holds no fp64 figure (tcgen05 has no f64 kind)',
+        'peak_source': 'algorithmic fp64 flops 2*N*S*D against the FP64 tensor (DMMA mma.sync m16n8k4 f64) peak measured on this pool, '
+                       'profiles/r01_fp64_peaks.jsonl -- the fastest NATIVE fp64 contraction rate of the chip; MEASURED_PEAKS.json '
+                       'holds no fp64 figure and tcgen05 has no f64 kind (the q route emulates fp64 exactly on int8 tensor cores)',
         'launch_ms': col_mean, 'launches_timed': len(col_ms), 'rows_per_launch': n_local,
         'algorithmic_flops_per_launch': flops, 'evals_per_s_kernel': n_local*S/(col_mean*1e-3),
         'hbm': {'algorithmic_bytes_per_launch': alg_bytes, 'achieved_gbs': alg_bytes/(col_mean*1e-3)/1e9, 'peak_gbs': hbm_peak,
@@ -297,6 +322,17 @@ def b200_arm(a):
         'score_pass_ms': sco_mean,
         'share_of_step': (sum(col_ms) + sum(sco_ms))*1e-3/dt,
     }
+    roofline.update(extra)
+    if route == 'q':
+        qbytes = ((n_local + 127)//128)*7*128*128 + 8.*n_local + 7.*S*128*((n_local + 127)//128)*0   # image + row scales
+        roofline['hbm'].update({'algorithmic_bytes_per_launch': qbytes, 'achieved_gbs': qbytes/(col_mean*1e-3)/1e9,
+                                'frac': qbytes/(col_mean*1e-3)/1e9/hbm_peak,
+                                'note': 'int8 digit image of the rows (7 B per feature) + row scales; samples stay in L2'})
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r01_ncu_k_project_q_v3.txt: 910.2 MB for a
+        # 1,000,000-row launch (= the algorithmic 904 MB; the operands are read exactly once); it scales linearly in rows
+        roofline['traffic'] = 910.2*n_local
+        roofline['traffic_source'] = 'ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v3.txt), scaled by rows'
+        roofline['bound_detail'] = 'fp64 pipe of the fused potential epilogue (see fp64_pipe); tensor and HBM pipes are far from their limits'
     idcs_value = [int(i) for i in alg.idcs]
 
     # ------------------------------------------------- e2e: public API from host buffers --
