@@ -423,8 +423,18 @@ def b200_arm(a):
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """libraries (NCCL's version banner, ...) write to fd 1: point it at stderr while the bench runs so that stdout carries
+    exactly one JSON line; returns a file object on the real stdout"""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == '__main__':
     args = parse()
+    sys.stdout = _quiet_stdout()
     if args.impl == 'reference':
         reference_arm(args)
     else:

@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 python bench.py > gpurun_out/bench_r01_q.json 2> gpurun_out/bench_r01_q.err; echo "bench rc=$?"
-tail -c 2500 gpurun_out/bench_r01_q.json; tail -3 gpurun_out/bench_r01_q.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_ref2.json 2> gpurun_out/bench_r01_ref2.err; echo "ref rc=$?"
-cat gpurun_out/bench_r01_ref2.json | cut -c1-600
-CMD="python bench.py --n 1000000 --steps 1 --warmup 1 --opt-itrs 2 --no-e2e --no-cpu-baseline"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches_q.csv $CMD > gpurun_out/ncu_l.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_project_q -c 2 -f -o gpurun_out/prof_bench_q $CMD > gpurun_out/ncu_f.log 2>&1; echo "ncu full rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_r01_q_n2.json 2> gpurun_out/bench_r01_q_n2.err; echo "bench2 rc=$?"
+python -c "
+import json;d=json.load(open('gpurun_out/bench_r01_q_n2.json'));r=d['roofline'];print(d['n_gpus'],d['value'],d['ms_per_step'],r['launch_ms'],r['score_pass_ms'],d['e2e']['value'],d['selected_indices'],r['share_of_step'])"
+tail -5 gpurun_out/bench_r01_q_n2.err
