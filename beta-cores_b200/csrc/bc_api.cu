@@ -183,6 +183,7 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
   if (model == BC_MODEL_LOGISTIC && kind == BC_KIND_BETALIK) {
     const double beta = h_params[0];
     if (!(beta > 0.0)) return BC_ERR_ARG;
+    c->mp.p[2] = 700.0 / (beta > 1.0 ? beta : 1.0);  // clamp of |m| ahead of the exponentials (LogisticF::evalv)
     const int degs[2] = {20, kPowPolyMax};
     for (int i = 0; i < 2 && c->poly == 0; ++i) {
       double q[kPowPolyMax + 1];
@@ -214,10 +215,10 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
   if (c->Dk <= kQK) {
     const size_t chunks = (size_t)(S + kQChunk - 1) / kQChunk;
     if ((rc = grow(&c->qB, &c->cap_qB, chunks * kQChunkBytes / sizeof(double)))) return rc;
-    if ((rc = grow(&c->colscale, &c->cap_cs, chunks * kQChunk))) return rc;
+    if ((rc = grow(&c->colscale, &c->cap_cs, 2))) return rc;   // [0] = scale, [1] = the shared exponent (int)
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    (cudaStream_t)stream));
-    BC_LAUNCHED(1);
+                                    reinterpret_cast<int*>(c->colscale + 1), (cudaStream_t)stream));
+    BC_LAUNCHED(2);
     c->q_ready = true;
   }
   c->samples_set = true;

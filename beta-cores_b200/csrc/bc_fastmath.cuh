@@ -37,6 +37,15 @@ BC_HD int fm_lo(double x) {
   return (int)(uint32_t)u;
 #endif
 }
+BC_HD int fm_hi(double x) {
+#if defined(__CUDACC__)
+  return __double2hiint(x);
+#else
+  uint64_t u;
+  memcpy(&u, &x, 8);
+  return (int)(uint32_t)(u >> 32);
+#endif
+}
 BC_HD double fm_add_exponent(double p, int k) {  // p * 2^k for results that stay normal
 #if defined(__CUDACC__)
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));

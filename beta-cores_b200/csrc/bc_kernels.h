@@ -56,7 +56,7 @@ struct QProjArgs {
   const unsigned char* imgA;  // [tiles][7][128][128] swizzled
   const double* rowscale;     // [n]
   const unsigned char* imgB;  // [chunks][7][32][128] swizzled
-  const double* colscale;     // [S]
+  const double* colscale;     // [1]: the samples share one power-of-two scale
   long long n;
   long long idx_offset;
   int S;
@@ -73,7 +73,8 @@ struct QProjArgs {
 };
 cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
                                  double* aux_out, int aux_col, cudaStream_t st);
-cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, cudaStream_t st);
+cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
+                                    cudaStream_t st);
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----

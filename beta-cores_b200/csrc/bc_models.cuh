@@ -56,30 +56,32 @@ struct LogisticF {
       return (m != m) ? m : r;
     }
   }
-  // the same arithmetic on W independent elements, stage by stage (instruction-level parallelism for the FP64 pipe);
-  // bit-identical to eval() element by element
+  // W independent elements, stage by stage (instruction-level parallelism for the FP64 pipe).  Same arithmetic as eval()
+  // for finite arguments.  Used by the tensor-core kernel, which supplies its own NaN handling (a non-finite row poisons
+  // the row's pivot) -- a NaN argument here gives an unspecified result.
+  //   p[2] = largest |m| passed to the exponentials: 700 / max(1, beta)  (one clamp serves e^-a and e^(-beta a); beyond
+  //          it both terms are below 1e-300 of the result)
   template <int W>
   BC_HD static void evalv(const double (&c)[W], double, const double (&)[W], const ModelParams& mp, double (&out)[W]) {
     double a[W], x[W], t[W];
-    BC_UNROLL for (int i = 0; i < W; ++i) a[i] = fabs(c[i]);
-    BC_UNROLL for (int i = 0; i < W; ++i) x[i] = (-a[i] < -700.0) ? -700.0 : -a[i];
-    exp_core_v<W>(x, t);
     if (KIND == KIND_LOGLIK) {
+      BC_UNROLL for (int i = 0; i < W; ++i) a[i] = fabs(c[i]);
+      BC_UNROLL for (int i = 0; i < W; ++i) x[i] = (a[i] > 700.0) ? -700.0 : -a[i];
+      exp_core_v<W>(x, t);
       double u[W], l[W];
       BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
       horner_v<22, W>(kLog1pPoly, u, l);
-      BC_UNROLL for (int i = 0; i < W; ++i) {
-        const double m = -c[i];
-        const double r = -(fmax(m, 0.0) + l[i]);
-        out[i] = (m != m) ? m : r;
-      }
+      BC_UNROLL for (int i = 0; i < W; ++i) out[i] = -(fmax(-c[i], 0.0) + l[i]);
     } else {
-      const double beta = mp.p[0], k1 = mp.p[1];
+      const double beta = mp.p[0], k1 = mp.p[1], amax = mp.p[2];
       double G[W], big[W], E[W], u[W];
       BC_UNROLL for (int i = 0; i < W; ++i) {
-        const double y = -beta * a[i];
-        x[i] = (y < -700.0) ? -700.0 : y;
+        const double ai = fabs(c[i]);
+        a[i] = (ai > amax) ? amax : ai;
       }
+      BC_UNROLL for (int i = 0; i < W; ++i) x[i] = -a[i];
+      exp_core_v<W>(x, t);
+      BC_UNROLL for (int i = 0; i < W; ++i) x[i] = -beta * a[i];
       exp_core_v<W>(x, G);
       BC_UNROLL for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
       rcp_1to2_v<W>(u, big);
@@ -87,20 +89,16 @@ struct LogisticF {
         double l[W];
         BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
         horner_v<22, W>(kLog1pPoly, u, l);
-        BC_UNROLL for (int i = 0; i < W; ++i) {
-          const double y = -beta * l[i];
-          x[i] = (y < -700.0) ? -700.0 : y;
-        }
+        BC_UNROLL for (int i = 0; i < W; ++i) x[i] = -beta * l[i];
         exp_core_v<W>(x, E);
       } else {
         BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
         horner_v<(POLY > 0 ? POLY : 1), W>(mp.q + (kPowPolyMax - POLY), u, E);
       }
       BC_UNROLL for (int i = 0; i < W; ++i) {
-        const double m = -c[i];
-        const double sel = (m >= 0.0) ? k1 * G[i] : k1;
-        const double r = E[i] * fm_fma(big[i], fm_fma(G[i], t[i], 1.0), -sel);
-        out[i] = (m != m) ? m : r;
+        // m = -c >= 0  <=>  sign bit of c set (c = +0 gives G = 1 either way): an integer test, not an FP64 compare
+        const double sel = (fm_hi(c[i]) < 0) ? k1 * G[i] : k1;
+        out[i] = E[i] * fm_fma(big[i], fm_fma(G[i], t[i], 1.0), -sel);
       }
     }
   }

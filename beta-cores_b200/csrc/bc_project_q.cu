@@ -80,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 template <int R>
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src, long long ld, long long n, int D,
                                                    unsigned char* __restrict__ image, double* __restrict__ scale_out,
-                                                   double* __restrict__ aux_out, int aux_col) {
+                                                   double* __restrict__ aux_out, int aux_col, const int* __restrict__ common_e) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src
       bad = bad || (ob != 0);
     }
     // |x| 2^-e < 1/4  =>  top digit within [-64, 64], the others in [-128, 127]
-    const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
+    // common_e: every row shares one exponent (the samples: their magnitudes are alike, and a single scale keeps the
+    // projection epilogue free of per-column loads); a non-finite entry anywhere was flagged by k_common_exponent
+    const int e = common_e ? __ldg(common_e) : ((amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0);
+    if (common_e) bad = !(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]) && isfinite(x[3]));
     uint32_t dig[kQSlices] = {0, 0, 0, 0, 0, 0, 0};
     if (!bad) {
 #pragma unroll
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src
     unsigned char* base = image + (size_t)tile * (kQSlices * R * kQK) + q_swizzle_off(rr, (uint32_t)lane * 4u);
 #pragma unroll
     for (int s = 0; s < kQSlices; ++s) *reinterpret_cast<uint32_t*>(base + (size_t)s * (R * kQK)) = dig[s];
-    if (r < n && lane == 0) scale_out[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
+    if (scale_out && r < n && lane == 0) scale_out[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
   }
 }
 
@@ -135,14 +138,49 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
   long long warps = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
   long long blocks = (warps + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col);
+  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col, nullptr);
   return cudaGetLastError();
 }
 
-cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale,
+// exponent shared by all S samples: ilogb(max |B|) + 3, and the matching scale 2^(e - 32) (NaN if any entry is not finite:
+// the reference's own result is NaN in every quantity downstream of such a sample set)
+__global__ void __launch_bounds__(1024) k_common_exponent(const double* __restrict__ B, int ldb, int S, int D, int* __restrict__ e_out,
+                                                          double* __restrict__ scale_out) {
+  __shared__ double smax[32];
+  __shared__ int sbad[32];
+  double amax = 0.0;
+  int bad = 0;
+  for (long long i = threadIdx.x; i < (long long)S * D; i += blockDim.x) {
+    const double v = B[(i / D) * ldb + (i % D)];
+    bad |= !isfinite(v);
+    amax = fmax(amax, fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smax[threadIdx.x >> 5] = amax;
+    sbad[threadIdx.x >> 5] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      amax = fmax(amax, smax[w]);
+      bad |= sbad[w];
+    }
+    const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
+    *e_out = e;
+    *scale_out = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
+  }
+}
+
+cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
                                     cudaStream_t st) {
+  k_common_exponent<<<1, 1024, 0, st>>>(B, ldb, S, D, common_e, colscale);
   const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
-  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, colscale, nullptr, 0);
+  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, common_e);
   return cudaGetLastError();
 }
 
@@ -302,21 +340,30 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kQDiagCols + half * kQHalfCols);
     const double dS = (double)S;
     const double rsum = (MODE == QMODE_SCORE) ? __ldg(P.resid + S) : 0.0;
+    const double cs = __ldg(P.colscale);   // one scale for all samples
+    const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+    constexpr int NB = kQHalfCols / 4;     // batches of 4 columns per chunk
     Best best = {0.0, -1};
     uint32_t use = 0, tcount = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const long long p = tile * kQTileRows + row;
       const bool rv = p < n;
       const double rs = rv ? __ldg(P.rowscale + p) : 0.0;
+      const double rsc = rs * cs;          // NaN for a non-finite row / sample set
       const double ra = (F::kRowAux && rv) ? __ldg(P.rowaux + p) : 0.0;
+      const bool tail_rows = (tile + 1) * kQTileRows > n;   // warp-uniform
       double piv = 0.0;
       double s1 = 0.0, s2 = 0.0, sr = 0.0;
       bool have_piv = (MODE == QMODE_DOT) || grp == 0;
       for (int c = buf; c < nchunks; c += 2) {
         const uint32_t itb = tcount * (uint32_t)nchunks + (uint32_t)c;
+        const bool need_mask = tail_rows || (c + 1) * kQChunk > S;   // warp-uniform: last row tile / ragged last chunk
         mbar_wait(tmem_full + buf, use & 1);
         ++use;
         tc_fence_after();
+        uint32_t dg[kQSlices][4];
+#pragma unroll
+        for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk), dg[d]);
         if (!have_piv) {
           // group 0 publishes the row pivots right after its first four columns of the tile
           mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
@@ -324,68 +371,70 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           have_piv = true;
         }
         const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
-#pragma unroll 1
-        for (int sub = 0; sub < kQHalfCols / 8; ++sub) {
-          double fv[8];
+        double fv[8];
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {
-            uint32_t dg[kQSlices][4];
-            const int co = sub * 8 + hb * 4;  // column offset inside this group's half
+        for (int b = 0; b < NB; ++b) {
+          const int cb = c * kQChunk + half * kQHalfCols + b * 4;
+          double cval[4], ca[4], fr[4];
+          tmem_wait_ld();
 #pragma unroll
-            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + co), dg[d]);
-            tmem_wait_ld();
-            if (sub == kQHalfCols / 8 - 1 && hb == 1) {
-              // every accumulator column this group owns is in registers: hand the buffer back to the MMA issuer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tmem_empty + buf);
-            }
-            const int cb = c * kQChunk + half * kQHalfCols + co;
-            double cval[4], ca[4], fr[4];
+          for (int e = 0; e < 4; ++e) {
+            cval[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
+                                      (int)dg[6][e]);
+          }
+          if (b + 1 < NB) {
+            // the digits are consumed: fetch the next four columns while this batch is evaluated
+#pragma unroll
+            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + (b + 1) * 4), dg[d]);
+          } else {
+            // every accumulator column this group owns has been read: hand the buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);
+          }
+          if (MODE == QMODE_DOT) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int col = cb + e;
-              const int colc = (col < S) ? col : S - 1;
-              const double h = q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e],
-                                         (int)dg[5][e], (int)dg[6][e]);
-              cval[e] = h * (rs * __ldg(P.colscale + colc));
-              ca[e] = F::kColAux ? __ldg(P.colaux + colc) : 0.0;
+              if (rv && cb + e < S) P.V[p * P.ldv + cb + e] = cval[e];
+              fv[(b & 1) * 4 + e] = 0.0;
             }
-            if (MODE == QMODE_DOT) {
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ca[e] = F::kColAux ? __ldg(P.colaux + min(cb + e, S - 1)) : 0.0;
+            F::template evalv<4>(cval, ra, ca, P.mp, fr);
+            if (grp == 0 && c == 0 && b == 0) {
+              // pivot = the potential at the first sample: any per-row constant near the row mean keeps
+              // sum f^2 - S mean^2 well conditioned; the other groups read it from shared memory.
+              // A non-finite row (or sample set) has rsc = NaN: its pivot, hence every centred value of the row, is NaN
+              // -- the reference's NaN propagation (evalv itself does not promise NaN in -> NaN out).
+              piv = (rsc != rsc) ? kNaN : fr[0];
+              pivs[(tcount & 1) * 128 + row] = piv;
+              __syncwarp();
+              if (lane == 0) mbar_arrive(piv_full + (tcount & 1));
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // __dsub_rn: never contracted -- a row whose potential is the same double for every sample must centre
+              // to exactly 0 (-> 0/0 = NaN score, as in the reference, bcores.py:78)
+              fr[e] = __dsub_rn(fr[e], piv);
+            }
+            if (need_mask) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) fr[e] = (rv && cb + e < S) ? fr[e] : 0.0;
+            }
+            if (MODE == QMODE_SCORE) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (rv && cb + e < S) P.V[p * P.ldv + cb + e] = cval[e];
-                fv[hb * 4 + e] = 0.0;
-              }
-            } else {
-              F::template evalv<4>(cval, ra, ca, P.mp, fr);
-              if (grp == 0 && c == 0 && sub == 0 && hb == 0) {
-                // pivot = the potential at the first sample: any per-row constant near the row mean keeps
-                // sum f^2 - S mean^2 well conditioned; the other groups read it from shared memory
-                piv = fr[0];
-                pivs[(tcount & 1) * 128 + row] = piv;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(piv_full + (tcount & 1));
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int col = cb + e;
-                const bool cv = col < S;
-                // __dsub_rn: never contracted -- a row whose potential is the same double for every sample must centre
-                // to exactly 0 (-> 0/0 = NaN score, as in the reference, bcores.py:78)
-                double f = __dsub_rn(fr[e], piv);
-                f = (rv && cv) ? f : 0.0;
-                if (MODE == QMODE_SCORE) {
-                  const double rr = __ldg(P.resid + (cv ? col : S - 1));
-                  s1 += f;
-                  s2 = fma(f, f, s2);
-                  sr = fma(f, rr, sr);
-                }
-                fv[hb * 4 + e] = f;
+                const double rr = __ldg(P.resid + min(cb + e, S - 1));
+                s1 += fr[e];
+                s2 = fma(fr[e], fr[e], s2);
+                sr = fma(fr[e], rr, sr);
               }
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) fv[(b & 1) * 4 + e] = fr[e];
           }
-          if (want_cols) {
+          if (want_cols && (b & 1)) {
             // transposed butterfly: 32 rows x 8 columns -> lanes with (lane & 3) == 0 own one column total each
             int off = 0;
 #pragma unroll
@@ -403,8 +452,8 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
             }
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 2);
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 1);
-            if (sub == 0) mbar_wait(ring_empty + slot, rph ^ 1);
-            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + sub * 8 + off] = fv[0];
+            if (b == 1) mbar_wait(ring_empty + slot, rph ^ 1);
+            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + (b >> 1) * 8 + off] = fv[0];
           }
         }
         if (want_cols) {

@@ -185,9 +185,10 @@ def test_tensor_core_contraction_is_fp64_exact(bc):
         V = eng.empty(n, S)
         nv.call('bc_contraction_q', ctx, ptr(img), ptr(rs), n, ptr(V), S, stream_ptr())
         ref = (X.astype(np.longdouble) @ Th.T.astype(np.longdouble)).astype(np.float64)
-        bound = np.abs(X).max(axis=1)[:, None]*np.abs(Th).max(axis=1)[None, :]
+        # rows carry their own power-of-two scale, the samples share one: the error is relative to max|x_n| * max|Theta|
+        bound = np.abs(X).max(axis=1)[:, None]*np.abs(Th).max()
         err = np.abs(V.cpu().numpy() - ref)
-        assert (err <= 4e-14*bound + 1e-320).all(), (n, D, S, float((err/np.maximum(bound, 1e-300)).max()))
+        assert (err <= 2e-14*bound + 1e-320).all(), (n, D, S, float((err/np.maximum(bound, 1e-300)).max()))
 
 
 def test_score_nan_and_tie_semantics(bc, route):

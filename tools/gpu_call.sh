@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_r01_q_n2.json 2> gpurun_out/bench_r01_q_n2.err; echo "bench2 rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/gpu_tests.log
+timeout 900 python bench.py --no-cpu-baseline --no-e2e --steps 2 > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.err; echo "bench rc=$?"
 python -c "
-import json;d=json.load(open('gpurun_out/bench_r01_q_n2.json'));r=d['roofline'];print(d['n_gpus'],d['value'],d['ms_per_step'],r['launch_ms'],r['score_pass_ms'],d['e2e']['value'],d['selected_indices'],r['share_of_step'])"
-tail -5 gpurun_out/bench_r01_q_n2.err
+import json;d=json.load(open('gpurun_out/bench_v5.json'));r=d['roofline'];print(d['value'],d['ms_per_step'],r['launch_ms'],r['score_pass_ms'],r['frac'],d['clocks'],d['selected_indices'])"
+tail -5 gpurun_out/bench_v5.err
