@@ -39,6 +39,7 @@ for p in (ROOT, PKG, os.path.join(PKG, 'examples', 'common')):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+SAMPLER = 'newton'   # mode finder of the host Laplace sampler (examples/common/model_lr.py); 'bfgs' = the reference's scipy call
 BLK = 65536          # rows per generator block: the dataset does not depend on how many ranks generate it
 FP64_DMMA_PEAK_TFLOPS = 36.9   # measured on this pool's B200 (profiles/r01_fp64_peaks.jsonl); MEASURED_PEAKS.json has no fp64 entry
 
@@ -88,7 +89,7 @@ def run_oracle_build(Z, S, beta, opt_itrs, steps, warmup, seed=1):
     from oracle import np_models as om, np_coresets as oc
     D = Z.shape[1]
     np.random.seed(seed)
-    o = oc.GreedyVI(Z, model_lr.make_laplace_sampler(D), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
+    o = oc.GreedyVI(Z, model_lr.make_laplace_sampler(D, method=SAMPLER), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
     for m in range(1, warmup+1):
         o.build(1, m)
     evals = 0
@@ -130,7 +131,8 @@ def workload_config(a, world):
                         % (a.n, a.d, a.s, a.beta),
             'N': a.n, 'D': a.d, 'S': a.s, 'beta': a.beta, 'opt_itrs': a.opt_itrs,
             'step': 'one BetaCoreset.build(1, m): 1 selection + opt_itrs ADAM steps = (1+opt_itrs) N x S projections',
-            'sampler': 'host Laplace approximation (scipy BFGS) of the weighted coreset posterior, called every optimiser step',
+            'sampler': 'host Laplace approximation of the weighted coreset posterior (mode by damped Newton steps, D x D Cholesky '
+                       'factor, S x D normal draws), called every optimiser step; the same callback in both arms',
             'sharding': 'rows over %d rank(s), fixed total N' % world,
             'l2': 'inputs (%.2f GB of rows) exceed the 126 MB L2; no flush' % (a.n*a.d*8/1e9)}
 
@@ -225,6 +227,13 @@ def b200_arm(a):
     from bayesiancoresets._shard import partition_rows
 
     N, D, S, beta, K, W = a.n, a.d, a.s, a.beta, a.steps, a.warmup
+    # the host side of this arm is the sampler's D x D algebra: BLAS thread pools only thrash on it
+    blas_default = blas_threads()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1, user_api='blas')
+    except Exception:
+        threadpool_limits = None
     eng = Engine.get()
     row0, n_local = partition_rows(N, world, rank)
     Zdev = gen_rows(torch, row0, n_local, D, a.seed, dev)
@@ -242,9 +251,21 @@ def b200_arm(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler_clock = [0, 0.]
+
+    def timed_sampler(fn):
+        def sampler(Sn, w, pts):
+            t = time.perf_counter()
+            out = fn(Sn, w, pts)
+            sampler_clock[0] += 1
+            sampler_clock[1] += time.perf_counter() - t
+            return out
+        return sampler
+
     def make_alg(rows):
         np.random.seed(1)     # every rank draws the same stream; rank 0's samples are broadcast anyway
-        prj = bc.BetaBlackBoxProjector(model_lr.make_laplace_sampler(D), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        prj = bc.BetaBlackBoxProjector(timed_sampler(model_lr.make_laplace_sampler(D, method=SAMPLER)), S, model_lr.beta_likelihood,
+                                       model_lr.log_likelihood, None)
         return bc.BetaCoreset(rows, prj, opt_itrs=a.opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
 
     # ------------------------------------------------------------ value: rows resident in HBM --
@@ -253,6 +274,7 @@ def b200_arm(a):
         alg.build(1, m)
     clocks = ClockSampler(local) if rank == 0 else None
     _fused.PASS_TIMERS = []
+    sampler_clock[0], sampler_clock[1] = 0, 0.
     launches0 = nv.lib().bc_launch_count()
     evals = 0
     barrier()
@@ -268,6 +290,7 @@ def b200_arm(a):
     torch.cuda.profiler.stop()
     dt = max_over_ranks(e0.elapsed_time(e1)*1e-3)
     launches = nv.lib().bc_launch_count() - launches0
+    sampler_calls, sampler_s = sampler_clock[0], sampler_clock[1]
     timers, _fused.PASS_TIMERS = _fused.PASS_TIMERS, None
     clk = clocks.stop() if clocks else None
     value = evals/dt
@@ -374,20 +397,15 @@ def b200_arm(a):
         ns = min(a.cpu_rows, n_local)
         Zs = Zdev[:ns, :D].cpu().numpy().copy()
         best = None
-        for threads in (None, 1):
-            try:
-                from threadpoolctl import threadpool_limits
-                ctxm = threadpool_limits(limits=threads) if threads else None
-            except Exception:
-                ctxm = None
-            if ctxm is not None:
-                with ctxm:
+        for threads in (blas_default, 1):
+            if threadpool_limits is not None:
+                with threadpool_limits(limits=threads, user_api='blas'):
                     o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, 1, 0)
             else:
                 if threads == 1:
                     continue
                 o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, 1, 0)
-            used = 1 if threads == 1 else blas_threads()
+            used = threads
             if best is None or ev/t > best[0]:
                 best = (ev/t, used, t)
         cpu = {'value': best[0], 'unit': 'evals/s', 'cores': best[1], 'kind': 'port',
@@ -396,7 +414,7 @@ def b200_arm(a):
                          % (ns, D, S, a.cpu_opt_itrs, best[2], os.cpu_count())}
         # the same sample through the CUDA path: identical index, weights within 1e-6
         np.random.seed(1)
-        prj = bc.BetaBlackBoxProjector(model_lr.make_laplace_sampler(D), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        prj = bc.BetaBlackBoxProjector(model_lr.make_laplace_sampler(D, method=SAMPLER), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         algs = bc.BetaCoreset(Zs, prj, opt_itrs=a.cpu_opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
         algs.build(1, 1)
         ow, _, oi = o.get()
@@ -410,7 +428,8 @@ def b200_arm(a):
             'ms_per_step': 1e3*dt/K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(a, world), 'build_seconds_per_point': dt/K,
             'selected_indices': idcs_value, 'roofline': roofline, 'gpu_launches': int(launches), 'clocks': clk,
-            'host': {'cpu_count': os.cpu_count()},
+            'host': {'cpu_count': os.cpu_count(), 'sampler_calls': sampler_calls, 'sampler_ms_per_call': 1e3*sampler_s/max(sampler_calls, 1),
+                     'sampler_share_of_step': sampler_s/dt},
         }
         if e2e is not None:
             line['e2e'] = e2e

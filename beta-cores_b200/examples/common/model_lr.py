@@ -67,22 +67,48 @@ def hess_th_log_joint(Z, th, wts):
     return -np.eye(th.shape[0]) - (Z*(wts*c)[:, np.newaxis]).T.dot(Z)
 
 
-def get_laplace(wts, Z, mu0, diag=False):
+def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200):
+    """mode of the (strictly concave) weighted log-joint by damped Newton steps: a few D x D Cholesky solves instead of
+    scipy's BFGS iterations on a dense D x D inverse-Hessian estimate (tens of ms at D = 128, every optimiser step)"""
+    th = np.array(mu0, dtype=np.float64)
+    f = log_joint(Zw, th, ww)
+    for _ in range(maxit):
+        g = grad_th_log_joint(Zw, th, ww)
+        H = -hess_th_log_joint(Zw, th, ww)
+        step = sl.cho_solve(sl.cho_factor(H, lower=True, check_finite=False), g, check_finite=False)
+        t = 1.
+        while True:
+            th_new = th + t*step
+            f_new = log_joint(Zw, th_new, ww)
+            if f_new >= f - 1e-15*abs(f) or t < 1e-8:
+                break
+            t *= .5
+        done = np.abs(th_new-th).max() <= tol*(1.+np.abs(th_new).max())
+        th, f = th_new, f_new
+        if done:
+            break
+    return th
+
+
+def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
     """N(mu, L L^T) Laplace approximation of the weighted posterior; returns (mu, L, Linv^T-factor)
-    like bayesiancoresets/util/opt.py:10-33 (same optimiser: scipy BFGS with analytic gradient,
-    up to 10 restarts from a jittered start)."""
+    like bayesiancoresets/util/opt.py:10-33.  method='bfgs': the reference's optimiser (scipy BFGS with analytic
+    gradient, up to 10 restarts from a jittered start); method='newton': the same mode by damped Newton steps."""
     keep = wts > 0
     Zw, ww = Z[keep, :], wts[keep]
-    res = None
-    for _ in range(10):
-        try:
-            res = minimize(lambda mu: -log_joint(Zw, mu, ww), mu0, jac=lambda mu: -grad_th_log_joint(Zw, mu, ww))
-            break
-        except Exception:
-            mu0 = mu0 + np.sqrt((mu0**2).sum())*0.1*np.random.randn(mu0.shape[0])
-    if res is None:
-        raise RuntimeError('Laplace optimisation failed 10 times')
-    mu = res.x
+    if method == 'newton':
+        mu = _newton_mode(Zw, ww, mu0)
+    else:
+        res = None
+        for _ in range(10):
+            try:
+                res = minimize(lambda mu: -log_joint(Zw, mu, ww), mu0, jac=lambda mu: -grad_th_log_joint(Zw, mu, ww))
+                break
+            except Exception:
+                mu0 = mu0 + np.sqrt((mu0**2).sum())*0.1*np.random.randn(mu0.shape[0])
+        if res is None:
+            raise RuntimeError('Laplace optimisation failed 10 times')
+        mu = res.x
     H = -hess_th_log_joint(Zw, mu, ww)
     if diag:
         LSigInv = np.sqrt(np.diag(H))
@@ -92,7 +118,7 @@ def get_laplace(wts, Z, mu0, diag=False):
     return mu, LSig, LSigInv
 
 
-def make_laplace_sampler(D, mu0=None):
+def make_laplace_sampler(D, mu0=None, method='bfgs'):
     """sampler(S, wts, pts) -> (S, D): the callback the logistic drivers hand to the projector
     (examples/zellner_logreg/main.py:139-144).  Empty coreset -> the N(0, I) prior."""
     mu0 = np.zeros(D) if mu0 is None else mu0
@@ -101,6 +127,6 @@ def make_laplace_sampler(D, mu0=None):
         if pts.shape[0] == 0:
             wts = np.zeros(1)
             pts = np.zeros((1, D))
-        mu, LSig, _ = get_laplace(wts, pts, mu0)
+        mu, LSig, _ = get_laplace(wts, pts, mu0, method=method)
         return mu + np.random.randn(S, mu.shape[0]).dot(LSig.T)
     return sampler

@@ -169,3 +169,17 @@ def test_gloo_world2_exchange_matches_single_process():
         assert best[1] == int(np.argmax(V.dot(resid)))
         assert cnt == 200
         assert (t == 7.).all()
+
+
+def test_newton_laplace_mode_is_the_bfgs_mode():
+    """the bench's host sampler finds the Laplace mode by Newton steps; it is the stationary point scipy's BFGS (the
+    reference's optimiser, util/opt.py:10-33) converges towards"""
+    import model_lr
+    r = np.random.RandomState(3)
+    Z = r.randn(6, 12)
+    w = np.abs(r.randn(6))*50.
+    mu_b, L_b, _ = model_lr.get_laplace(w, Z, np.zeros(12))
+    mu_n, L_n, _ = model_lr.get_laplace(w, Z, np.zeros(12), method='newton')
+    assert np.abs(model_lr.grad_th_log_joint(Z, mu_n, w)).max() < 1e-10
+    np.testing.assert_allclose(mu_n, mu_b, atol=1e-4)
+    np.testing.assert_allclose(L_n, L_b, atol=1e-4)
