@@ -358,6 +358,54 @@ def b200_arm(a):
         roofline['bound_detail'] = 'fp64 pipe of the fused potential epilogue (see fp64_pipe); tensor and HBM pipes are far from their limits'
     idcs_value = [int(i) for i in alg.idcs]
 
+    # ---- stage 2 (materialised n x S matrix: snnls / Hilbert scoring) and stage 3 (coreset-side step), timed on their own ----
+    stage2 = stage3 = None
+    if rank == 0 and world == 1:
+        from bayesiancoresets._device import ptr, stream_ptr
+        ctx2 = eng.ctx('bench-stage2')
+        n2 = min(1_000_000, N)
+        V = torch.randn(n2, S, dtype=torch.float64, device=dev)
+        nrm = torch.empty(n2, dtype=torch.float64, device=dev)
+        uu = torch.randn(2*S, dtype=torch.float64, device=dev)
+        o4 = torch.zeros(4, dtype=torch.float64, device=dev)
+
+        def ev_time(fn, reps):
+            for _ in range(3):
+                fn()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1)/reps
+        nv.call('bc_dense_rownorms', ctx2, ptr(V), n2, S, S, ptr(nrm), stream_ptr())
+        stage2 = {'bytes_per_launch': 8.*n2*S, 'rows': n2, 'S': S, 'peak_gbs': hbm_peak, 'bound': 'hbm', 'kernels': {}}
+        for nm, mode in (('k_dense_score<FW> (frankwolfe.py:15-17)', nv.SCORE_FW), ('k_dense_score<GIGA> (giga.py:20-38)', nv.SCORE_GIGA),
+                         ('k_dense_score<CORR> (bcores.py:78-81)', nv.SCORE_CORR)):
+            ms = ev_time(lambda: nv.call('bc_dense_score', ctx2, mode, ptr(V), n2, S, S, ptr(nrm), ptr(uu), None, 0, ptr(o4), None,
+                                         stream_ptr()), 10)
+            stage2['kernels'][nm] = {'ms': ms, 'achieved_gbs': 8.*n2*S/ms/1e6, 'frac': 8.*n2*S/ms/1e6/hbm_peak}
+        del V, nrm
+        # stage 3: residual + gradient + ADAM on an M = 64 coreset (latency-bound: microseconds per optimiser step)
+        M3 = 64
+        Vc = torch.randn(M3, S, dtype=torch.float64, device=dev)
+        cs_ = torch.randn(S, dtype=torch.float64, device=dev)
+        w3 = torch.rand(M3, dtype=torch.float64, device=dev)
+        m1 = torch.zeros(M3, dtype=torch.float64, device=dev)
+        m2 = torch.zeros(M3, dtype=torch.float64, device=dev)
+        g3 = torch.zeros(M3, dtype=torch.float64, device=dev)
+        rs3 = torch.zeros(S+1, dtype=torch.float64, device=dev)
+
+        def step3():
+            nv.call('bc_core_resid', ctx2, ptr(cs_), 1.0, ptr(Vc), M3, S, S, ptr(w3), ptr(rs3), stream_ptr())
+            nv.call('bc_core_grad', ctx2, ptr(Vc), M3, S, S, ptr(rs3), ptr(g3), stream_ptr())
+            nv.call('bc_adam_step', ctx2, ptr(g3), ptr(w3), ptr(m1), ptr(m2), M3, 0.1, 0.9, 0.999, 0.1, 0.001, 1e-8, None, stream_ptr())
+        stage3 = {'M': M3, 'S': S, 'us_per_step': 1e3*ev_time(step3, 50),
+                  'kernels': 'k_core_resid + k_core_rows (gradient) + k_adam (bcores.py:145-146, util/opt.py:45-52)',
+                  'bound': 'launch latency (3 launches, M x S = 0.5 MB)'}
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------- e2e: public API from host buffers --
     e2e = None
     if not a.no_e2e:
@@ -431,6 +479,9 @@ def b200_arm(a):
             'host': {'cpu_count': os.cpu_count(), 'sampler_calls': sampler_calls, 'sampler_ms_per_call': 1e3*sampler_s/max(sampler_calls, 1),
                      'sampler_share_of_step': sampler_s/dt},
         }
+        if stage2 is not None:
+            line['stage2'] = stage2
+            line['stage3'] = stage3
         if e2e is not None:
             line['e2e'] = e2e
         if cpu is not None:

@@ -79,10 +79,19 @@ struct LogisticF {
         const double ai = fabs(c[i]);
         a[i] = (ai > amax) ? amax : ai;
       }
-      BC_UNROLL for (int i = 0; i < W; ++i) x[i] = -a[i];
-      exp_core_v<W>(x, t);
-      BC_UNROLL for (int i = 0; i < W; ++i) x[i] = -beta * a[i];
-      exp_core_v<W>(x, G);
+      {
+        // both exponentials of all W elements advance together: 2W independent dependency chains
+        double xx[2 * W], yy[2 * W];
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          xx[i] = -a[i];
+          xx[W + i] = -beta * a[i];
+        }
+        exp_core_v<2 * W>(xx, yy);
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          t[i] = yy[i];
+          G[i] = yy[W + i];
+        }
+      }
       BC_UNROLL for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
       rcp_1to2_v<W>(u, big);
       if (POLY == 0) {
