@@ -35,17 +35,32 @@ __device__ __forceinline__ void row_dots(const double* __restrict__ v, int S, co
                                          double& d0, double& d1, double& n2) {
   d0 = d1 = n2 = 0.0;
   if (vec_ok) {
-    for (int c = lane * 2; c < S; c += 64) {  // S even and row 16-byte aligned
-      const double2 x = ld_stream2(v + c);
-      d0 = fma(x.x, u_s[c], d0);
-      d0 = fma(x.y, u_s[c + 1], d0);
-      if (NU > 1) {
-        d1 = fma(x.x, u_s[S + c], d1);
-        d1 = fma(x.y, u_s[S + c + 1], d1);
+    // S even and row 16-byte aligned.  Four 16-byte loads per lane are issued before the first is consumed: with one
+    // warp per row the memory-level parallelism has to come from here (HBM latency x bandwidth needs ~40 KB in flight per SM)
+    for (int c0 = lane * 2; c0 < S; c0 += 256) {
+      double2 x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 64 * k;
+        x[k] = (c < S) ? ld_stream2(v + c) : make_double2(0.0, 0.0);
       }
-      if (NORM) {
-        n2 = fma(x.x, x.x, n2);
-        n2 = fma(x.y, x.y, n2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 64 * k;
+        if (c < S) {
+          const double2 ua = *reinterpret_cast<const double2*>(u_s + c);
+          d0 = fma(x[k].x, ua.x, d0);
+          d0 = fma(x[k].y, ua.y, d0);
+          if (NU > 1) {
+            const double2 ub = *reinterpret_cast<const double2*>(u_s + S + c);
+            d1 = fma(x[k].x, ub.x, d1);
+            d1 = fma(x[k].y, ub.y, d1);
+          }
+          if (NORM) {
+            n2 = fma(x[k].x, x[k].x, n2);
+            n2 = fma(x[k].y, x[k].y, n2);
+          }
+        }
       }
     }
   } else {
@@ -216,8 +231,25 @@ cudaError_t launch_dense_score(const double* V, long long n, int S, long long ld
                                double* scores, cudaStream_t st) {
   long long want = (n + 7) / 8;
   if (want < 1) want = 1;
-  if (want < nparts) nparts = (int)want;
   const size_t smem = (size_t)((mode == 1) ? 2 : 1) * S * sizeof(double);
+  // one wave of resident blocks: the rows are dealt out grid-stride, so a partial second wave would only add a tail
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int o = 0;
+  switch (mode) {
+    case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<0>, 256, smem); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<1>, 256, smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<2>, 256, smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<3>, 256, smem); break;
+  }
+  if (o < 1) o = 1;
+  int resident = sms * o;
+  if (resident < nparts) nparts = resident;
+  if (want < nparts) nparts = (int)want;
   switch (mode) {
     case 0: k_dense_score<0><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
     case 1: k_dense_score<1><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
