@@ -50,7 +50,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=10_000_000)
+    ap.add_argument('--n', '--rows', dest='n', type=int, default=10_000_000)
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--s', type=int, default=1024)
     ap.add_argument('--beta', type=float, default=0.1)
@@ -82,14 +82,28 @@ def blas_threads():
 
 
 # ---------------------------------------------------------------------------- reference arm (CPU) --
+_SAMPLERS = []
+
+
+def new_sampler(D, seed):
+    """the host sampler of both arms; numpy's global stream is re-seeded only once no prefetched draw is in flight"""
+    import numpy as np
+    import model_lr
+    for s in _SAMPLERS:
+        s.drain()
+    np.random.seed(seed)
+    s = model_lr.make_laplace_sampler(D, method=SAMPLER, prefetch=True)
+    _SAMPLERS.append(s)
+    return s
+
+
 def run_oracle_build(Z, S, beta, opt_itrs, steps, warmup, seed=1):
     """time `steps` build(1, m) iterations of the numpy restatement of the reference on rows Z"""
     import numpy as np
     import model_lr
     from oracle import np_models as om, np_coresets as oc
     D = Z.shape[1]
-    np.random.seed(seed)
-    o = oc.GreedyVI(Z, model_lr.make_laplace_sampler(D, method=SAMPLER), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
+    o = oc.GreedyVI(Z, new_sampler(D, seed), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
     for m in range(1, warmup+1):
         o.build(1, m)
     evals = 0
@@ -131,8 +145,9 @@ def workload_config(a, world):
                         % (a.n, a.d, a.s, a.beta),
             'N': a.n, 'D': a.d, 'S': a.s, 'beta': a.beta, 'opt_itrs': a.opt_itrs,
             'step': 'one BetaCoreset.build(1, m): 1 selection + opt_itrs ADAM steps = (1+opt_itrs) N x S projections',
-            'sampler': 'host Laplace approximation of the weighted coreset posterior (mode by damped Newton steps, D x D Cholesky '
-                       'factor, S x D normal draws), called every optimiser step; the same callback in both arms',
+            'sampler': 'host Laplace approximation of the weighted coreset posterior (mode by warm-started damped Newton steps, D x D '
+                       'Cholesky factor, S x D normal draws from the global numpy stream, drawn one call ahead on a helper thread), '
+                       'called every optimiser step; the same callback in both arms',
             'sharding': 'rows over %d rank(s), fixed total N' % world,
             'l2': 'inputs (%.2f GB of rows) exceed the 126 MB L2; no flush' % (a.n*a.d*8/1e9)}
 
@@ -263,9 +278,8 @@ def b200_arm(a):
         return sampler
 
     def make_alg(rows):
-        np.random.seed(1)     # every rank draws the same stream; rank 0's samples are broadcast anyway
-        prj = bc.BetaBlackBoxProjector(timed_sampler(model_lr.make_laplace_sampler(D, method=SAMPLER)), S, model_lr.beta_likelihood,
-                                       model_lr.log_likelihood, None)
+        # every rank draws the same stream (seed 1); rank 0's samples are broadcast anyway
+        prj = bc.BetaBlackBoxProjector(timed_sampler(new_sampler(D, 1)), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         return bc.BetaCoreset(rows, prj, opt_itrs=a.opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
 
     # ------------------------------------------------------------ value: rows resident in HBM --
@@ -461,8 +475,7 @@ def b200_arm(a):
                          'D=%d S=%d opt_itrs=%d (%.1f s); faster of default BLAS threads and 1 thread; host has %d cpus'
                          % (ns, D, S, a.cpu_opt_itrs, best[2], os.cpu_count())}
         # the same sample through the CUDA path: identical index, weights within 1e-6
-        np.random.seed(1)
-        prj = bc.BetaBlackBoxProjector(model_lr.make_laplace_sampler(D, method=SAMPLER), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        prj = bc.BetaBlackBoxProjector(new_sampler(D, 1), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         algs = bc.BetaCoreset(Zs, prj, opt_itrs=a.cpu_opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
         algs.build(1, 1)
         ow, _, oi = o.get()

@@ -118,15 +118,46 @@ def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
     return mu, LSig, LSigInv
 
 
-def make_laplace_sampler(D, mu0=None, method='bfgs'):
+def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
     """sampler(S, wts, pts) -> (S, D): the callback the logistic drivers hand to the projector
-    (examples/zellner_logreg/main.py:139-144).  Empty coreset -> the N(0, I) prior."""
+    (examples/zellner_logreg/main.py:139-144).  Empty coreset -> the N(0, I) prior.
+
+    method='newton' additionally warm-starts each mode search at the previous mode (consecutive optimiser steps move the
+    weights a little).  prefetch=True draws the NEXT call's S x D standard normals on a helper thread while the caller is
+    busy (the draw does not depend on the weights); the global numpy stream is consumed in exactly the same order and
+    amounts as without it, provided nothing else draws from it between two sampler calls (true for full-data builds)."""
     mu0 = np.zeros(D) if mu0 is None else mu0
+    state = {'mu': None, 'fut': None, 'shape': None}
+    pool = None
+    if prefetch:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+
+    def normals(S, d):
+        if pool is None:
+            return np.random.randn(S, d)
+        if state['fut'] is not None and state['shape'] == (S, d):
+            out = state['fut'].result()
+        else:
+            if state['fut'] is not None:
+                state['fut'].result()       # a draw of another shape was in flight: it has consumed the stream; keep order
+            out = np.random.randn(S, d)
+        state['fut'], state['shape'] = pool.submit(np.random.randn, S, d), (S, d)
+        return out
 
     def sampler(S, wts, pts):
         if pts.shape[0] == 0:
             wts = np.zeros(1)
             pts = np.zeros((1, D))
-        mu, LSig, _ = get_laplace(wts, pts, mu0, method=method)
-        return mu + np.random.randn(S, mu.shape[0]).dot(LSig.T)
+        start = state['mu'] if (method == 'newton' and state['mu'] is not None) else mu0
+        mu, LSig, _ = get_laplace(wts, pts, start, method=method)
+        state['mu'] = mu
+        return mu + normals(S, mu.shape[0]).dot(LSig.T)
+
+    def drain():
+        """wait for the draw in flight (call before re-seeding numpy's global stream)"""
+        if state['fut'] is not None:
+            state['fut'].result()
+            state['fut'] = None
+    sampler.drain = drain
     return sampler
