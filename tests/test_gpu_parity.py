@@ -359,3 +359,54 @@ def test_c_abi_host_project(models):
     np.testing.assert_allclose(out, g['lr_project_f'], rtol=1e-10, atol=1e-14)
     # argument errors come back as codes, not crashes
     assert nv.lib().bc_host_project(0, 0, 1, D, params, None, None, n, D, None, S, None, 1) == -1
+
+
+# ------------------------------------------------------- full north-star size: size-independent properties --
+def test_full_size_properties_north_star_shape(bc):
+    """N = 10M, D = 128, S = 1024 (BASELINE.json north star; the oracle cannot run this size): properties that hold for
+    any size -- (1) every centred row sums to zero over the samples, so the column sums add up to ~0; (2) the column sum
+    of the whole block equals the sum over two row shards (what the multi-GPU exchange relies on); (3) the tensor-core
+    route and the FP64 DMMA route agree on the column sums and pick the same row; (4) the reported arg-max is the arg-max
+    of the per-row scores."""
+    import torch
+    from bayesiancoresets import _fused
+    from bayesiancoresets._fused import FusedProjection
+    from bayesiancoresets._device import Engine, DeviceRows
+    from bayesiancoresets.potentials import DevicePotential
+    N, D, S = int(os.environ.get('BC_TEST_FULL_N', 10_000_000)), 128, 1024
+    eng = Engine.get()
+    g = torch.Generator(device=eng.device)
+    g.manual_seed(11)
+    X = torch.randn(N, D, generator=g, dtype=torch.float64, device=eng.device)
+    Th = torch.randn(S, D, generator=g, dtype=torch.float64, device=eng.device)/np.sqrt(D) + 1./np.sqrt(D)
+    fp = FusedProjection(eng, DevicePotential('logistic', 'betalik'), D)
+    fp.configure(0.1)
+    fp.set_samples(Th)
+    rows = DeviceRows.from_device(eng, X)
+    h = N//2 + 37
+    lo, hi = DeviceRows.from_device(eng, X[:h]), DeviceRows.from_device(eng, X[h:])
+    old = _fused.ROUTE
+    try:
+        out = {}
+        for route in ('q', 'dmma'):
+            _fused.ROUTE = route
+            cs = fp.combine(fp.colsum_parts(rows), 1).cpu().numpy()
+            parts = torch.stack((fp.colsum_parts(lo).clone(), fp.colsum_parts(hi).clone()))
+            cs2 = fp.combine(parts, 2).cpu().numpy()
+            scale = np.abs(cs).max()
+            assert abs(cs.sum()) <= 1e-9*scale*S                                 # (1)
+            np.testing.assert_allclose(cs2, cs, rtol=0, atol=1e-12*scale)        # (2)
+            r = np.cos(np.arange(S))                                             # any fixed direction
+            resid = eng.upload(np.concatenate((r, [r.sum()])))
+            best = eng.zeros(4)
+            scores = eng.empty(N)
+            fp.score(rows, None, resid, 0, best, scores=scores)
+            b = best.cpu().numpy()
+            am = int(torch.argmax(scores).item())
+            assert int(b[1:2].view(np.int64)[0]) == am and b[0] == float(scores[am].item())   # (4)
+            out[route] = (cs, am, scores[:100000].cpu().numpy())
+        np.testing.assert_allclose(out['q'][0], out['dmma'][0], rtol=0, atol=1e-11*np.abs(out['dmma'][0]).max())   # (3)
+        assert out['q'][1] == out['dmma'][1]
+        np.testing.assert_allclose(out['q'][2], out['dmma'][2], rtol=1e-9, atol=1e-12)
+    finally:
+        _fused.ROUTE = old
