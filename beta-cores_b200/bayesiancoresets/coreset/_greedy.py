@@ -39,6 +39,8 @@ class _Tangent(object):
         self.comm = Comm.current()
         self.resid = None
         self.out4 = self.eng.zeros(4)
+        self.core_out = self.eng.zeros(1)      # max |correlation| of the coreset rows (kept apart from out4: the dense
+                                               # score kernel writes all four entries of its output)
 
     # residual = scaling * colsum - w . Vc      (bcores.py:77 / :145); element S = its sum
     def residual(self, colsum, scaling, Vc, w_dev):
@@ -57,6 +59,23 @@ class _Tangent(object):
     def core_max(self, Vc, resid, skip, out):
         nv.call('bc_core_maxcorr', self.ctx, ptr(Vc), Vc.shape[0], Vc.shape[1], int(Vc.stride(0)), ptr(resid), int(skip), ptr(out),
                 stream_ptr())
+
+
+    # group-wise selection (bcores.py:91-123): `gv` = one row per candidate group (sum of the group's centred rows)
+    def group_colsum(self, gv):
+        G, S = gv.shape
+        dd = self.eng.empty(2*(S+1))
+        nv.call('bc_dense_colsum', self.ctx, ptr(gv), G, S, int(gv.stride(0)), ptr(dd), stream_ptr())
+        out = self.eng.empty(S)
+        nv.call('bc_colsum_combine', self.ctx, ptr(dd), 1, S, ptr(out), stream_ptr())
+        return out
+
+    def group_best(self, gv, resid):
+        G, S = gv.shape
+        nv.call('bc_dense_score', self.ctx, nv.SCORE_CORR, ptr(gv), G, S, int(gv.stride(0)), None, ptr(resid), None, 0,
+                ptr(self.out4), None, stream_ptr())
+        v = self.out4[:2].cpu().numpy()
+        return float(v[0]), int(v[1:2].view(np.int64)[0])
 
 
 class _FusedTangent(_Tangent):
@@ -109,6 +128,25 @@ class _FusedTangent(_Tangent):
         V, _, _ = self.fp.materialise(pts_rows)
         return V
 
+    def group_rows(self, groups, gi):
+        """(len(gi), S) device matrix: row j = column sum of the centred projection of the rows of group gi[j]
+        (bcores.py:50,60) -- one gathered fused pass per group, nothing of size rows x S is formed; all ranks combined"""
+        Sld, S = self.fp.Sld, self.S
+        if not hasattr(self, '_group_loc'):
+            self._group_loc = {}
+        parts = self.eng.empty(len(gi), 2*Sld)
+        for j, g in enumerate(gi):
+            g = int(g)
+            if g not in self._group_loc:
+                _, loc = local_subsample(np.asarray(groups[g], dtype=np.int64), self.rows.row0, self.rows.n_local)
+                self._group_loc[g] = self.eng.upload(loc, dtype=torch.int64)
+            self.fp.colsum_parts(self.rows, self._group_loc[g], out=parts[j])
+        allparts = self.comm.allgather(parts)                       # (world, G', 2 Sld)
+        gv = self.eng.empty(len(gi), S)
+        for j in range(len(gi)):
+            self.fp.combine(allparts[:, j].contiguous(), self.comm.world, out=gv[j])
+        return gv
+
     def best_row(self, sub_idcs, resid):
         """(score, position) of np.argmax(corrs) over the rows of the last colsum() call"""
         n_here = self.rows.n_local if sub_idcs is None else int(self._loc.numel())
@@ -158,6 +196,19 @@ class _DenseTangent(_Tangent):
     def core_rows(self, pts_host):
         return self.eng.upload(_as_f64_2d(self.project(pts_host)))
 
+    def group_rows(self, groups, gi):
+        data = self.o.data
+        first = self.eng.upload(_as_f64_2d(self.project(data[groups[int(gi[0])], :])))
+        S = first.shape[1]
+        self.S = S
+        gv = self.eng.empty(len(gi), S)
+        dd = self.eng.empty(2*(S+1))
+        for j, g in enumerate(gi):
+            V = first if j == 0 else self.eng.upload(_as_f64_2d(self.project(data[groups[int(g)], :])))
+            nv.call('bc_dense_colsum', self.ctx, ptr(V), V.shape[0], S, int(V.stride(0)), ptr(dd), stream_ptr())
+            nv.call('bc_colsum_combine', self.ctx, ptr(dd), 1, S, ptr(gv[j]), stream_ptr())
+        return gv
+
     def best_row(self, sub_idcs, resid):
         n, S = self.V.shape
         nv.call('bc_dense_score', self.ctx, nv.SCORE_CORR, ptr(self.V), n, S, int(self.V.stride(0)), None, ptr(resid), None, 0,
@@ -187,8 +238,12 @@ class GreedyVICoreset(Coreset):
         self.opt_itrs = opt_itrs
         self.groups = groups
         self.selected_groups = []
+        self._groups_cover = None
         if groups is not None:
-            raise NotImplementedError('group-wise selection is not on the accelerated path yet (SURVEY 8f.1)')
+            flat = np.array([r for g in groups for r in g], dtype=np.int64)
+            # when the groups list every row exactly once, in order, a pass over "all grouped rows" is a full-block pass
+            self._groups_cover = flat.shape[0] == n_total and bool(np.all(flat == np.arange(n_total)))
+            self._groups_flat = flat
         Coreset.__init__(self, **kw)
         self.initialized = int(initialized)*len(self.wts)
         self._tangent = None
@@ -227,15 +282,57 @@ class GreedyVICoreset(Coreset):
         return self.pts
 
     def _build(self, itrs, sz):
-        if self.size()+itrs > sz:
+        if self.groups is None and self.size()+itrs > sz:      # bcores.py:28-30: group mode has no size guard
             raise ValueError('%s._build(): # itrs + current size cannot exceed total desired size sz. # itr = %s cur sz: %s '
                              'desired sz: %s' % (self.alg_name, itrs, self.size(), sz))
         for i in range(itrs):
             self._select()
             self._optimize()
 
+    # bcores.py:91-123 / sparsevi.py:93-126
+    def _select_group(self):
+        t = self._get_tangent()
+        t.begin(self.wts, self.pts, self._beta())
+        G = len(self.groups)
+        if self.n_subsample_select is None:
+            gi, scaling = list(range(G)), 1.
+        else:
+            gi = np.random.randint(G, size=self.n_subsample_select)                       # bcores.py:57
+            scaling = G/self.n_subsample_select
+        gv = t.group_rows(self.groups, gi)
+        colsum = t.group_colsum(gv)
+        if self.pts.size > 0:
+            Vc = t.core_rows(self._core_operand(t))
+            w_dev = t.eng.upload(self.wts)
+            resid = t.residual(colsum, scaling, Vc, w_dev)
+            M = Vc.shape[0]
+            if M > self.initialized:
+                t.core_max(Vc, resid, self.initialized, t.core_out)
+        else:
+            Vc = None
+            resid = t.residual(colsum, scaling, None, None)
+        best, pos = t.group_best(gv, resid)
+        if Vc is None:
+            take = True
+        elif Vc.shape[0] > self.initialized:
+            take = best > float(t.core_out.cpu().numpy()[0])           # NaN on either side -> False
+        else:
+            take = best > -np.inf                                       # bcores.py:107-108 (False for NaN)
+        if take and pos >= 0:
+            f = int(pos) if self.n_subsample_select is None else int(gi[pos])
+            if f not in self.selected_groups:
+                self.selected_groups.append(f)
+                rows_f = np.asarray(self.groups[f], dtype=np.int64)
+                new = np.vstack([np.asarray(self.data[int(r)], dtype=np.float64).reshape(1, -1) for r in rows_f]) \
+                    if self.rows is not None and not isinstance(self.data, np.ndarray) else np.asarray(self.data[rows_f, :], dtype=np.float64)
+                self.wts = np.append(self.wts, np.zeros(new.shape[0]))
+                self.idcs = np.append(self.idcs, rows_f).astype(np.int64)
+                self.pts = np.vstack((self.pts.reshape(-1, self._ncols), new))
+
     # bcores.py:75-90 / sparsevi.py:73-92
     def _select(self):
+        if self.groups is not None:
+            return self._select_group()
         t = self._get_tangent()
         M = self.wts.shape[0]
         t.begin(self.wts, self.pts, self._beta())
@@ -249,13 +346,13 @@ class GreedyVICoreset(Coreset):
             Vc = t.core_rows(self._core_operand(t))
             w_dev = t.eng.upload(self.wts)
             resid = t.residual(colsum, scaling, Vc, w_dev)
-            t.core_max(Vc, resid, 0, t.out4[2:3])
+            t.core_max(Vc, resid, 0, t.core_out)
         else:
             Vc = None
             resid = t.residual(colsum, scaling, None, None)
         best, pos = t.best_row(sub_idcs, resid)
         if Vc is not None:
-            core_best = float(t.out4[2:3].cpu().numpy()[0])
+            core_best = float(t.core_out.cpu().numpy()[0])
             take = best > core_best                          # NaN on either side -> False, like `corrs.max() > corecorrs.max()`
         else:
             take = True
@@ -286,7 +383,12 @@ class GreedyVICoreset(Coreset):
 
         def grd(w_host, w_dev):
             t.begin(w_host, self.pts, beta)
-            sub_idcs = None if self.n_subsample_opt is None else np.random.randint(self._n_total, size=self.n_subsample_opt)
+            if self.n_subsample_opt is not None:
+                sub_idcs = np.random.randint(self._n_total, size=self.n_subsample_opt)
+            elif self.groups is not None and not self._groups_cover:
+                sub_idcs = self._groups_flat        # bcores.py:46-51: the data term is the sum over the grouped rows
+            else:
+                sub_idcs = None
             colsum = t.colsum(sub_idcs)
             Vc = t.core_rows(core)
             resid = t.residual(colsum, scaling, Vc, w_dev)

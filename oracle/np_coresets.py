@@ -41,7 +41,7 @@ class GreedyVI(object):
     """
 
     def __init__(self, data, sampler, S, potential, n_sub_select=None, n_sub_opt=None,
-                 opt_itrs=100, sched=lambda i: 1./(1.+i)):
+                 opt_itrs=100, sched=lambda i: 1./(1.+i), groups=None, initialized=False):
         self.data = data
         self.sampler = sampler
         self.S = S
@@ -54,6 +54,9 @@ class GreedyVI(object):
         self.wts = np.array([])
         self.idcs = np.array([], dtype=np.int64)
         self.pts = np.array([])
+        self.groups = groups                                   # bcores.py:22 / sparsevi.py:20: list of row-index lists
+        self.selected_groups = []
+        self.initialized = int(initialized)*len(self.wts)      # bcores.py:25
         self.samples = sampler(S, np.array([]), np.array([]))   # projector.py:18,46 (ctor draws once)
         self.log = []   # oracle extra: per-select diagnostics
 
@@ -64,13 +67,28 @@ class GreedyVI(object):
         keep = self.wts > 0                              # coreset.py:25-26
         return self.wts[keep], self.pts[keep, :], self.idcs[keep]
 
-    def _tangent(self, n_sub, w, p):
-        """bcores.py:37-72 / sparsevi.py:35-70, individual-point branches."""
+    def _group_rows(self, gi):
+        """bcores.py:50,60: one row per listed group = the sum of the group's centred rows"""
+        return np.array([np.sum(centred(self.potential(self.data[self.groups[i], :], self.samples)), axis=0) for i in gi])
+
+    def _tangent(self, n_sub, w, p, select=False):
+        """bcores.py:37-72 / sparsevi.py:35-70."""
         self.samples = self.sampler(self.S, w, p)        # update() first: consumes np.random
-        if n_sub is None:
+        self._gi = None
+        if n_sub is None and self.groups is None:
             sub = None
             vecs = centred(self.potential(self.data, self.samples))
             scale = 1.
+        elif n_sub is None:                                              # bcores.py:46-51
+            self._gi = list(range(len(self.groups)))
+            sub = [r for i in self._gi for r in self.groups[i]]
+            vecs = self._group_rows(self._gi)
+            scale = 1.
+        elif self.groups is not None and select:                         # bcores.py:56-61
+            self._gi = np.random.randint(len(self.groups), size=n_sub)
+            sub = [r for i in self._gi for r in self.groups[i]]
+            vecs = self._group_rows(self._gi)
+            scale = len(self.groups)/n_sub
         else:
             sub = np.random.randint(self.data.shape[0], size=n_sub)     # bcores.py:53
             vecs = centred(self.potential(self.data[sub], self.samples))
@@ -84,8 +102,30 @@ class GreedyVI(object):
         # passes it: rows whose centred vector is exactly 0 stay in and score 0/0 = NaN.
         return vecs, scale, sub, core
 
+    def select_group(self):
+        """bcores.py:91-123 / sparsevi.py:93-126: add a whole group of rows."""
+        gv, scale, sub, core = self._tangent(self.n_sub_select, self.wts, self.pts, select=True)
+        if self.n_sub_select is None:
+            resid = gv.sum(axis=0) - self.wts.dot(core)
+        else:
+            resid = scale*gv.sum(axis=0) - self.wts.dot(core)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            corrs = gv.dot(resid) / np.sqrt((gv**2).sum(axis=1)) / gv.shape[1]
+            ccorrs = np.fabs(core.dot(resid) / np.sqrt((core**2).sum(axis=1))) / core.shape[1]
+        maxcc = ccorrs[self.initialized:].max() if ccorrs.shape[0] > self.initialized else -np.inf
+        if ccorrs.size == 0 or corrs.max() > maxcc:
+            f = np.argmax(corrs) if self.n_sub_select is None else self._gi[np.argmax(corrs)]
+            if f not in self.selected_groups:
+                self.selected_groups.append(f)
+                new = self.data[self.groups[f], :]
+                self.wts = np.append(self.wts, np.zeros(new.shape[0]))
+                self.idcs = np.append(self.idcs, np.asarray(self.groups[f], dtype=np.int64))
+                self.pts = np.vstack((self.pts.reshape(-1, self.data.shape[1]), new))
+
     def select(self):
         """bcores.py:75-90 / sparsevi.py:73-92."""
+        if self.groups is not None:
+            return self.select_group()
         vecs, scale, sub, core = self._tangent(self.n_sub_select, self.wts, self.pts)
         resid = scale*vecs.sum(axis=0) - self.wts.dot(core)
         with np.errstate(invalid='ignore', divide='ignore'):
@@ -116,7 +156,7 @@ class GreedyVI(object):
         """coreset.py:33-45 + bcores.py:27-35."""
         if sz < self.size():
             raise ValueError('cannot shrink')
-        if self.size()+itrs > sz:
+        if self.groups is None and self.size()+itrs > sz:      # bcores.py:28-30: no size guard in group mode
             raise ValueError('itrs + size > sz')
         for _ in range(itrs):
             self.select()

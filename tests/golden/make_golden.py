@@ -129,18 +129,19 @@ def main():
             prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], prob['ref_betalik'](model_lr, gaussian, model_neurlinr),
                                            prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
             alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
-                                 opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False, **empty_kw())
+                                 opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False,
+                                 groups=case['groups'], **empty_kw())
         elif case['alg'] == 'svi':
             prj = bc.BlackBoxProjector(prob['sampler'], case['S'], prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
             alg = bc.SparseVICoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
-                                     opt_itrs=case['opt_itrs'], step_sched=case['sched'], **empty_kw())
+                                     opt_itrs=case['opt_itrs'], step_sched=case['sched'], groups=case['groups'], **empty_kw())
         else:
             prj = bc.BlackBoxProjector(prob['sampler'], case['S'], prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
             alg = bc.HilbertCoreset(prob['data'], prj, n_subsample=case['n_sel'], snnls=getattr(bc.snnls, case['solver']), **empty_kw())
         hist_i, hist_w = [], []
         with contextlib.redirect_stdout(io.StringIO()):
             for m in range(1, case['M']+1):
-                alg.build(1, m)
+                alg.build(1, problems.build_size(case, m))
                 r = alg.get()
                 hist_i.append(np.array(r[2]).copy()); hist_w.append(np.array(r[0]).copy())
         # oracle run, same seeds
@@ -149,12 +150,12 @@ def main():
         if case['alg'] in ('beta', 'svi'):
             pot = prob['oracle_betalik'](case['beta']) if case['alg'] == 'beta' else prob['oracle_loglik']()
             o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], pot, n_sub_select=case['n_sel'], n_sub_opt=case['n_opt'],
-                            opt_itrs=case['opt_itrs'], sched=case['sched'])
+                            opt_itrs=case['opt_itrs'], sched=case['sched'], groups=case['groups'])
         else:
             o = oc.Hilbert(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), n_sub=case['n_sel'],
                            solver={'GIGA': 'giga', 'FrankWolfe': 'fw', 'OrthoPursuit': 'omp'}[case['solver']])
         for m in range(1, case['M']+1):
-            o.build(1, m)
+            o.build(1, problems.build_size(case, m))
             if case['alg'] in ('beta', 'svi'):
                 ow, _, oi = o.get()
             else:

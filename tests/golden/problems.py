@@ -152,9 +152,31 @@ def _sched(i0):
     return lambda i: i0/(1.+i)
 
 
+def contiguous_groups(n, size):
+    return [list(range(i, min(i+size, n))) for i in range(0, n, size)]
+
+
+def ragged_groups(n, seed):
+    """a random partition of the rows into groups of 5..20 rows (row order shuffled)"""
+    r = np.random.RandomState(seed)
+    perm = r.permutation(n)
+    out, i = [], 0
+    while i < n:
+        k = int(r.randint(5, 21))
+        out.append([int(v) for v in perm[i:i+k]])
+        i += k
+    return out
+
+
+def build_size(case, m):
+    """`sz` argument of build(1, sz) at step m: group mode adds whole groups, so the reference's only guard is
+    sz >= current size (coreset.py:38-39)"""
+    return 10**9 if case.get('groups') is not None else m
+
+
 def coreset_cases(heavy=True):
     c = []
-    base = dict(n_sel=None, n_opt=None, beta=0.1, solver=None)
+    base = dict(n_sel=None, n_opt=None, beta=0.1, solver=None, groups=None)
     c.append(dict(base, name='lr_beta_small', alg='beta', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
     c.append(dict(base, name='lr_svi_small', alg='svi', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
     c.append(dict(base, name='lr_beta_zero_rows', alg='beta', make=make_logistic(1500, 4, 5, zero_rows=(0, 7, 450, 1499)), seed=2, S=64, opt_itrs=10, M=5, sched=_sched(1.)))
@@ -166,6 +188,13 @@ def coreset_cases(heavy=True):
     c.append(dict(base, name='lr_hilbert_giga', alg='hilbert', make=make_logistic(500, 5, 13), seed=8, S=50, opt_itrs=0, M=10, sched=None, solver='GIGA'))
     c.append(dict(base, name='lr_hilbert_fw_sub', alg='hilbert', make=make_logistic(800, 5, 14), seed=9, S=50, opt_itrs=0, M=10, sched=None, solver='FrankWolfe', n_sel=200))
     c.append(dict(base, name='gauss_hilbert_omp', alg='hilbert', make=make_gaussian(300, 6, 4), seed=10, S=48, opt_itrs=0, M=7, sched=None, solver='OrthoPursuit'))
+    # group-wise selection (bcores.py:46-61,91-123 / sparsevi.py:93-126): whole groups of rows enter the coreset
+    c.append(dict(base, name='lr_beta_groups', alg='beta', make=make_logistic(600, 5, 21), seed=11, S=40, opt_itrs=15, M=4, sched=_sched(1.),
+                  groups=contiguous_groups(600, 15)))
+    c.append(dict(base, name='lr_beta_groups_sub', alg='beta', make=make_logistic(900, 4, 22), seed=12, S=32, opt_itrs=12, M=4, sched=_sched(1.),
+                  groups=contiguous_groups(900, 10), n_sel=25, n_opt=150))
+    c.append(dict(base, name='nl_svi_groups', alg='svi', make=make_neurlin(480, 6, 23), seed=13, S=32, opt_itrs=12, M=3, sched=_sched(.1),
+                  groups=ragged_groups(480, 17)))
     if heavy:
         # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
         c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))

@@ -290,17 +290,17 @@ def _run_product_case(bc, models, case, blackbox=False):
     if case['alg'] == 'beta':
         prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
         alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
-                             opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False)
+                             opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False, groups=case['groups'])
     elif case['alg'] == 'svi':
         prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
         alg = bc.SparseVICoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
-                                 opt_itrs=case['opt_itrs'], step_sched=case['sched'])
+                                 opt_itrs=case['opt_itrs'], step_sched=case['sched'], groups=case['groups'])
     else:
         prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
         alg = bc.HilbertCoreset(prob['data'], prj, n_subsample=case['n_sel'], snnls=getattr(bc.snnls, case['solver']))
     sizes, sumw = [], []
     for m in range(1, case['M']+1):
-        alg.build(1, m)
+        alg.build(1, problems.build_size(case, m))
         r = alg.get()
         sizes.append(len(r[2])); sumw.append(r[0].sum())
     return r[0], r[2], np.array(sizes), np.array(sumw)
@@ -317,7 +317,7 @@ def test_coreset_builds_match_reference(bc, models, route, case):
     np.testing.assert_allclose(sumw, g[nm+'_sumw'], rtol=1e-6, atol=1e-9)
 
 
-@pytest.mark.parametrize('name', ['lr_beta_small', 'gauss_beta_sub', 'nl_svi_small'])
+@pytest.mark.parametrize('name', ['lr_beta_small', 'gauss_beta_sub', 'nl_svi_small', 'lr_beta_groups_sub'])
 def test_blackbox_callbacks_take_the_dense_path(bc, models, name):
     """likelihoods hidden behind lambdas (as the reference drivers pass them) give the same coreset"""
     g = np.load(os.path.join(G, 'g3_coresets.npz'))

@@ -67,14 +67,14 @@ def run_oracle_case(case):
     if case['alg'] in ('beta', 'svi'):
         pot = prob['oracle_betalik'](case['beta']) if case['alg'] == 'beta' else prob['oracle_loglik']()
         o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], pot, n_sub_select=case['n_sel'], n_sub_opt=case['n_opt'],
-                        opt_itrs=case['opt_itrs'], sched=case['sched'])
+                        opt_itrs=case['opt_itrs'], sched=case['sched'], groups=case['groups'])
     else:
         o = oc.Hilbert(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), n_sub=case['n_sel'],
                        solver={'GIGA': 'giga', 'FrankWolfe': 'fw', 'OrthoPursuit': 'omp'}[case['solver']])
     sizes, sumw = [], []
     with np.errstate(all='ignore'):
         for m in range(1, case['M']+1):
-            o.build(1, m)
+            o.build(1, problems.build_size(case, m))
             if case['alg'] in ('beta', 'svi'):
                 w, _, i = o.get()
             else:

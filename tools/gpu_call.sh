@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "full_size" > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"
-tail -15 gpurun_out/gpu_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"
+tail -25 gpurun_out/gpu_tests.log
