@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libbetacores.so')
+LIB_PATH = os.environ.get('BC_LIB_PATH') or os.path.join(os.path.dirname(_HERE), 'lib', 'libbetacores.so')
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 

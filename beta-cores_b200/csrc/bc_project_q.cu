@@ -372,37 +372,32 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         }
         const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
         double fv[8];
-        double cnext[4];   // batch 3, converted one batch early so that the buffer can go back half-way through the chunk
+        // software pipeline inside the warp: while batch b is evaluated (FP64 pipe) the digits of batch b+1 -- fetched one
+        // step earlier -- are recombined (integer pipe) in the same straight-line block, and the fetch of batch b+2 is in
+        // flight.  Without it the four warps of a sub-partition fall into step (all converting, then all evaluating) and
+        // the phases add up instead of overlapping.
+        double ccur[4], cnext[4];
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ccur[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
+                                    (int)dg[6][e]);
+        }
+#pragma unroll
+        for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + 4), dg[d]);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const int cb = c * kQChunk + half * kQHalfCols + b * 4;
           double cval[4], ca[4], fr[4];
-          if (b < NB - 1) {
-            tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cval[e] = ccur[e];
+          if (b + 1 < NB) {
+            tmem_wait_ld();   // digits of batch b+1
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              cval[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
-                                        (int)dg[6][e]);
+              cnext[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
+                                         (int)dg[6][e]);
             }
-            // the digits are consumed: fetch the next four columns while this batch is evaluated
-#pragma unroll
-            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + (b + 1) * 4), dg[d]);
-            if (b == NB - 2) {
-              // last fetch of the chunk: convert it right away and hand the accumulator buffer back to the MMA issuer --
-              // two evaluation batches (half a chunk period) before this group needs the chunk after next
-              tmem_wait_ld();
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                cnext[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e],
-                                           (int)dg[5][e], (int)dg[6][e]);
-              }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tmem_empty + buf);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) cval[e] = cnext[e];
           }
           if (MODE == QMODE_DOT) {
 #pragma unroll
@@ -446,6 +441,17 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) fv[(b & 1) * 4 + e] = fr[e];
           }
+          if (b + 2 < NB) {
+#pragma unroll
+            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + (b + 2) * 4), dg[d]);
+          } else if (b + 2 == NB) {
+            // the last digits of the chunk are converted: hand the accumulator buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ccur[e] = cnext[e];
           if (want_cols && (b & 1)) {
             // transposed butterfly: 32 rows x 8 columns -> lanes with (lane & 3) == 0 own one column total each
             int off = 0;
