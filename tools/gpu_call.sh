@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 300 python tools/q_probe.py > gpurun_out/q_probe.log 2>&1; echo "probe rc=$?"
-tail -6 gpurun_out/q_probe.log
+for v in DEC DECFEW; do
+  BC_LIB_PATH=$PWD/beta-cores_b200/lib/libbc_$v.so timeout 120 python tools/q_time.py
+done 2>&1 | grep "ms/pass"
