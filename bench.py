@@ -331,7 +331,7 @@ def b200_arm(a):
     if route == 'q':
         kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
                  'column sums, fused)')
-        digit_pairs, fp64_inst = 28, 74          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
+        digit_pairs, fp64_inst = 28, 69          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
         int8_ops = digit_pairs*2.*n_local*S*128
         extra = {
             'route': 'q',
@@ -365,11 +365,13 @@ def b200_arm(a):
         roofline['hbm'].update({'algorithmic_bytes_per_launch': qbytes, 'achieved_gbs': qbytes/(col_mean*1e-3)/1e9,
                                 'frac': qbytes/(col_mean*1e-3)/1e9/hbm_peak,
                                 'note': 'int8 digit image of the rows (7 B per feature) + row scales; samples stay in L2'})
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r01_ncu_k_project_q_v3.txt: 910.2 MB for a
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for a
         # 1,000,000-row launch (= the algorithmic 904 MB; the operands are read exactly once); it scales linearly in rows
-        roofline['traffic'] = 910.2*n_local
-        roofline['traffic_source'] = 'ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v3.txt), scaled by rows'
-        roofline['bound_detail'] = 'fp64 pipe of the fused potential epilogue (see fp64_pipe); tensor and HBM pipes are far from their limits'
+        roofline['traffic'] = 911.4*n_local
+        roofline['traffic_source'] = 'ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v4.txt), scaled by rows'
+        roofline['bound_detail'] = ('FP64 pipe of the fused potential epilogue PLUS the tensor time of the int8 digit MMAs: on B200 the FP64 pipe '
+                                    'makes no progress while the tensor core is busy (profiles/r01_q_ablation.txt), so the two add up; '
+                                    'HBM is at 2 % of its peak')
     idcs_value = [int(i) for i in alg.idcs]
 
     # ---- stage 2 (materialised n x S matrix: snnls / Hilbert scoring) and stage 3 (coreset-side step), timed on their own ----
