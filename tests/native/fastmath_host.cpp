@@ -18,6 +18,21 @@ double fm_logistic(int kind, int poly, double c, double beta, const double* q) {
   if (poly == bc::kPowPolyMax) return bc::LogisticF<bc::KIND_BETALIK, bc::kPowPolyMax>::eval(c, 0, 0, mp);
   return bc::LogisticF<bc::KIND_BETALIK, 0>::eval(c, 0, 0, mp);
 }
+// the 4-wide stage-interleaved form the tensor-core kernel uses (bc_project_q.cu)
+void fm_logistic_v4(int kind, int poly, const double* c4, double beta, const double* q, double* out4) {
+  bc::ModelParams mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = 0.0;
+  mp.p[0] = beta;
+  mp.p[1] = (beta + 1.) / beta;
+  mp.p[2] = 700.0 / (beta > 1.0 ? beta : 1.0);
+  for (int i = 0; i <= bc::kPowPolyMax; ++i) mp.q[i] = q ? q[i] : 0.0;
+  double c[4] = {c4[0], c4[1], c4[2], c4[3]}, ca[4] = {0, 0, 0, 0}, o[4];
+  if (kind == bc::KIND_LOGLIK) bc::LogisticF<bc::KIND_LOGLIK, 0>::evalv<4>(c, 0, ca, mp, o);
+  else if (poly == 20) bc::LogisticF<bc::KIND_BETALIK, 20>::evalv<4>(c, 0, ca, mp, o);
+  else if (poly == bc::kPowPolyMax) bc::LogisticF<bc::KIND_BETALIK, bc::kPowPolyMax>::evalv<4>(c, 0, ca, mp, o);
+  else bc::LogisticF<bc::KIND_BETALIK, 0>::evalv<4>(c, 0, ca, mp, o);
+  for (int i = 0; i < 4; ++i) out4[i] = o[i];
+}
 double fm_gaussian(int kind, double c, double ra, double ca, const double* p8) {
   bc::ModelParams mp;
   for (int i = 0; i < 8; ++i) mp.p[i] = p8[i];

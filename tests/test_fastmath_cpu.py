@@ -32,6 +32,7 @@ def fm():
     L.fm_logistic.argtypes, L.fm_logistic.restype = [i, i, d, d, dp], d
     L.fm_gaussian.argtypes, L.fm_gaussian.restype = [i, d, d, d, dp], d
     L.fm_neurlin.argtypes, L.fm_neurlin.restype = [i, d, d, dp], d
+    L.fm_logistic_v4.argtypes, L.fm_logistic_v4.restype = [i, i, dp, d, dp, dp], None
     return L
 
 
@@ -120,3 +121,24 @@ def test_logistic_loglik_rewrite(fm):
     ref = om.lr_loglik(-ms[:, None], np.ones((1, 1)))[:, 0]
     got = np.array([fm.fm_logistic(0, 0, float(-m), 0.1, None) for m in ms])
     assert np.allclose(got, ref, rtol=1e-15, atol=1e-15)
+
+
+@pytest.mark.parametrize('kind,beta,poly', [(1, 0.1, 20), (1, 0.9, 24), (1, 0.1, 0), (1, 3.0, 0), (0, 0.1, 0)])
+def test_logistic_vector_forms(fm, kind, beta, poly):
+    """evalv<4> -- the stage-interleaved form k_project_q runs (single clamp, integer sign test, no NaN selects) -- against
+    60-digit arithmetic"""
+    q = _fit(beta, poly)[0] if poly > 0 else (ctypes.c_double*25)()
+    r = np.random.RandomState(4)
+    ms = np.concatenate([r.normal(0, 12, 3000), np.linspace(-60, 60, 1201), [0., -0.0, 700., -700., 745., -745., 5000., -5000.]])
+    if kind == 0:
+        ms = np.concatenate([ms, [99.9, 100., 100.1, 1e4]])
+    ms = ms[:4*(len(ms)//4)]
+    worst = 0.
+    out = (ctypes.c_double*4)()
+    for k in range(0, len(ms), 4):
+        c4 = (ctypes.c_double*4)(*[float(-m) for m in ms[k:k+4]])
+        fm.fm_logistic_v4(kind, poly, c4, beta, q, out)
+        for m, got in zip(ms[k:k+4], out):
+            want = _lr_beta_exact(m, beta) if kind == 1 else -mp.log1p(mp.exp(mp.mpf(float(m))))
+            worst = max(worst, float(abs(mp.mpf(got)-want)/max(1, abs(want))))
+    assert worst < 5e-16*(max(1., (beta+1)/beta) if kind == 1 else 1.), worst
