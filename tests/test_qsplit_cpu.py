@@ -1,0 +1,95 @@
+"""CPU checks of the error-free integer split behind the tensor-core route (csrc/bc_project_q.cu): the digit
+decomposition and the truncated diagonal recombination are restated here in exact integer arithmetic, next to the
+operand-image geometry compiled from the kernel's own header.  No GPU needed."""
+import ctypes
+import math
+import os
+import subprocess
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'native', 'qsplit_host.cpp')
+OUT = os.path.join(HERE, 'native', '_build', 'libqsplit_host.so')
+K = 7     # digits
+
+
+@pytest.fixture(scope='module')
+def geo():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.run(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I/usr/local/cuda/include', SRC, '-o', OUT], check=True)
+    L = ctypes.CDLL(OUT)
+    L.q_off.argtypes, L.q_off.restype = [ctypes.c_uint, ctypes.c_uint], ctypes.c_uint
+    return L
+
+
+def split(vec):
+    """k_quantise: one power-of-two exponent per vector, 7 signed base-256 digits per entry (top digit within +-64)"""
+    amax = float(np.abs(vec).max())
+    e = (math.frexp(amax)[1] - 1) + 3 if amax > 0 else 0          # ilogb(amax) + 3
+    digs = np.zeros((K, len(vec)), dtype=np.int64)
+    for i, x in enumerate(vec):
+        Q = int(round(Fraction(float(x))*Fraction(2)**(56-e)))   # round-half-even on an exact rational = __double2ll_rn
+        q = Q
+        for s in range(K-1, 0, -1):
+            d = ((q + 128) % 256) - 128                           # sign-extended low byte
+            digs[s, i] = d
+            q = (q - d) >> 8
+        digs[0, i] = q
+        assert sum(int(digs[s, i])*256**(K-1-s) for s in range(K)) == Q
+    return e, digs
+
+
+def test_digits_are_int8_and_exact():
+    r = np.random.RandomState(0)
+    for trial in range(40):
+        v = r.randn(128)*math.exp(6*r.randn())
+        if trial % 5 == 0:
+            v[r.randint(128, size=20)] = 0.
+        e, d = split(v)
+        assert np.abs(d[0]).max() <= 64 and d[1:].min() >= -128 and d[1:].max() <= 127
+        # the digits reproduce the entries to 2^-56 of the scale 2^e (at most 2^-53 of the largest entry)
+        back = sum(d[s].astype(object)*Fraction(256)**(-(s+1)) for s in range(K))
+        err = max(abs(Fraction(float(x)) - b*Fraction(2)**e) for x, b in zip(v, back))
+        assert err <= Fraction(2)**(e-57)
+
+
+def test_truncated_diagonals_reproduce_the_fp64_contraction():
+    """sum_{d<=6} 256^(6-d) D_d, D_d = sum_{i+j=d} a_i . b_j in int32 range, times 2^(e_x + e_th - 64): within 2e-14 of the
+    exact dot product relative to max|x| max|theta| (numpy's own dgemm is at ~5e-15)"""
+    r = np.random.RandomState(1)
+    worst = 0.
+    for trial in range(30):
+        D = int(r.choice([1, 5, 20, 64, 128]))
+        x = r.randn(D)*math.exp(3*r.randn())
+        th = r.randn(D)*math.exp(r.randn())
+        ex, a = split(x)
+        et, b = split(th)
+        H = 0
+        for d in range(K):
+            Dd = sum(int(np.dot(a[i], b[d-i])) for i in range(d+1))
+            assert abs(Dd) < 2**24                      # what the kernel keeps in an int32 TMEM accumulator
+            H += Dd*256**(K-1-d)
+        hi = sum(sum(int(np.dot(a[i], b[d-i])) for i in range(d+1))*256**(3-d) for d in range(4))
+        assert abs(hi) < 2**51                          # exact_ll2d's range (q_combine's upper half)
+        got = Fraction(H)*Fraction(2)**(ex+et-64)
+        exact = sum(Fraction(float(u))*Fraction(float(v)) for u, v in zip(x, th))
+        worst = max(worst, float(abs(got-exact))/(np.abs(x).max()*np.abs(th).max()))
+    assert worst < 2e-14, worst
+
+
+def test_swizzled_image_geometry(geo):
+    """q_swizzle_off is a bijection of a digit plane onto itself, keeps 16-byte chunks intact inside their 128-byte row
+    and XORs the chunk index with (row mod 8) -- the SWIZZLE_128B pattern the UMMA descriptors declare"""
+    rows, kk = geo.q_tile_rows(), geo.q_k()
+    assert (geo.q_slices(), rows, geo.q_chunk(), kk) == (7, 128, 32, 128)
+    seen = set()
+    for rr in range(rows):
+        for c in range(kk):
+            o = geo.q_off(rr, c)
+            assert o // 128 == rr and o % 16 == c % 16
+            assert (o % 128) // 16 == (c // 16) ^ (rr % 8)
+            seen.add(o)
+    assert len(seen) == rows*kk and max(seen) == rows*kk - 1
