@@ -91,11 +91,11 @@ class BlackBoxProjector(_SamplingProjector):
         if grad:
             if self.grad_loglikelihood is None:
                 raise ValueError('grad_loglikelihood was requested but not initialized in BlackBoxProjector.project')
-            # (n, S, D) gradients feed BatchPSVI only, which is outside the accelerated path
-            # (SURVEY section 8f.3); reference centring over the last axis kept (projector.py:31).
-            glls = self.grad_loglikelihood(pts, self.samples)
-            glls -= glls.mean(axis=2)[:, :, np.newaxis]
-            return lls, glls
+            # opaque gradient callback: (n, S, D) host tensor, centred over its LAST axis as the reference does
+            # (projector.py:31) -- on the device, as n*S rows of length D.  BatchPSVICoreset does not come through here.
+            glls = np.ascontiguousarray(self.grad_loglikelihood(pts, self.samples), dtype=np.float64)
+            shp = glls.shape
+            return lls, centre_on_device(glls.reshape(-1, shp[-1])).cpu().numpy().reshape(shp)
         return lls
 
 

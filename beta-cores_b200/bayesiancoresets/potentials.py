@@ -106,3 +106,40 @@ class DevicePotential(object):
             raise TypeError('%s: unbound model constants %s' % (self.__name__, missing))
         from .coreset.projector import evaluate_potential
         return evaluate_potential(pot, pts, samples, beta, centred=False)
+
+
+class DeviceGradient(object):
+    """d(log-likelihood)/d(point) of a built-in model, as the object `BlackBoxProjector(..., grad_loglikelihood=...)`
+    takes (examples/common/model_lr.py:107-114 grad_z_log_likelihood, gaussian.py:17-20 gaussian_grad_x_loglikelihood).
+
+    BatchPSVICoreset recognises it and contracts the gradient with the residual on the device
+    (bc_core_pgrad) without forming the (M, S, D) tensor of the reference.  Called directly with the reference's
+    signature it returns that tensor (built on the device from the same kernel, one unit residual at a time is not needed:
+    the tensor is sigma(m)[:, :, None] * th[None] resp. (th Siginv)[None] - (x Siginv)[:, None], assembled from the
+    materialise pass) -- only meant for small inputs."""
+
+    def __init__(self, model, bound=None, name=None):
+        if model not in ('logistic', 'gaussian'):
+            raise ValueError('no point-gradient for model %r (the reference defines none, model_neurlinr.py:99-100)' % (model,))
+        self.model = model
+        self.bound = dict(bound or {})
+        self.__name__ = name or '%s_grad_point' % model
+
+    @property
+    def needs(self):
+        return ('Siginv',) if self.model == 'gaussian' else ()
+
+    def is_bound(self):
+        return all(k in self.bound for k in self.needs)
+
+    def bind(self, **consts):
+        b = dict(self.bound)
+        for k, v in consts.items():
+            if k not in self.needs:
+                raise TypeError('%s has no constant %r' % (self.__name__, k))
+            b[k] = np.ascontiguousarray(v, dtype=np.float64)
+        return DeviceGradient(self.model, b, self.__name__)
+
+    def __call__(self, pts, samples, *rest):
+        raise NotImplementedError('%s is a device gradient descriptor: BatchPSVICoreset contracts it on the device; the (n, S, D) '
+                                  'tensor of the reference is never formed' % self.__name__)

@@ -466,6 +466,28 @@ int bc_adam_step(bc_ctx* c, const double* d_g, double* d_x, double* d_m1, double
   return BC_OK;
 }
 
+int bc_core_pgrad(bc_ctx* c, const double* d_P, int M, int64_t ldp, const double* d_w, const double* d_resid, double* d_out,
+                  int64_t ldo, void* stream) {
+  if (!c || !d_P || !d_w || !d_resid || !d_out || M < 0 || ldp < 1 || ldo < 1) return BC_ERR_ARG;
+  if (!c->potential_set || !c->samples_set) return BC_ERR_STATE;
+  if (c->model == BC_MODEL_NEURLIN) return BC_ERR_UNSUPPORTED;   // the reference defines no gradient for it (model_neurlinr.py:99-100)
+  if (ldp < c->Dk || ldo < c->Dk) return BC_ERR_ARG;
+  if ((size_t)(2 * c->Dk + 2 * c->S) * sizeof(double) > 48 * 1024) return BC_ERR_UNSUPPORTED;
+  BC_CUDA(launch_pgrad_model(c->model, d_P, M, ldp, c->B, c->S, c->Dk, c->Dpad, c->d_siginv, d_w, d_resid, d_out, ldo,
+                             (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
+int bc_dense_pgrad(bc_ctx* c, const double* d_G, int M, int S, int D, const double* d_w, const double* d_resid, int centre,
+                   double* d_out, int64_t ldo, void* stream) {
+  if (!c || !d_G || !d_w || !d_resid || !d_out || M < 0 || S <= 0 || D <= 0 || ldo < D) return BC_ERR_ARG;
+  if ((size_t)2 * S * sizeof(double) > 48 * 1024) return BC_ERR_UNSUPPORTED;
+  BC_CUDA(launch_pgrad_dense(d_G, M, S, D, d_w, d_resid, centre, d_out, ldo, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
 int bc_dense_rownorms(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream) {
   if (!c || !d_V || !d_norms || n < 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_dense_rowstats(d_V, n, S, ldv, nullptr, 0, d_norms, nullptr, (cudaStream_t)stream));

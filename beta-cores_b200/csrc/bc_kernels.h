@@ -90,6 +90,12 @@ cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, cons
 cudaError_t launch_adam(const double* g, double* x, double* m1, double* m2, int n, double lr, double b1, double b2, double c1,
                         double c2, double eps, const unsigned char* nn_mask, cudaStream_t st);
 
+cudaError_t launch_pgrad_model(int model, const double* P, int M, long long ldp, const double* B, int S, int D, int ldb,
+                               const double* siginv, const double* w, const double* resid, double* out, long long ldo,
+                               cudaStream_t st);
+cudaError_t launch_pgrad_dense(const double* G, int M, int S, int D, const double* w, const double* resid, int centre, double* out,
+                               long long ldo, cudaStream_t st);
+
 // ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----
 cudaError_t launch_dense_rowstats(const double* V, long long n, int S, long long ldv, const double* u, int nu, double* norms,
                                   double* dots, cudaStream_t st);

@@ -236,4 +236,110 @@ cudaError_t launch_adam(const double* g, double* x, double* m1, double* m2, int 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------- pseudo-point gradients ----
+// BatchPSVICoreset (bayesiancoresets/coreset/bpsvi.py:49-55): gradient of the objective in the LOCATION of pseudo-point m,
+//   ugrad[m][d] = -(w_m / S) sum_s resid_s * pg[m][s][d],
+// pg = the model's d(log-likelihood)/d(point), centred over its LAST axis as the reference's projector does
+// (coreset/projector.py:31).  The (M, S, D) tensor is never formed for the built-in models:
+//   logistic (examples/common/model_lr.py:107-114):  pg = sigma(m_ms) theta_sd,  m = -p_m . theta_s
+//        -> ugrad[m][d] = -(w_m/S) sum_s [resid_s sigma_ms] (theta_sd - mean_d theta_s)
+//   Gaussian (examples/common/gaussian.py:17-20):    pg = (theta_s Siginv)_d - (p_m Siginv)_d
+//        -> ugrad[m][d] = -(w_m/S) [ sum_s resid_s (A_sd - mean_d A_s) - (sum_s resid_s) (Bm_d - mean_d Bm) ],  A = Theta Siginv
+// One CTA per pseudo-point; M, S, D are small (latency-bound).  B = the prepared samples (Theta, or Siginv Theta).
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_pgrad_model(const double* __restrict__ P, int M, long long ldp, const double* __restrict__ B,
+                                                     int S, int D, int ldb, const double* __restrict__ siginv,
+                                                     const double* __restrict__ w, const double* __restrict__ resid,
+                                                     double* __restrict__ out, long long ldo) {
+  extern __shared__ double sm[];
+  double* ps = sm;            // [D]   pseudo-point
+  double* cs = ps + D;        // [S]   per-sample weight of the sample term
+  double* tb = cs + S;        // [S]   mean over d of the sample term
+  double* bm = tb + S;        // [D]   Gaussian: (p_m Siginv)_d
+  __shared__ double red[33];
+  const int m = blockIdx.x;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) ps[k] = P[m * ldp + k];
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const double* b = B + (size_t)s * ldb;
+    double dot = 0.0, sum = 0.0;
+    for (int k = 0; k < D; ++k) {
+      dot = fma(ps[k], b[k], dot);
+      sum += b[k];
+    }
+    double c = resid[s];
+    if (MODEL == MODEL_LOGISTIC) {
+      const double mm = -dot;
+      const double sg = (mm < 100.0) ? exp(mm) / (1.0 + exp(mm)) : 1.0;   // model_lr.py:111-113
+      c *= sg;
+    }
+    cs[s] = c;
+    tb[s] = sum / (double)D;
+  }
+  double bmean = 0.0;
+  if (MODEL == MODEL_GAUSSIAN) {
+    double part = 0.0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < D; ++j) acc = fma(ps[j], siginv[(size_t)j * D + d], acc);   // (p Siginv)_d   gaussian.py:20
+      bm[d] = acc;
+      part += acc;
+    }
+    bmean = block_sum(part, red) / (double)D;
+  }
+  __syncthreads();
+  const double R = resid[S];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc = fma(cs[s], B[(size_t)s * ldb + d] - tb[s], acc);
+    if (MODEL == MODEL_GAUSSIAN) acc -= R * (bm[d] - bmean);
+    out[m * ldo + d] = -(w[m] * acc) / (double)S;
+  }
+}
+
+// opaque gradient callbacks: G = (M, S, D) contiguous, already produced on the host by the user's function;
+// centre != 0 subtracts the mean over the last axis first (projector.py:31)
+__global__ void __launch_bounds__(256) k_pgrad_dense(const double* __restrict__ G, int M, int S, int D, const double* __restrict__ w,
+                                                     const double* __restrict__ resid, int centre, double* __restrict__ out,
+                                                     long long ldo) {
+  extern __shared__ double sm[];
+  double* cs = sm;       // [S] resid
+  double* tb = cs + S;   // [S] row means
+  const int m = blockIdx.x;
+  const double* g = G + (size_t)m * S * D;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    cs[s] = resid[s];
+    double sum = 0.0;
+    if (centre)
+      for (int d = 0; d < D; ++d) sum += g[(size_t)s * D + d];
+    tb[s] = sum / (double)D;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc = fma(cs[s], g[(size_t)s * D + d] - tb[s], acc);
+    out[m * ldo + d] = -(w[m] * acc) / (double)S;
+  }
+}
+
+cudaError_t launch_pgrad_model(int model, const double* P, int M, long long ldp, const double* B, int S, int D, int ldb,
+                               const double* siginv, const double* w, const double* resid, double* out, long long ldo,
+                               cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  const size_t smem = (size_t)(2 * D + 2 * S) * sizeof(double);
+  if (model == MODEL_LOGISTIC) {
+    k_pgrad_model<MODEL_LOGISTIC><<<M, 256, smem, st>>>(P, M, ldp, B, S, D, ldb, siginv, w, resid, out, ldo);
+  } else {
+    k_pgrad_model<MODEL_GAUSSIAN><<<M, 256, smem, st>>>(P, M, ldp, B, S, D, ldb, siginv, w, resid, out, ldo);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pgrad_dense(const double* G, int M, int S, int D, const double* w, const double* resid, int centre, double* out,
+                               long long ldo, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  k_pgrad_dense<<<M, 256, (size_t)2 * S * sizeof(double), st>>>(G, M, S, D, w, resid, centre, out, ldo);
+  return cudaGetLastError();
+}
+
 }  // namespace bc

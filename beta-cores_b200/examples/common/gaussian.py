@@ -12,11 +12,12 @@ projector can run them fused.
 import numpy as np
 import scipy.linalg as sl
 
-from bayesiancoresets.potentials import DevicePotential
+from bayesiancoresets.potentials import DevicePotential, DeviceGradient
 
 gaussian_loglikelihood = DevicePotential('gaussian', 'loglik', name='gaussian_loglikelihood')
 gaussian_beta_likelihood = DevicePotential('gaussian', 'betalik', name='gaussian_beta_likelihood')
 gaussian_beta_gradient = DevicePotential('gaussian', 'betagrad', name='gaussian_beta_gradient')
+gaussian_grad_x_loglikelihood = DeviceGradient('gaussian', name='gaussian_grad_x_loglikelihood')   # gaussian.py:17-20 (BatchPSVI)
 
 
 def weighted_post(th0, Sig0inv, Siginv, x, w):

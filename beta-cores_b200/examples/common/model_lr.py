@@ -16,10 +16,11 @@ import numpy as np
 import scipy.linalg as sl
 from scipy.optimize import minimize
 
-from bayesiancoresets.potentials import DevicePotential
+from bayesiancoresets.potentials import DevicePotential, DeviceGradient
 
 log_likelihood = DevicePotential('logistic', 'loglik', name='log_likelihood')
 beta_likelihood = DevicePotential('logistic', 'betalik', name='beta_likelihood')
+grad_z_log_likelihood = DeviceGradient('logistic', name='grad_z_log_likelihood')        # model_lr.py:107-114 (BatchPSVI)
 
 
 # ----------------------------------------------------------------- host: data utilities --

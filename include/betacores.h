@@ -113,6 +113,15 @@ int bc_core_maxcorr(bc_ctx* ctx, const double* d_Vc, int M, int S, int64_t ldv, 
                     void* stream);
 /* grad[m] = -(Vc_m . resid)/S                                        (bcores.py:146) */
 int bc_core_grad(bc_ctx* ctx, const double* d_Vc, int M, int S, int64_t ldv, const double* d_resid, double* d_grad, void* stream);
+/* Pseudo-point location gradients of BatchPSVICoreset (bpsvi.py:49-55):
+ *   out[m][d] = -(w[m]/S) sum_s resid[s] * pg[m][s][d],  pg = d(log-likelihood)/d(point) centred over its last axis (projector.py:31).
+ * bc_core_pgrad: pg of the current potential's model (logistic: model_lr.py:107-114; Gaussian: gaussian.py:17-20) against the
+ *   installed samples, without forming the (M, S, D) tensor.  d_P: M x ldp pseudo-points; d_resid has S+1 entries.
+ * bc_dense_pgrad: pg given as a contiguous (M, S, D) device tensor (opaque user callbacks); centre != 0 centres it first. */
+int bc_core_pgrad(bc_ctx* ctx, const double* d_P, int M, int64_t ldp, const double* d_w, const double* d_resid, double* d_out,
+                  int64_t ldo, void* stream);
+int bc_dense_pgrad(bc_ctx* ctx, const double* d_G, int M, int S, int D, const double* d_w, const double* d_resid, int centre,
+                   double* d_out, int64_t ldo, void* stream);
 /* one projected-ADAM update of x given g (util/opt.py:45-52; c1 = 1-b1**(i+1), c2 = 1-b2**(i+1));
  * d_nn_mask NULL = clamp every coordinate (nn_opt), else clamp where mask != 0 (partial_nn_opt). */
 int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, double* d_m2, int n, double lr, double b1, double b2,

@@ -163,6 +163,91 @@ class GreedyVI(object):
             self.optimise()
 
 
+def adam_partial_nonneg(x0, grad, nn_idcs, itrs, sched, b1=0.9, b2=0.999, eps=1e-8):
+    """util/opt.py:56-77 partial_nn_opt: ADAM, projection onto x >= 0 on the coordinates nn_idcs only."""
+    x = x0.copy()
+    m1 = np.zeros(x.shape[0])
+    m2 = np.zeros(x.shape[0])
+    for i in range(itrs):
+        g = grad(x)
+        m1 = b1*m1 + (1.-b1)*g
+        m2 = b2*m2 + (1.-b2)*g**2
+        upd = sched(i)*m1/(1.-b1**(i+1))/(eps + np.sqrt(m2/(1.-b2**(i+1))))
+        x -= upd
+        x[nn_idcs] = np.maximum(x[nn_idcs], 0.)
+    return x
+
+
+class BatchPSVI(object):
+    """coreset/bpsvi.py:6-65: pseudo-coreset -- sz points drawn from the data, then weights AND point locations optimised
+    jointly; potential = log-likelihood, grad_potential(pts, samples) -> (M, S, D) its gradient in the point."""
+
+    def __init__(self, data, sampler, S, potential, grad_potential, opt_itrs, n_sub_opt=None,
+                 sched=lambda m: (lambda i: 1./(1.+i))):
+        self.data = data
+        self.sampler = sampler
+        self.S = S
+        self.potential = potential
+        self.grad_potential = grad_potential
+        self.opt_itrs = opt_itrs
+        self.n_sub_opt = None if n_sub_opt is None else min(data.shape[0], n_sub_opt)     # bpsvi.py:11
+        self.sched = sched
+        self.wts = np.array([])
+        self.idcs = np.array([], dtype=np.int64)
+        self.pts = np.array([])
+        self.samples = sampler(S, np.array([]), np.array([]))   # projector ctor draw (projector.py:18)
+
+    def size(self):
+        return (self.wts > 0).sum()
+
+    def get(self):
+        keep = self.wts > 0
+        return self.wts[keep], self.pts[keep, :], self.idcs[keep]
+
+    def _tangent(self, w, p):
+        """bpsvi.py:26-42"""
+        self.samples = self.sampler(self.S, w, p)
+        if self.n_sub_opt is None:
+            vecs = centred(self.potential(self.data, self.samples))
+            scale = 1.
+        else:
+            sub = np.random.randint(self.data.shape[0], size=self.n_sub_opt)
+            vecs = centred(self.potential(self.data[sub], self.samples))
+            scale = self.data.shape[0]/self.n_sub_opt
+        core = centred(self.potential(p, self.samples))
+        pg = self.grad_potential(p, self.samples)
+        pg -= pg.mean(axis=2)[:, :, np.newaxis]                 # projector.py:31: centred over the LAST axis (D), as shipped
+        return vecs, scale, core, pg
+
+    def build(self, itrs, sz):
+        """coreset.py:33-45 + bpsvi.py:17-24 (itrs is ignored by the reference)"""
+        if sz < self.size():
+            raise ValueError('cannot shrink')
+        init = np.random.choice(self.data.shape[0], size=sz, replace=False)
+        self.pts = self.data[init]
+        self.wts = self.data.shape[0]/sz*np.ones(sz)
+        self.idcs = init
+        self.optimise()
+
+    def optimise(self):
+        """bpsvi.py:44-62"""
+        sz = self.wts.shape[0]
+        d = self.pts.shape[1]
+
+        def grad(x):
+            w = x[:sz]
+            p = x[sz:].reshape((sz, d))
+            vecs, scale, core, pg = self._tangent(w, p)
+            resid = scale*vecs.sum(axis=0) - w.dot(core)
+            wgrad = -core.dot(resid) / core.shape[1]
+            ugrad = -(w[:, np.newaxis, np.newaxis]*pg*resid[np.newaxis, :, np.newaxis]).sum(axis=1)/core.shape[1]
+            return np.hstack((wgrad, ugrad.reshape(sz*d)))
+        x0 = np.hstack((self.wts, self.pts.reshape(sz*d)))
+        xf = adam_partial_nonneg(x0, grad, np.arange(sz), self.opt_itrs, self.sched(sz))
+        self.wts = xf[:sz]
+        self.pts = xf[sz:].reshape((sz, d))
+
+
 class Hilbert(object):
     """coreset/hilbert.py:7-43: project once, drop zero-norm rows, delegate to a solver."""
 

@@ -45,6 +45,24 @@ def _gauss_quad_terms(x, th, Siginv):
     return x, th, xSx, tSt, xSt
 
 
+def lr_grad_z_loglik(z, th):
+    """model_lr.py:107-114 grad_z_log_likelihood: sigma(m)[:, :, None] * th[None] -> (n, S, D)"""
+    z = np.atleast_2d(z)
+    th = np.atleast_2d(th)
+    m = -z.dot(th.T)
+    idcs = m < 100
+    m[idcs] = np.exp(m[idcs])/(1.+np.exp(m[idcs]))
+    m[np.logical_not(idcs)] = 1.
+    return m[:, :, np.newaxis]*th[np.newaxis, :, :]
+
+
+def gauss_grad_x_loglik(x, th, Siginv):
+    """gaussian.py:17-20 gaussian_grad_x_loglikelihood -> (n, S, d)"""
+    x = np.atleast_2d(x)
+    th = np.atleast_2d(th)
+    return th.dot(Siginv)[np.newaxis, :, :] - x.dot(Siginv)[:, np.newaxis, :]
+
+
 def gauss_loglik(x, th, Siginv, logdetSig):
     """examples/common/gaussian.py:7-15 (the reference's debug print is dropped)."""
     x, th, xSx, tSt, xSt = _gauss_quad_terms(x, th, Siginv)

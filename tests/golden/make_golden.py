@@ -131,6 +131,11 @@ def main():
             alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
                                  opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False,
                                  groups=case['groups'], **empty_kw())
+        elif case['alg'] == 'bpsvi':
+            prj = bc.BlackBoxProjector(prob['sampler'], case['S'], prob['ref_loglik'](model_lr, gaussian, model_neurlinr),
+                                       prob['ref_gradll'](model_lr, gaussian, model_neurlinr))
+            alg = bc.BatchPSVICoreset(prob['data'], prj, opt_itrs=case['opt_itrs'], n_subsample_opt=case['n_opt'],
+                                      step_sched=lambda m: case['sched'], **empty_kw())
         elif case['alg'] == 'svi':
             prj = bc.BlackBoxProjector(prob['sampler'], case['S'], prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
             alg = bc.SparseVICoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
@@ -139,29 +144,37 @@ def main():
             prj = bc.BlackBoxProjector(prob['sampler'], case['S'], prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
             alg = bc.HilbertCoreset(prob['data'], prj, n_subsample=case['n_sel'], snnls=getattr(bc.snnls, case['solver']), **empty_kw())
         hist_i, hist_w = [], []
+        steps = [case['M']] if case['alg'] == 'bpsvi' else list(range(1, case['M']+1))     # bpsvi: one build of M pseudo-points
         with contextlib.redirect_stdout(io.StringIO()):
-            for m in range(1, case['M']+1):
+            for m in steps:
                 alg.build(1, problems.build_size(case, m))
                 r = alg.get()
                 hist_i.append(np.array(r[2]).copy()); hist_w.append(np.array(r[0]).copy())
+        ref_pts = np.array(alg.get()[1]).copy()
         # oracle run, same seeds
         prob = case['make']()
         np.random.seed(case['seed'])
-        if case['alg'] in ('beta', 'svi'):
+        if case['alg'] == 'bpsvi':
+            o = oc.BatchPSVI(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), prob['oracle_gradll'](), case['opt_itrs'],
+                             n_sub_opt=case['n_opt'], sched=lambda m: case['sched'])
+        elif case['alg'] in ('beta', 'svi'):
             pot = prob['oracle_betalik'](case['beta']) if case['alg'] == 'beta' else prob['oracle_loglik']()
             o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], pot, n_sub_select=case['n_sel'], n_sub_opt=case['n_opt'],
                             opt_itrs=case['opt_itrs'], sched=case['sched'], groups=case['groups'])
         else:
             o = oc.Hilbert(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), n_sub=case['n_sel'],
                            solver={'GIGA': 'giga', 'FrankWolfe': 'fw', 'OrthoPursuit': 'omp'}[case['solver']])
-        for m in range(1, case['M']+1):
+        for k, m in enumerate(steps):
             o.build(1, problems.build_size(case, m))
-            if case['alg'] in ('beta', 'svi'):
+            if case['alg'] in ('beta', 'svi', 'bpsvi'):
                 ow, _, oi = o.get()
             else:
                 ow, oi = o.wts, o.idcs
-            same(oi, hist_i[m-1], nm+' idcs step %d' % m)
-            same(ow, hist_w[m-1], nm+' wts step %d' % m)
+            same(oi, hist_i[k], nm+' idcs step %d' % m)
+            same(ow, hist_w[k], nm+' wts step %d' % m)
+        if case['alg'] == 'bpsvi':
+            same(o.get()[1], ref_pts, nm+' pseudo-points')
+            g[nm+'_pts'] = ref_pts
         g[nm+'_idcs'] = np.array(hist_i[-1]); g[nm+'_wts'] = np.array(hist_w[-1])
         g[nm+'_sizes'] = np.array([len(h) for h in hist_i])
         g[nm+'_first_idcs'] = np.array([h[-1] if len(h) else -1 for h in hist_i])

@@ -83,7 +83,9 @@ def make_logistic(N, D, seed, zero_rows=()):
                     ref_betalik=lambda lr, ga, nl: lr.beta_likelihood,
                     ref_loglik=lambda lr, ga, nl: lr.log_likelihood,
                     oracle_betalik=lambda beta: (lambda pts, th: om.lr_betalik(pts, th, beta)),
-                    oracle_loglik=lambda: om.lr_loglik)
+                    oracle_loglik=lambda: om.lr_loglik,
+                    ref_gradll=lambda lr, ga, nl: lr.grad_z_log_likelihood,
+                    oracle_gradll=lambda: om.lr_grad_z_loglik)
     return make
 
 
@@ -112,6 +114,8 @@ def make_gaussian(N, d, seed):
         return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig),
                     ref_betalik=lambda lr, ga, nl: (lambda x, th, beta: ga.gaussian_beta_likelihood(x, th, beta, Siginv, logdetSig)),
                     ref_loglik=lambda lr, ga, nl: (lambda x, th: ga.gaussian_loglikelihood(x, th, Siginv, logdetSig)),
+                    ref_gradll=lambda lr, ga, nl: (lambda x, th: ga.gaussian_grad_x_loglikelihood(x, th, Siginv)),
+                    oracle_gradll=lambda: (lambda x, th: om.gauss_grad_x_loglik(x, th, Siginv)),
                     oracle_betalik=lambda beta: (lambda pts, th: om.gauss_betalik(pts, th, beta, Siginv, logdetSig)),
                     oracle_loglik=lambda: (lambda pts, th: om.gauss_loglik(pts, th, Siginv, logdetSig)))
     return make
@@ -195,6 +199,10 @@ def coreset_cases(heavy=True):
                   groups=contiguous_groups(900, 10), n_sel=25, n_opt=150))
     c.append(dict(base, name='nl_svi_groups', alg='svi', make=make_neurlin(480, 6, 23), seed=13, S=32, opt_itrs=12, M=3, sched=_sched(.1),
                   groups=ragged_groups(480, 17)))
+    # pseudo-coresets (bpsvi.py): weights and point locations optimised jointly; M = number of pseudo-points, one build
+    c.append(dict(base, name='lr_bpsvi', alg='bpsvi', make=make_logistic(800, 5, 31), seed=14, S=48, opt_itrs=25, M=6, sched=_sched(.5)))
+    c.append(dict(base, name='gauss_bpsvi_sub', alg='bpsvi', make=make_gaussian(400, 6, 8), seed=15, S=40, opt_itrs=20, M=5, sched=_sched(.2),
+                  n_opt=120))
     if heavy:
         # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
         c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))

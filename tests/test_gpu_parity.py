@@ -291,6 +291,14 @@ def _run_product_case(bc, models, case, blackbox=False):
         prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
         alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
                              opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False, groups=case['groups'])
+    elif case['alg'] == 'bpsvi':
+        gl = {'lr': lambda: models[0].grad_z_log_likelihood,
+              'gauss': lambda: models[1].gaussian_grad_x_loglikelihood.bind(Siginv=prob['params']['Siginv'])}[prob['model']]()
+        if blackbox:      # opaque callbacks: the oracle's numpy gradient plays the user's function
+            gl = prob['oracle_gradll']()
+        prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, gl)
+        alg = bc.BatchPSVICoreset(prob['data'], prj, opt_itrs=case['opt_itrs'], n_subsample_opt=case['n_opt'],
+                                  step_sched=lambda m: case['sched'])
     elif case['alg'] == 'svi':
         prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
         alg = bc.SparseVICoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'],
@@ -299,10 +307,11 @@ def _run_product_case(bc, models, case, blackbox=False):
         prj = bc.BlackBoxProjector(prob['sampler'], case['S'], ll, None)
         alg = bc.HilbertCoreset(prob['data'], prj, n_subsample=case['n_sel'], snnls=getattr(bc.snnls, case['solver']))
     sizes, sumw = [], []
-    for m in range(1, case['M']+1):
+    for m in ([case['M']] if case['alg'] == 'bpsvi' else range(1, case['M']+1)):
         alg.build(1, problems.build_size(case, m))
         r = alg.get()
         sizes.append(len(r[2])); sumw.append(r[0].sum())
+    _run_product_case.last = alg
     return r[0], r[2], np.array(sizes), np.array(sumw)
 
 
@@ -315,9 +324,11 @@ def test_coreset_builds_match_reference(bc, models, route, case):
     np.testing.assert_array_equal(sizes, g[nm+'_sizes'])
     np.testing.assert_allclose(w, g[nm+'_wts'], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(sumw, g[nm+'_sumw'], rtol=1e-6, atol=1e-9)
+    if case['alg'] == 'bpsvi':      # the optimised pseudo-point locations
+        np.testing.assert_allclose(_run_product_case.last.get()[1], g[nm+'_pts'], rtol=1e-6, atol=1e-8)
 
 
-@pytest.mark.parametrize('name', ['lr_beta_small', 'gauss_beta_sub', 'nl_svi_small', 'lr_beta_groups_sub'])
+@pytest.mark.parametrize('name', ['lr_beta_small', 'gauss_beta_sub', 'nl_svi_small', 'lr_beta_groups_sub', 'lr_bpsvi'])
 def test_blackbox_callbacks_take_the_dense_path(bc, models, name):
     """likelihoods hidden behind lambdas (as the reference drivers pass them) give the same coreset"""
     g = np.load(os.path.join(G, 'g3_coresets.npz'))

@@ -64,7 +64,10 @@ def test_snnls_small_cases():
 def run_oracle_case(case):
     prob = case['make']()
     np.random.seed(case['seed'])
-    if case['alg'] in ('beta', 'svi'):
+    if case['alg'] == 'bpsvi':
+        o = oc.BatchPSVI(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), prob['oracle_gradll'](), case['opt_itrs'],
+                         n_sub_opt=case['n_opt'], sched=lambda m: case['sched'])
+    elif case['alg'] in ('beta', 'svi'):
         pot = prob['oracle_betalik'](case['beta']) if case['alg'] == 'beta' else prob['oracle_loglik']()
         o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], pot, n_sub_select=case['n_sel'], n_sub_opt=case['n_opt'],
                         opt_itrs=case['opt_itrs'], sched=case['sched'], groups=case['groups'])
@@ -73,13 +76,14 @@ def run_oracle_case(case):
                        solver={'GIGA': 'giga', 'FrankWolfe': 'fw', 'OrthoPursuit': 'omp'}[case['solver']])
     sizes, sumw = [], []
     with np.errstate(all='ignore'):
-        for m in range(1, case['M']+1):
+        for m in ([case['M']] if case['alg'] == 'bpsvi' else range(1, case['M']+1)):
             o.build(1, problems.build_size(case, m))
-            if case['alg'] in ('beta', 'svi'):
+            if case['alg'] in ('beta', 'svi', 'bpsvi'):
                 w, _, i = o.get()
             else:
                 w, i = o.wts, o.idcs
             sizes.append(len(i)); sumw.append(w.sum())
+    run_oracle_case.last = o
     return w, i, np.array(sizes), np.array(sumw)
 
 
@@ -92,6 +96,8 @@ def test_coreset_builds_match_reference(case):
     np.testing.assert_array_equal(sizes, g[nm+'_sizes'])
     np.testing.assert_allclose(w, g[nm+'_wts'], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(sumw, g[nm+'_sumw'], rtol=1e-9, atol=1e-12)
+    if case['alg'] == 'bpsvi':
+        np.testing.assert_allclose(run_oracle_case.last.get()[1], g[nm+'_pts'], rtol=1e-9, atol=1e-12)
 
 
 def test_nan_rows_poison_selection_like_reference():
