@@ -365,6 +365,7 @@ static int q_common(bc_ctx* c, const void* d_image, const double* d_rowscale, in
   P.n = n;
   P.idx_offset = 0;
   P.S = c->S;
+  P.ksteps = (c->Dk + 31) / 32;
   P.colaux = (c->model == BC_MODEL_GAUSSIAN) ? c->colaux : nullptr;
   P.rowaux = (c->model != BC_MODEL_LOGISTIC) ? d_rowaux : nullptr;
   P.mp = c->mp;

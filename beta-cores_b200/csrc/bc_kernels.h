@@ -60,6 +60,7 @@ struct QProjArgs {
   long long n;
   long long idx_offset;
   int S;
+  int ksteps;            // 32-byte K blocks that hold features: ceil(D / 32), 1..4
   const double* colaux;  // [S] or null
   const double* rowaux;  // [n] or null
   ModelParams mp;

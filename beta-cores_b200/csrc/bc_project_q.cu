@@ -185,6 +185,19 @@ cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsi
 }
 
 // ------------------------------------------------------------------ projection --
+// The MMAs of one 128-row x 32-sample chunk: row digit i against the sample digits 0..6-i stacked along N, KS blocks of
+// 32 bytes along K.  +32 bytes along K inside the swizzle atom = +2 in the (>>4) start-address field of a descriptor.
+template <int KS>
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t d0, uint64_t adesc0, uint64_t bdesc0, const uint32_t (&idesc)[kQSlices]) {
+#pragma unroll
+  for (int i = 0; i < kQSlices; ++i) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      umma_i8(d0 + (uint32_t)(i * kQChunk), adesc0 + (uint64_t)(i * (kQSliceA >> 4) + k * 2), bdesc0 + (uint64_t)(k * 2), idesc[i],
+              (i | k) ? 1u : 0u);
+    }
+  }
+}
 
 
 template <class F, int MODE>
@@ -283,14 +296,13 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           tc_fence_after();
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(Bs + (size_t)st * kQChunkBytes));
           const uint32_t d0 = tmem_base + (uint32_t)(buf * kQDiagCols);
-#pragma unroll
-          for (int i = 0; i < kQSlices; ++i) {
-#pragma unroll
-            for (int k = 0; k < kQK / 32; ++k) {
-              // +32 bytes along K inside the swizzle atom = +2 in the (>>4) start-address field
-              umma_i8(d0 + (uint32_t)(i * kQChunk), adesc0 + (uint64_t)(i * (kQSliceA >> 4) + k * 2), bdesc0 + (uint64_t)(k * 2),
-                      idesc[i], (i | k) ? 1u : 0u);
-            }
+          // K blocks beyond the feature count hold only zero digits: not multiplied (D = 20 issues 7 MMAs per chunk
+          // instead of 28).  Fully unrolled per block count: the issue rate of this one thread is on the critical path.
+          switch (P.ksteps) {
+            case 1: issue_chunk_mmas<1>(d0, adesc0, bdesc0, idesc); break;
+            case 2: issue_chunk_mmas<2>(d0, adesc0, bdesc0, idesc); break;
+            case 3: issue_chunk_mmas<3>(d0, adesc0, bdesc0, idesc); break;
+            default: issue_chunk_mmas<4>(d0, adesc0, bdesc0, idesc); break;
           }
           umma_commit(empty_b + st);
           umma_commit(tmem_full + buf);
