@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "bc_npmean.h"
 
 namespace bc {
 
@@ -82,6 +83,8 @@ __device__ __forceinline__ dd dd_add(dd a, dd b) {
   r.lo = e - (r.hi - s);
   return r;
 }
+
+// numpy's rounding of the mean of a constant row (np_sum_const / np_centred_const / np_score_const): bc_npmean.h
 
 // ----------------------------------------------------------------- arg-max --
 // numpy semantics: np.argmax returns the FIRST NaN if any NaN is present, else the first

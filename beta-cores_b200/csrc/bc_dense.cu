@@ -284,8 +284,15 @@ __global__ void k_dense_center(double* __restrict__ V, long long n, int S, long 
   for (long long r = (long long)blockIdx.x * nw + warp; r < n; r += (long long)gridDim.x * nw) {
     double* v = V + r * ldv;
     double a = 0.0;
-    for (int c = lane; c < S; c += 32) a += v[c];
+    const double first = v[0];
+    bool same = true;
+    for (int c = lane; c < S; c += 32) {
+      a += v[c];
+      same = same && (v[c] == first);
+    }
     a = warp_sum(a) / (double)S;
+    // a row of S identical values is centred the way numpy rounds its mean (bc_common.cuh, np_sum_const)
+    if (__all_sync(0xffffffffu, same)) a = np_sum_const(first, S) / (double)S;
     for (int c = lane; c < S; c += 32) v[c] -= a;
   }
 }

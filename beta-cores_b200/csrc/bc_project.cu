@@ -305,7 +305,9 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
         if (nrm2 < 0.0) nrm2 = 0.0;
         const double dot = SR - gb * rsum;
         // bcores.py:78  corrs = vecs.dot(resid) / sqrt((vecs**2).sum(1)) / S
-        const double score = dot / sqrt(nrm2) / dS;
+        double score = dot / sqrt(nrm2) / dS;
+        // every sample gave exactly the pivot value: a constant row -- centred the way numpy rounds it (bc_common.cuh)
+        if (S2 == 0.0) score = np_score_const(t ? piv1 : piv0, S, rsum);
         if (p < n) {
           if (P.scores) P.scores[p] = score;
           Best mine = {score, P.idx_offset + p};
@@ -342,6 +344,28 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
       q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
       q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
       q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      // constant rows (every centred value exactly 0): the reference leaves numpy's rounding residue in every column
+      // (usually 0, else one ulp) -- reproduced, since it decides zero-norm filters and NaN correlations downstream
+      if (q0 == 0.0 && v0) {
+        const double v = np_centred_const(piv0, S);
+        if (v != 0.0) {
+          for (int col = 2 * t; col < S; col += 8) {
+            P.V[p0 * P.ldv + col] = v;
+            if (col + 1 < S) P.V[p0 * P.ldv + col + 1] = v;
+          }
+          q0 = np_sum_const(v * v, S);
+        }
+      }
+      if (q1 == 0.0 && v1) {
+        const double v = np_centred_const(piv1, S);
+        if (v != 0.0) {
+          for (int col = 2 * t; col < S; col += 8) {
+            P.V[p1 * P.ldv + col] = v;
+            if (col + 1 < S) P.V[p1 * P.ldv + col + 1] = v;
+          }
+          q1 = np_sum_const(v * v, S);
+        }
+      }
       if (P.norms && t == 0) {
         if (v0) P.norms[p0] = sqrt(q0);
         if (v1) P.norms[p1] = sqrt(q1);

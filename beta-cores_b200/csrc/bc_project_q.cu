@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           if (nrm2 < 0.0) nrm2 = 0.0;
           const double dot = sr - gb * rsum;
           // bcores.py:78  corrs = vecs.dot(resid) / sqrt((vecs**2).sum(1)) / S
-          const double score = dot / sqrt(nrm2) / dS;
+          double score = dot / sqrt(nrm2) / dS;
+          // every sample gave exactly the pivot value: a constant row -- centred the way numpy rounds it (bc_common.cuh)
+          if (s2 == 0.0) score = np_score_const(piv, S, rsum);
           if (rv) {
             if (P.scores) P.scores[p] = score;
             Best mine = {score, P.idx_offset + p};

@@ -124,7 +124,7 @@ def main():
         t0 = time.time()
         # reference run
         prob = case['make']()
-        np.random.seed(case['seed'])
+        problems.reseed(case)
         if case['alg'] == 'beta':
             prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], prob['ref_betalik'](model_lr, gaussian, model_neurlinr),
                                            prob['ref_loglik'](model_lr, gaussian, model_neurlinr), None)
@@ -153,7 +153,7 @@ def main():
         ref_pts = np.array(alg.get()[1]).copy()
         # oracle run, same seeds
         prob = case['make']()
-        np.random.seed(case['seed'])
+        problems.reseed(case)
         if case['alg'] == 'bpsvi':
             o = oc.BatchPSVI(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), prob['oracle_gradll'](), case['opt_itrs'],
                              n_sub_opt=case['n_opt'], sched=lambda m: case['sched'])
@@ -175,6 +175,8 @@ def main():
         if case['alg'] == 'bpsvi':
             same(o.get()[1], ref_pts, nm+' pseudo-points')
             g[nm+'_pts'] = ref_pts
+        if nm == 'c1_zellner_gaussian':     # the restated setup reproduces the unmodified driver's selections
+            same(hist_i[-1][:len(problems.C1_DRIVER_FIRST_ROWS)], problems.C1_DRIVER_FIRST_ROWS, 'C1 driver fingerprint')
         g[nm+'_idcs'] = np.array(hist_i[-1]); g[nm+'_wts'] = np.array(hist_w[-1])
         g[nm+'_sizes'] = np.array([len(h) for h in hist_i])
         g[nm+'_first_idcs'] = np.array([h[-1] if len(h) else -1 for h in hist_i])

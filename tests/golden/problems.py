@@ -152,6 +152,62 @@ def make_neurlin(N, D, seed):
     return make
 
 
+def make_c1_zellner_gaussian():
+    """BASELINE config 1 -- examples/zellner_gaussian/main.py with its run.sh arguments `BCORES 0`, restated line by line up
+    to the point where the driver starts its build loop: the driver seeds numpy's GLOBAL stream once (main.py:14) and
+    everything -- data (:43,:51-53), the perturbed proposal (:79-85), the constructor draws of the four projectors
+    (:75,:87,:94,:95) -- consumes it in order.  The case runner constructs the last projector (prj_bw) itself, so the
+    stream is left positioned right before that draw; `seed` is None so that nothing re-seeds it."""
+    def make():
+        np.random.seed(0)                                  # main.py:13-14, tr = 0
+        N, d = 5000, 100
+        mu0 = np.zeros(d)
+        Sig0 = np.eye(d)
+        Sig = 500*np.eye(d)
+        th = np.zeros(d)
+        Sig0inv = np.linalg.inv(Sig0)
+        Siginv = np.linalg.inv(Sig)
+        logdetSig = np.linalg.slogdet(Sig)[1]
+        X = np.random.multivariate_normal(th, Sig, N)      # :43
+        mup, LSigp, _ = om.gauss_weighted_post(mu0, Sig0inv, Siginv, X, np.ones(X.shape[0]))
+        Sigp = LSigp.dot(LSigp.T)
+        X1 = np.random.multivariate_normal(th+200, 0.5*Sig, int(N/50.))   # :51
+        X2 = np.random.multivariate_normal(th+150, 0.1*Sig, int(N/50.))   # :52
+        X3 = np.random.multivariate_normal(th, 10*Sig, int(N/10.))        # :53
+        data = np.concatenate((X, X1, X2, X3))
+        np.random.randn(200, d)                            # prj_optimal's constructor draw (:75; projector.py:18)
+        U = np.random.rand()                               # :78
+        muhat = U*mup + (1.-U)*mu0
+        muhat += 0.75*np.sqrt((muhat**2).sum())*np.random.randn(muhat.shape[0])    # :82
+        np.random.randn()                                  # :83
+        np.random.randn(200, d)                            # prj_realistic's constructor draw (:87)
+        np.random.randn(200, d)                            # prj_w's constructor draw (:94): sampler_w(200, [], [])
+
+        def sampler(S, w, pts):                            # sampler_w, main.py:88-92
+            if pts.shape[0] == 0:
+                w = np.zeros(1)
+                pts = np.zeros((1, d))
+            mu, Lp, _ = om.gauss_weighted_post(mu0, Sig0inv, Siginv, pts, w)
+            return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
+        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig),
+                    ref_betalik=lambda lr, ga, nl: (lambda x, th, beta: ga.gaussian_beta_likelihood(x, th, beta, Siginv, logdetSig)),
+                    ref_loglik=lambda lr, ga, nl: (lambda x, th: ga.gaussian_loglikelihood(x, th, Siginv, logdetSig)),
+                    ref_gradll=lambda lr, ga, nl: (lambda x, th: ga.gaussian_grad_x_loglikelihood(x, th, Siginv)),
+                    oracle_gradll=lambda: (lambda x, th: om.gauss_grad_x_loglik(x, th, Siginv)),
+                    oracle_betalik=lambda beta: (lambda pts, th: om.gauss_betalik(pts, th, beta, Siginv, logdetSig)),
+                    oracle_loglik=lambda: (lambda pts, th: om.gauss_loglik(pts, th, Siginv, logdetSig)))
+    return make
+
+
+# first selected rows of the UNMODIFIED driver `python3 main.py BCORES 0` (SURVEY.md section 6: 619 s on one CPU thread)
+C1_DRIVER_FIRST_ROWS = [3650, 3950, 435, 3281, 1108, 933, 1640, 4214, 4372, 1164, 30, 3726]
+
+
+def reseed(case):
+    if case['seed'] is not None:
+        np.random.seed(case['seed'])
+
+
 def _sched(i0):
     return lambda i: i0/(1.+i)
 
@@ -204,6 +260,10 @@ def coreset_cases(heavy=True):
     c.append(dict(base, name='gauss_bpsvi_sub', alg='bpsvi', make=make_gaussian(400, 6, 8), seed=15, S=40, opt_itrs=20, M=5, sched=_sched(.2),
                   n_opt=120))
     if heavy:
+        # BASELINE config 1: the reference's own driver configuration (N = 5700, d = 100, S = 200, 1000 ADAM steps per point,
+        # sub-samples 1000 / 200, step 0.1/(1+i), beta = 0.1), first 12 of its 200 build iterations
+        c.append(dict(base, name='c1_zellner_gaussian', alg='beta', make=make_c1_zellner_gaussian(), seed=None, S=200, opt_itrs=1000, M=12,
+                      sched=_sched(.1), n_sel=1000, n_opt=200, beta=0.1, heavy=True))
         # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
         c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))
     return c

@@ -281,7 +281,7 @@ def _device_potentials(prob, models):
 
 def _run_product_case(bc, models, case, blackbox=False):
     prob = case['make']()
-    np.random.seed(case['seed'])
+    problems.reseed(case)
     bl, ll = _device_potentials(prob, models)
     if blackbox:      # hide the potentials behind lambdas, as the reference drivers do
         bl0, ll0 = bl, ll

@@ -63,7 +63,7 @@ def test_snnls_small_cases():
 
 def run_oracle_case(case):
     prob = case['make']()
-    np.random.seed(case['seed'])
+    problems.reseed(case)
     if case['alg'] == 'bpsvi':
         o = oc.BatchPSVI(prob['data'], prob['sampler'], case['S'], prob['oracle_loglik'](), prob['oracle_gradll'](), case['opt_itrs'],
                          n_sub_opt=case['n_opt'], sched=lambda m: case['sched'])

@@ -22,6 +22,8 @@ def geo():
     subprocess.run(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I/usr/local/cuda/include', SRC, '-o', OUT], check=True)
     L = ctypes.CDLL(OUT)
     L.q_off.argtypes, L.q_off.restype = [ctypes.c_uint, ctypes.c_uint], ctypes.c_uint
+    L.np_sum_const.argtypes, L.np_sum_const.restype = [ctypes.c_double, ctypes.c_int], ctypes.c_double
+    L.np_score_const.argtypes, L.np_score_const.restype = [ctypes.c_double, ctypes.c_int, ctypes.c_double], ctypes.c_double
     return L
 
 
@@ -93,3 +95,21 @@ def test_swizzled_image_geometry(geo):
             assert (o % 128) // 16 == (c // 16) ^ (rr % 8)
             seen.add(o)
     assert len(seen) == rows*kk and max(seen) == rows*kk - 1
+
+
+def test_constant_rows_are_centred_like_numpy(geo):
+    """a row of S identical values: the reference's `x -= x.mean(axis=1)` leaves 0 or one ulp depending on how numpy's
+    pairwise summation rounds -- which decides between a NaN and a finite correlation (bcores.py:78).  The kernels use
+    bc::np_sum_const; it must agree with numpy bit for bit for every S."""
+    r = np.random.RandomState(7)
+    for trial in range(4000):
+        S = int(r.choice([1, 2, 3, 7, 8, 9, 31, 32, 33, 40, 64, 100, 127, 128, 129, 136, 200, 255, 256, 257, 500, 1000, 1024, 1025, 2000, 4096, 5000]))
+        x = float(r.randn()*10.**r.uniform(-8, 8))
+        A = np.full((3, S), x)
+        assert geo.np_sum_const(x, S) == A.sum(axis=1)[1], (x, S)
+        V = A - A.mean(axis=1)[:, np.newaxis]
+        res = r.randn(S)
+        with np.errstate(all='ignore'):
+            want = (V.dot(res)/np.sqrt((V**2).sum(axis=1))/S)[1]
+        got = geo.np_score_const(x, S, float(res.sum()))
+        assert (np.isnan(want) and np.isnan(got)) or np.isclose(got, want, rtol=1e-9, atol=0), (x, S, got, want)
