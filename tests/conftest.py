@@ -28,3 +28,12 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if 'gpu' in it.keywords:
             it.add_marker(skip)
+
+
+# The samplers of the test problems do D x D linear algebra (D <= 100) thousands of times: a multi-threaded BLAS pool only
+# thrashes on such sizes (111.7 s vs 2.9 s per build iteration of the Gaussian example).
+try:
+    from threadpoolctl import threadpool_limits
+    _BLAS_LIMIT = threadpool_limits(limits=1, user_api='blas')
+except Exception:      # pragma: no cover
+    _BLAS_LIMIT = None

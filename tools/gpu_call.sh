@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python tools/debug_c1.py 30 > gpurun_out/debug_c1.log 2>&1; echo "rc=$?"
-tail -12 gpurun_out/debug_c1.log
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=4 > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"
+tail -12 gpurun_out/gpu_tests.log
