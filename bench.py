@@ -60,6 +60,8 @@ def parse():
     ap.add_argument('--cpu-opt-itrs', type=int, default=2)
     ap.add_argument('--ref-rows', type=int, default=16384, help='rows per step of the --impl reference arm')
     ap.add_argument('--ref-opt-itrs', type=int, default=4)
+    ap.add_argument('--sampler', default='newton', choices=['newton', 'hybrid', 'device', 'bfgs'],
+                    help="product arm's Laplace sampler: host Newton (default), the device kernels of csrc/bc_sampler.cu, or scipy BFGS")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -85,14 +87,15 @@ def blas_threads():
 _SAMPLERS = []
 
 
-def new_sampler(D, seed):
-    """the host sampler of both arms; numpy's global stream is re-seeded only once no prefetched draw is in flight"""
+def new_sampler(D, seed, method=None):
+    """the sampler of both arms (the product arm may run its algebra on the device: --sampler device); numpy's global
+    stream is re-seeded only once no prefetched draw is in flight"""
     import numpy as np
     import model_lr
     for s in _SAMPLERS:
         s.drain()
     np.random.seed(seed)
-    s = model_lr.make_laplace_sampler(D, method=SAMPLER, prefetch=True)
+    s = model_lr.make_laplace_sampler(D, method=method or SAMPLER, prefetch=True)
     _SAMPLERS.append(s)
     return s
 
@@ -145,9 +148,13 @@ def workload_config(a, world):
                         % (a.n, a.d, a.s, a.beta),
             'N': a.n, 'D': a.d, 'S': a.s, 'beta': a.beta, 'opt_itrs': a.opt_itrs,
             'step': 'one BetaCoreset.build(1, m): 1 selection + opt_itrs ADAM steps = (1+opt_itrs) N x S projections',
-            'sampler': 'host Laplace approximation of the weighted coreset posterior (mode by warm-started damped Newton steps, D x D '
-                       'Cholesky factor, S x D normal draws from the global numpy stream, drawn one call ahead on a helper thread), '
-                       'called every optimiser step; the same callback in both arms',
+            'sampler': ('Laplace approximation of the weighted coreset posterior on the device (csrc/bc_sampler.cu: warm-started damped Newton '
+                        'mode search, D x D Cholesky factor and inverse, affine map of S x D normals drawn from the global numpy stream one '
+                        'call ahead on a helper thread), called every optimiser step; the reference arm runs the same algebra on the host'
+                        if getattr(a, 'sampler', 'newton') == 'device' else
+                        'host Laplace approximation of the weighted coreset posterior (mode by warm-started damped Newton steps, D x D '
+                        'Cholesky factor, S x D normal draws from the global numpy stream, drawn one call ahead on a helper thread), '
+                        'called every optimiser step; the same callback in both arms'),
             'sharding': 'rows over %d rank(s), fixed total N' % world,
             'l2': 'inputs (%.2f GB of rows) exceed the 126 MB L2; no flush' % (a.n*a.d*8/1e9)}
 
@@ -279,7 +286,7 @@ def b200_arm(a):
 
     def make_alg(rows):
         # every rank draws the same stream (seed 1); rank 0's samples are broadcast anyway
-        prj = bc.BetaBlackBoxProjector(timed_sampler(new_sampler(D, 1)), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        prj = bc.BetaBlackBoxProjector(timed_sampler(new_sampler(D, 1, a.sampler)), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         return bc.BetaCoreset(rows, prj, opt_itrs=a.opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
 
     # ------------------------------------------------------------ value: rows resident in HBM --
@@ -477,7 +484,7 @@ def b200_arm(a):
                          'D=%d S=%d opt_itrs=%d (%.1f s); faster of default BLAS threads and 1 thread; host has %d cpus'
                          % (ns, D, S, a.cpu_opt_itrs, best[2], os.cpu_count())}
         # the same sample through the CUDA path: identical index, weights within 1e-6
-        prj = bc.BetaBlackBoxProjector(new_sampler(D, 1), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        prj = bc.BetaBlackBoxProjector(new_sampler(D, 1, a.sampler), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         algs = bc.BetaCoreset(Zs, prj, opt_itrs=a.cpu_opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
         algs.build(1, 1)
         ow, _, oi = o.get()

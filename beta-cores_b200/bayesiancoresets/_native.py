@@ -33,6 +33,8 @@ SIGNATURES = {
     'bc_core_grad': [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp],
     'bc_core_pgrad': [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp],
     'bc_dense_pgrad': [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp],
+    'bc_laplace_logistic': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
+    'bc_sample_affine': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
     'bc_dense_rownorms': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp],
     'bc_dense_center': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp],

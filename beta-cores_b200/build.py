@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib')
 OUT = os.path.join(LIB, 'libbetacores.so')
-UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_dense.cu', 'bc_api.cu']
+UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_sampler.cu', 'bc_dense.cu', 'bc_api.cu']
 HEADERS = ['bc_common.cuh', 'bc_npmean.h', 'bc_umma.cuh', 'bc_fastmath.cuh', 'bc_models.cuh', 'bc_kernels.h', os.path.join('..', '..', 'include', 'betacores.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']

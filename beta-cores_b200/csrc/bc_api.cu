@@ -489,6 +489,23 @@ int bc_dense_pgrad(bc_ctx* c, const double* d_G, int M, int S, int D, const doub
   return BC_OK;
 }
 
+int bc_laplace_logistic(bc_ctx* c, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_L, int maxit,
+                        double tol, int* d_info, void* stream) {
+  if (!c || !d_Z || !d_w || !d_mu || !d_L || !d_info || M < 1 || D < 1 || D > 160 || ldz < D || maxit < 1) return BC_ERR_ARG;
+  if (((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)M + 70) * sizeof(double) > kMaxSmem - 1024) return BC_ERR_UNSUPPORTED;
+  BC_CUDA(launch_laplace_logistic(d_Z, ldz, d_w, M, D, d_mu, d_L, maxit, tol, d_info, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
+int bc_sample_affine(bc_ctx* c, const double* d_mu, const double* d_L, const double* d_R, int S, int D, double* d_theta, int ldt,
+                     void* stream) {
+  if (!c || !d_mu || !d_L || !d_R || !d_theta || S < 0 || D < 1 || ldt < D) return BC_ERR_ARG;
+  BC_CUDA(launch_sample_affine(d_mu, d_L, d_R, S, D, d_theta, ldt, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
 int bc_dense_rownorms(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream) {
   if (!c || !d_V || !d_norms || n < 0 || S <= 0) return BC_ERR_ARG;
   BC_CUDA(launch_dense_rowstats(d_V, n, S, ldv, nullptr, 0, d_norms, nullptr, (cudaStream_t)stream));

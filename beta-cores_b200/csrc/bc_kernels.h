@@ -97,6 +97,11 @@ cudaError_t launch_pgrad_model(int model, const double* P, int M, long long ldp,
 cudaError_t launch_pgrad_dense(const double* G, int M, int S, int D, const double* w, const double* resid, int centre, double* out,
                                long long ldo, cudaStream_t st);
 
+// ---- bc_sampler.cu: device-side posterior samplers ----
+cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
+                                    double tol, int* info, cudaStream_t st);
+cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
+
 // ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----
 cudaError_t launch_dense_rowstats(const double* V, long long n, int S, long long ldv, const double* u, int nu, double* norms,
                                   double* dots, cudaStream_t st);

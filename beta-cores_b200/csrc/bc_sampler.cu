@@ -1,0 +1,321 @@
+// beta-cores B200: device-side posterior samplers.
+//
+// The coreset classes call the user's sampler once per optimiser step; in the reference it is host numpy
+// (examples/zellner_logreg/main.py:86-111,139-144 -> bayesiancoresets/util/opt.py:10-33 get_laplace; examples/common/gaussian.py:28-32).
+// With the projection pass at a few milliseconds per GPU that host call (mode search, D x D Cholesky, triangular
+// inverse, S x D x D product, 1 MB upload) is the largest non-kernel item of a step.  These kernels do the same algebra
+// on the device.  Everything is D x D with D <= 128 and M (coreset size) rows: one CTA, latency-bound.
+//   k_laplace_logistic : mode of the weighted logistic log-joint with N(0, I) prior by damped Newton steps (the same
+//                        iteration as examples/common/model_lr.py::_newton_mode), then L = inverse of the lower Cholesky
+//                        factor of the negative Hessian at the mode -- get_laplace's (mu, LSig).
+//   k_sample_affine    : Theta = mu + R L^T for S x D standard normals R drawn by the HOST stream (so that the random
+//                        numbers are the reference's), sampler line `mu + randn(S, D).dot(LSig.T)`.
+#include "bc_kernels.h"
+#include "bc_common.cuh"
+
+namespace bc {
+
+constexpr int kLapThreads = 1024;   // one CTA; every phase is latency-bound, so as many warps as a CTA can hold
+
+__device__ __forceinline__ double blk_sum(double x, double* red) {  // all threads get the result
+  x = warp_sum(x);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = x;
+  __syncthreads();
+  double y = (l < nw) ? red[l] : 0.0;
+  y = warp_sum(y);
+  return y;
+}
+
+// In-place lower Cholesky of the D x D matrix H (row-major, leading dimension ld = D + 1 so that column walks are free of
+// shared-memory bank conflicts) in shared memory, blocked: warp 0 factorises a panel of kPanel columns with warp-level
+// synchronisation only, then every warp applies the rank-kPanel update to the trailing block.  2 CTA barriers per panel
+// instead of 3 per column: at D = 128 the unblocked form spent most of its time in barriers.  rd[j] = 1 / L[j][j].
+// Returns false if H is not positive definite.
+constexpr int kPanel = 16;
+__device__ bool chol_lower(double* H, int D, int ld, double* rd, int* flag) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  if (tid == 0) *flag = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < D; j0 += kPanel) {
+    const int nb = min(kPanel, D - j0);
+    if (wid == 0) {
+      for (int c = 0; c < nb; ++c) {
+        const int j = j0 + c;
+        const double d = H[j * ld + j];
+        if (!(d > 0.0)) {
+          if (lane == 0) *flag = 1;
+          break;
+        }
+        const double s = sqrt(d), inv = 1.0 / s;
+        __syncwarp();
+        for (int i = j + lane; i < D; i += 32) H[i * ld + j] = (i == j) ? s : H[i * ld + j] * inv;
+        if (lane == 0) rd[j] = inv;
+        __syncwarp();
+        for (int i = j + 1 + lane; i < D; i += 32) {   // the panel's remaining columns
+          const double lij = H[i * ld + j];
+          for (int k = j + 1; k < j0 + nb; ++k)
+            if (i >= k) H[i * ld + k] = fma(-lij, H[k * ld + j], H[i * ld + k]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (*flag) return false;
+    // trailing block: H[i][k] -= sum_c L[i][j0+c] L[k][j0+c], j0+nb <= k <= i; one warp per row, lanes over k
+    const int r0 = j0 + nb;
+    for (int i = r0 + wid; i < D; i += nw) {
+      for (int k = r0 + lane; k <= i; k += 32) {
+        double a = H[i * ld + k];
+        for (int c = 0; c < nb; ++c) a = fma(-H[i * ld + j0 + c], H[k * ld + j0 + c], a);
+        H[i * ld + k] = a;
+      }
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// x <- (L L^T)^-1 x by warp 0 alone (warp-level synchronisation; the other warps wait at the closing barrier)
+__device__ void chol_solve(const double* L, const double* rd, int D, int ld, double* x) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    for (int j = 0; j < D; ++j) {          // L y = x, column-oriented
+      const double xj = x[j] * rd[j];
+      __syncwarp();
+      if (lane == 0) x[j] = xj;
+      for (int i = j + 1 + lane; i < D; i += 32) x[i] = fma(-L[i * ld + j], xj, x[i]);
+      __syncwarp();
+    }
+    for (int j = D - 1; j >= 0; --j) {     // L^T z = y
+      const double xj = x[j] * rd[j];
+      __syncwarp();
+      if (lane == 0) x[j] = xj;
+      for (int i = lane; i < j; i += 32) x[i] = fma(-L[j * ld + i], xj, x[i]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// out (D x D, row-major, global) = L^-1 for the lower-triangular L in shared memory: one warp per column c solves
+// L x = e_c by column-oriented forward substitution with the residuals of rows 32 q + lane in registers.
+constexpr int kMaxQ = 6;   // D <= 192 (the shared-memory budget already limits D to 168)
+__device__ void tri_inverse_lower(const double* L, const double* rd, int D, int ld, double* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = wid; c < D; c += nw) {
+    double r[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) r[q] = (q * 32 + lane == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q0 = 0; q0 < kMaxQ; ++q0) {
+      if (q0 * 32 + 31 < c || q0 * 32 >= D) continue;
+      for (int l = 0; l < 32; ++l) {
+        const int i = q0 * 32 + l;
+        if (i >= D) break;
+        const double xi = __shfl_sync(0xffffffffu, r[q0], l) * rd[i];
+        if (i < c) {
+          if (lane == 0) out[i * D + c] = 0.0;
+          continue;
+        }
+        if (lane == 0) out[i * D + c] = xi;
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+          const int k = q * 32 + lane;
+          if (q >= q0 && k > i && k < D) r[q] = fma(-L[k * ld + i], xi, r[q]);
+        }
+      }
+    }
+    for (int i = lane; i < c && i < (c & ~31); i += 32) out[i * D + c] = 0.0;   // rows above the first visited block
+  }
+  __syncthreads();
+}
+
+// margins m_i = -z_i . th, one warp per row (coalesced)
+__device__ void margins(const double* Z, long long ldz, int M, int D, const double* th, double* mrg) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wid; i < M; i += nw) {
+    double a = 0.0;
+    for (int k = lane; k < D; k += 32) a = fma(Z[i * ldz + k], th[k], a);
+    a = warp_sum(a);
+    if (lane == 0) mrg[i] = -a;
+  }
+  __syncthreads();
+}
+
+// weighted log-joint (model_lr.py:88-93) from the margins at th: sum_i w_i ll(m_i) - D/2 log 2pi - |th|^2 / 2
+__device__ double log_joint(const double* w, const double* mrg, int M, int D, const double* th, double* red) {
+  double part = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const double m = mrg[i];
+    const double ll = (m < 100.0) ? -log1p(exp(m)) : -m;
+    part = fma(w[i], ll, part);
+  }
+  for (int k = threadIdx.x; k < D; k += blockDim.x) part -= 0.5 * th[k] * th[k];
+  return blk_sum(part, red) - 0.5 * (double)D * 1.8378770664093453;   // log(2 pi)
+}
+
+__global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* __restrict__ Z, long long ldz, const double* __restrict__ w,
+                                                                  int M, int D, double* __restrict__ mu_io, double* __restrict__ Lsig,
+                                                                  int maxit, double tol, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int ld = D + 1, Mp = (M + 1) & ~1;
+  double* H = sm;                 // [D*ld]
+  double* th = H + D * ld;        // [D]
+  double* tn = th + D;            // [D] trial point
+  double* g = tn + D;             // [D] gradient, then Newton step
+  double* sw = g + D;             // [Mp] w_i s_i, then w_i c_i
+  double* mrg = sw + Mp;          // [Mp] margins at th
+  double* mtr = mrg + Mp;         // [Mp] margins at the trial point
+  double* red = mtr + Mp;         // [64]
+  double* rd = red + 64;          // [D] reciprocal diagonal of the Cholesky factor
+  __shared__ int flag;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int k = tid; k < D; k += nt) th[k] = mu_io[k];
+  __syncthreads();
+  margins(Z, ldz, M, D, th, mrg);
+  double f = log_joint(w, mrg, M, D, th, red);
+  int it = 0, status = 0;
+  auto hessian = [&]() {   // H = I + Z^T diag(w c) Z (lower triangle) from the margins at th
+    for (int i = tid; i < M; i += nt) {
+      const double m = mrg[i];
+      double c = 0.0;
+      if (m < 100.0) {
+        const double e = exp(m), s = e / (1.0 + e);
+        c = s * (1.0 - s);
+      }
+      sw[i] = w[i] * c;
+    }
+    __syncthreads();
+    for (int a = wid; a < D; a += nw) {
+      for (int b = lane; b <= a; b += 32) {
+        double a0 = (a == b) ? 1.0 : 0.0, a1 = 0.0;
+        int i = 0;
+        for (; i + 1 < M; i += 2) {
+          a0 = fma(sw[i] * Z[i * ldz + a], Z[i * ldz + b], a0);
+          a1 = fma(sw[i + 1] * Z[(i + 1) * ldz + a], Z[(i + 1) * ldz + b], a1);
+        }
+        if (i < M) a0 = fma(sw[i] * Z[i * ldz + a], Z[i * ldz + b], a0);
+        H[a * ld + b] = a0 + a1;
+      }
+    }
+    __syncthreads();
+  };
+  for (; it < maxit; ++it) {
+    // gradient -th + Z^T (w s)
+    for (int i = tid; i < M; i += nt) {
+      const double m = mrg[i];
+      double s = 1.0;
+      if (m < 100.0) {
+        const double e = exp(m);
+        s = e / (1.0 + e);
+      }
+      sw[i] = w[i] * s;
+    }
+    __syncthreads();
+    for (int k = tid; k < D; k += nt) {
+      double acc = -th[k];
+      for (int i = 0; i < M; ++i) acc = fma(sw[i], Z[i * ldz + k], acc);
+      g[k] = acc;
+    }
+    __syncthreads();
+    hessian();
+    if (!chol_lower(H, D, ld, rd, &flag)) {
+      status = 2;
+      break;
+    }
+    chol_solve(H, rd, D, ld, g);   // g <- Newton step
+    // damped step: halve until the log-joint does not decrease (it is strictly concave)
+    double t = 1.0, fn = f;
+    for (;;) {
+      for (int k = tid; k < D; k += nt) tn[k] = fma(t, g[k], th[k]);
+      __syncthreads();
+      margins(Z, ldz, M, D, tn, mtr);
+      fn = log_joint(w, mtr, M, D, tn, red);
+      if (fn >= f - 1e-15 * fabs(f) || t < 1e-8) break;
+      t *= 0.5;
+    }
+    double dm = 0.0, am = 0.0;
+    for (int k = tid; k < D; k += nt) {
+      dm = fmax(dm, fabs(tn[k] - th[k]));
+      am = fmax(am, fabs(tn[k]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+      am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[wid] = dm;
+      red[32 + wid] = am;
+    }
+    __syncthreads();
+    dm = 0.0;
+    am = 0.0;
+    for (int q = 0; q < nw; ++q) {
+      dm = fmax(dm, red[q]);
+      am = fmax(am, red[32 + q]);
+    }
+    __syncthreads();
+    for (int k = tid; k < D; k += nt) th[k] = tn[k];
+    for (int i = tid; i < M; i += nt) mrg[i] = mtr[i];
+    f = fn;
+    __syncthreads();
+    // a full step this small is in the quadratic regime: the point it lands on is within ~|z| dm^2 of the mode
+    if (dm <= tol * (1.0 + am) || (t == 1.0 && dm <= 1e-7 * (1.0 + am))) {
+      ++it;
+      break;
+    }
+  }
+  if (status == 0) {
+    hessian();
+    if (!chol_lower(H, D, ld, rd, &flag)) status = 2;
+  }
+  if (status == 0) {
+    tri_inverse_lower(H, rd, D, ld, Lsig);   // get_laplace's LSig
+    for (int k = tid; k < D; k += nt) mu_io[k] = th[k];
+  }
+  if (tid == 0) {
+    info[0] = status;
+    info[1] = it;
+  }
+}
+
+// Theta[s][d] = mu[d] + sum_k R[s][k] L[d][k]      (mu + randn(S, D).dot(L.T))
+__global__ void __launch_bounds__(128) k_sample_affine(const double* __restrict__ mu, const double* __restrict__ L, const double* __restrict__ R,
+                                                       int S, int D, double* __restrict__ out, int ldo) {
+  extern __shared__ double rs[];   // this sample's normals
+  const int s = blockIdx.x;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) rs[k] = R[(size_t)s * D + k];
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k <= d; ++k) acc = fma(rs[k], L[(size_t)d * D + k], acc);   // L is lower triangular
+    out[(size_t)s * ldo + d] = mu[d] + acc;
+  }
+}
+
+cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
+                                    double tol, int* info, cudaStream_t st) {
+  const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
+  const size_t cap = kMaxSmem - 1024;   // the kernel also has a few bytes of static shared memory
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_laplace_logistic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (smem > cap) return cudaErrorInvalidValue;
+  k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st) {
+  if (S <= 0) return cudaSuccess;
+  k_sample_affine<<<S, 128, (size_t)D * sizeof(double), st>>>(mu, L, R, S, D, out, ldo);
+  return cudaGetLastError();
+}
+
+}  // namespace bc

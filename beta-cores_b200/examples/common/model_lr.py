@@ -84,7 +84,9 @@ def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200):
             if f_new >= f - 1e-15*abs(f) or t < 1e-8:
                 break
             t *= .5
-        done = np.abs(th_new-th).max() <= tol*(1.+np.abs(th_new).max())
+        dm, am = np.abs(th_new-th).max(), np.abs(th_new).max()
+        # a full step this small is in the quadratic regime: the point it lands on is within ~|z| dm^2 of the mode
+        done = dm <= tol*(1.+am) or (t == 1. and dm <= 1e-7*(1.+am))
         th, f = th_new, f_new
         if done:
             break
@@ -123,6 +125,7 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
     """sampler(S, wts, pts) -> (S, D): the callback the logistic drivers hand to the projector
     (examples/zellner_logreg/main.py:139-144).  Empty coreset -> the N(0, I) prior.
 
+    method='hybrid' / 'device' form the samples on the GPU and return a device tensor (see `_device_laplace_sampler`).
     method='newton' additionally warm-starts each mode search at the previous mode (consecutive optimiser steps move the
     weights a little).  prefetch=True draws the NEXT call's S x D standard normals on a helper thread while the caller is
     busy (the draw does not depend on the weights); the global numpy stream is consumed in exactly the same order and
@@ -160,5 +163,78 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
         if state['fut'] is not None:
             state['fut'].result()
             state['fut'] = None
+
+    if method in ('device', 'hybrid'):
+        sampler = _device_laplace_sampler(D, mu0, normals, host_factor=(method == 'hybrid'))
     sampler.drain = drain
+    return sampler
+
+
+def _device_laplace_sampler(D, mu0, normals, host_factor):
+    """method='device' / 'hybrid': the S x D samples are formed on the GPU and returned as a device tensor (the projector's
+    fused path takes it without a host round trip).  The standard normals still come from numpy's global stream, so the
+    sampler consumes it exactly like the host one.
+      'hybrid': mode, Cholesky factor and its inverse on the host (`get_laplace(method='newton')`, warm-started), only the
+                S x D x D affine map mu + R L^T on the device (csrc/bc_sampler.cu::k_sample_affine) -- it takes the GEMM and
+                the 8 S D-byte sample upload off the host's critical path (the normals go up instead, and do not wait for the weights);
+      'device': the Newton mode search and the factorisations too (k_laplace_logistic, one CTA; D <= 160).  Same iteration and
+                tolerance as `_newton_mode`; the two agree to rounding.  At D = 128 the single-CTA factorisations are
+                latency-bound and no faster than the host's LAPACK, so 'hybrid' is the quicker of the two."""
+    import torch
+    from bayesiancoresets import _native as nv
+    from bayesiancoresets._device import Engine, ptr, stream_ptr
+    st = {'mu': None, 'L': None, 'info': None, 'pin': [None, None], 'ev': [None, None], 'k': 0, 'mu_host': None, 'ml': None}
+
+    def sampler(S, wts, pts):
+        eng = Engine.get()
+        ctx = eng.ctx('sampler')
+        wts = np.asarray(wts, dtype=np.float64)
+        pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
+        if st['mu'] is None:
+            st['ml'] = eng.empty(D*D + D)                  # [mu | L] in one buffer: one upload in 'hybrid'
+            st['mu'], st['L'] = st['ml'][:D], st['ml'][D:].view(D, D)
+            st['mu'].copy_(torch.from_numpy(np.asarray(mu0, dtype=np.float64)))
+            st['info'] = torch.zeros(2, dtype=torch.int32, device=eng.device)
+            st['ml_pin'] = torch.empty(D*D + D, dtype=torch.float64).pin_memory()
+        R = normals(S, D)
+        k = st['k'] = st['k'] ^ 1                          # two pinned staging buffers, alternating
+        if st['pin'][k] is None or tuple(st['pin'][k].shape) != (S, D):
+            st['pin'][k] = torch.empty(S, D, dtype=torch.float64).pin_memory()
+        if st['ev'][k] is not None:
+            st['ev'][k].synchronize()                      # the upload that last used this buffer has left it
+        st['pin'][k].numpy()[...] = R
+        Rd = st['pin'][k].to(eng.device, non_blocking=True)
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
+        theta = eng.empty(S, D)
+        keep = wts > 0
+        if pts.shape[0] == 0 or not keep.any():           # empty coreset: the N(0, I) prior
+            st['mu'].zero_()
+            st['L'].copy_(torch.eye(D, dtype=torch.float64, device=eng.device))
+            st['mu_host'] = None
+        elif host_factor:
+            start = st['mu_host'] if st['mu_host'] is not None else mu0
+            mu, LSig, _ = get_laplace(wts, pts, start, method='newton')
+            st['mu_host'] = mu
+            if st.get('ml_ev') is not None:
+                st['ml_ev'].synchronize()
+            buf = st['ml_pin'].numpy()
+            buf[:D] = mu
+            buf[D:] = LSig.ravel()
+            st['ml'].copy_(st['ml_pin'], non_blocking=True)
+            st['ml_ev'] = torch.cuda.Event()
+            st['ml_ev'].record()
+        else:
+            Zd = eng.upload(pts[keep])
+            wd = eng.upload(wts[keep])
+            nv.call('bc_laplace_logistic', ctx, ptr(Zd), int(Zd.stride(0)), ptr(wd), int(Zd.shape[0]), D, ptr(st['mu']), ptr(st['L']),
+                    200, 1e-13, ptr(st['info']), stream_ptr())
+        nv.call('bc_sample_affine', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        return theta
+
+    def status():
+        """(status, newton steps) of the last device mode search: 0 = converged"""
+        return tuple(int(v) for v in st['info'].cpu()) if st['info'] is not None else (0, 0)
+    sampler.status = status
+    sampler.state = st
     return sampler

@@ -127,6 +127,19 @@ int bc_dense_pgrad(bc_ctx* ctx, const double* d_G, int M, int S, int D, const do
 int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, double* d_m2, int n, double lr, double b1, double b2,
                  double c1, double c2, double eps, const unsigned char* d_nn_mask, void* stream);
 
+/* ---- device-side posterior samplers (the reference's samplers are host callbacks) ----------------
+ * bc_laplace_logistic: Laplace approximation of the weighted logistic posterior with N(0, I) prior -- what
+ *   bayesiancoresets/util/opt.py:10-33 get_laplace / examples/zellner_logreg/main.py:86-111 compute on the host: d_mu holds
+ *   the start on entry and the mode on return (damped Newton, |step|_inf <= tol (1 + |mu|_inf)), d_L (D x D) the inverse of
+ *   the lower Cholesky factor of the negative Hessian there (get_laplace's LSig).  d_Z: M x ldz coreset rows, d_w their
+ *   weights (rows with weight 0 do not contribute).  d_info[0] = 0 ok / 2 Hessian not positive definite, d_info[1] = steps.
+ * bc_sample_affine: d_theta[s][:] = d_mu + d_R[s][:] . d_L^T for S x D standard normals d_R -- the sampler line
+ *   `mu + np.random.randn(S, D).dot(LSig.T)` (main.py:144), with the normals drawn by the caller's own stream. */
+int bc_laplace_logistic(bc_ctx* ctx, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_L,
+                        int maxit, double tol, int* d_info, void* stream);
+int bc_sample_affine(bc_ctx* ctx, const double* d_mu, const double* d_L, const double* d_R, int S, int D, double* d_theta, int ldt,
+                     void* stream);
+
 /* ---- stage 2 on a materialised n x S matrix (snnls solvers, black-box projections) --------- */
 int bc_dense_rownorms(bc_ctx* ctx, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream);
 /* V[r][:] -= mean(V[r][:])  (projector.py:26, :55) for matrices produced by host callbacks */

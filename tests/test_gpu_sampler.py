@@ -1,0 +1,64 @@
+"""Device-side Laplace sampler (csrc/bc_sampler.cu) against the host one (examples/common/model_lr.py), same numpy stream."""
+import numpy as np
+import pytest
+
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(M, D, seed):
+    r = np.random.RandomState(seed)
+    Z = r.randn(M, D)
+    w = r.rand(M)*50
+    w[1::5] = 0.         # rows the optimiser has clamped to zero do not contribute
+    return Z, w
+
+
+@pytest.mark.parametrize('M,D,S', [(1, 3, 7), (40, 10, 64), (200, 128, 1024), (300, 51, 100)])
+@pytest.mark.parametrize('method', ['device', 'hybrid'])
+def test_device_sampler_matches_host(M, D, S, method):
+    import torch
+    import model_lr
+    Z, w = _problem(M, D, 3)
+    np.random.seed(11)
+    host = model_lr.make_laplace_sampler(D, method='newton')
+    th_h = [host(S, w, Z), host(S, w*1.1, Z)]
+    np.random.seed(11)
+    dev = model_lr.make_laplace_sampler(D, method=method)
+    th_d = [dev(S, w, Z).cpu().numpy(), dev(S, w*1.1, Z).cpu().numpy()]
+    assert dev.status()[0] == 0
+    for a, b in zip(th_h, th_d):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(b, a, rtol=0, atol=1e-9*max(1., np.abs(a).max()))
+    torch.cuda.synchronize()
+
+
+def test_device_sampler_empty_coreset_is_prior():
+    import model_lr
+    D, S = 6, 50
+    np.random.seed(5)
+    R = np.random.randn(S, D)
+    np.random.seed(5)
+    dev = model_lr.make_laplace_sampler(D, method='device')
+    th = dev(S, np.zeros(0), np.zeros((0, D))).cpu().numpy()
+    np.testing.assert_array_equal(th, R)
+
+
+def test_build_with_device_sampler_selects_like_host():
+    """a short beta-coreset build: same first selections and weights to 1e-6 with either sampler"""
+    import bayesiancoresets as bc
+    import model_lr
+    r = np.random.RandomState(0)
+    N, D, S = 3000, 12, 128
+    Z = r.randn(N, D)
+    out = []
+    for method in ('newton', 'hybrid', 'device'):
+        np.random.seed(2)
+        prj = bc.BetaBlackBoxProjector(model_lr.make_laplace_sampler(D, method=method), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        alg = bc.BetaCoreset(Z, prj, opt_itrs=10, step_sched=lambda i: 1./(1.+i), beta=0.3, learn_beta=False)
+        for m in range(1, 6):
+            alg.build(1, m)
+        out.append((alg.idcs.copy(), alg.wts.copy()))
+    for o in out[1:]:
+        np.testing.assert_array_equal(out[0][0], o[0])
+        np.testing.assert_allclose(o[1], out[0][1], rtol=1e-6)
