@@ -137,16 +137,20 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1)
 
-    def normals(S, d):
+    def normals(S, d, stage=None):
+        """S x d standard normals from numpy's global stream; `stage` (optional) post-processes a draw on the thread that made it"""
+        def draw():
+            r = np.random.randn(S, d)
+            return r if stage is None else stage(r)
         if pool is None:
-            return np.random.randn(S, d)
+            return draw()
         if state['fut'] is not None and state['shape'] == (S, d):
             out = state['fut'].result()
         else:
             if state['fut'] is not None:
                 state['fut'].result()       # a draw of another shape was in flight: it has consumed the stream; keep order
-            out = np.random.randn(S, d)
-        state['fut'], state['shape'] = pool.submit(np.random.randn, S, d), (S, d)
+            out = draw()
+        state['fut'], state['shape'] = pool.submit(draw), (S, d)
         return out
 
     def sampler(S, wts, pts):
@@ -185,6 +189,16 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
     from bayesiancoresets._device import Engine, ptr, stream_ptr
     st = {'mu': None, 'L': None, 'info': None, 'pin': [None, None], 'ev': [None, None], 'k': 0, 'mu_host': None, 'ml': None}
 
+    def stage(r):
+        """copy a draw into one of two pinned staging buffers (runs on the thread that drew it)"""
+        k = st['k'] = st['k'] ^ 1
+        if st['pin'][k] is None or tuple(st['pin'][k].shape) != r.shape:
+            st['pin'][k] = torch.empty(*r.shape, dtype=torch.float64).pin_memory()
+        if st['ev'][k] is not None:
+            st['ev'][k].synchronize()                      # the upload that last used this buffer has left it
+        st['pin'][k].numpy()[...] = r
+        return k, st['pin'][k]
+
     def sampler(S, wts, pts):
         eng = Engine.get()
         ctx = eng.ctx('sampler')
@@ -196,16 +210,6 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
             st['mu'].copy_(torch.from_numpy(np.asarray(mu0, dtype=np.float64)))
             st['info'] = torch.zeros(2, dtype=torch.int32, device=eng.device)
             st['ml_pin'] = torch.empty(D*D + D, dtype=torch.float64).pin_memory()
-        R = normals(S, D)
-        k = st['k'] = st['k'] ^ 1                          # two pinned staging buffers, alternating
-        if st['pin'][k] is None or tuple(st['pin'][k].shape) != (S, D):
-            st['pin'][k] = torch.empty(S, D, dtype=torch.float64).pin_memory()
-        if st['ev'][k] is not None:
-            st['ev'][k].synchronize()                      # the upload that last used this buffer has left it
-        st['pin'][k].numpy()[...] = R
-        Rd = st['pin'][k].to(eng.device, non_blocking=True)
-        st['ev'][k] = torch.cuda.Event()
-        st['ev'][k].record()
         theta = eng.empty(S, D)
         keep = wts > 0
         if pts.shape[0] == 0 or not keep.any():           # empty coreset: the N(0, I) prior
@@ -229,6 +233,11 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
             wd = eng.upload(wts[keep])
             nv.call('bc_laplace_logistic', ctx, ptr(Zd), int(Zd.stride(0)), ptr(wd), int(Zd.shape[0]), D, ptr(st['mu']), ptr(st['L']),
                     200, 1e-13, ptr(st['info']), stream_ptr())
+        # the normals last: the next draw starts on the helper thread here, after the Python-heavy part of this call
+        k, pin = normals(S, D, stage)
+        Rd = pin.to(eng.device, non_blocking=True)
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
         nv.call('bc_sample_affine', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
         return theta
 
