@@ -34,3 +34,29 @@ def make_conjugate_sampler(mu0, Sig0inv, sigsq):
         mu, L, _ = weighted_post(mu0, Sig0inv, sigsq, pts, wts)
         return mu + np.random.randn(S, D).dot(L.T)
     return sampler
+
+
+def encode_dataset(nl, Z, batch=1 << 20):
+    """rows z_n = [phi(x_n), y_n] (float64) for the whole dataset, computed ONCE with a fixed encoder.
+
+    The reference re-encodes the rows inside every likelihood call (examples/zellner_neural_linear/main.py:110-114:
+    `deep_encoder(nl, pts)` is part of the lambdas), which keeps the potentials opaque to the projector and, with the
+    BatchNorm layers of examples/common/neural.py:126-133 in training mode, makes phi depend on which rows share a call.
+    With the encoder frozen (`nl.feature_extractor.eval()` for the torch module, or any object with `encode`), encoding
+    the data up front gives the same features for every call, and the coreset classes can take the result as `data` with
+    the bound device potentials above -- the fused tensor-core path -- instead of the black-box route.  `nl.encode`
+    may take / return numpy arrays or torch tensors; features come back in the encoder's precision (fp32 in the
+    reference) and are widened to float64 exactly like `np.hstack` does in the reference's lambda."""
+    Z = np.atleast_2d(np.asarray(Z))
+    out = []
+    for s in range(0, Z.shape[0], batch):
+        x = Z[s:s+batch, :-1].astype(np.float32)
+        try:
+            import torch
+            phi = nl.encode(torch.from_numpy(x)) if isinstance(nl, torch.nn.Module) else nl.encode(x)
+            if isinstance(phi, torch.Tensor):
+                phi = phi.detach().cpu().numpy()
+        except ImportError:
+            phi = nl.encode(x)
+        out.append(np.hstack((np.asarray(phi), Z[s:s+batch, -1][:, np.newaxis].astype(np.float32))).astype(np.float64))
+    return np.vstack(out) if out else np.zeros((0, 0))

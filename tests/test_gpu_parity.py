@@ -421,3 +421,88 @@ def test_full_size_properties_north_star_shape(bc):
         np.testing.assert_allclose(out['q'][2], out['dmma'][2], rtol=1e-9, atol=1e-12)
     finally:
         _fused.ROUTE = old
+
+
+# ------------------------------------------------------- learned-feature encoder forwarded to the callbacks --
+class _FixedEncoder(object):
+    """stands in for examples/common/neural.py::NeuralLinear: `encode` maps raw inputs to features (fp32, as the reference's
+    torch encoder returns them); two fixed ReLU layers, no batch statistics (the reference's BatchNorm in train
+    mode makes the features depend on which rows are passed; a fixed encoder is the documented way to run config 4)"""
+
+    def __init__(self, din, dout, seed):
+        r = np.random.RandomState(seed)
+        self.W1, self.b1 = (r.randn(din, dout)/np.sqrt(din)).astype(np.float32), (0.1*r.randn(dout)).astype(np.float32)
+        self.W2, self.b2 = (r.randn(dout, dout)/np.sqrt(dout)).astype(np.float32), (0.1*r.randn(dout)).astype(np.float32)
+
+    def encode(self, x):
+        h = np.maximum(x.astype(np.float32).dot(self.W1) + self.b1, 0)
+        return np.maximum(h.dot(self.W2) + self.b2, 0)
+
+
+@pytest.mark.parametrize('alg', ['beta', 'svi'])
+def test_encoder_kwarg_is_forwarded_like_the_reference(bc, alg):
+    """examples/zellner_neural_linear/main.py:110-140: likelihood lambdas take the encoder as a last argument and the
+    projector is built with nl=encoder (projector.py:40-54).  The callbacks are opaque Python: stage 1 is theirs, the
+    centring, scoring and the optimiser run on the device.  Checked against the oracle driven by the same callbacks."""
+    r = np.random.RandomState(5)
+    N, din, D, S, sigsq, beta = 500, 6, 8, 48, 0.7, 0.4
+    nl = _FixedEncoder(din, D, 1)
+    X = r.randn(N, din)
+    y = nl.encode(X).astype(np.float64).dot(r.randn(D)/np.sqrt(D)) + np.sqrt(sigsq)*r.randn(N)
+    Z = np.hstack((X, y[:, None]))
+    deep_encoder = lambda nl, pts: np.hstack((nl.encode(pts[:, :-1].astype(np.float32)), pts[:, -1][:, None].astype(np.float32)))
+    log_likelihood = lambda pts, th, nl: om.nl_loglik(deep_encoder(nl, pts), th, sigsq)
+    beta_likelihood = lambda pts, th, b, nl: om.nl_betalik(deep_encoder(nl, pts), th, b, sigsq)
+    mu0, Sig0inv = np.zeros(D), np.eye(D)
+
+    def sampler(n, wts, pts):
+        if pts.shape[0] == 0:
+            wts, pts = np.zeros(1), np.zeros((1, Z.shape[1]))
+        mu, L, _ = om.nl_weighted_post(mu0, Sig0inv, sigsq, deep_encoder(nl, pts).astype(np.float64), wts)
+        return mu + np.random.randn(n, D).dot(L.T)
+    sched = lambda i: 1./(1.+i)
+    np.random.seed(3)
+    if alg == 'beta':
+        prj = bc.BetaBlackBoxProjector(sampler, S, beta_likelihood, log_likelihood, None, nl=nl)
+        a = bc.BetaCoreset(Z, prj, opt_itrs=15, step_sched=sched, beta=beta, learn_beta=False)
+        pot = lambda p, t: om.nl_betalik(deep_encoder(nl, p), t, beta, sigsq)
+    else:
+        prj = bc.BlackBoxProjector(sampler, S, log_likelihood, None, nl=nl)
+        a = bc.SparseVICoreset(Z, prj, opt_itrs=15, step_sched=sched)
+        pot = lambda p, t: om.nl_loglik(deep_encoder(nl, p), t, sigsq)
+    for m in range(1, 7):
+        a.build(1, m)
+    np.random.seed(3)
+    o = oc.GreedyVI(Z, sampler, S, pot, opt_itrs=15, sched=sched)
+    for m in range(1, 7):
+        o.build(1, m)
+    np.testing.assert_array_equal(a.idcs, o.idcs)
+    np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
+
+
+def test_precomputed_features_take_the_fused_path(bc, models):
+    """the same problem with the rows encoded once (model_neurlinr.encode_dataset) and the bound device potential: the
+    fused path selects the same rows as the black-box route through the encoder lambdas"""
+    _, _, nlm = models
+    r = np.random.RandomState(5)
+    N, din, D, S, sigsq, beta = 500, 6, 8, 48, 0.7, 0.4
+    nl = _FixedEncoder(din, D, 1)
+    X = r.randn(N, din)
+    y = nl.encode(X).astype(np.float64).dot(r.randn(D)/np.sqrt(D)) + np.sqrt(sigsq)*r.randn(N)
+    Z = np.hstack((X, y[:, None]))
+    F = nlm.encode_dataset(nl, Z, batch=128)
+    assert F.shape == (N, D+1) and F.dtype == np.float64
+    sampler = nlm.make_conjugate_sampler(np.zeros(D), np.eye(D), sigsq)
+    pot = lambda p, t: om.nl_betalik(p, t, beta, sigsq)
+    sched = lambda i: 1./(1.+i)
+    np.random.seed(3)
+    prj = bc.BetaBlackBoxProjector(sampler, S, nlm.neurlinr_beta_likelihood.bind(sigsq=sigsq), nlm.neurlinr_loglikelihood.bind(sigsq=sigsq), None)
+    a = bc.BetaCoreset(F, prj, opt_itrs=15, step_sched=sched, beta=beta, learn_beta=False)
+    for m in range(1, 7):
+        a.build(1, m)
+    np.random.seed(3)
+    o = oc.GreedyVI(F, sampler, S, pot, opt_itrs=15, sched=sched)
+    for m in range(1, 7):
+        o.build(1, m)
+    np.testing.assert_array_equal(a.idcs, o.idcs)
+    np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
