@@ -49,6 +49,7 @@ class Engine(object):
         self.index = index
         self.device = torch.device('cuda', index)
         self._ctx = {}
+        self.fexp_applied = {}     # ctx name -> feature-exponent tensor last handed to bc_set_feature_exponents
         self.sms = None
 
     def ctx(self, name='main'):
@@ -126,20 +127,29 @@ class DeviceRows(object):
         return self
 
     def quantised(self, ctx, D, aux_col=None):
-        """(image, rowscale, aux) for the tensor-core route: the rows split once into 7 int8 digit planes, stored in
-        the tensor core's own swizzled tile layout (bc_quantise_rows); aux = column `aux_col` of every row."""
+        """(image, rowscale, aux, fexp) for the tensor-core route: the rows split once into 7 int8 digit planes, stored
+        in the tensor core's own swizzled tile layout (bc_quantise_rows); aux = column `aux_col` of every row; fexp = the
+        per-feature power-of-two exponents the image was built with (bc_feature_exponents; the maximum over the row
+        shards of a sharded job, so that the image -- and every result -- does not depend on how the rows are split)."""
         key = (int(D), aux_col)
         if key not in self._q:
             from ._native import call, c_i64
+            from ._shard import Comm
             nb = c_i64()
             call('bc_q_image_bytes', self.n_local, ctypes.byref(nb))
             img = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=self.engine.device)
             rs = self.engine.empty(max(self.n_local, 1))
             aux = self.engine.empty(max(self.n_local, 1)) if aux_col is not None else None
+            fexp = torch.empty(int(D), dtype=torch.int32, device=self.engine.device)
+            call('bc_feature_exponents', ctx, ptr(self.t), self.ld, self.n_local, int(D), ptr(fexp), stream_ptr())
+            comm = Comm.current()
+            if self.sharded and comm.world > 1:
+                fexp = comm.allgather(fexp).amax(dim=0).to(torch.int32)
+            fexp = torch.where(fexp < -(1 << 20), torch.zeros_like(fexp), fexp).contiguous()
             if self.n_local:
                 call('bc_quantise_rows', ctx, ptr(self.t), self.ld, self.n_local, int(D), 0 if aux_col is None else int(aux_col),
-                     ptr(img), ptr(rs), ptr(aux), stream_ptr())
-            self._q[key] = (img, rs, aux)
+                     ptr(img), ptr(rs), ptr(aux), ptr(fexp), stream_ptr())
+            self._q[key] = (img, rs, aux, fexp)
         return self._q[key]
 
     @property

@@ -41,6 +41,7 @@ class FusedProjection(object):
         self.pot = potential
         self.ncols = ncols
         self.D = potential.feature_dim(ncols)
+        self.ctx_name = ctx_name
         self.ctx = engine.ctx(ctx_name)
         self.siginv = engine.upload(potential.bound['Siginv']) if potential.model == 'gaussian' else None
         self._beta = ()
@@ -87,7 +88,10 @@ class FusedProjection(object):
         if ROUTE != 'q' or sub is not None or self.D > nv.lib().bc_q_max_features() or rows.n_local == 0:
             return None
         aux_col = self.D if self.pot.model == 'neurlin' else None
-        img, rs, aux = rows.quantised(self.ctx, self.D, aux_col)
+        img, rs, aux, fexp = rows.quantised(self.ctx, self.D, aux_col)
+        if self.eng.fexp_applied.get(self.ctx_name) is not fexp:     # the ctx's sample image must match this row image
+            nv.call('bc_set_feature_exponents', self.ctx, ptr(fexp), self.D, stream_ptr())
+            self.eng.fexp_applied[self.ctx_name] = fexp
         ra = self._rowaux(rows) if self.pot.model == 'gaussian' else aux
         return img, rs, ra
 

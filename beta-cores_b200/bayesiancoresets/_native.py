@@ -23,7 +23,9 @@ SIGNATURES = {
     'bc_project_score': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_project_materialise': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp],
     'bc_q_image_bytes': [c_i64, ctypes.POINTER(c_i64)],
-    'bc_quantise_rows': [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    'bc_quantise_rows': [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'bc_feature_exponents': [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
+    'bc_set_feature_exponents': [c_vp, c_vp, c_int, c_vp],
     'bc_project_colsum_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_project_score_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_contraction_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp],

@@ -40,6 +40,10 @@ struct bc_ctx {
   size_t cap_qB = 0;
   double* colscale = nullptr;
   size_t cap_cs = 0;
+  // feature exponents of the row image in use (bc_set_feature_exponents); the sample image is built with their negatives
+  bool fexp_on = false;
+  int* fexp = nullptr;                     // kQK ints
+  unsigned long long* fscratch = nullptr;  // kQK column maxima (bc_feature_exponents)
 };
 
 static int cuda_fail(cudaError_t e) {
@@ -134,6 +138,9 @@ int bc_create(int device, bc_ctx** out) {
   BC_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sms = prop.multiProcessorCount;
   BC_CUDA(cudaMalloc((void**)&c->part_misc, (size_t)4 * 1024 * sizeof(double)));
+  BC_CUDA(cudaMalloc((void**)&c->fexp, kQK * sizeof(int)));
+  BC_CUDA(cudaMemset(c->fexp, 0, kQK * sizeof(int)));
+  BC_CUDA(cudaMalloc((void**)&c->fscratch, kQK * sizeof(unsigned long long)));
   *out = c;
   return BC_OK;
 }
@@ -148,6 +155,8 @@ int bc_destroy(bc_ctx* c) {
   cudaFree(c->dense_part);
   cudaFree(c->qB);
   cudaFree(c->colscale);
+  cudaFree(c->fexp);
+  cudaFree(c->fscratch);
   delete c;
   return BC_OK;
 }
@@ -217,11 +226,33 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
     if ((rc = grow(&c->qB, &c->cap_qB, chunks * kQChunkBytes / sizeof(double)))) return rc;
     if ((rc = grow(&c->colscale, &c->cap_cs, 2))) return rc;   // [0] = scale, [1] = the shared exponent (int)
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    reinterpret_cast<int*>(c->colscale + 1), (cudaStream_t)stream));
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, (cudaStream_t)stream));
     BC_LAUNCHED(2);
     c->q_ready = true;
   }
   c->samples_set = true;
+  return BC_OK;
+}
+
+int bc_feature_exponents(bc_ctx* c, const double* d_X, int64_t ldx, int64_t n, int D, int32_t* d_fexp_out, void* stream) {
+  if (!c || !d_X || !d_fexp_out || n < 0 || D <= 0 || ldx < D) return BC_ERR_ARG;
+  if (D > kQK) return BC_ERR_UNSUPPORTED;
+  BC_CUDA(launch_feature_exponents(d_X, ldx, n, D, c->fscratch, d_fexp_out, (cudaStream_t)stream));
+  BC_LAUNCHED(n > 0 ? 2 : 1);
+  return BC_OK;
+}
+
+int bc_set_feature_exponents(bc_ctx* c, const int32_t* d_fexp, int D, void* stream) {
+  if (!c || D < 0 || D > kQK || (d_fexp && D == 0)) return BC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  BC_CUDA(cudaMemsetAsync(c->fexp, 0, kQK * sizeof(int), st));
+  if (d_fexp) BC_CUDA(cudaMemcpyAsync(c->fexp, d_fexp, (size_t)D * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  c->fexp_on = d_fexp != nullptr;
+  if (c->samples_set && c->q_ready) {   // the sample image in place was built for other exponents
+    BC_CUDA(launch_quantise_samples(c->B, c->Dpad, c->S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, st));
+    BC_LAUNCHED(2);
+  }
   return BC_OK;
 }
 
@@ -340,12 +371,12 @@ int bc_q_image_bytes(int64_t n, int64_t* bytes) {
 }
 
 int bc_quantise_rows(bc_ctx* c, const double* d_X, int64_t ldx, int64_t n, int D, int aux_col, void* d_image, double* d_rowscale,
-                     double* d_aux_out, void* stream) {
+                     double* d_aux_out, const int32_t* d_fexp, void* stream) {
   if (!c || !d_X || !d_image || !d_rowscale || n < 0 || D <= 0 || ldx < D) return BC_ERR_ARG;
   if (D > kQK) return BC_ERR_UNSUPPORTED;
   if (d_aux_out && (aux_col < 0 || aux_col >= ldx)) return BC_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(d_image) & 15) return BC_ERR_ALIGN;
-  BC_CUDA(launch_quantise_rows(d_X, ldx, n, D, reinterpret_cast<unsigned char*>(d_image), d_rowscale, d_aux_out, aux_col,
+  BC_CUDA(launch_quantise_rows(d_X, ldx, n, D, reinterpret_cast<unsigned char*>(d_image), d_rowscale, d_aux_out, aux_col, d_fexp,
                                (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;

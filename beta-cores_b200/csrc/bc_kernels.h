@@ -72,10 +72,12 @@ struct QProjArgs {
   double* V;            // QMODE_DOT: the contraction itself, n x ldv
   long long ldv;
 };
+cudaError_t launch_feature_exponents(const double* X, long long ldx, long long n, int D, unsigned long long* scratch, int* out,
+                                     cudaStream_t st);
 cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
-                                 double* aux_out, int aux_col, cudaStream_t st);
+                                 double* aux_out, int aux_col, const int* fexp, cudaStream_t st);
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    cudaStream_t st);
+                                    const int* fexp, cudaStream_t st);
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----

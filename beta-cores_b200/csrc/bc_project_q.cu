@@ -80,7 +80,8 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 template <int R>
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src, long long ld, long long n, int D,
                                                    unsigned char* __restrict__ image, double* __restrict__ scale_out,
-                                                   double* __restrict__ aux_out, int aux_col, const int* __restrict__ common_e) {
+                                                   double* __restrict__ aux_out, int aux_col, const int* __restrict__ common_e,
+                                                   const int* __restrict__ fexp, int fsign) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = lane * 4 + i;
-        if (k < D) x[i] = p[k];
+        if (k < D) x[i] = fexp ? scalbn(p[k], fsign * __ldg(fexp + k)) : p[k];   // feature exponents: see k_feature_exponents
       }
       if (aux_out && lane == 0) aux_out[r] = p[aux_col];
     }
@@ -132,26 +133,76 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src
   }
 }
 
+// Feature exponents.  The digit split keeps 56 bits below the largest entry of a ROW, so a feature whose entries are all
+// tiny next to another feature's (unstandardised data: an income column beside a 0/1 flag) would keep few significant
+// bits, while an fp64 dot product rounds every product relative to itself.  Both operands are therefore rescaled per
+// feature by a power of two -- x_k 2^-c_k with theta_k 2^+c_k, c_k = ilogb(max_n |x_nk|): exact, the products are
+// unchanged, and every feature of the row image is O(1).  out[k] = c_k, or kFexpEmpty for a column with no finite
+// non-zero entry (the caller maps it to 0 after taking the maximum over row shards).
+constexpr int kFexpEmpty = -(1 << 30);
+__global__ void __launch_bounds__(256) k_feature_absmax(const double* __restrict__ X, long long ld, long long n, int D,
+                                                        unsigned long long* __restrict__ colmax_bits) {
+  // blockDim = (32, 8): lane -> features lane + 32 j, 8 row groups per block; |x| compares like its bit pattern
+  unsigned long long m[4] = {0, 0, 0, 0};
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (long long)gridDim.x * blockDim.y) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = threadIdx.x + 32 * j;
+      if (k < D) {
+        const double v = fabs(X[r * ld + k]);
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        if (isfinite(v) && b > m[j]) m[j] = b;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = threadIdx.x + 32 * j;
+    if (k < D && m[j]) atomicMax(colmax_bits + k, m[j]);
+  }
+}
+__global__ void k_feature_exponents(const unsigned long long* __restrict__ colmax_bits, int D, int* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < D) {
+    const double v = __longlong_as_double((long long)colmax_bits[k]);
+    out[k] = (v > 0.0) ? ilogb(v) : kFexpEmpty;
+  }
+}
+
+cudaError_t launch_feature_exponents(const double* X, long long ldx, long long n, int D, unsigned long long* scratch, int* out,
+                                     cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * kQK, st);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    long long blocks = (n + 63) / 64;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_feature_absmax<<<(int)blocks, dim3(32, 8), 0, st>>>(X, ldx, n, D, scratch);
+  }
+  k_feature_exponents<<<1, kQK, 0, st>>>(scratch, D, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
-                                 double* aux_out, int aux_col, cudaStream_t st) {
+                                 double* aux_out, int aux_col, const int* fexp, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   long long warps = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
   long long blocks = (warps + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col, nullptr);
+  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col, nullptr, fexp, -1);
   return cudaGetLastError();
 }
 
 // exponent shared by all S samples: ilogb(max |B|) + 3, and the matching scale 2^(e - 32) (NaN if any entry is not finite:
 // the reference's own result is NaN in every quantity downstream of such a sample set)
 __global__ void __launch_bounds__(1024) k_common_exponent(const double* __restrict__ B, int ldb, int S, int D, int* __restrict__ e_out,
-                                                          double* __restrict__ scale_out) {
+                                                          double* __restrict__ scale_out, const int* __restrict__ fexp) {
   __shared__ double smax[32];
   __shared__ int sbad[32];
   double amax = 0.0;
   int bad = 0;
   for (long long i = threadIdx.x; i < (long long)S * D; i += blockDim.x) {
-    const double v = B[(i / D) * ldb + (i % D)];
+    const int k = (int)(i % D);
+    const double v = fexp ? scalbn(B[(i / D) * ldb + k], __ldg(fexp + k)) : B[(i / D) * ldb + k];
     bad |= !isfinite(v);
     amax = fmax(amax, fabs(v));
   }
@@ -177,10 +228,10 @@ __global__ void __launch_bounds__(1024) k_common_exponent(const double* __restri
 }
 
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    cudaStream_t st) {
-  k_common_exponent<<<1, 1024, 0, st>>>(B, ldb, S, D, common_e, colscale);
+                                    const int* fexp, cudaStream_t st) {
+  k_common_exponent<<<1, 1024, 0, st>>>(B, ldb, S, D, common_e, colscale, fexp);
   const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
-  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, common_e);
+  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, common_e, fexp, +1);
   return cudaGetLastError();
 }
 

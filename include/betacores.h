@@ -89,10 +89,21 @@ int bc_project_materialise(bc_ctx* ctx, const double* d_X, int64_t ldx, const in
  * The row image is built ONCE per dataset; bc_set_samples() builds the sample image. */
 int bc_q_max_features(void);
 int bc_q_image_bytes(int64_t n, int64_t* bytes);     /* device bytes of the quantised image of n rows */
+/* Feature exponents (optional, recommended for data whose columns differ much in magnitude).  The digit split keeps 56
+ * bits below the largest entry of a row; with x_k 2^-c_k in the row image and theta_k 2^+c_k in the sample image
+ * (c_k = ilogb max_n |x_nk|, powers of two: the products are unchanged) every feature is O(1) in its row and the
+ * truncation is relative to the largest PRODUCT, as in an fp64 dot product, not to the largest entries.
+ *   bc_feature_exponents: d_fexp_out[k] = c_k of the n rows given, or -2^30 for a column with no finite non-zero entry
+ *                         (row shards: take the element-wise maximum over the shards, then replace -2^30 by 0);
+ *   bc_set_feature_exponents: the exponents of the row image the next _q passes will use (NULL: none).  They stay in
+ *                         force across bc_set_samples / bc_set_potential; a sample image already built is rebuilt. */
+int bc_feature_exponents(bc_ctx* ctx, const double* d_X, int64_t ldx, int64_t n, int D, int32_t* d_fexp_out, void* stream);
+int bc_set_feature_exponents(bc_ctx* ctx, const int32_t* d_fexp, int D, void* stream);
 /* d_image (16-byte aligned, bc_q_image_bytes(n)), d_rowscale[n]; optional d_aux_out[n] = column aux_col of every row
- * (the neural-linear target y, model_neurlinr.py:104). */
+ * (the neural-linear target y, model_neurlinr.py:104); d_fexp: D feature exponents applied to the rows (NULL: none) --
+ * the passes over this image then need bc_set_feature_exponents(ctx, d_fexp, D). */
 int bc_quantise_rows(bc_ctx* ctx, const double* d_X, int64_t ldx, int64_t n, int D, int aux_col, void* d_image, double* d_rowscale,
-                     double* d_aux_out, void* stream);
+                     double* d_aux_out, const int32_t* d_fexp, void* stream);
 /* d_rowaux[n]: Gaussian x Siginv x (bc_rowquad) / neural-linear y (d_aux_out above); NULL for the logistic model. */
 int bc_project_colsum_q(bc_ctx* ctx, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
                         double* d_out_dd, void* stream);

@@ -181,14 +181,64 @@ def test_tensor_core_contraction_is_fp64_exact(bc):
         T = eng.upload(Th)
         nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_LOGLIK, D, nv.params8([0]*8), None)
         nv.call('bc_set_samples', ctx, ptr(T), S, int(T.stride(0)), stream_ptr())
-        img, rs, _ = rows.quantised(ctx, D)
+        img, rs, _, fexp = rows.quantised(ctx, D)
+        nv.call('bc_set_feature_exponents', ctx, ptr(fexp), D, stream_ptr())
         V = eng.empty(n, S)
         nv.call('bc_contraction_q', ctx, ptr(img), ptr(rs), n, ptr(V), S, stream_ptr())
         ref = (X.astype(np.longdouble) @ Th.T.astype(np.longdouble)).astype(np.float64)
         # rows carry their own power-of-two scale, the samples share one: the error is relative to max|x_n| * max|Theta|
-        bound = np.abs(X).max(axis=1)[:, None]*np.abs(Th).max()
+        # of the operands as split, i.e. after the per-feature exponents (x_k 2^-c_k, theta_k 2^+c_k)
+        c = fexp.cpu().numpy().astype(np.float64)
+        bound = np.abs(X*2.**-c).max(axis=1)[:, None]*np.abs(Th*2.**c).max()
         err = np.abs(V.cpu().numpy() - ref)
         assert (err <= 2e-14*bound + 1e-320).all(), (n, D, S, float((err/np.maximum(bound, 1e-300)).max()))
+
+
+def test_tensor_core_contraction_with_unstandardised_features(bc):
+    """columns 16 orders of magnitude apart (and the samples scaled the other way, so that every feature contributes
+    O(1) to the product): the per-feature exponents keep the error at the level of an fp64 dot product, relative to
+    sum_k |x_k theta_k| -- without them the small columns would keep only a few bits next to the large ones"""
+    import torch
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    from bayesiancoresets import _native as nv
+    eng = Engine.get()
+    ctx = eng.ctx('qtest')
+    for n, D, S, seed in [(300, 128, 64, 4), (1000, 20, 100, 5)]:
+        r = np.random.RandomState(seed)
+        col = 10.**r.uniform(-8, 8, size=D)
+        col[0] = 0.                                   # an all-zero feature
+        X = r.randn(n, D)*col
+        Th = r.randn(S, D)/np.where(col > 0, col, 1.)
+        rows = DeviceRows(eng, X)
+        T = eng.upload(Th)
+        nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_LOGLIK, D, nv.params8([0]*8), None)
+        nv.call('bc_set_samples', ctx, ptr(T), S, int(T.stride(0)), stream_ptr())
+        img, rs, _, fexp = rows.quantised(ctx, D)
+        fe = fexp.cpu().numpy()
+        assert fe[0] == 0 and (np.abs(fe[1:] - np.floor(np.log2(np.abs(X[:, 1:]).max(axis=0)))) <= 1).all()
+        nv.call('bc_set_feature_exponents', ctx, ptr(fexp), D, stream_ptr())      # rebuilds the sample image
+        V = eng.empty(n, S)
+        nv.call('bc_contraction_q', ctx, ptr(img), ptr(rs), n, ptr(V), S, stream_ptr())
+        ref = (X.astype(np.longdouble) @ Th.T.astype(np.longdouble)).astype(np.float64)
+        natural = np.abs(X) @ np.abs(Th).T            # what an fp64 dot product's rounding is relative to
+        err = np.abs(V.cpu().numpy() - ref)
+        assert (err <= 1e-13*natural).all(), float((err/natural).max())
+        # and the fused passes (which apply the exponents themselves) agree with the FP64 DMMA route
+        from bayesiancoresets import _fused
+        from bayesiancoresets._fused import FusedProjection
+        from bayesiancoresets.potentials import DevicePotential
+        fp = FusedProjection(eng, DevicePotential('logistic', 'betalik'), D)
+        fp.configure(0.3)
+        fp.set_samples(Th)
+        old = _fused.ROUTE
+        try:
+            cs = {}
+            for route in ('q', 'dmma'):
+                _fused.ROUTE = route
+                cs[route] = fp.combine(fp.colsum_parts(rows), 1).cpu().numpy()
+        finally:
+            _fused.ROUTE = old
+        np.testing.assert_allclose(cs['q'], cs['dmma'], rtol=1e-9, atol=1e-11*np.abs(cs['dmma']).max())
 
 
 def test_score_nan_and_tie_semantics(bc, route):

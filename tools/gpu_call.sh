@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "encoder or precomputed" 2>&1 | tail -15
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8

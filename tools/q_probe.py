@@ -20,7 +20,7 @@ def quantise(X, D, aux_col=None):
     img = torch.empty(nb.value, dtype=torch.uint8, device=dev)
     rs = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
     aux = torch.empty(max(n, 1), dtype=torch.float64, device=dev) if aux_col is not None else None
-    nv.call('bc_quantise_rows', ctx, ptr(X), int(X.stride(0)), n, D, 0 if aux_col is None else aux_col, ptr(img), ptr(rs), ptr(aux), stream_ptr())
+    nv.call('bc_quantise_rows', ctx, ptr(X), int(X.stride(0)), n, D, 0 if aux_col is None else aux_col, ptr(img), ptr(rs), ptr(aux), None, stream_ptr())
     return img, rs, aux
 
 

@@ -13,7 +13,7 @@ nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_BETALIK, D, nv.param
 nv.call('bc_set_samples', ctx, ptr(T), S, D, stream_ptr())
 nb = ctypes.c_int64(); nv.call('bc_q_image_bytes', N, ctypes.byref(nb))
 img = torch.empty(nb.value, dtype=torch.uint8, device=dev); rs = torch.empty(N, dtype=torch.float64, device=dev)
-nv.call('bc_quantise_rows', ctx, ptr(X), D, N, D, 0, ptr(img), ptr(rs), None, stream_ptr())
+nv.call("bc_quantise_rows", ctx, ptr(X), D, N, D, 0, ptr(img), ptr(rs), None, None, stream_ptr())
 o = torch.empty(2*(S+1), dtype=torch.float64, device=dev)
 fn = lambda: nv.call('bc_project_colsum_q', ctx, ptr(img), ptr(rs), N, None, ptr(o), stream_ptr())
 for _ in range(2): fn()
