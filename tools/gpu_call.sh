@@ -1,9 +1,5 @@
 cd /root/repo
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2_final.json 2> gpurun_out/bench_n2_final.err
-echo rc=$?
-tail -c 800 gpurun_out/bench_n2_final.err
-python - <<'PY'
-import json
-d=json.loads(open('/root/repo/gpurun_out/bench_n2_final.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','n_gpus','scaling')}, d['e2e']['value'], d.get('parity'), d['roofline']['launch_ms'])
-PY
+for v in notab tab notab tab; do
+BC_LIB_PATH=/root/repo/beta-cores_b200/lib/lib_$v.so timeout 300 python tools/q_time.py 2>&1 | tail -1
+done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "fused or potentials or project_f" 2>&1 | tail -4
