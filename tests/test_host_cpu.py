@@ -183,3 +183,26 @@ def test_newton_laplace_mode_is_the_bfgs_mode():
     assert np.abs(model_lr.grad_th_log_joint(Z, mu_n, w)).max() < 1e-10
     np.testing.assert_allclose(mu_n, mu_b, atol=1e-4)
     np.testing.assert_allclose(L_n, L_b, atol=1e-4)
+
+
+def test_c_abi_argument_errors_need_no_device():
+    """every entry point checks its handle / pointers before touching CUDA: misuse comes back as a code (no device here)"""
+    import ctypes
+    from bayesiancoresets import _native as nv
+    L = nv.lib()
+    null = None
+    assert L.bc_set_samples(null, null, 4, 4, null) == -1
+    assert L.bc_project_colsum(null, null, 0, null, 0, null, null, null) == -1
+    assert L.bc_project_colsum_q(null, null, null, 0, null, null, null) == -1
+    assert L.bc_quantise_rows(null, null, 0, 0, 1, 0, null, null, null, null, null) == -1
+    assert L.bc_feature_exponents(null, null, 0, 0, 1, null, null) == -1
+    assert L.bc_set_feature_exponents(null, null, 0, null) == -1
+    assert L.bc_laplace_logistic(null, null, 0, null, 1, 1, null, null, 1, 1e-9, null, null) == -1
+    assert L.bc_sample_affine(null, null, null, null, 1, 1, null, 1, null) == -1
+    assert L.bc_destroy(null) == 0
+    nb = ctypes.c_int64()
+    assert L.bc_q_image_bytes(1000, ctypes.byref(nb)) == 0 and nb.value == 8*128*7*128   # 8 tiles of 128 rows x 7 digit planes x 128 B
+    assert L.bc_q_max_features() == 128
+    L.bc_error_string.restype = ctypes.c_char_p
+    msgs = {L.bc_error_string(c) for c in (0, -1, -2, -3, -4, -5)}
+    assert len(msgs) == 6 and all(m for m in msgs)
