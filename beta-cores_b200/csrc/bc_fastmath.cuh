@@ -46,6 +46,13 @@ BC_HD int fm_hi(double x) {
   return (int)(uint32_t)(u >> 32);
 #endif
 }
+BC_HD double fm_i2d(int k) {
+#if defined(__CUDACC__)
+  return __int2double_rn(k);
+#else
+  return (double)k;
+#endif
+}
 BC_HD double fm_add_exponent(double p, int k) {  // p * 2^k for results that stay normal
 #if defined(__CUDACC__)
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
@@ -77,7 +84,7 @@ BC_HD void exp_core_v(const double (&x)[W], double (&y)[W]) {
   BC_UNROLL for (int i = 0; i < W; ++i) kf[i] = fm_fma(x[i], 1.4426950408889634, kMagic);
   BC_UNROLL for (int i = 0; i < W; ++i) {
     k[i] = fm_lo(kf[i]);
-    kf[i] -= kMagic;
+    kf[i] = fm_i2d(k[i]);      // the same value as kf - kMagic, from the conversion unit instead of the FP64 pipe
   }
   BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(kf[i], -6.93147180369123816490e-01, x[i]);
   BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(kf[i], -1.90821492927058770002e-10, r[i]);

@@ -80,11 +80,9 @@ __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// exact conversion of an integer |t| < 2^51 to fp64 with one integer add and one FP64 add
-// (the bit pattern of 2^52 + 2^51 + t is 0x4338000000000000 + t).
-__device__ __forceinline__ double exact_ll2d(long long t) {
-  return __longlong_as_double(t + 0x4338000000000000LL) - 6755399441055744.0;
-}
+// exact conversion of an integer |t| < 2^53 to fp64 (I2F.F64.S64 on the conversion unit: measured a little faster here than
+// the integer-add + FP64-add magic-number form, which occupies the contended FP64 pipe)
+__device__ __forceinline__ double exact_ll2d(long long t) { return __ll2double_rn(t); }
 // the seven int32 digit diagonals D_d = sum_{i+j=d} A_i B_j^T  ->  sum_d D_d 256^(6-d)  as an fp64 (one rounding)
 __device__ __forceinline__ double q_combine(int d0, int d1, int d2, int d3, int d4, int d5, int d6) {
   const long long hi = ((long long)d0 << 24) + ((long long)d1 << 16) + ((long long)d2 << 8) + (long long)d3;
