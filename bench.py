@@ -60,8 +60,10 @@ def parse():
     ap.add_argument('--cpu-opt-itrs', type=int, default=2)
     ap.add_argument('--ref-rows', type=int, default=16384, help='rows per step of the --impl reference arm')
     ap.add_argument('--ref-opt-itrs', type=int, default=4)
-    ap.add_argument('--sampler', default='newton', choices=['newton', 'hybrid', 'device', 'bfgs'],
-                    help="product arm's Laplace sampler: host Newton (default), the device kernels of csrc/bc_sampler.cu, or scipy BFGS")
+    ap.add_argument('--sampler', default='hybrid', choices=['newton', 'hybrid', 'device', 'bfgs'],
+                    help="product arm's Laplace sampler: 'hybrid' (default) = mode and Cholesky factor on the host, the S x D x D affine map "
+                         "of the normals on the device; 'newton' = all on the host (what the reference arm runs); 'device' = all on the "
+                         "device (csrc/bc_sampler.cu); 'bfgs' = the reference's scipy optimiser")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -148,13 +150,18 @@ def workload_config(a, world):
                         % (a.n, a.d, a.s, a.beta),
             'N': a.n, 'D': a.d, 'S': a.s, 'beta': a.beta, 'opt_itrs': a.opt_itrs,
             'step': 'one BetaCoreset.build(1, m): 1 selection + opt_itrs ADAM steps = (1+opt_itrs) N x S projections',
-            'sampler': ('Laplace approximation of the weighted coreset posterior on the device (csrc/bc_sampler.cu: warm-started damped Newton '
-                        'mode search, D x D Cholesky factor and inverse, affine map of S x D normals drawn from the global numpy stream one '
-                        'call ahead on a helper thread), called every optimiser step; the reference arm runs the same algebra on the host'
-                        if getattr(a, 'sampler', 'newton') == 'device' else
-                        'host Laplace approximation of the weighted coreset posterior (mode by warm-started damped Newton steps, D x D '
-                        'Cholesky factor, S x D normal draws from the global numpy stream, drawn one call ahead on a helper thread), '
-                        'called every optimiser step; the same callback in both arms'),
+            'sampler': {'hybrid': 'Laplace approximation of the weighted coreset posterior: mode (warm-started damped Newton steps) and D x D '
+                                  'Cholesky factor / inverse on the host, samples mu + R L^T formed on the device (k_sample_affine) from S x D '
+                                  'normals drawn from the global numpy stream one call ahead on a helper thread; called every optimiser '
+                                  'step.  The reference arm runs the same algebra entirely on the host (same random numbers)',
+                        'device': 'Laplace approximation of the weighted coreset posterior on the device (csrc/bc_sampler.cu: warm-started '
+                                  'damped Newton mode search, D x D Cholesky factor and inverse, affine map of S x D normals drawn from '
+                                  'the global numpy stream one call ahead on a helper thread), called every optimiser step; the reference '
+                                  'arm runs the same algebra on the host'}.get(
+                            getattr(a, 'sampler', 'newton'),
+                            'host Laplace approximation of the weighted coreset posterior (mode by warm-started damped Newton steps, D x D '
+                            'Cholesky factor, S x D normal draws from the global numpy stream, drawn one call ahead on a helper thread), '
+                            'called every optimiser step; the same callback in both arms'),
             'sharding': 'rows over %d rank(s), fixed total N' % world,
             'l2': 'inputs (%.2f GB of rows) exceed the 126 MB L2; no flush' % (a.n*a.d*8/1e9)}
 

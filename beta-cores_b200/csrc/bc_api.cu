@@ -44,6 +44,7 @@ struct bc_ctx {
   bool fexp_on = false;
   int* fexp = nullptr;                     // kQK ints
   unsigned long long* fscratch = nullptr;  // kQK column maxima (bc_feature_exponents)
+  unsigned long long* sscratch = nullptr;  // 2 words: max bits / non-finite flag of the samples, zero between calls
 };
 
 static int cuda_fail(cudaError_t e) {
@@ -141,6 +142,8 @@ int bc_create(int device, bc_ctx** out) {
   BC_CUDA(cudaMalloc((void**)&c->fexp, kQK * sizeof(int)));
   BC_CUDA(cudaMemset(c->fexp, 0, kQK * sizeof(int)));
   BC_CUDA(cudaMalloc((void**)&c->fscratch, kQK * sizeof(unsigned long long)));
+  BC_CUDA(cudaMalloc((void**)&c->sscratch, 2 * sizeof(unsigned long long)));
+  BC_CUDA(cudaMemset(c->sscratch, 0, 2 * sizeof(unsigned long long)));
   *out = c;
   return BC_OK;
 }
@@ -157,6 +160,7 @@ int bc_destroy(bc_ctx* c) {
   cudaFree(c->colscale);
   cudaFree(c->fexp);
   cudaFree(c->fscratch);
+  cudaFree(c->sscratch);
   delete c;
   return BC_OK;
 }
@@ -226,8 +230,8 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
     if ((rc = grow(&c->qB, &c->cap_qB, chunks * kQChunkBytes / sizeof(double)))) return rc;
     if ((rc = grow(&c->colscale, &c->cap_cs, 2))) return rc;   // [0] = scale, [1] = the shared exponent (int)
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, (cudaStream_t)stream));
-    BC_LAUNCHED(2);
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, (cudaStream_t)stream));
+    BC_LAUNCHED(3);
     c->q_ready = true;
   }
   c->samples_set = true;
@@ -250,8 +254,8 @@ int bc_set_feature_exponents(bc_ctx* c, const int32_t* d_fexp, int D, void* stre
   c->fexp_on = d_fexp != nullptr;
   if (c->samples_set && c->q_ready) {   // the sample image in place was built for other exponents
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, c->S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, st));
-    BC_LAUNCHED(2);
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, st));
+    BC_LAUNCHED(3);
   }
   return BC_OK;
 }
@@ -265,7 +269,7 @@ int bc_rowquad(bc_ctx* c, const double* d_X, int64_t n, int64_t ldx, double* d_o
 }
 
 static int project_common(bc_ctx* c, int mode, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n,
-                          const double* d_rowaux, ProjArgs& P, int* grid) {
+                          const double* d_rowaux, ProjArgs& P, int* grid, int* cfg, size_t* smem) {
   if (!c || !d_X || n < 0) return BC_ERR_ARG;
   if (!c->potential_set || !c->samples_set) return BC_ERR_STATE;
   if ((reinterpret_cast<uintptr_t>(d_X) & 15) || (ldx & 1) || ldx < c->Dc) return BC_ERR_ALIGN;
@@ -296,7 +300,9 @@ static int project_common(bc_ctx* c, int mode, const double* d_X, int64_t ldx, c
   P.norms = nullptr;
   P.raw = 0;
   P.want_colsum = 0;
-  const int64_t tiles = (n + c->BM - 1) / c->BM;
+  *cfg = project_tile_config_for_rows(c->tile_cfg, n, c->sms, c->Dpad, smem);
+  const int bm = project_tile_rows(*cfg);
+  const int64_t tiles = (n + bm - 1) / bm;
   *grid = (int)(tiles < c->sms ? tiles : c->sms);
   (void)mode;
   return BC_OK;
@@ -305,15 +311,16 @@ static int project_common(bc_ctx* c, int mode, const double* d_X, int64_t ldx, c
 int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
                       double* d_out_dd, void* stream) {
   ProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   if (!d_out_dd) return BC_ERR_ARG;
-  if ((rc = project_common(c, MODE_COLSUM, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  if ((rc = project_common(c, MODE_COLSUM, d_X, ldx, d_rows, n, d_rowaux, P, &grid, &cfg, &smem))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
     return BC_OK;
   }
-  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_COLSUM, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_COLSUM, cfg, grid, smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -322,14 +329,15 @@ int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* 
 int bc_project_score(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
                      const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream) {
   ProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   if (!d_resid || !d_best || n <= 0) return BC_ERR_ARG;
-  if ((rc = project_common(c, MODE_SCORE, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  if ((rc = project_common(c, MODE_SCORE, d_X, ldx, d_rows, n, d_rowaux, P, &grid, &cfg, &smem))) return rc;
   P.resid = d_resid;
   P.scores = d_scores;
   P.idx_offset = idx_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_SCORE, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_SCORE, cfg, grid, smem, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -338,9 +346,10 @@ int bc_project_score(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d
 int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* d_rows, int64_t n, const double* d_rowaux,
                            double* d_V, int64_t ldv, double* d_norms, double* d_out_dd, int raw, void* stream) {
   ProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   if (!d_V) return BC_ERR_ARG;
-  if ((rc = project_common(c, MODE_MATERIALISE, d_X, ldx, d_rows, n, d_rowaux, P, &grid))) return rc;
+  if ((rc = project_common(c, MODE_MATERIALISE, d_X, ldx, d_rows, n, d_rowaux, P, &grid, &cfg, &smem))) return rc;
   if (ldv < c->S) return BC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
@@ -352,7 +361,7 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
   P.norms = raw ? nullptr : d_norms;
   P.raw = raw ? 1 : 0;
   P.want_colsum = d_out_dd ? 1 : 0;
-  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, c->tile_cfg, grid, c->smem, st));
+  BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, cfg, grid, smem, st));
   BC_LAUNCHED(1);
   if (d_out_dd) {
     BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_MATERIALISE, st));
@@ -415,7 +424,8 @@ static int q_common(bc_ctx* c, const void* d_image, const double* d_rowscale, in
 int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
                         double* d_out_dd, void* stream) {
   QProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   if (!d_out_dd) return BC_ERR_ARG;
   if ((rc = q_common(c, d_image, d_rowscale, n, d_rowaux, P, &grid))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -432,7 +442,8 @@ int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale
 int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux,
                        const double* d_resid, int64_t idx_offset, double* d_best, double* d_scores, void* stream) {
   QProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   if (!d_resid || !d_best || n <= 0) return BC_ERR_ARG;
   if ((rc = q_common(c, d_image, d_rowscale, n, d_rowaux, P, &grid))) return rc;
   P.resid = d_resid;
@@ -447,7 +458,8 @@ int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale,
 
 int bc_contraction_q(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, double* d_V, int64_t ldv, void* stream) {
   QProjArgs P;
-  int grid, rc;
+  int grid, rc, cfg;
+  size_t smem;
   static const double dummy = 0.0;
   if (!d_V || n <= 0) return BC_ERR_ARG;
   if ((rc = q_common(c, d_image, d_rowscale, n, &dummy, P, &grid))) return rc;

@@ -45,6 +45,8 @@ struct ProjArgs {
 };
 
 int project_tile_config(int Dpad, int* BM, int* BN, int* ss, size_t* smem);
+int project_tile_config_for_rows(int base_cfg, long long n, int sms, int Dpad, size_t* smem_out);
+int project_tile_rows(int cfg);
 cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld, double* out_dd,
                                     double* out_best, int mode, cudaStream_t st);
@@ -77,7 +79,7 @@ cudaError_t launch_feature_exponents(const double* X, long long ldx, long long n
 cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
                                  double* aux_out, int aux_col, const int* fexp, cudaStream_t st);
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    const int* fexp, cudaStream_t st);
+                                    const int* fexp, unsigned long long* scratch2, cudaStream_t st);
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----

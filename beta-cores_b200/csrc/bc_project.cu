@@ -508,6 +508,17 @@ int project_tile_config(int Dpad, int* BM, int* BN, int* ss_out, size_t* smem_ou
   return -1;
 }
 
+// Few rows (the M coreset points, every optimiser step): a smaller row tile spreads them over more SMs and does not pay for
+// 128 rows when 16 are valid.  Returns the configuration index >= base_cfg to use for n rows, with its shared memory size.
+int project_tile_config_for_rows(int base_cfg, long long n, int sms, int Dpad, size_t* smem_out) {
+  const int ss = (Dpad % 8 == 4) ? Dpad : Dpad + 4;
+  int cfg = base_cfg;
+  while (cfg < 2 && (n + kCfgs[cfg][0] - 1) / kCfgs[cfg][0] < sms) ++cfg;
+  *smem_out = smem_layout(kCfgs[cfg][0], kCfgs[cfg][1], ss, Dpad).total;
+  return cfg;
+}
+int project_tile_rows(int cfg) { return kCfgs[cfg][0]; }
+
 cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem,
                            cudaStream_t st) {
   if (model == MODEL_LOGISTIC) {

@@ -192,44 +192,48 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
   return cudaGetLastError();
 }
 
-// exponent shared by all S samples: ilogb(max |B|) + 3, and the matching scale 2^(e - 32) (NaN if any entry is not finite:
-// the reference's own result is NaN in every quantity downstream of such a sample set)
-__global__ void __launch_bounds__(1024) k_common_exponent(const double* __restrict__ B, int ldb, int S, int D, int* __restrict__ e_out,
-                                                          double* __restrict__ scale_out, const int* __restrict__ fexp) {
-  __shared__ double smax[32];
-  __shared__ int sbad[32];
-  double amax = 0.0;
-  int bad = 0;
-  for (long long i = threadIdx.x; i < (long long)S * D; i += blockDim.x) {
-    const int k = (int)(i % D);
-    const double v = fexp ? scalbn(B[(i / D) * ldb + k], __ldg(fexp + k)) : B[(i / D) * ldb + k];
-    bad |= !isfinite(v);
-    amax = fmax(amax, fabs(v));
+// exponent shared by all S samples: ilogb(max |B'|) + 3 over the feature-scaled samples B'[s][k] = B[s][k] 2^fexp[k], and
+// the matching scale 2^(e - 32) (NaN if any entry is not finite: the reference's own result is NaN in every quantity
+// downstream of such a sample set).  Two steps: a grid-wide max of the bit patterns (|x| orders like its bits; a
+// non-finite entry sets the flag word), then one thread turns it into (e, scale) and clears the scratch for the next call.
+__global__ void __launch_bounds__(256) k_sample_absmax(const double* __restrict__ B, int ldb, int S, int D, const int* __restrict__ fexp,
+                                                       unsigned long long* __restrict__ scratch /* [0] max bits, [1] bad */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long m = 0, bad = 0;
+  for (int s = blockIdx.x * nw + wid; s < S; s += gridDim.x * nw) {
+    for (int k = lane; k < D; k += 32) {
+      const double b = B[(size_t)s * ldb + k];
+      const double v = fabs(fexp ? scalbn(b, __ldg(fexp + k)) : b);
+      if (!isfinite(v)) bad = 1;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+      if (isfinite(v) && bits > m) m = bits;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const unsigned long long om = __shfl_xor_sync(0xffffffffu, m, o);
+    m = om > m ? om : m;
     bad |= __shfl_xor_sync(0xffffffffu, bad, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    smax[threadIdx.x >> 5] = amax;
-    sbad[threadIdx.x >> 5] = bad;
+  if (lane == 0) {
+    if (m) atomicMax(scratch, m);
+    if (bad) atomicOr(scratch + 1, 1ull);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-      amax = fmax(amax, smax[w]);
-      bad |= sbad[w];
-    }
-    const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
-    *e_out = e;
-    *scale_out = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
-  }
+}
+__global__ void k_common_exponent(unsigned long long* __restrict__ scratch, int* __restrict__ e_out, double* __restrict__ scale_out) {
+  const double amax = __longlong_as_double((long long)scratch[0]);
+  const bool bad = scratch[1] != 0;
+  const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
+  *e_out = e;
+  *scale_out = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
+  scratch[0] = 0;
+  scratch[1] = 0;
 }
 
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    const int* fexp, cudaStream_t st) {
-  k_common_exponent<<<1, 1024, 0, st>>>(B, ldb, S, D, common_e, colscale, fexp);
+                                    const int* fexp, unsigned long long* scratch2 /* two words, zero between calls */, cudaStream_t st) {
+  k_sample_absmax<<<(S + 7) / 8 < 148 ? (S + 7) / 8 : 148, 256, 0, st>>>(B, ldb, S, D, fexp, scratch2);
+  k_common_exponent<<<1, 1, 0, st>>>(scratch2, common_e, colscale);
   const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
   k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, common_e, fexp, +1);
   return cudaGetLastError();

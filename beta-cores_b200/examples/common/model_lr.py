@@ -68,29 +68,63 @@ def hess_th_log_joint(Z, th, wts):
     return -np.eye(th.shape[0]) - (Z*(wts*c)[:, np.newaxis]).T.dot(Z)
 
 
-def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200):
+def _margin_terms(m):
+    """sigma(m) and sigma(m)(1 - sigma(m)) with the reference's m < 100 guard (model_lr.py:98-105,123-137)"""
+    s = np.ones_like(m)
+    ok = m < 100
+    e = np.exp(m[ok])
+    s[ok] = e/(1.+e)
+    return s, np.where(ok, s*(1.-s), 0.)
+
+
+_MASKS = {}
+
+
+def _lower_mask(D):
+    if D not in _MASKS:
+        _MASKS[D] = np.tril(np.ones((D, D)))
+    return _MASKS[D]
+
+
+def _neg_hessian(Zw, ww, c):
+    return np.eye(Zw.shape[1]) + (Zw*(ww*c)[:, np.newaxis]).T.dot(Zw)
+
+
+def _log_joint_from_margins(m, th, ww):
+    ll = np.where(m < 100, -np.log1p(np.exp(np.minimum(m, 100.))), -m)
+    return ww.dot(ll) - 0.5*th.shape[0]*np.log(2.*np.pi) - 0.5*(th**2).sum()
+
+
+def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200, want_margins=False):
     """mode of the (strictly concave) weighted log-joint by damped Newton steps: a few D x D Cholesky solves instead of
-    scipy's BFGS iterations on a dense D x D inverse-Hessian estimate (tens of ms at D = 128, every optimiser step)"""
+    scipy's BFGS iterations on a dense D x D inverse-Hessian estimate (tens of ms at D = 128, every optimiser step).
+    The margins -Z th are computed once per point and shared by value, gradient and Hessian; LAPACK is called through
+    scipy's thin f2py wrappers (dpotrf / dpotrs) -- at D = 128 the checked high-level wrappers cost as much as the solves."""
     th = np.array(mu0, dtype=np.float64)
-    f = log_joint(Zw, th, ww)
+    m = -Zw.dot(th)
+    f = _log_joint_from_margins(m, th, ww)
     for _ in range(maxit):
-        g = grad_th_log_joint(Zw, th, ww)
-        H = -hess_th_log_joint(Zw, th, ww)
-        step = sl.cho_solve(sl.cho_factor(H, lower=True, check_finite=False), g, check_finite=False)
+        s, c = _margin_terms(m)
+        g = -th + Zw.T.dot(ww*s)
+        L, info = sl.lapack.dpotrf(_neg_hessian(Zw, ww, c), lower=1, overwrite_a=1)
+        if info != 0:
+            raise np.linalg.LinAlgError('negative Hessian not positive definite (dpotrf info %d)' % info)
+        step, _ = sl.lapack.dpotrs(L, g, lower=1)
         t = 1.
         while True:
             th_new = th + t*step
-            f_new = log_joint(Zw, th_new, ww)
+            m_new = -Zw.dot(th_new)
+            f_new = _log_joint_from_margins(m_new, th_new, ww)
             if f_new >= f - 1e-15*abs(f) or t < 1e-8:
                 break
             t *= .5
         dm, am = np.abs(th_new-th).max(), np.abs(th_new).max()
         # a full step this small is in the quadratic regime: the point it lands on is within ~|z| dm^2 of the mode
         done = dm <= tol*(1.+am) or (t == 1. and dm <= 1e-7*(1.+am))
-        th, f = th_new, f_new
+        th, f, m = th_new, f_new, m_new
         if done:
             break
-    return th
+    return (th, m) if want_margins else th
 
 
 def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
@@ -100,7 +134,16 @@ def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
     keep = wts > 0
     Zw, ww = Z[keep, :], wts[keep]
     if method == 'newton':
-        mu = _newton_mode(Zw, ww, mu0)
+        mu, m = _newton_mode(Zw, ww, mu0, want_margins=True)
+        if not diag:
+            # factor and invert through the LAPACK routines directly: L = chol(-Hessian), LSig = L^-1 (both lower)
+            L, info = sl.lapack.dpotrf(_neg_hessian(Zw, ww, _margin_terms(m)[1]), lower=1, overwrite_a=1)
+            if info != 0:
+                raise np.linalg.LinAlgError('negative Hessian not positive definite (dpotrf info %d)' % info)
+            mask = _lower_mask(L.shape[0])         # dpotrf / dtrtri leave the other triangle untouched
+            LSigInv = L*mask
+            LSig, info = sl.lapack.dtrtri(LSigInv, lower=1)
+            return mu, LSig*mask, LSigInv
     else:
         res = None
         for _ in range(10):
