@@ -361,6 +361,25 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
   P.norms = raw ? nullptr : d_norms;
   P.raw = raw ? 1 : 0;
   P.want_colsum = d_out_dd ? 1 : 0;
+  // Few rows (the M coreset points of every optimiser step): one 16-row warp would walk all S samples alone.  Split the
+  // sample range over CTAs instead -- each writes raw potentials for its chunks -- and centre the rows in a second
+  // small kernel, the reference's own arithmetic (projector.py:26,55: bls -= bls.mean(axis=1)).
+  const int64_t tiles = (n + project_tile_rows(cfg) - 1) / project_tile_rows(cfg);
+  if (tiles * 4 <= c->sms && !d_out_dd && (raw || !d_norms)) {
+    int csplit = (int)(c->sms / tiles);
+    if (csplit > project_chunks(c->S)) csplit = project_chunks(c->S);
+    if (csplit > 1) {
+      P.raw = 1;
+      P.norms = nullptr;
+      BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, cfg, grid, smem, st, csplit));
+      BC_LAUNCHED(1);
+      if (!raw) {
+        BC_CUDA(launch_dense_center(d_V, n, c->S, ldv, st));
+        BC_LAUNCHED(1);
+      }
+      return BC_OK;
+    }
+  }
   BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_MATERIALISE, cfg, grid, smem, st));
   BC_LAUNCHED(1);
   if (d_out_dd) {

@@ -47,7 +47,8 @@ struct ProjArgs {
 int project_tile_config(int Dpad, int* BM, int* BN, int* ss, size_t* smem);
 int project_tile_config_for_rows(int base_cfg, long long n, int sms, int Dpad, size_t* smem_out);
 int project_tile_rows(int cfg);
-cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st, int csplit = 1);
+int project_chunks(int S);
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld, double* out_dd,
                                     double* out_best, int mode, cudaStream_t st);
 

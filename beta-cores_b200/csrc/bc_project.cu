@@ -70,6 +70,9 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
   const long long n = P.n;
   const long long ntiles = (n + BM - 1) / BM;
   const int nchunks = (S + BN - 1) / BN;
+  // sample-range split (raw materialise of few rows only): blockIdx.y owns the chunks [c_lo, c_hi) of every tile
+  const int c_lo = (MODE == MODE_MATERIALISE) ? (int)(((long long)nchunks * blockIdx.y) / gridDim.y) : 0;
+  const int c_hi = (MODE == MODE_MATERIALISE) ? (int)(((long long)nchunks * (blockIdx.y + 1)) / gridDim.y) : nchunks;
   const uint32_t a_row_bytes = (uint32_t)P.Dc * 8u;
   const uint32_t b_row_bytes = (uint32_t)Dpad * 8u;
   const bool want_cols = (MODE == MODE_COLSUM) || (MODE == MODE_MATERIALISE && P.want_colsum);
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
         const long long rid = P.rows ? P.rows[p] : p;
         bulk_g2s(As + (size_t)r * ss, P.A + rid * P.lda, a_row_bytes, full_a);
       }
-      for (int c = 0; c < nchunks; ++c, ++itb) {
+      for (int c = c_lo; c < c_hi; ++c, ++itb) {
         const uint32_t st = itb % NST, ph = (itb / NST) & 1;
         mbar_wait(empty_b + st, ph ^ 1);
         if (lane == 0) mbar_arrive_expect_tx(full_b + st, (uint32_t)BN * b_row_bytes);
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
     __syncwarp();
     uint32_t itb = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int c = 0; c < nchunks; ++c, ++itb) {
+      for (int c = c_lo; c < c_hi; ++c, ++itb) {
         const uint32_t slot = itb % kSlots, ph = (itb / kSlots) & 1;
         mbar_wait(ring_full + slot, ph);
         const double* rs = ring + (size_t)slot * CW * BN + lane;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
     const bool v0 = p0 < n, v1 = p1 < n;
     double s1_0 = 0, s1_1 = 0, s2_0 = 0, s2_1 = 0, sr_0 = 0, sr_1 = 0;
 
-    for (int c = 0; c < nchunks; ++c, ++itb) {
+    for (int c = c_lo; c < c_hi; ++c, ++itb) {
       const uint32_t st = itb % NST, ph = (itb / NST) & 1;
       double acc[NT][4];
 #pragma unroll
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(empty_b + st);
-        if (c == nchunks - 1) mbar_arrive(empty_a);
+        if (c == c_hi - 1) mbar_arrive(empty_a);
       }
 
       // ---- epilogue: potential, pivot shift, row / column partial sums ----
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(1024) k_project_finalize(const double* __restr
 
 // ------------------------------------------------------------------ launch --
 template <class F, int MODE, int BM, int NST>
-static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStream_t st, int csplit = 1) {
   auto kern = k_project<F, MODE, BM, NST>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
@@ -470,7 +473,7 @@ static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStre
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  kern<<<grid, (BM / 16 + 2) * 32, smem, st>>>(P);
+  kern<<<dim3(grid, MODE == MODE_MATERIALISE ? csplit : 1), (BM / 16 + 2) * 32, smem, st>>>(P);
   return cudaGetLastError();
 }
 
@@ -478,18 +481,18 @@ static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStre
 static const int kCfgs[3][2] = {{128, 2}, {64, 2}, {32, 2}};
 
 template <class F, int MODE>
-static cudaError_t launch_tile(const ProjArgs& P, int tile_cfg, int grid, size_t smem, cudaStream_t st) {
-  if (tile_cfg == 0) return launch_one<F, MODE, 128, 2>(P, grid, smem, st);
-  if (tile_cfg == 1) return launch_one<F, MODE, 64, 2>(P, grid, smem, st);
-  return launch_one<F, MODE, 32, 2>(P, grid, smem, st);
+static cudaError_t launch_tile(const ProjArgs& P, int tile_cfg, int grid, size_t smem, cudaStream_t st, int csplit) {
+  if (tile_cfg == 0) return launch_one<F, MODE, 128, 2>(P, grid, smem, st, csplit);
+  if (tile_cfg == 1) return launch_one<F, MODE, 64, 2>(P, grid, smem, st, csplit);
+  return launch_one<F, MODE, 32, 2>(P, grid, smem, st, csplit);
 }
 
 template <class F>
-static cudaError_t launch_mode(const ProjArgs& P, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_mode(const ProjArgs& P, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st, int csplit) {
   switch (mode) {
-    case MODE_COLSUM: return launch_tile<F, MODE_COLSUM>(P, tile_cfg, grid, smem, st);
-    case MODE_SCORE: return launch_tile<F, MODE_SCORE>(P, tile_cfg, grid, smem, st);
-    default: return launch_tile<F, MODE_MATERIALISE>(P, tile_cfg, grid, smem, st);
+    case MODE_COLSUM: return launch_tile<F, MODE_COLSUM>(P, tile_cfg, grid, smem, st, 1);
+    case MODE_SCORE: return launch_tile<F, MODE_SCORE>(P, tile_cfg, grid, smem, st, 1);
+    default: return launch_tile<F, MODE_MATERIALISE>(P, tile_cfg, grid, smem, st, csplit);
   }
 }
 
@@ -519,20 +522,22 @@ int project_tile_config_for_rows(int base_cfg, long long n, int sms, int Dpad, s
 }
 int project_tile_rows(int cfg) { return kCfgs[cfg][0]; }
 
+int project_chunks(int S) { return (S + kBN - 1) / kBN; }
+
 cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem,
-                           cudaStream_t st) {
+                           cudaStream_t st, int csplit) {
   if (model == MODEL_LOGISTIC) {
-    if (kind == KIND_LOGLIK) return launch_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, tile_cfg, grid, smem, st);
-    if (poly == 20) return launch_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, tile_cfg, grid, smem, st);
-    if (poly == kPowPolyMax) return launch_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, tile_cfg, grid, smem, st);
-    return launch_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, tile_cfg, grid, smem, st);
+    if (kind == KIND_LOGLIK) return launch_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    if (poly == 20) return launch_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    if (poly == kPowPolyMax) return launch_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    return launch_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, tile_cfg, grid, smem, st, csplit);
   } else if (model == MODEL_GAUSSIAN) {
-    if (kind == KIND_LOGLIK) return launch_mode<GaussianF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st);
-    if (kind == KIND_BETALIK) return launch_mode<GaussianF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st);
-    return launch_mode<GaussianF<KIND_BETAGRAD>>(P, mode, tile_cfg, grid, smem, st);
+    if (kind == KIND_LOGLIK) return launch_mode<GaussianF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    if (kind == KIND_BETALIK) return launch_mode<GaussianF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    return launch_mode<GaussianF<KIND_BETAGRAD>>(P, mode, tile_cfg, grid, smem, st, csplit);
   } else {
-    if (kind == KIND_LOGLIK) return launch_mode<NeurlinF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st);
-    return launch_mode<NeurlinF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st);
+    if (kind == KIND_LOGLIK) return launch_mode<NeurlinF<KIND_LOGLIK>>(P, mode, tile_cfg, grid, smem, st, csplit);
+    return launch_mode<NeurlinF<KIND_BETALIK>>(P, mode, tile_cfg, grid, smem, st, csplit);
   }
 }
 
