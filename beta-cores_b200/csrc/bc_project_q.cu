@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     __syncwarp();
   } else if (warp == kQEpiWarps + 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // All 32 lanes run the loop so that control flow and operands (descriptors, TMEM addresses) stay warp-uniform -- ptxas
+    // then feeds tcgen05.mma from uniform registers directly; inside an `if (lane == 0)` region it wraps every MMA in an
+    // ELECT / R2UR.BROADCAST loop (89 cycles per MMA measured, more than the MMA takes to execute).  One elected lane issues.
+    {
       uint32_t idesc[kQSlices];
 #pragma unroll
       for (int i = 0; i < kQSlices; ++i) idesc[i] = umma_idesc_i8(kQChunk * (kQSlices - i));
@@ -351,17 +354,20 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           tc_fence_after();
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(Bs + (size_t)st * kQChunkBytes));
           const uint32_t d0 = tmem_base + (uint32_t)(buf * kQDiagCols);
-          // K blocks beyond the feature count hold only zero digits: not multiplied (D = 20 issues 7 MMAs per chunk
-          // instead of 28).  Fully unrolled per block count: the issue rate of this one thread is on the critical path.
-          switch (P.ksteps) {
-            case 1: issue_chunk_mmas<1>(d0, adesc0, bdesc0, idesc); break;
-            case 2: issue_chunk_mmas<2>(d0, adesc0, bdesc0, idesc); break;
-            case 3: issue_chunk_mmas<3>(d0, adesc0, bdesc0, idesc); break;
-            default: issue_chunk_mmas<4>(d0, adesc0, bdesc0, idesc); break;
+          if (elect_one()) {
+            // K blocks beyond the feature count hold only zero digits: not multiplied (D = 20 issues 7 MMAs per chunk
+            // instead of 28).  Fully unrolled per block count: the issue rate of this one thread is on the critical path.
+            switch (P.ksteps) {
+              case 1: issue_chunk_mmas<1>(d0, adesc0, bdesc0, idesc); break;
+              case 2: issue_chunk_mmas<2>(d0, adesc0, bdesc0, idesc); break;
+              case 3: issue_chunk_mmas<3>(d0, adesc0, bdesc0, idesc); break;
+              default: issue_chunk_mmas<4>(d0, adesc0, bdesc0, idesc); break;
+            }
+            umma_commit(empty_b + st);
+            umma_commit(tmem_full + buf);
+            if (c == nchunks - 1) umma_commit(empty_a);
           }
-          umma_commit(empty_b + st);
-          umma_commit(tmem_full + buf);
-          if (c == nchunks - 1) umma_commit(empty_a);
+          __syncwarp();
         }
       }
     }
@@ -465,6 +471,13 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
               cnext[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
                                          (int)dg[6][e]);
             }
+            if (b + 2 == NB) {
+              // the last digits of the chunk are in registers: hand the accumulator buffer back to the MMA issuer now,
+              // with two batches of evaluation still to go -- the next chunk's MMAs then finish before this group needs them
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tmem_empty + buf);
+            }
           }
           if (MODE == QMODE_DOT) {
 #pragma unroll
@@ -511,11 +524,6 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           if (b + 2 < NB) {
 #pragma unroll
             for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + (b + 2) * 4), dg[d]);
-          } else if (b + 2 == NB) {
-            // the last digits of the chunk are converted: hand the accumulator buffer back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + buf);
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) ccur[e] = cnext[e];

@@ -62,14 +62,31 @@ __global__ void k_prepare_rows(int model, const double* __restrict__ theta, int 
 __global__ void k_prepare_mean(const double* __restrict__ B, int S, int ldb, const double* __restrict__ colaux,
                                double* __restrict__ bbar) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  // sequential sum over the samples (the order is part of the result); the loads of 8 samples are issued together so that
+  // the chain is bound by the adds, not by 8 x the L2 latency
   if (k < ldb) {
     double acc = 0.0;
-    for (int s = 0; s < S; ++s) acc += B[(size_t)s * ldb + k];
+    for (int s = 0; s < S; s += 8) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (s + j < S) ? B[(size_t)(s + j) * ldb + k] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (s + j < S) acc += v[j];
+    }
     bbar[k] = acc / (double)S;
   } else if (k == ldb) {
     double acc = 0.0;
-    if (colaux)
-      for (int s = 0; s < S; ++s) acc += colaux[s];
+    if (colaux) {
+      for (int s = 0; s < S; s += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (s + j < S) ? colaux[s + j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (s + j < S) acc += v[j];
+      }
+    }
     bbar[ldb] = acc / (double)S;
   }
 }

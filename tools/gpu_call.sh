@@ -1,9 +1,5 @@
 cd /root/repo
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_n8_final.json 2> gpurun_out/bench_n8_final.err
-echo rc=$?
-tail -c 400 gpurun_out/bench_n8_final.err
-python - <<'PY'
-import json
-d=json.loads(open('/root/repo/gpurun_out/bench_n8_final.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','n_gpus','scaling')}, d['e2e']['value'], d['host'], d['roofline']['launch_ms'], d['roofline']['share_of_step'])
-PY
+for v in base elect base elect; do
+BC_LIB_PATH=/root/repo/beta-cores_b200/lib/lib_$v.so timeout 300 python tools/q_time.py 2>&1 | tail -1
+done
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
