@@ -85,10 +85,13 @@ class FusedProjection(object):
 
     def _q_operands(self, rows, sub):
         """(image, rowscale, rowaux) when the tensor-core route applies to this pass, else None"""
-        if ROUTE != 'q' or sub is not None or self.D > nv.lib().bc_q_max_features() or rows.n_local == 0:
+        if ROUTE != 'q' or sub is not None or self.D > nv.lib().bc_q_max_features():
             return None
         aux_col = self.D if self.pot.model == 'neurlin' else None
+        # in a sharded job the first call exchanges the feature exponents: every rank comes through here, rows or not
         img, rs, aux, fexp = rows.quantised(self.ctx, self.D, aux_col)
+        if rows.n_local == 0:
+            return None
         if self.eng.fexp_applied.get(self.ctx_name) is not fexp:     # the ctx's sample image must match this row image
             nv.call('bc_set_feature_exponents', self.ctx, ptr(fexp), self.D, stream_ptr())
             self.eng.fexp_applied[self.ctx_name] = fexp
