@@ -95,6 +95,7 @@ class DeviceRows(object):
         self.n_local, self.ncols = host_rows.shape
         self.row0 = int(row0)
         self.n_total = int(n_total) if n_total is not None else self.n_local
+        self.is_shard = n_total is not None      # built as one rank's slice of a larger set (even if this rank got all of it)
         self.ld = padded_ld(self.ncols)
         if self.ld == self.ncols:
             self.t = engine.upload(host_rows)
@@ -119,6 +120,7 @@ class DeviceRows(object):
         self.n_local, self.ncols = int(t.shape[0]), int(t.shape[1])
         self.row0 = int(row0)
         self.n_total = int(n_total) if n_total is not None else self.n_local
+        self.is_shard = n_total is not None
         self.ld = self.ncols
         self.t = t
         self.rowaux = None
@@ -154,7 +156,10 @@ class DeviceRows(object):
 
     @property
     def sharded(self):
-        return self.n_total != self.n_local
+        """rows split over the ranks of the current process group.  A job-level property: every rank must answer alike (it
+        guards collectives), so it cannot be read off the local row count -- a rank may own all of a tiny set, or none"""
+        from ._shard import Comm
+        return self.is_shard and Comm.current().world > 1
 
     @property
     def shape(self):
