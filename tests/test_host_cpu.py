@@ -144,6 +144,19 @@ def _gloo_worker(rank, world, port, q):
         if rank == 1:
             t += 7.
         comm.broadcast(t, 1)
+        # "sharded" guards collectives, so every rank must answer alike -- also when one rank owns all rows of a tiny set
+        # and the other none (no device needed for the property itself)
+        from bayesiancoresets._device import DeviceRows
+        flags = []
+        for n_tot in (1, 3, 1001):
+            r0t, nlt = partition_rows(n_tot, world, rank)
+            rows = DeviceRows.__new__(DeviceRows)
+            rows.n_local, rows.n_total, rows.row0, rows.is_shard = nlt, n_tot, r0t, True
+            flags.append(bool(rows.sharded))
+        whole = DeviceRows.__new__(DeviceRows)
+        whole.n_local, whole.n_total, whole.row0, whole.is_shard = 5, 5, 0, False
+        flags.append(bool(whole.sharded))
+        assert flags == [True, True, True, False], flags
         q.put((rank, colsum, best, int(cnt), t.numpy()))
     finally:
         dist.destroy_process_group()
