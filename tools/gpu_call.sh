@@ -1,3 +1,5 @@
 cd /root/repo
-timeout 90 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 tools/shard_edge.py 2>&1 | grep "^N \|Error\|error" | head
-echo rc=$?
+for v in base mid base mid; do
+BC_LIB_PATH=/root/repo/beta-cores_b200/lib/lib_$v.so timeout 120 python tools/q_time.py 2>&1 | tail -1
+done
+BC_LIB_PATH=/root/repo/beta-cores_b200/lib/lib_mid.so timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "fused or tensor_core or score_nan" 2>&1 | tail -3
