@@ -10,6 +10,9 @@
 //   z_n = 2^(e_n) sum_i a_i 256^-(i+1),  theta_s = 2^(e_s) sum_j b_j 256^-(j+1),   a_i, b_j int8 digits (7 each, 55 bits)
 //   z_n . theta_s = 2^(e_n + e_s) sum_d 256^-(d+2) D_d,     D_d = sum_{i+j=d} a_i . b_j   (int32, exact)
 // keeping the diagonals d <= 6 (28 of the 49 digit pairs; the dropped ones are below 6*128*2^-58 of |z|max |theta|max).
+// Every row carries its own exponent e_n, the samples share one, and both operands are first rescaled per FEATURE by a power
+// of two (z_k 2^-c_k, theta_k 2^+c_k, c_k = ilogb max_n |z_nk|: exact, products unchanged) so that columns of very different
+// magnitude keep their bits -- see k_feature_absmax below.
 // tcgen05.mma.kind::i8 computes D_0..D_6 for a 128-row x 32-sample chunk into 7 x 32 TMEM columns: the MMA for row digit
 // i multiplies against the sample digits 0..6-i STACKED along N (N = 32 (7 - i)), i.e. 7 x 4 instructions per chunk.
 //
@@ -17,14 +20,14 @@
 //   warps 0-15 : four epilogue groups of four warps (a warp may only read its own TMEM lane quarter).  Groups 0,1 take
 //                the even chunks (accumulator buffer 0), groups 2,3 the odd chunks (buffer 1); within a pair each group
 //                owns 16 of the chunk's 32 sample columns.  Thread = data row (TMEM lane): tcgen05.ld the 7 diagonals,
-//                recombine in int64 (integer pipe), convert exactly, apply the model's potential four columns at a time
+//                recombine in int64 (integer pipe), convert exactly (conversion unit), apply the model's potential four columns at a time
 //                (FP64 pipe, four independent dependency chains), pivot shift, per-row statistics in registers, column
 //                partials by a transposed warp butterfly -> shared-memory ring.  Four warps per SM sub-partition is what
 //                keeps the FP64 pipe fed (8-cycle DFMA latency, measured tools/fp64_ipc.cu).
 //   warp 16    : producer -- cp.async.bulk (TMA engine) of the row tile (112 KB, once per tile) and of the sample
 //                chunks (28 KB, 3-stage ring).  Both images are stored in HBM already in the swizzled layout the tensor
 //                core reads, so a copy is one contiguous burst.
-//   warp 17    : MMA issuer (one lane) + TMEM allocation.
+//   warp 17    : MMA issuer (warp-uniform loop, one elected lane issues) + TMEM allocation.
 //   warp 18    : reducer -- adds the four 32-row column partials of a chunk in fixed order and accumulates them per
 //                column in double-double (order-insensitive S-vector).
 #include "bc_common.cuh"
