@@ -16,9 +16,12 @@ from .. import _native as nv
 def evaluate_potential(pot, pts, samples, beta=None, centred=True):
     """(n, S) host array of `pot` on host inputs, through the device materialise pass."""
     pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
-    samples = np.atleast_2d(np.asarray(samples, dtype=np.float64))
+    if not hasattr(samples, 'is_cuda'):               # a device-side sampler hands its samples over as a CUDA tensor
+        samples = np.atleast_2d(np.asarray(samples, dtype=np.float64))
     eng = Engine.get()
-    fp = FusedProjection(eng, pot, pts.shape[1])
+    # its own workspace: a coreset object may be in the middle of a fused pass on the main one (learn_beta evaluates the
+    # beta-gradient of the coreset points between begin() and the data pass)
+    fp = FusedProjection(eng, pot, pts.shape[1], ctx_name='eval')
     fp.configure(beta)
     fp.set_samples(samples)
     rows = DeviceRows(eng, pts)

@@ -163,6 +163,42 @@ class GreedyVI(object):
             self.optimise()
 
 
+class GreedyVILearnBeta(GreedyVI):
+    """BetaCoreset with learn_beta=True.  PARITY UNPINNED: the reference's own branch (coreset/bcores.py:127-140) calls
+    `self._get_projection_ii`, which no file of the reference defines, so it raises AttributeError on the first
+    optimisation and there is no reference output to pin against.  This class restates what that branch spells out
+    around the missing call:
+        grd(x):  w, beta = x[:-1], x[-1]                                               bcores.py:129-130
+                 vecs, sum_scaling, sub_idcs, corevecs, betagrads = projection at (w, pts, beta)       :131
+                     with betagrads = the centred beta-gradient of the coreset points, what
+                     BetaBlackBoxProjector.project_f(pts, beta, grad=True) returns second     projector.py:56-61
+                 resid = sum_scaling vecs.sum(0) - w.corevecs                                           :132
+                 wgrad = -corevecs.resid / S;  betagrad = -1e-5 w.(betagrads.resid) / S              :133-134
+        x0 = [wts, beta];  xf = partial_nn_opt(x0, grd, all coordinates clamped at 0);  wts, beta = xf[:-1], xf[-1]   :137-140
+    potential_beta(pts, samples, beta) and beta_gradient(pts, samples, beta) return un-centred (n, S) matrices."""
+
+    def __init__(self, data, sampler, S, potential_beta, beta_gradient, beta, **kw):
+        self.beta = beta
+        self.potential_beta = potential_beta
+        self.beta_gradient = beta_gradient
+        GreedyVI.__init__(self, data, sampler, S, lambda p, th: self.potential_beta(p, th, self.beta), **kw)
+
+    def optimise(self):
+        saved = self.beta
+
+        def grad(x):
+            w, self.beta = x[:-1], x[-1]           # the projection below evaluates the potential at the iterate's beta
+            vecs, scale, _, core = self._tangent(self.n_sub_opt, w, self.pts)
+            bg = centred(self.beta_gradient(self.pts, self.samples, self.beta)) if self.pts.size > 0 else np.zeros((0, vecs.shape[1]))
+            resid = scale*vecs.sum(axis=0) - w.dot(core)
+            wgrad = -core.dot(resid)/core.shape[1]
+            bgrad = -1e-5*w.dot(bg.dot(resid))/core.shape[1]
+            return np.hstack((wgrad, bgrad))
+        x0 = np.hstack((self.wts, np.asarray([saved])))
+        xf = adam_partial_nonneg(x0, grad, np.arange(x0.shape[0]), self.opt_itrs, self.sched)
+        self.wts, self.beta = xf[:-1], xf[-1]          # a numpy float64, as in the reference (:140)
+
+
 def adam_partial_nonneg(x0, grad, nn_idcs, itrs, sched, b1=0.9, b2=0.999, eps=1e-8):
     """util/opt.py:56-77 partial_nn_opt: ADAM, projection onto x >= 0 on the coordinates nn_idcs only."""
     x = x0.copy()

@@ -556,3 +556,38 @@ def test_precomputed_features_take_the_fused_path(bc, models):
         o.build(1, m)
     np.testing.assert_array_equal(a.idcs, o.idcs)
     np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
+
+
+# ------------------------------------------------------- learn_beta (parity unpinned: see the oracle class) --
+@pytest.mark.parametrize('blackbox', [False, True])
+def test_learn_beta_matches_the_restated_branch(bc, models, blackbox):
+    """BetaCoreset(learn_beta=True): the reference's branch (bcores.py:127-140) crashes on a method it never defines, so
+    there is no reference output; the product and oracle/np_coresets.py::GreedyVILearnBeta both follow the lines around the
+    missing call.  Gaussian model (the only one with a beta-gradient in the reference, gaussian.py:46-62); device
+    potentials and opaque lambdas."""
+    _, ga, _ = models
+    prob = problems.make_gaussian(400, 5, 7)()
+    X, sampler, P = prob['data'], prob['sampler'], prob['params']
+    S, itrs, beta0 = 40, 12, 0.02
+    sched = lambda i: 0.002/(1.+i)      # beta shares the weights' step size (bcores.py:138): with steps of 1 it leaves (0, 1) at once
+    if blackbox:
+        bl = lambda x, th, b: om.gauss_betalik(x, th, b, P['Siginv'], P['logdetSig'])
+        ll = lambda x, th: om.gauss_loglik(x, th, P['Siginv'], P['logdetSig'])
+        bg = lambda x, th, b: om.gauss_betagrad(x, th, b, P['Siginv'], P['logdetSig'])
+    else:
+        bl, ll, bg = ga.gaussian_beta_likelihood.bind(**P), ga.gaussian_loglikelihood.bind(**P), ga.gaussian_beta_gradient.bind(**P)
+    np.random.seed(9)
+    prj = bc.BetaBlackBoxProjector(sampler, S, bl, ll, bg)
+    a = bc.BetaCoreset(X, prj, opt_itrs=itrs, step_sched=sched, beta=beta0, learn_beta=True)
+    for m in range(1, 6):
+        a.build(1, m)
+    np.random.seed(9)
+    o = oc.GreedyVILearnBeta(X, sampler, S, lambda p, th, b: om.gauss_betalik(p, th, b, P['Siginv'], P['logdetSig']),
+                             lambda p, th, b: om.gauss_betagrad(p, th, b, P['Siginv'], P['logdetSig']), beta0, opt_itrs=itrs, sched=sched)
+    for m in range(1, 6):
+        o.build(1, m)
+    np.testing.assert_array_equal(a.idcs, o.idcs)
+    np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(a.beta, o.beta, rtol=1e-9)
+    assert a.beta != beta0                                   # beta did move
+    assert len(a.get()) == 4 and a.get()[3] == a.beta        # bcores.py:155-156
