@@ -36,8 +36,9 @@ def gaussian_KL(mu0, Sig0, mu1, Sig1inv):
     return 0.5*(t1+t2+t3-mu0.shape[0])
 
 
-def make_conjugate_sampler(mu0, Sig0inv, Siginv):
-    """sampler(S, wts, pts) as in examples/zellner_gaussian/main.py:87-92."""
+def make_conjugate_sampler(mu0, Sig0inv, Siginv, device=False):
+    """sampler(S, wts, pts) as in examples/zellner_gaussian/main.py:87-92.  device=True: the S x d x d product of the last
+    line runs on the GPU and the samples stay there (bayesiancoresets/util/samplers.py); same numpy stream, same (mu, L)."""
     d = mu0.shape[0]
 
     def sampler(S, wts, pts):
@@ -45,5 +46,8 @@ def make_conjugate_sampler(mu0, Sig0inv, Siginv):
             wts = np.zeros(1)
             pts = np.zeros((1, d))
         mu, L, _ = weighted_post(mu0, Sig0inv, Siginv, pts, wts)
+        if device:
+            from bayesiancoresets.util.samplers import affine_samples
+            return affine_samples(mu, L, np.random.randn(S, d))
         return mu + np.random.randn(S, d).dot(L.T)
     return sampler

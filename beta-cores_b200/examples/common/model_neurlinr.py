@@ -24,7 +24,9 @@ def weighted_post(th0, Sig0inv, sigsq, z, w):
     return mup, LSigp, LSigpInv
 
 
-def make_conjugate_sampler(mu0, Sig0inv, sigsq):
+def make_conjugate_sampler(mu0, Sig0inv, sigsq, device=False):
+    """sampler(S, wts, pts) with the conjugate posterior of the linear head (model_neurlinr.py:115-122).  device=True: the
+    S x D x D product of the last line runs on the GPU and the samples stay there (bayesiancoresets/util/samplers.py)."""
     D = mu0.shape[0]
 
     def sampler(S, wts, pts):
@@ -32,6 +34,9 @@ def make_conjugate_sampler(mu0, Sig0inv, sigsq):
             wts = np.zeros(1)
             pts = np.zeros((1, D+1))
         mu, L, _ = weighted_post(mu0, Sig0inv, sigsq, pts, wts)
+        if device:
+            from bayesiancoresets.util.samplers import affine_samples
+            return affine_samples(mu, L, np.random.randn(S, D))
         return mu + np.random.randn(S, D).dot(L.T)
     return sampler
 

@@ -62,3 +62,36 @@ def test_build_with_device_sampler_selects_like_host():
     for o in out[1:]:
         np.testing.assert_array_equal(out[0][0], o[0])
         np.testing.assert_allclose(o[1], out[0][1], rtol=1e-6)
+
+
+@pytest.mark.parametrize('model', ['gaussian', 'neurlin'])
+def test_conjugate_samplers_device_form(model):
+    """make_conjugate_sampler(device=True): the last line of the reference's samplers, mu + randn(S, D).dot(L.T), formed on
+    the GPU from the same numpy stream"""
+    import gaussian, model_neurlinr
+    r = np.random.RandomState(2)
+    D, M, S = 9, 30, 77
+    A = r.randn(D, D)
+    Sig0inv = np.eye(D) + 0.1*A.dot(A.T)
+    mu0 = r.randn(D)
+    w = r.rand(M)*3
+    if model == 'gaussian':
+        B = r.randn(D, D)
+        Siginv = np.linalg.inv(np.eye(D)*4 + B.dot(B.T))
+        pts = r.randn(M, D)
+        make = lambda dev: gaussian.make_conjugate_sampler(mu0, Sig0inv, Siginv, device=dev)
+    else:
+        pts = np.hstack((np.maximum(r.randn(M, D), 0), r.randn(M, 1)))
+        make = lambda dev: model_neurlinr.make_conjugate_sampler(mu0, Sig0inv, 0.6, device=dev)
+    np.random.seed(21)
+    host = [make(False)(S, w, pts), make(False)(S, np.zeros(0), np.zeros((0, pts.shape[1])))]
+    np.random.seed(21)
+    dev = [make(True)(S, w, pts).cpu().numpy(), make(True)(S, np.zeros(0), np.zeros((0, pts.shape[1]))).cpu().numpy()]
+    for a, b in zip(host, dev):
+        np.testing.assert_allclose(b, a, rtol=0, atol=1e-12*max(1., np.abs(a).max()))
+
+
+def test_affine_samples_rejects_a_full_matrix():
+    from bayesiancoresets.util.samplers import affine_samples
+    with pytest.raises(ValueError):
+        affine_samples(np.zeros(3), np.ones((3, 3)), np.zeros((4, 3)))

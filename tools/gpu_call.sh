@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "learn_beta" 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q 2>&1 | tail -8
