@@ -49,6 +49,7 @@ class Engine(object):
         self.index = index
         self.device = torch.device('cuda', index)
         self._ctx = {}
+        self._stage = []           # pinned staging buffers of _staged_upload
         self.fexp_applied = {}     # ctx name -> feature-exponent tensor last handed to bc_set_feature_exponents
         self.sms = None
 
@@ -71,7 +72,49 @@ class Engine(object):
 
     def upload(self, arr, dtype=torch.float64):
         a = np.ascontiguousarray(arr)
-        return torch.from_numpy(a).to(self.device, dtype=dtype, non_blocking=False)
+        src = torch.from_numpy(a)
+        if (a.nbytes >= self.STAGED_UPLOAD_MIN_BYTES and a.ndim == 2 and src.dtype == dtype and not src.is_pinned()):
+            return self._staged_upload(src)
+        return src.to(self.device, dtype=dtype, non_blocking=False)
+
+    # A large PAGEABLE host matrix (what a numpy user hands to the coreset classes) goes up at ~11 GB/s through the
+    # driver's own bounce buffers -- 0.9 s for the 10 GB of the north-star rows -- against 55 GB/s from pinned memory.
+    # Row blocks are copied into pinned staging buffers by a few host threads (the copies release the GIL) and sent from
+    # there asynchronously on a side stream, so the host copies and the DMA overlap.
+    STAGED_UPLOAD_MIN_BYTES = 256 << 20
+    STAGED_UPLOAD_BLOCK_BYTES = 64 << 20
+    STAGED_UPLOAD_THREADS = 4
+
+    def _staged_upload(self, src):
+        from concurrent.futures import ThreadPoolExecutor
+        n, row_bytes = src.shape[0], src.shape[1]*src.element_size()
+        rows_per = max(1, self.STAGED_UPLOAD_BLOCK_BYTES // row_bytes)
+        dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+        nbuf = self.STAGED_UPLOAD_THREADS
+        if len(self._stage) < nbuf:                   # pinned staging buffers are kept: page-locking costs more than the copy
+            self._stage += [torch.empty(self.STAGED_UPLOAD_BLOCK_BYTES, dtype=torch.uint8).pin_memory()
+                            for _ in range(nbuf - len(self._stage))]
+        stage = [self._stage[k][:rows_per*row_bytes].view(src.dtype).view(rows_per, src.shape[1]) for k in range(nbuf)]
+        side = torch.cuda.Stream(device=self.device)
+        blocks = [(s, min(s + rows_per, n)) for s in range(0, n, rows_per)]
+
+        def send(k):
+            # worker k owns staging buffer k: blocks k, k + nbuf, ...; an event guards the buffer's reuse
+            ev = None
+            for s, e in blocks[k::nbuf]:
+                if ev is not None:
+                    ev.synchronize()
+                stage[k][:e-s].copy_(src[s:e])
+                with torch.cuda.stream(side):
+                    dst[s:e].copy_(stage[k][:e-s], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+        with torch.cuda.device(self.device):
+            with ThreadPoolExecutor(max_workers=nbuf) as ex:
+                list(ex.map(send, range(nbuf)))
+            side.synchronize()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return dst
 
 
 def padded_ld(ncols):

@@ -591,3 +591,24 @@ def test_learn_beta_matches_the_restated_branch(bc, models, blackbox):
     np.testing.assert_allclose(a.beta, o.beta, rtol=1e-9)
     assert a.beta != beta0                                   # beta did move
     assert len(a.get()) == 4 and a.get()[3] == a.beta        # bcores.py:155-156
+
+
+def test_staged_upload_of_pageable_rows_is_exact(bc):
+    """large pageable host matrices go up through pinned staging buffers filled by several threads (Engine._staged_upload):
+    every block, the ragged last one included, must arrive bit for bit"""
+    import torch
+    from bayesiancoresets._device import Engine
+    eng = Engine.get()
+    old = (Engine.STAGED_UPLOAD_MIN_BYTES, Engine.STAGED_UPLOAD_BLOCK_BYTES)
+    stage_old = eng._stage
+    try:
+        Engine.STAGED_UPLOAD_MIN_BYTES, Engine.STAGED_UPLOAD_BLOCK_BYTES = 1 << 16, 1 << 18
+        eng._stage = []
+        for n, d in [(20011, 12), (4099, 128), (70001, 4)]:
+            Z = np.random.RandomState(n).randn(n, d)
+            got = eng.upload(Z)
+            assert torch.equal(got.cpu(), torch.from_numpy(Z))
+        rows = bc.DeviceRows(eng, np.random.RandomState(1).randn(30000, 20)) if hasattr(bc, 'DeviceRows') else None
+    finally:
+        Engine.STAGED_UPLOAD_MIN_BYTES, Engine.STAGED_UPLOAD_BLOCK_BYTES = old
+        eng._stage = stage_old
