@@ -345,13 +345,17 @@ def b200_arm(a):
     if route == 'q':
         kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
                  'column sums, fused)')
-        digit_pairs, fp64_inst = 28, 69          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
+        digit_pairs, fp64_inst = 28, 65          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
         int8_ops = digit_pairs*2.*n_local*S*128
+        # measured on this pool (tools/mma_i8_rate.cu, profiles/r01_mma_i8_rate.txt): 8192 int8 MACs per cycle per SM from N = 128 up
+        int8_peak = eng.sms*8192*2.*1965e6/1e12
         extra = {
             'route': 'q',
-            'int8_tensor': {'ops_per_launch': int8_ops, 'achieved_tops': int8_ops/(col_mean*1e-3)/1e12, 'peak_tops': 2*bf16_peak,
-                            'frac': int8_ops/(col_mean*1e-3)/1e12/(2*bf16_peak),
-                            'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate; no int8 figure measured)'},
+            'int8_tensor': {'ops_per_launch': int8_ops, 'achieved_tops': int8_ops/(col_mean*1e-3)/1e12, 'peak_tops': int8_peak,
+                            'frac': int8_ops/(col_mean*1e-3)/1e12/int8_peak,
+                            'peak_source': 'tcgen05.mma.kind::i8 rate measured on this pool: 8192 MACs/cycle/SM x SMs x 1965 MHz '
+                                           '(profiles/r01_mma_i8_rate.txt; MEASURED_PEAKS.json has no int8 figure, 2 x its bf16_tflops '
+                                           '= %.0f would be the estimate)' % (2*bf16_peak)},
             'fp64_pipe': {'instructions_per_eval': fp64_inst,
                           'frac_of_issue_peak': n_local*S*fp64_inst/32./(eng.sms*4*0.5*sm_clock_hz*col_mean*1e-3),
                           'note': 'the potential (two exp, one reciprocal, one degree-20 polynomial per evaluation) runs on the FP64 pipe '
