@@ -212,18 +212,40 @@ __global__ void __launch_bounds__(256) k_dense_score(const double* __restrict__ 
     part[blockIdx.x * 4 + 3] = __longlong_as_double(nbest.i);
   }
 }
-__global__ void k_dense_score_fin(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+// merge of the per-CTA candidates: the order (NaN first, larger value, lower index) is total, so any merge tree gives the
+// sequential result; one block, each thread takes a strided share (a single thread walking several hundred partials cost
+// 0.1 ms per scoring pass)
+__global__ void __launch_bounds__(256) k_dense_score_fin(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+  __shared__ double sv[2][8];
+  __shared__ long long si[2][8];
   Best b = {0.0, -1}, nb = {0.0, -1};
-  for (int p = 0; p < nparts; ++p) {  // fixed order; nparts is a few hundred
+  for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
     Best o = {part[p * 4 + 0], __double_as_longlong(part[p * 4 + 1])};
     Best on = {part[p * 4 + 2], __double_as_longlong(part[p * 4 + 3])};
     b = best_merge(b, o);
     nb = best_merge(nb, on);
   }
-  out[0] = b.v;
-  out[1] = __longlong_as_double(b.i);
-  out[2] = nb.v;
-  out[3] = __longlong_as_double(nb.i);
+  b = best_warp(b);
+  nb = best_warp(nb);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sv[0][w] = b.v;
+    si[0][w] = b.i;
+    sv[1][w] = nb.v;
+    si[1][w] = nb.i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      Best o = {sv[0][k], si[0][k]}, on = {sv[1][k], si[1][k]};
+      b = best_merge(b, o);
+      nb = best_merge(nb, on);
+    }
+    out[0] = b.v;
+    out[1] = __longlong_as_double(b.i);
+    out[2] = nb.v;
+    out[3] = __longlong_as_double(nb.i);
+  }
 }
 
 cudaError_t launch_dense_score(const double* V, long long n, int S, long long ldv, const double* norms, const double* u, int mode,
@@ -258,7 +280,7 @@ cudaError_t launch_dense_score(const double* V, long long n, int S, long long ld
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_dense_score_fin<<<1, 1, 0, st>>>(part, nparts, out);
+  k_dense_score_fin<<<1, 256, 0, st>>>(part, nparts, out);
   return cudaGetLastError();
 }
 
