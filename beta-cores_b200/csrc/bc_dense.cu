@@ -127,14 +127,27 @@ __global__ void k_dense_colsum_part(const double* __restrict__ V, long long n, i
     part[(size_t)blockIdx.x * S + s] = (a0 + a1) + (a2 + a3);
   }
 }
-__global__ void k_dense_colsum_fin(const double* __restrict__ part, int nparts, int S, int Sld, double* __restrict__ out_dd) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: the lanes add strided shares of the per-block partials in double-double, then merge -- the sum is
+// order-insensitive at double-double precision (a single thread per column adding ~1200 partials in sequence cost 0.1-0.2 ms)
+__global__ void __launch_bounds__(256) k_dense_colsum_fin(const double* __restrict__ part, int nparts, int S, int Sld,
+                                                          double* __restrict__ out_dd) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s > S) return;
   dd a = {0.0, 0.0};
   if (s < S)
-    for (int p = 0; p < nparts; ++p) a = dd_add_d(a, part[(size_t)p * S + s]);
-  out_dd[s] = a.hi;  // element S (sum of row means) is 0: V is already centred
-  out_dd[Sld + s] = a.lo;
+    for (int p = lane; p < nparts; p += 32) a = dd_add_d(a, part[(size_t)p * S + s]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dd b;
+    b.hi = __shfl_xor_sync(0xffffffffu, a.hi, o);
+    b.lo = __shfl_xor_sync(0xffffffffu, a.lo, o);
+    a = dd_add(a, b);
+  }
+  if (lane == 0) {
+    out_dd[s] = a.hi;  // element S (sum of row means) is 0: V is already centred
+    out_dd[Sld + s] = a.lo;
+  }
 }
 
 cudaError_t launch_dense_colsum(const double* V, long long n, int S, long long ldv, double* part, int nparts, double* out_dd,
@@ -143,7 +156,7 @@ cudaError_t launch_dense_colsum(const double* V, long long n, int S, long long l
   k_dense_colsum_part<<<nparts, 256, 0, st>>>(V, n, S, ldv, part);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_dense_colsum_fin<<<(S + 1 + 127) / 128, 128, 0, st>>>(part, nparts, S, Sld, out_dd);
+  k_dense_colsum_fin<<<(S + 1 + 7) / 8, 256, 0, st>>>(part, nparts, S, Sld, out_dd);
   return cudaGetLastError();
 }
 
