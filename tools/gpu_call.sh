@@ -1,4 +1,9 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "blackbox or groups or hilbert or encoder or learn_beta or fused" 2>&1 | tail -3
-python tools/dense_probe.py 1000000 2>&1 | grep colsum
-python tools/dense_probe.py 500000 2>&1 | grep colsum
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_last.json 2> gpurun_out/bench_last.err; echo b200 rc=$?
+python - <<'PY'
+import json
+d=json.loads(open('/root/repo/gpurun_out/bench_last.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d['parity'], {k:v['achieved_gbs'] for k,v in d['stage2']['kernels'].items()})
+PY
