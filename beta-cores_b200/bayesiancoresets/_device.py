@@ -51,6 +51,7 @@ class Engine(object):
         self._ctx = {}
         self._stage = []           # pinned staging buffers of _staged_upload
         self.fexp_applied = {}     # ctx name -> feature-exponent tensor last handed to bc_set_feature_exponents
+        self.ctx_state = {}        # ctx name -> which potential / whose samples are applied to that workspace (_fused.py)
         self.sms = None
 
     def ctx(self, name='main'):
@@ -96,6 +97,9 @@ class Engine(object):
                             for _ in range(nbuf - len(self._stage))]
         stage = [self._stage[k][:rows_per*row_bytes].view(src.dtype).view(rows_per, src.shape[1]) for k in range(nbuf)]
         side = torch.cuda.Stream(device=self.device)
+        # `dst` may be a recycled block whose previous owner still has kernels queued on the current stream
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        dst.record_stream(side)
         blocks = [(s, min(s + rows_per, n)) for s in range(0, n, rows_per)]
 
         def send(k):

@@ -22,6 +22,18 @@ PASS_TIMERS = None
 # 'dmma' = FP64 mma.sync (csrc/bc_project.cu, any shape; always used for gathered sub-samples and materialisation).
 ROUTE = os.environ.get('BC_CONTRACTION', 'q')
 
+# Precision tier of the tensor-core route: leading int8 digits of the 7-digit operand images a pass contracts
+# (bc_set_contraction_digits: 7 = 28 digit pairs, the accuracy of an fp64 dgemm; 6 = 21 pairs, operands as if rounded
+# to 46 bits; 5 = 15 pairs, 38 bits).  tests/test_gpu_parity.py::test_precision_tiers pins what each tier keeps exact.
+DIGITS = int(os.environ.get('BC_Q_DIGITS', '7'))
+
+
+def set_contraction_digits(n):
+    global DIGITS
+    if n not in (5, 6, 7):
+        raise ValueError('contraction digits must be 5, 6 or 7')
+    DIGITS = int(n)
+
 
 def _timed(kind, n, fn):
     if PASS_TIMERS is None:
@@ -44,18 +56,30 @@ class FusedProjection(object):
         self.ctx_name = ctx_name
         self.ctx = engine.ctx(ctx_name)
         self.siginv = engine.upload(potential.bound['Siginv']) if potential.model == 'gaussian' else None
-        self._beta = ()
         self.S = None
         self.Sld = None
         self._theta = None
 
     # ---- configuration ----
+    # The bc_ctx workspace behind `ctx_name` is shared by every FusedProjection of the engine (one potential and one
+    # prepared sample set live in it at a time), so what is currently applied is remembered ON THE ENGINE, per workspace:
+    # two coreset objects built alternately (a SparseVICoreset and a BetaCoreset, say) each find the other's potential
+    # in place and re-apply their own.
+    def _applied(self):
+        return self.eng.ctx_state.setdefault(self.ctx_name, {'potential': None, 'samples_of': None})
+
     def configure(self, beta=None):
-        if self._beta == (beta,):
+        st = self._applied()
+        key = (id(self), beta)      # per projection object: the workspace also points at THIS object's Siginv copy
+        if st['potential'] == key:
+            if st['samples_of'] is not self:
+                self.S = None      # another projection's samples are in place
             return
         p = nv.params8(self.pot.params(self.D, beta))
         nv.call('bc_set_potential', self.ctx, self.pot.model_id, self.pot.kind_id, self.D, p, ptr(self.siginv))
-        self._beta = (beta,)
+        st['potential'] = key
+        st['potential_owner'] = self       # keeps id(self) from being recycled while the key is in place
+        st['samples_of'] = None
         self.S = None          # bc_set_potential invalidates the prepared samples
 
     def set_samples(self, theta):
@@ -67,10 +91,14 @@ class FusedProjection(object):
             t = self.eng.upload(theta)
         if t.shape[1] != self.D:
             raise ValueError('samples have %d columns, potential expects %d' % (t.shape[1], self.D))
+        st = self._applied()
+        if st['potential'] is None or st['potential'][0] != id(self):
+            raise nv.NativeError('set_samples() must follow configure()')
         self._theta = t
         self.S = int(t.shape[0])
         self.Sld = nv.lib().bc_colsum_ld(self.S)
         nv.call('bc_set_samples', self.ctx, ptr(t), self.S, int(t.stride(0)), stream_ptr())
+        st['samples_of'] = self
 
     # ---- helpers ----
     def _rowaux(self, rows):
@@ -95,12 +123,15 @@ class FusedProjection(object):
         if self.eng.fexp_applied.get(self.ctx_name) is not fexp:     # the ctx's sample image must match this row image
             nv.call('bc_set_feature_exponents', self.ctx, ptr(fexp), self.D, stream_ptr())
             self.eng.fexp_applied[self.ctx_name] = fexp
+        if self._applied().get('digits') != DIGITS:
+            nv.call('bc_set_contraction_digits', self.ctx, DIGITS)
+            self._applied()['digits'] = DIGITS
         ra = self._rowaux(rows) if self.pot.model == 'gaussian' else aux
         return img, rs, ra
 
     def _check(self, rows):
-        if self.S is None:
-            raise nv.NativeError('set_samples() must follow configure()')
+        if self.S is None or self._applied()['samples_of'] is not self:
+            raise nv.NativeError('set_samples() must follow configure() (another projection has used this workspace since)')
         if rows.ncols != self.ncols:
             raise ValueError('data rows have %d columns, projector was built for %d' % (rows.ncols, self.ncols))
 

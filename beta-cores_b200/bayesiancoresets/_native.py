@@ -26,6 +26,7 @@ SIGNATURES = {
     'bc_quantise_rows': [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     'bc_feature_exponents': [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     'bc_set_feature_exponents': [c_vp, c_vp, c_int, c_vp],
+    'bc_set_contraction_digits': [c_vp, c_int],
     'bc_project_colsum_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_project_score_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     'bc_contraction_q': [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp],
@@ -49,7 +50,7 @@ SIGNATURES = {
     'bc_fit_pow_poly': [c_dbl, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }
-PLAIN = {'bc_version': ([], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+PLAIN = {'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
 MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2

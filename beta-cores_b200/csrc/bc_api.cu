@@ -45,6 +45,7 @@ struct bc_ctx {
   int* fexp = nullptr;                     // kQK ints
   unsigned long long* fscratch = nullptr;  // kQK column maxima (bc_feature_exponents)
   unsigned long long* sscratch = nullptr;  // 2 words: max bits / non-finite flag of the samples, zero between calls
+  int q_digits = 7;                        // leading digits of the 7-digit images a launch contracts (bc_set_contraction_digits)
 };
 
 static int cuda_fail(cudaError_t e) {
@@ -392,6 +393,13 @@ int bc_project_materialise(bc_ctx* c, const double* d_X, int64_t ldx, const int6
 // ---- tensor-core route ------------------------------------------------------------------------
 int bc_q_max_features(void) { return kQK; }
 
+int bc_set_contraction_digits(bc_ctx* c, int digits) {
+  if (!c || digits < 5 || digits > kQSlices) return BC_ERR_ARG;
+  c->q_digits = digits;
+  return BC_OK;
+}
+int bc_contraction_digits(const bc_ctx* c) { return c ? c->q_digits : 0; }
+
 int bc_q_image_bytes(int64_t n, int64_t* bytes) {
   if (n < 0 || !bytes) return BC_ERR_ARG;
   *bytes = ((n + kQTileRows - 1) / kQTileRows) * (int64_t)kQTileBytes;
@@ -452,7 +460,7 @@ int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale
     BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
     return BC_OK;
   }
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_COLSUM, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_COLSUM, c->q_digits, grid, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -469,7 +477,7 @@ int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale,
   P.scores = d_scores;
   P.idx_offset = idx_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_SCORE, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_SCORE, c->q_digits, grid, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -486,7 +494,7 @@ int bc_contraction_q(bc_ctx* c, const void* d_image, const double* d_rowscale, i
   P.rowaux = nullptr;
   P.V = d_V;
   P.ldv = ldv;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_DOT, grid, (cudaStream_t)stream));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_DOT, c->q_digits, grid, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

@@ -267,19 +267,41 @@ cudaError_t launch_dense_score(const double* V, long long n, int S, long long ld
   long long want = (n + 7) / 8;
   if (want < 1) want = 1;
   const size_t smem = (size_t)((mode == 1) ? 2 : 1) * S * sizeof(double);
-  // one wave of resident blocks: the rows are dealt out grid-stride, so a partial second wave would only add a tail
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  // one wave of resident blocks: the rows are dealt out grid-stride, so a partial second wave would only add a tail.
+  // SM count, the opt-in shared-memory limit (S > 6144 samples need more than the default 48 KB) and the occupancy are
+  // per device and per instantiation: looked up once each.
+  constexpr size_t kScoreSmemMax = 200 * 1024;
+  static DeviceOnce once[4];
+  static int sms_of[64];
+  const int dev = current_device();
+  if (smem > kScoreSmemMax) return cudaErrorInvalidValue;
   int o = 0;
-  switch (mode) {
-    case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<0>, 256, smem); break;
-    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<1>, 256, smem); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<2>, 256, smem); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<3>, 256, smem); break;
+  {
+    cudaError_t e;
+    switch (mode) {
+      case 0:
+        e = raise_dynamic_smem(k_dense_score<0>, kScoreSmemMax, once[0]);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<0>, 256, smem);
+        break;
+      case 1:
+        e = raise_dynamic_smem(k_dense_score<1>, kScoreSmemMax, once[1]);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<1>, 256, smem);
+        break;
+      case 2:
+        e = raise_dynamic_smem(k_dense_score<2>, kScoreSmemMax, once[2]);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<2>, 256, smem);
+        break;
+      default:
+        e = raise_dynamic_smem(k_dense_score<3>, kScoreSmemMax, once[3]);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dense_score<3>, 256, smem);
+        break;
+    }
+    if (e != cudaSuccess) return e;
+  }
+  int sms = (dev >= 0 && dev < 64) ? sms_of[dev] : 0;
+  if (!sms) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) sms_of[dev] = sms;
   }
   if (o < 1) o = 1;
   int resident = sms * o;

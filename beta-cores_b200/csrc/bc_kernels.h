@@ -5,7 +5,33 @@
 #include <stdint.h>
 #include "bc_models.cuh"
 
+#include <atomic>
+
 namespace bc {
+
+// One flag per CUDA device ordinal: function attributes (the opt-in dynamic shared-memory limit) and SM counts belong to a
+// DEVICE, and one process may drive several (Engine.get(device)); a per-process `static bool` would leave the second
+// device's kernels without their attribute.  Thread-safe; ordinals >= 64 simply repeat the (idempotent) call.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+  void set(int dev) {
+    if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+template <class K>
+inline cudaError_t raise_dynamic_smem(K kern, size_t bytes, DeviceOnce& once) {
+  const int dev = current_device();
+  if (once.done(dev)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) once.set(dev);
+  return e;
+}
 
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
@@ -81,7 +107,7 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
                                  double* aux_out, int aux_col, const int* fexp, cudaStream_t st);
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
                                     const int* fexp, unsigned long long* scratch2, cudaStream_t st);
-cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st);
+cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,

@@ -17,22 +17,49 @@ namespace bc {
 // values of one ulp, whose correlation is +-sum(resid)/S^1.5.  Which of the two happens decides the reference's
 // selection, so the kernels reproduce it: np_sum_const is numpy's pairwise summation (8 interleaved accumulators up to
 // 128 elements, halving above; numpy/core/src/umath/loops_utils.h.src) specialised to equal addends.
-BC_NP_HD double np_sum_const(double x, int n) {
+BC_NP_HD double np_sum_leaf(double x, int n) {   // n <= 128: numpy's unrolled-by-8 loop
   if (n < 8) {
     double r = 0.0;
     for (int i = 0; i < n; ++i) r += x;
     return r;
   }
-  if (n <= 128) {
-    double rr = x;
-    for (int i = 8; i < n - (n % 8); i += 8) rr += x;
-    double res = ((rr + rr) + (rr + rr)) + ((rr + rr) + (rr + rr));
-    for (int i = 0; i < n % 8; ++i) res += x;
-    return res;
+  double rr = x;
+  for (int i = 8; i < n - (n % 8); i += 8) rr += x;
+  double res = ((rr + rr) + (rr + rr)) + ((rr + rr) + (rr + rr));
+  for (int i = 0; i < n % 8; ++i) res += x;
+  return res;
+}
+// sum(n) = sum(n2) + sum(n - n2), n2 = n/2 rounded down to a multiple of 8, down to leaves of <= 128 elements: the tree is
+// walked in post-order with an explicit stack (a recursive device function would be an ABI call, which also makes ptxas
+// drop the kernel's setmaxnreg register hand-over).  Depth <= log2(n / 64).
+BC_NP_HD double np_sum_const(double x, int n) {
+  if (n <= 128) return np_sum_leaf(x, n);
+  int size[32];       // pending right-hand sizes
+  double left[32];    // value of the left sibling once it is known
+  bool have[32];
+  int top = 0;
+  int cur = n;
+  double val = 0.0;
+  while (true) {
+    while (cur > 128) {            // descend along left children
+      int n2 = cur / 2;
+      n2 -= n2 % 8;
+      size[top] = cur - n2;
+      have[top] = false;
+      ++top;
+      cur = n2;
+    }
+    val = np_sum_leaf(x, cur);
+    // climb: a finished left child starts its right sibling, a finished right child is added to the stored left value
+    while (top > 0 && have[top - 1]) {
+      val = left[top - 1] + val;
+      --top;
+    }
+    if (top == 0) return val;
+    left[top - 1] = val;
+    have[top - 1] = true;
+    cur = size[top - 1];
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return np_sum_const(x, n2) + np_sum_const(x, n - n2);
 }
 // what the reference's centring leaves in every column of a row that is constantly x
 BC_NP_HD double np_centred_const(double x, int S) { return x - np_sum_const(x, S) / (double)S; }

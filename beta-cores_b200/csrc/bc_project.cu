@@ -467,12 +467,9 @@ __global__ void __launch_bounds__(1024) k_project_finalize(const double* __restr
 template <class F, int MODE, int BM, int NST>
 static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStream_t st, int csplit = 1) {
   auto kern = k_project<F, MODE, BM, NST>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static DeviceOnce once;  // per instantiation, per device
+  cudaError_t e = raise_dynamic_smem(kern, kMaxSmem, once);
+  if (e != cudaSuccess) return e;
   kern<<<dim3(grid, MODE == MODE_MATERIALISE ? csplit : 1), (BM / 16 + 2) * 32, smem, st>>>(P);
   return cudaGetLastError();
 }

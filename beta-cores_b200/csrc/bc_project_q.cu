@@ -16,7 +16,12 @@
 // tcgen05.mma.kind::i8 computes D_0..D_6 for a 128-row x 32-sample chunk into 7 x 32 TMEM columns: the MMA for row digit
 // i multiplies against the sample digits 0..6-i STACKED along N (N = 32 (7 - i)), i.e. 7 x 4 instructions per chunk.
 //
-// One persistent CTA per SM, 19 warps:
+// The images always hold 7 digits; a launch may contract only the leading NS of them (NS = 5, 6, 7: 15 / 21 / 28 digit
+// pairs, diagonals d < NS) -- the operands are then read as if rounded to 8 NS - 2 bits below the row / sample maximum
+// (balanced digits: dropping the tail is a round-to-nearest), bc_set_contraction_digits.
+//
+// One persistent CTA per SM, 20 warps (five warpgroups: the register file is re-divided with setmaxnreg so that the sixteen
+// epilogue warps run with 112 registers instead of the 96 a 640-thread launch gets, the four service warps with 32):
 //   warps 0-15 : four epilogue groups of four warps (a warp may only read its own TMEM lane quarter).  Groups 0,1 take
 //                the even chunks (accumulator buffer 0), groups 2,3 the odd chunks (buffer 1); within a pair each group
 //                owns 16 of the chunk's 32 sample columns.  Thread = data row (TMEM lane): tcgen05.ld the 7 diagonals,
@@ -41,7 +46,13 @@ constexpr int kQStagesB = 3;
 constexpr int kQSlots = 4;
 constexpr int kQGroups = 4;                       // epilogue groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int kQEpiWarps = 4 * kQGroups;          // 16
-constexpr int kQThreads = (kQEpiWarps + 3) * 32;  // + producer, MMA issuer, reducer
+constexpr int kQThreads = (kQEpiWarps + 4) * 32;  // + producer, MMA issuer, reducer, one idle warp (setmaxnreg works on whole warpgroups)
+#ifndef BC_Q_REGS_EPI          // experiment knobs (tools/build_variants.py); the defaults are what ships
+#define BC_Q_REGS_EPI 112
+#define BC_Q_REGS_SVC 32
+#endif
+constexpr int kQRegsEpi = BC_Q_REGS_EPI;          // 16 x 32 x 112 + 4 x 32 x 32 = 61440 = the CTA's pool at 96 registers x 640 threads
+constexpr int kQRegsSvc = BC_Q_REGS_SVC;
 constexpr int kQHalfCols = kQChunk / 2;           // columns of a chunk one group handles
 
 struct QSmem {
@@ -245,10 +256,10 @@ cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsi
 // ------------------------------------------------------------------ projection --
 // The MMAs of one 128-row x 32-sample chunk: row digit i against the sample digits 0..6-i stacked along N, KS blocks of
 // 32 bytes along K.  +32 bytes along K inside the swizzle atom = +2 in the (>>4) start-address field of a descriptor.
-template <int KS>
+template <int KS, int NS>
 __device__ __forceinline__ void issue_chunk_mmas(uint32_t d0, uint64_t adesc0, uint64_t bdesc0, const uint32_t (&idesc)[kQSlices]) {
 #pragma unroll
-  for (int i = 0; i < kQSlices; ++i) {
+  for (int i = 0; i < NS; ++i) {
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       umma_i8(d0 + (uint32_t)(i * kQChunk), adesc0 + (uint64_t)(i * (kQSliceA >> 4) + k * 2), bdesc0 + (uint64_t)(k * 2), idesc[i],
@@ -257,8 +268,7 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t d0, uint64_t adesc0, u
   }
 }
 
-
-template <class F, int MODE>
+template <class F, int MODE, int NS>
 __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -315,34 +325,37 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // setmaxnreg sits at the head of each role's branch: ptxas allocates registers for the code a setmaxnreg dominates
   if (warp == kQEpiWarps) {
     // ======================= producer: TMA-engine bulk copies =======================
+    reg_dealloc<kQRegsSvc>();
     if (lane == 0) {
       uint32_t itb = 0, tcount = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         mbar_wait_relaxed(empty_a, (tcount & 1) ^ 1);
-        mbar_arrive_expect_tx(full_a, (uint32_t)kQTileBytes);
+        mbar_arrive_expect_tx(full_a, (uint32_t)(NS * kQSliceA));
         const unsigned char* srcA = P.imgA + (size_t)tile * kQTileBytes;
 #pragma unroll
-        for (int s = 0; s < kQSlices; ++s) bulk_g2s(As + (size_t)s * kQSliceA, srcA + (size_t)s * kQSliceA, kQSliceA, full_a);
+        for (int s = 0; s < NS; ++s) bulk_g2s(As + (size_t)s * kQSliceA, srcA + (size_t)s * kQSliceA, kQSliceA, full_a);
         for (int c = 0; c < nchunks; ++c, ++itb) {
           const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
           mbar_wait_relaxed(empty_b + st, ph ^ 1);
-          mbar_arrive_expect_tx(full_b + st, (uint32_t)kQChunkBytes);
-          bulk_g2s(Bs + (size_t)st * kQChunkBytes, P.imgB + (size_t)c * kQChunkBytes, kQChunkBytes, full_b + st);
+          mbar_arrive_expect_tx(full_b + st, (uint32_t)(NS * kQSliceB));
+          bulk_g2s(Bs + (size_t)st * kQChunkBytes, P.imgB + (size_t)c * kQChunkBytes, NS * kQSliceB, full_b + st);
         }
       }
     }
     __syncwarp();
   } else if (warp == kQEpiWarps + 1) {
     // ======================= MMA issuer =======================
+    reg_dealloc<kQRegsSvc>();
     // All 32 lanes run the loop so that control flow and operands (descriptors, TMEM addresses) stay warp-uniform -- ptxas
     // then feeds tcgen05.mma from uniform registers directly; inside an `if (lane == 0)` region it wraps every MMA in an
     // ELECT / R2UR.BROADCAST loop (89 cycles per MMA measured, more than the MMA takes to execute).  One elected lane issues.
     {
       uint32_t idesc[kQSlices];
 #pragma unroll
-      for (int i = 0; i < kQSlices; ++i) idesc[i] = umma_idesc_i8(kQChunk * (kQSlices - i));
+      for (int i = 0; i < kQSlices; ++i) idesc[i] = umma_idesc_i8(kQChunk * (i < NS ? NS - i : 1));
       const uint64_t adesc0 = umma_desc_sw128(smem_u32(As));
       uint32_t itb = 0, tcount = 0, use0 = 0, use1 = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -361,10 +374,10 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
             // K blocks beyond the feature count hold only zero digits: not multiplied (D = 20 issues 7 MMAs per chunk
             // instead of 28).  Fully unrolled per block count: the issue rate of this one thread is on the critical path.
             switch (P.ksteps) {
-              case 1: issue_chunk_mmas<1>(d0, adesc0, bdesc0, idesc); break;
-              case 2: issue_chunk_mmas<2>(d0, adesc0, bdesc0, idesc); break;
-              case 3: issue_chunk_mmas<3>(d0, adesc0, bdesc0, idesc); break;
-              default: issue_chunk_mmas<4>(d0, adesc0, bdesc0, idesc); break;
+              case 1: issue_chunk_mmas<1, NS>(d0, adesc0, bdesc0, idesc); break;
+              case 2: issue_chunk_mmas<2, NS>(d0, adesc0, bdesc0, idesc); break;
+              case 3: issue_chunk_mmas<3, NS>(d0, adesc0, bdesc0, idesc); break;
+              default: issue_chunk_mmas<4, NS>(d0, adesc0, bdesc0, idesc); break;
             }
             umma_commit(empty_b + st);
             umma_commit(tmem_full + buf);
@@ -375,8 +388,11 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
       }
     }
     __syncwarp();
+  } else if (warp == kQEpiWarps + 3) {
+    reg_dealloc<kQRegsSvc>();   // idle: pads the service warps to a full warpgroup
   } else if (warp == kQEpiWarps + 2) {
     // ============ reducer: 4 partials per chunk -> double-double column accumulators ============
+    reg_dealloc<kQRegsSvc>();
     if (want_cols) {
       double* acc_hi = P.part_colsum + (size_t)blockIdx.x * 2 * P.Sld;
       double* acc_lo = acc_hi + P.Sld;
@@ -408,6 +424,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     }
   } else {
     // ================================ epilogue groups ================================
+    reg_alloc<kQRegsEpi>();
     const int grp = warp >> 2;   // 0..3
     const int buf = grp >> 1;    // accumulator buffer = chunk parity this group serves
     const int half = grp & 1;    // which 16 of the chunk's 32 columns
@@ -416,7 +433,8 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kQDiagCols + half * kQHalfCols);
     const double dS = (double)S;
     const double rsum = (MODE == QMODE_SCORE) ? __ldg(P.resid + S) : 0.0;
-    const double cs = __ldg(P.colscale);   // one scale for all samples
+    // one scale for all samples; the stored scales are those of the full 7-digit split: 2^-32 each, 256^-(NS+1) is needed
+    const double cs = __ldg(P.colscale) * (double)(1ull << (8 * (kQSlices - NS)));
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
     constexpr int NB = kQHalfCols / 4;     // batches of 4 columns per chunk
     Best best = {0.0, -1};
@@ -437,9 +455,27 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         mbar_wait(tmem_full + buf, use & 1);
         ++use;
         tc_fence_after();
-        uint32_t dg[kQSlices][4];
+        int dg[4][NS];   // [column of the batch][diagonal]
+        auto fetch = [&](int batch) {
 #pragma unroll
-        for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk), dg[d]);
+          for (int d = 0; d < NS; ++d) {
+            uint32_t v[4];
+            tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + batch * 4), v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dg[e][d] = (int)v[e];
+          }
+        };
+        // tcgen05.ld is asynchronous: its destination registers are defined only after tcgen05.wait::ld.  The empty asm
+        // statements pin every use of the digits behind the wait (volatile asm statements keep their order).
+        auto landed = [&]() {
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int d = 0; d < NS; ++d) asm volatile("" : "+r"(dg[e][d]));
+          }
+        };
+        fetch(0);
         if (!have_piv) {
           // group 0 publishes the row pivots right after its first four columns of the tile
           mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
@@ -449,18 +485,14 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
         double fv[8];
         // software pipeline inside the warp: while batch b is evaluated (FP64 pipe) the digits of batch b+1 -- fetched one
-        // step earlier -- are recombined (integer pipe) in the same straight-line block, and the fetch of batch b+2 is in
-        // flight.  Without it the four warps of a sub-partition fall into step (all converting, then all evaluating) and
-        // the phases add up instead of overlapping.
+        // step earlier -- have just been recombined (integer pipe), and the fetch of batch b+2 is in flight: it is issued
+        // BEFORE the evaluation, into the digit registers the recombination has just released (this is what the 112
+        // registers of the epilogue warps are for -- at 96 the in-flight destinations spilled).
         double ccur[4], cnext[4];
-        tmem_wait_ld();
+        landed();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ccur[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
-                                    (int)dg[6][e]);
-        }
-#pragma unroll
-        for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + 4), dg[d]);
+        for (int e = 0; e < 4; ++e) ccur[e] = rsc * q_combine_n<NS>(dg[e]);
+        fetch(1);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const int cb = c * kQChunk + half * kQHalfCols + b * 4;
@@ -468,13 +500,14 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) cval[e] = ccur[e];
           if (b + 1 < NB) {
-            tmem_wait_ld();   // digits of batch b+1
+            landed();   // digits of batch b+1
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              cnext[e] = rsc * q_combine((int)dg[0][e], (int)dg[1][e], (int)dg[2][e], (int)dg[3][e], (int)dg[4][e], (int)dg[5][e],
-                                         (int)dg[6][e]);
-            }
-            if (b + 2 == NB) {
+            for (int e = 0; e < 4; ++e) cnext[e] = rsc * q_combine_n<NS>(dg[e]);
+            if (b + 2 < NB) {
+#ifndef BC_Q_LATE_FETCH
+              fetch(b + 2);
+#endif
+            } else {
               // the last digits of the chunk are in registers: hand the accumulator buffer back to the MMA issuer now,
               // with two batches of evaluation still to go -- the next chunk's MMAs then finish before this group needs them
               tc_fence_before();
@@ -524,10 +557,9 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) fv[(b & 1) * 4 + e] = fr[e];
           }
-          if (b + 2 < NB) {
-#pragma unroll
-            for (int d = 0; d < kQSlices; ++d) tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + (b + 2) * 4), dg[d]);
-          }
+#ifdef BC_Q_LATE_FETCH
+          if (b + 2 < NB) fetch(b + 2);
+#endif
 #pragma unroll
           for (int e = 0; e < 4; ++e) ccur[e] = cnext[e];
           if (want_cols && (b & 1)) {
@@ -623,39 +655,46 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 }
 
 // ------------------------------------------------------------------ launch --
-template <class F, int MODE>
+template <class F, int MODE, int NS>
 static cudaError_t launch_q_one(const QProjArgs& P, int grid, cudaStream_t st) {
-  auto kern = k_project_q<F, MODE>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QSmem::total);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  auto kern = k_project_q<F, MODE, NS>;
+  static DeviceOnce once;  // per instantiation, per device
+  cudaError_t e = raise_dynamic_smem(kern, QSmem::total, once);
+  if (e != cudaSuccess) return e;
   kern<<<grid, kQThreads, QSmem::total, st>>>(P);
   return cudaGetLastError();
 }
 
-template <class F>
-static cudaError_t launch_q_mode(const QProjArgs& P, int mode, int grid, cudaStream_t st) {
-  if (mode == QMODE_COLSUM) return launch_q_one<F, QMODE_COLSUM>(P, grid, st);
-  return launch_q_one<F, QMODE_SCORE>(P, grid, st);
+template <class F, int MODE>
+static cudaError_t launch_q_digits(const QProjArgs& P, int digits, int grid, cudaStream_t st) {
+  switch (digits) {
+    case 5: return launch_q_one<F, MODE, 5>(P, grid, st);
+    case 6: return launch_q_one<F, MODE, 6>(P, grid, st);
+    case 7: return launch_q_one<F, MODE, 7>(P, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
-cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int grid, cudaStream_t st) {
-  if (mode == QMODE_DOT) return launch_q_one<LogisticF<KIND_LOGLIK, 0>, QMODE_DOT>(P, grid, st);
+template <class F>
+static cudaError_t launch_q_mode(const QProjArgs& P, int mode, int digits, int grid, cudaStream_t st) {
+  if (mode == QMODE_COLSUM) return launch_q_digits<F, QMODE_COLSUM>(P, digits, grid, st);
+  return launch_q_digits<F, QMODE_SCORE>(P, digits, grid, st);
+}
+
+cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st) {
+  if (mode == QMODE_DOT) return launch_q_digits<LogisticF<KIND_LOGLIK, 0>, QMODE_DOT>(P, digits, grid, st);
   if (model == MODEL_LOGISTIC) {
-    if (kind == KIND_LOGLIK) return launch_q_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, grid, st);
-    if (poly == 20) return launch_q_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, grid, st);
-    if (poly == kPowPolyMax) return launch_q_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, grid, st);
-    return launch_q_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, grid, st);
+    if (kind == KIND_LOGLIK) return launch_q_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, digits, grid, st);
+    if (poly == 20) return launch_q_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, digits, grid, st);
+    if (poly == kPowPolyMax) return launch_q_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, digits, grid, st);
+    return launch_q_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, digits, grid, st);
   } else if (model == MODEL_GAUSSIAN) {
-    if (kind == KIND_LOGLIK) return launch_q_mode<GaussianF<KIND_LOGLIK>>(P, mode, grid, st);
-    if (kind == KIND_BETALIK) return launch_q_mode<GaussianF<KIND_BETALIK>>(P, mode, grid, st);
-    return launch_q_mode<GaussianF<KIND_BETAGRAD>>(P, mode, grid, st);
+    if (kind == KIND_LOGLIK) return launch_q_mode<GaussianF<KIND_LOGLIK>>(P, mode, digits, grid, st);
+    if (kind == KIND_BETALIK) return launch_q_mode<GaussianF<KIND_BETALIK>>(P, mode, digits, grid, st);
+    return launch_q_mode<GaussianF<KIND_BETAGRAD>>(P, mode, digits, grid, st);
   } else {
-    if (kind == KIND_LOGLIK) return launch_q_mode<NeurlinF<KIND_LOGLIK>>(P, mode, grid, st);
-    return launch_q_mode<NeurlinF<KIND_BETALIK>>(P, mode, grid, st);
+    if (kind == KIND_LOGLIK) return launch_q_mode<NeurlinF<KIND_LOGLIK>>(P, mode, digits, grid, st);
+    return launch_q_mode<NeurlinF<KIND_BETALIK>>(P, mode, digits, grid, st);
   }
 }
 

@@ -301,12 +301,9 @@ cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double
                                     double tol, int* info, cudaStream_t st) {
   const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
   const size_t cap = kMaxSmem - 1024;   // the kernel also has a few bytes of static shared memory
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_laplace_logistic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  cudaError_t e = raise_dynamic_smem(k_laplace_logistic, cap, once);
+  if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
   k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info);
   return cudaGetLastError();

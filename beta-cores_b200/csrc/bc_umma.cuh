@@ -89,12 +89,27 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // exact conversion of an integer |t| < 2^53 to fp64 (I2F.F64.S64 on the conversion unit: measured a little faster here than
 // the integer-add + FP64-add magic-number form, which occupies the contended FP64 pipe)
 __device__ __forceinline__ double exact_ll2d(long long t) { return __ll2double_rn(t); }
-// the seven int32 digit diagonals D_d = sum_{i+j=d} A_i B_j^T  ->  sum_d D_d 256^(6-d)  as an fp64 (one rounding)
-__device__ __forceinline__ double q_combine(int d0, int d1, int d2, int d3, int d4, int d5, int d6) {
-  const long long hi = ((long long)d0 << 24) + ((long long)d1 << 16) + ((long long)d2 << 8) + (long long)d3;
-  const long long lo = ((long long)d4 << 16) + ((long long)d5 << 8) + (long long)d6;
+// the NS int32 digit diagonals D_d = sum_{i+j=d} A_i B_j^T  ->  sum_d D_d 256^(NS-1-d)  as an fp64 (one rounding):
+// the last three diagonals and the leading NS-3 are summed exactly in two int64 halves (integer pipe), each below 2^53.
+template <int NS>
+__device__ __forceinline__ double q_combine_n(const int (&d)[NS]) {
+  static_assert(NS >= 4 && NS <= 7, "digit count");
+  long long hi = 0;
+#pragma unroll
+  for (int i = 0; i < NS - 3; ++i) hi = (hi << 8) + (long long)d[i];
+  const long long lo = ((long long)d[NS - 3] << 16) + ((long long)d[NS - 2] << 8) + (long long)d[NS - 1];
   return fma(exact_ll2d(hi), 16777216.0, exact_ll2d(lo));
 }
+__device__ __forceinline__ double q_combine(int d0, int d1, int d2, int d3, int d4, int d5, int d6) {
+  const int d[7] = {d0, d1, d2, d3, d4, d5, d6};
+  return q_combine_n<7>(d);
+}
+// register budget hand-over between warpgroups of one CTA (sm_90+): the service warps give registers back, the epilogue
+// warps take them (the CTA's pool is launch registers x threads; both counts are multiples of 8)
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 #endif
 
 }  // namespace bc

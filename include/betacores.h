@@ -88,6 +88,14 @@ int bc_project_materialise(bc_ctx* ctx, const double* d_X, int64_t ldx, const in
  * Feature count D <= bc_q_max_features() (128); full row blocks only (no gather list).
  * The row image is built ONCE per dataset; bc_set_samples() builds the sample image. */
 int bc_q_max_features(void);
+/* Precision tier of the tensor-core contraction.  The images always hold 7 digits (55 bits + sign below the row / sample
+ * maximum: the product of two fp64 operands to the accuracy of a dgemm, the reference's numpy `dot`,
+ * examples/common/model_lr.py:83); a launch contracts the leading `digits` of them: 7 (default) = 28 digit pairs,
+ * 6 = 21 pairs (operands as if rounded to 46 bits, |error| <= 2^-44 max|x_n| max|theta| sqrt(D) typical), 5 = 15 pairs
+ * (38 bits).  BASELINE.json's north star allows "FP64 DMMA or 3xTF32" accuracy (3xTF32 keeps about 30 bits); the tier that
+ * keeps the selected indices exact on every parity case is reported in DESIGN.md. */
+int bc_set_contraction_digits(bc_ctx* ctx, int digits);   /* 5, 6 or 7 */
+int bc_contraction_digits(const bc_ctx* ctx);
 int bc_q_image_bytes(int64_t n, int64_t* bytes);     /* device bytes of the quantised image of n rows */
 /* Feature exponents (optional, recommended for data whose columns differ much in magnitude).  The digit split keeps 56
  * bits below the largest entry of a row; with x_k 2^-c_k in the row image and theta_k 2^+c_k in the sample image

@@ -55,6 +55,16 @@ def main():
     bc, model_lr, gaussian, model_neurlinr = import_reference()
     from oracle import np_models as om, np_snnls as osn, np_coresets as oc
     out = {}
+    # --only name1,name2 : regenerate just these coreset cases and merge them into the existing g3 fixture
+    only = None
+    if '--only' in sys.argv:
+        only = set(sys.argv[sys.argv.index('--only')+1].split(','))
+    if only is not None:
+        g = dict(np.load(os.path.join(HERE, 'g3_coresets.npz')))
+        coreset_section(bc, model_lr, gaussian, model_neurlinr, oc, g, only)
+        np.savez_compressed(os.path.join(HERE, 'g3_coresets.npz'), **g)
+        print('updated', sorted(only))
+        return
 
     # ---- G1: model functions --------------------------------------------------
     p = problems.model_function_inputs()
@@ -119,8 +129,17 @@ def main():
 
     # ---- G3..: greedy coreset builds ------------------------------------------
     g = {}
+    coreset_section(bc, model_lr, gaussian, model_neurlinr, oc, g, None)
+    np.savez_compressed(os.path.join(HERE, 'g3_coresets.npz'), **g)
+    print('all golden fixtures written')
+
+
+def coreset_section(bc, model_lr, gaussian, model_neurlinr, oc, g, only):
+    import contextlib, io
     for case in problems.coreset_cases():
         nm = case['name']
+        if only is not None and nm not in only:
+            continue
         t0 = time.time()
         # reference run
         prob = case['make']()
@@ -181,9 +200,7 @@ def main():
         g[nm+'_sizes'] = np.array([len(h) for h in hist_i])
         g[nm+'_first_idcs'] = np.array([h[-1] if len(h) else -1 for h in hist_i])
         g[nm+'_sumw'] = np.array([h.sum() for h in hist_w])
-        print('G3 %s ok (%.1fs) idcs %s sumw %.9f' % (nm, time.time()-t0, list(hist_i[-1][:12]), hist_w[-1].sum()))
-    np.savez_compressed(os.path.join(HERE, 'g3_coresets.npz'), **g)
-    print('all golden fixtures written')
+        print('G3 %s ok (%.1fs) idcs %s sumw %.9f' % (nm, time.time()-t0, [int(v) for v in hist_i[-1][:12]], hist_w[-1].sum()))
 
 
 if __name__ == '__main__':

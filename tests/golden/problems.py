@@ -240,6 +240,10 @@ def coreset_cases(heavy=True):
     c.append(dict(base, name='lr_beta_small', alg='beta', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
     c.append(dict(base, name='lr_svi_small', alg='svi', make=make_logistic(2000, 5, 3), seed=1, S=50, opt_itrs=20, M=6, sched=_sched(1.)))
     c.append(dict(base, name='lr_beta_zero_rows', alg='beta', make=make_logistic(1500, 4, 5, zero_rows=(0, 7, 450, 1499)), seed=2, S=64, opt_itrs=10, M=5, sched=_sched(1.)))
+    # zero rows met only now and then (sub-sampled selection): the NaN-first arg-max / NaN gate rules (bcores.py:78-81) fire on
+    # some selections while the coreset keeps growing, so the weights that follow a NaN event are pinned too
+    c.append(dict(base, name='lr_beta_zero_rows_sub', alg='beta', make=make_logistic(1500, 4, 5, zero_rows=tuple(range(0, 1500, 100))), seed=3, S=64,
+                  opt_itrs=10, M=10, sched=_sched(1.), n_sel=150))
     c.append(dict(base, name='lr_beta_sub', alg='beta', make=make_logistic(3000, 6, 7), seed=4, S=40, opt_itrs=25, M=6, sched=_sched(1.), n_sel=300, n_opt=100))
     c.append(dict(base, name='gauss_beta_sub', alg='beta', make=make_gaussian(500, 10, 0), seed=5, S=40, opt_itrs=30, M=8, sched=_sched(1.), n_sel=100, n_opt=40, beta=0.01))
     c.append(dict(base, name='gauss_svi_full', alg='svi', make=make_gaussian(400, 7, 2), seed=6, S=32, opt_itrs=15, M=5, sched=_sched(.1)))
@@ -266,4 +270,15 @@ def coreset_cases(heavy=True):
                       sched=_sched(.1), n_sel=1000, n_opt=200, beta=0.1, heavy=True))
         # SURVEY 8c "logistic mini" fingerprint shape (N=10000, D=10, S=100, opt_itrs=50, M=10)
         c.append(dict(base, name='lr_beta_mini', alg='beta', make=make_logistic(10000, 10, 0), seed=1, S=100, opt_itrs=50, M=10, sched=_sched(1.), heavy=True))
+        # BASELINE config 3 at its stated size (examples/zellner_logreg: N = 100K, D = 20, S = 100, beta = 0.1, full data)
+        c.append(dict(base, name='c3_logreg_100k', alg='beta', make=make_logistic(100000, 20, 41), seed=21, S=100, opt_itrs=20, M=5,
+                      sched=_sched(1.), heavy=True))
+        # BASELINE config 4 at N = 100K of its 1M (examples/zellner_neural_linear: D = 64 random-init relu features, S = 256,
+        # conjugate sampler of the weighted posterior, 10 % of the targets replaced by outliers)
+        c.append(dict(base, name='c4_neurlin_100k', alg='beta', make=make_neurlin(100000, 64, 42), seed=22, S=256, opt_itrs=20, M=5,
+                      sched=_sched(.1), beta=0.2, heavy=True))
+        # the north-star SHAPE (D = 128, S = 1024, beta = 0.1, full data) at a row count the reference finishes in seconds:
+        # four build steps on the tensor-core route's home ground
+        c.append(dict(base, name='c5_northstar_16k', alg='beta', make=make_logistic(16384, 128, 43), seed=23, S=1024, opt_itrs=5, M=4,
+                      sched=_sched(1.), heavy=True))
     return c

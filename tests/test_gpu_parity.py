@@ -271,6 +271,96 @@ def test_score_nan_and_tie_semantics(bc, route):
     assert np.isnan(scores.cpu().numpy()[[77, 123]]).all()
 
 
+# ------------------------------------------------------------------ precision tiers of the tensor-core route --
+@pytest.fixture(params=[5, 6, 7])
+def digits(request):
+    from bayesiancoresets import _fused
+    old = _fused.DIGITS
+    _fused.set_contraction_digits(request.param)
+    yield request.param
+    _fused.set_contraction_digits(old)
+
+
+def test_precision_tier_contraction_error(bc, digits):
+    """bc_set_contraction_digits: a launch contracts the leading T of the 7 int8 digits.  Dropping one digit costs a
+    factor 256: |error| <= 2e-14 * 256^(7-T) * max|x_n| max|Theta| (T = 7: the accuracy of dgemm itself)"""
+    import torch
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    from bayesiancoresets import _native as nv
+    eng = Engine.get()
+    ctx = eng.ctx('qtest')
+    nv.call('bc_set_contraction_digits', ctx, digits)
+    try:
+        assert nv.lib().bc_contraction_digits(ctx) == digits
+        for n, D, S, seed in [(129, 128, 33, 1), (700, 37, 300, 2), (2500, 100, 1000, 3)]:
+            r = np.random.RandomState(seed)
+            X = r.randn(n, D)*np.exp(3.*r.randn(n, 1))
+            X[5] = 0.
+            Th = r.randn(S, D)*np.exp(r.randn(S, 1))
+            rows = DeviceRows(eng, X)
+            T = eng.upload(Th)
+            nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_LOGLIK, D, nv.params8([0]*8), None)
+            nv.call('bc_set_samples', ctx, ptr(T), S, int(T.stride(0)), stream_ptr())
+            img, rs, _, fexp = rows.quantised(ctx, D)
+            nv.call('bc_set_feature_exponents', ctx, ptr(fexp), D, stream_ptr())
+            V = eng.empty(n, S)
+            nv.call('bc_contraction_q', ctx, ptr(img), ptr(rs), n, ptr(V), S, stream_ptr())
+            ref = (X.astype(np.longdouble) @ Th.T.astype(np.longdouble)).astype(np.float64)
+            c = fexp.cpu().numpy().astype(np.float64)
+            bound = np.abs(X*2.**-c).max(axis=1)[:, None]*np.abs(Th*2.**c).max()
+            err = np.abs(V.cpu().numpy() - ref)
+            tol = 2e-14*256.**(7-digits)
+            assert (err <= tol*bound + 1e-320).all(), (digits, n, D, S, float((err/np.maximum(bound, 1e-300)).max()))
+            if digits < 7:      # and the tier really is coarser than the full split (the knob is wired through)
+                assert float((err/np.maximum(bound, 1e-300)).max()) > 2e-14*256.**(6-digits)*1e-3
+    finally:
+        nv.call('bc_set_contraction_digits', ctx, 7)
+
+
+@pytest.mark.parametrize('name', ['c5_northstar_16k', 'c3_logreg_100k', 'c4_neurlin_100k', 'lr_beta_mini', 'lr_beta_small', 'gauss_svi_full'])
+def test_precision_tiers_keep_reference_selections(bc, models, digits, name):
+    """which digit count keeps the reference's index sequence: every tier is run over golden builds written by the
+    unmodified reference (north-star shape D=128 S=1024; configs 3 and 4 at 100K rows; small cases).  Indices exact,
+    weights within the north star's 1e-6."""
+    g = np.load(os.path.join(G, 'g3_coresets.npz'))
+    case = [c for c in problems.coreset_cases(True) if c['name'] == name][0]
+    w, i, sizes, sumw = _run_product_case(bc, models, case)
+    np.testing.assert_array_equal(i, g[name+'_idcs'])
+    np.testing.assert_array_equal(sizes, g[name+'_sizes'])
+    np.testing.assert_allclose(w, g[name+'_wts'], rtol=1e-6, atol=1e-9)
+
+
+def test_alternating_algorithms_share_the_workspace(bc, models):
+    """two coreset objects built ALTERNATELY on one engine (the bc_ctx workspace holds one potential and one sample set
+    at a time): a SparseVICoreset (log-likelihood) and a BetaCoreset (beta-likelihood) must each re-apply their own
+    potential when the other has used the workspace in between; both compared with the oracle"""
+    lr, _, _ = models
+    prob = problems.make_logistic(1200, 5, 77)()
+    Z, sampler = prob['data'], prob['sampler']
+    S, itrs, beta, M = 48, 8, 0.1, 5
+    sched = lambda i: 1./(1.+i)
+
+    # the two objects draw from the one global numpy stream in the order of the alternating build calls
+    def run(make_a, make_b, get):
+        np.random.seed(21)
+        a, b = make_a(), make_b()
+        for m in range(1, M+1):
+            a.build(1, m)
+            b.build(1, m)
+        return get(a), get(b)
+    pa, pb = run(lambda: bc.SparseVICoreset(Z, bc.BlackBoxProjector(sampler, S, lr.log_likelihood, None), opt_itrs=itrs, step_sched=sched),
+                 lambda: bc.BetaCoreset(Z, bc.BetaBlackBoxProjector(sampler, S, lr.beta_likelihood, lr.log_likelihood, None), opt_itrs=itrs,
+                                        step_sched=sched, beta=beta, learn_beta=False),
+                 lambda x: (np.array(x.get()[0]), np.array(x.get()[2])))
+    oa, ob = run(lambda: oc.GreedyVI(Z, sampler, S, om.lr_loglik, opt_itrs=itrs, sched=sched),
+                 lambda: oc.GreedyVI(Z, sampler, S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=itrs, sched=sched),
+                 lambda x: (np.array(x.get()[0]), np.array(x.get()[2])))
+    for (gw, gi), (ow, oi) in ((pa, oa), (pb, ob)):
+        np.testing.assert_array_equal(gi, oi)
+        np.testing.assert_allclose(gw, ow, rtol=1e-6, atol=1e-9)
+    assert list(pa[1]) != list(pb[1])      # the two algorithms did select differently: a mix-up could not hide
+
+
 # ------------------------------------------------------------------------------ snnls --
 @pytest.mark.parametrize('name', ['giga', 'fw', 'omp'])
 def test_snnls_fingerprint_matches_reference(bc, name):
@@ -317,6 +407,14 @@ def test_snnls_small_cases_and_monotone_error(bc):
             tie_prone = tag.startswith('bin') or tag.startswith('axis')
             if not tie_prone and not ref_limit and not alg.reached_numeric_limit:
                 np.testing.assert_allclose(alg.weights(), ref_w, rtol=1e-5, atol=1e-7, err_msg=tag+name)
+            if tie_prone and name != 'fw':
+                # whichever of the tied columns is taken, the result must be as good as the reference's: the true
+                # error |A w - b| of the device build against the error of the reference's weights (GIGA and OMP;
+                # Frank-Wolfe's path, and with it its final error, depends on which vertex a tie picks)
+                b = A.sum(axis=0)
+                ref_err = np.sqrt(((A.T.dot(ref_w)-b)**2).sum())
+                got_err = np.sqrt(((A.T.dot(alg.weights())-b)**2).sum())
+                assert got_err <= ref_err*(1+1e-6) + 1e-6*np.sqrt((b**2).sum()), (tag, name, got_err, ref_err)
 
 
 # ---------------------------------------------------------------------- coreset builds --

@@ -219,3 +219,66 @@ def test_c_abi_argument_errors_need_no_device():
     L.bc_error_string.restype = ctypes.c_char_p
     msgs = {L.bc_error_string(c) for c in (0, -1, -2, -3, -4, -5)}
     assert len(msgs) == 6 and all(m for m in msgs)
+
+
+def test_uniform_sampling_coreset_matches_reference_outputs():
+    """bayesiancoresets/coreset/sampling.py:5-47 (host RNG bookkeeping only, no GPU): the constructor takes `groups` /
+    `selected_groups`, a warm start through wts/idcs/pts seeds one count per initial point, group mode takes whole groups.
+    Expected values: the unmodified reference run on the same seeds in the build container."""
+    import bayesiancoresets as bc
+    X = np.arange(60.).reshape(20, 3)
+    groups = [list(range(i, i+4)) for i in range(0, 20, 4)]
+    np.random.seed(5)
+    a = bc.UniformSamplingCoreset(X, wts=np.ones(2), idcs=np.array([3, 7]), pts=X[[3, 7]].copy())
+    a.build(6, 100)
+    assert a.wts.tolist() == [5.0, 2.5, 2.5, 2.5, 2.5, 2.5, 2.5] and a.idcs.tolist() == [3, 7, 14, 15, 6, 16, 9]
+    np.testing.assert_array_equal(a.pts, X[a.idcs])
+    np.random.seed(6)
+    b = bc.UniformSamplingCoreset(X, wts=np.ones(2), idcs=np.array([3, 7]), pts=X[[3, 7]].copy(), groups=groups, selected_groups=None)
+    b.build(3, 100)
+    assert b.idcs.tolist() == [3, 7, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15] and b.selected_groups == [2, 1, 3]
+    np.testing.assert_allclose(b.wts, np.full(14, 20./14.), rtol=1e-15)
+    np.testing.assert_array_equal(b.pts, X[b.idcs])
+    np.random.seed(7)
+    c = bc.UniformSamplingCoreset(X)
+    c.build(5, 100)
+    assert c.wts.tolist() == [4.0]*5 and c.idcs.tolist() == [15, 4, 3, 19, 7]
+    c.reset()
+    assert c.size() == 0 and c.cts == [] and c.ct_idcs == []
+
+
+def test_fused_projection_reapplies_its_potential_after_another_owner(monkeypatch):
+    """the bc_ctx workspace is shared by all FusedProjections of an engine.  A.configure -> B.configure ->
+    A.configure must issue bc_set_potential three times, and A must not keep using samples B has replaced."""
+    from bayesiancoresets import _fused, _native as nv
+    from bayesiancoresets.potentials import DevicePotential
+    calls = []
+    monkeypatch.setattr(nv, 'call', lambda name, *a: calls.append(name))
+    monkeypatch.setattr(nv, 'lib', lambda: type('L', (), {'bc_colsum_ld': staticmethod(lambda S: S+1)})())
+    monkeypatch.setattr(_fused, 'stream_ptr', lambda: None)
+
+    class Eng(object):
+        ctx_state = {}
+        fexp_applied = {}
+
+        def ctx(self, name='main'):
+            return 1
+
+        def upload(self, a, dtype=None):
+            import torch
+            return torch.from_numpy(np.ascontiguousarray(a))
+    eng = Eng()
+    A = _fused.FusedProjection(eng, DevicePotential('logistic', 'loglik'), 4)
+    B = _fused.FusedProjection(eng, DevicePotential('logistic', 'betalik'), 4)
+    th = np.zeros((3, 4))
+    A.configure(None); A.set_samples(th)
+    B.configure(0.1); B.set_samples(th)
+    assert A.S is not None
+    A.configure(None)
+    assert calls.count('bc_set_potential') == 3
+    assert A.S is None                       # its prepared samples are gone: set_samples() must follow
+    A.set_samples(th)
+    A.configure(None)                        # nothing changed hands: no further call
+    assert calls.count('bc_set_potential') == 3 and A.S == 3
+    with pytest.raises(nv.NativeError):
+        B.set_samples(th)                    # B never re-configured: the workspace holds A's potential
