@@ -25,7 +25,7 @@ ROUTE = os.environ.get('BC_CONTRACTION', 'q')
 # Precision tier of the tensor-core route: leading int8 digits of the 7-digit operand images a pass contracts
 # (bc_set_contraction_digits: 7 = 28 digit pairs, the accuracy of an fp64 dgemm; 6 = 21 pairs, operands as if rounded
 # to 46 bits; 5 = 15 pairs, 38 bits).  tests/test_gpu_parity.py::test_precision_tiers pins what each tier keeps exact.
-DIGITS = int(os.environ.get('BC_Q_DIGITS', '7'))
+DIGITS = int(os.environ.get('BC_Q_DIGITS', '6'))
 
 
 def set_contraction_digits(n):

@@ -88,6 +88,9 @@ class _FusedTangent(_Tangent):
         self.parts = None
         self.colsum_buf = None
         self._theta_buf = None
+        self._theta_mode = None        # None (unchecked) / 'replicated' / 'broadcast'
+        self._theta_calls = 0
+        self._check_next = False
 
     def begin(self, w, p, beta):
         prj = self.o.ll_projector
@@ -102,10 +105,36 @@ class _FusedTangent(_Tangent):
             if self._theta_buf is None or tuple(self._theta_buf.shape) != th.shape:
                 self._theta_buf = self.eng.empty(*th.shape)
             self._theta_buf.copy_(torch.from_numpy(th))
-        self.comm.broadcast(self._theta_buf, 0)            # bit-identical samples on every rank
+        self._replicate_samples()
         self.fp.configure(beta)
         self.fp.set_samples(self._theta_buf)
         self.S = self.fp.S
+
+    def _replicate_samples(self):
+        """Every rank runs the user's sampler on the same weights and the same numpy stream, so the samples are normally
+        bit-identical already and a per-step 8 S D-byte broadcast would only add latency to the optimiser loop.  That is
+        CHECKED, not assumed: the ranks compare a 64-bit checksum of the sample bits (one 8-byte all-gather) on the first
+        call and then at every selection; any mismatch switches this object to broadcasting rank 0's samples for good."""
+        if self.comm.world == 1:
+            return
+        if self._theta_mode == 'broadcast':
+            self.comm.broadcast(self._theta_buf, 0)
+            return
+        self._theta_calls += 1
+        if self._theta_mode is None or self._check_next:
+            self._check_next = False
+            h = self._theta_buf.view(torch.int64).sum().reshape(1)
+            allh = self.comm.allgather(h).cpu()
+            if bool((allh != allh[0]).any()):
+                import logging
+                logging.getLogger(__name__).warning('posterior samples differ between ranks (unseeded sampler?): broadcasting rank 0\'s every step')
+                self._theta_mode = 'broadcast'
+                self.comm.broadcast(self._theta_buf, 0)
+            else:
+                self._theta_mode = 'replicated'
+
+    def check_samples_at_next_call(self):
+        self._check_next = True
 
     def _sub_local(self, sub_idcs):
         if sub_idcs is None:
@@ -335,6 +364,8 @@ class GreedyVICoreset(Coreset):
             return self._select_group()
         t = self._get_tangent()
         M = self.wts.shape[0]
+        if hasattr(t, 'check_samples_at_next_call'):
+            t.check_samples_at_next_call()
         t.begin(self.wts, self.pts, self._beta())
         if self.n_subsample_select is None:
             sub_idcs, scaling = None, 1.

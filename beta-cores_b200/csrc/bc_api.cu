@@ -45,7 +45,7 @@ struct bc_ctx {
   int* fexp = nullptr;                     // kQK ints
   unsigned long long* fscratch = nullptr;  // kQK column maxima (bc_feature_exponents)
   unsigned long long* sscratch = nullptr;  // 2 words: max bits / non-finite flag of the samples, zero between calls
-  int q_digits = 7;                        // leading digits of the 7-digit images a launch contracts (bc_set_contraction_digits)
+  int q_digits = 6;                        // leading digits of the 7-digit images a launch contracts (bc_set_contraction_digits)
 };
 
 static int cuda_fail(cudaError_t e) {

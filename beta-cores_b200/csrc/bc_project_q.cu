@@ -485,9 +485,9 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
         double fv[8];
         // software pipeline inside the warp: while batch b is evaluated (FP64 pipe) the digits of batch b+1 -- fetched one
-        // step earlier -- have just been recombined (integer pipe), and the fetch of batch b+2 is in flight: it is issued
-        // BEFORE the evaluation, into the digit registers the recombination has just released (this is what the 112
-        // registers of the epilogue warps are for -- at 96 the in-flight destinations spilled).
+        // step earlier -- are recombined (integer pipe) in the same straight-line block, and the fetch of batch b+2 is
+        // issued right behind the evaluation.  (With the 112 registers of the epilogue warps the fetch can also be issued
+        // BEFORE the evaluation without spilling -- BC_Q_EARLY_FETCH -- but that measured 1 % slower.)
         double ccur[4], cnext[4];
         landed();
 #pragma unroll
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) cnext[e] = rsc * q_combine_n<NS>(dg[e]);
             if (b + 2 < NB) {
-#ifndef BC_Q_LATE_FETCH
+#ifdef BC_Q_EARLY_FETCH   // measured (profiles/r02_q_tiers.txt): issuing the fetch here, before the evaluation, is no faster
               fetch(b + 2);
 #endif
             } else {
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) fv[(b & 1) * 4 + e] = fr[e];
           }
-#ifdef BC_Q_LATE_FETCH
+#ifndef BC_Q_EARLY_FETCH
           if (b + 2 < NB) fetch(b + 2);
 #endif
 #pragma unroll

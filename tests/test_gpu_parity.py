@@ -170,6 +170,7 @@ def test_tensor_core_contraction_is_fp64_exact(bc):
     from bayesiancoresets import _native as nv
     eng = Engine.get()
     ctx = eng.ctx('qtest')
+    nv.call('bc_set_contraction_digits', ctx, 7)      # the full split (the shipped default contracts 6 digits)
     for n, D, S, seed in [(1, 1, 1, 0), (129, 128, 33, 1), (700, 37, 300, 2), (2500, 100, 1000, 3)]:
         r = np.random.RandomState(seed)
         X = r.randn(n, D)*np.exp(3.*r.randn(n, 1))
@@ -203,6 +204,7 @@ def test_tensor_core_contraction_with_unstandardised_features(bc):
     from bayesiancoresets import _native as nv
     eng = Engine.get()
     ctx = eng.ctx('qtest')
+    nv.call('bc_set_contraction_digits', ctx, 7)
     for n, D, S, seed in [(300, 128, 64, 4), (1000, 20, 100, 5)]:
         r = np.random.RandomState(seed)
         col = 10.**r.uniform(-8, 8, size=D)
@@ -314,7 +316,7 @@ def test_precision_tier_contraction_error(bc, digits):
             if digits < 7:      # and the tier really is coarser than the full split (the knob is wired through)
                 assert float((err/np.maximum(bound, 1e-300)).max()) > 2e-14*256.**(6-digits)*1e-3
     finally:
-        nv.call('bc_set_contraction_digits', ctx, 7)
+        nv.call('bc_set_contraction_digits', ctx, 6)
 
 
 @pytest.mark.parametrize('name', ['c5_northstar_16k', 'c3_logreg_100k', 'c4_neurlin_100k', 'lr_beta_mini', 'lr_beta_small', 'gauss_svi_full'])

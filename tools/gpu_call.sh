@@ -1,9 +1,8 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_last.json 2> gpurun_out/bench_last.err; echo b200 rc=$?
-python - <<'PY'
-import json
-d=json.loads(open('/root/repo/gpurun_out/bench_last.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d['parity'], {k:v['achieved_gbs'] for k,v in d['stage2']['kernels'].items()})
-PY
+mkdir -p gpurun_out
+for v in default latefetch r104; do
+  if [ $v = default ]; then unset BC_LIB_PATH; else export BC_LIB_PATH=/root/repo/beta-cores_b200/lib/variants/libbetacores_$v.so; fi
+  timeout 300 python tools/q_tiers.py 1000000 2>&1 | tail -1 | tee -a gpurun_out/r02_q_tiers.jsonl
+done
+unset BC_LIB_PATH
+timeout 2400 python -m pytest tests -m gpu -q -x --durations=15 2>&1 | tail -40 | tee gpurun_out/r02_pytest_1.txt
