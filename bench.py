@@ -56,10 +56,16 @@ def parse():
     ap.add_argument('--beta', type=float, default=0.1)
     ap.add_argument('--opt-itrs', type=int, default=20)
     ap.add_argument('--seed', type=int, default=0)
-    ap.add_argument('--cpu-rows', type=int, default=32768, help='rows of the cpu_baseline / parity sample')
-    ap.add_argument('--cpu-opt-itrs', type=int, default=2)
+    ap.add_argument('--cpu-rows', type=int, default=16384, help='rows of the cpu_baseline / parity sample')
+    ap.add_argument('--cpu-opt-itrs', type=int, default=5)
+    ap.add_argument('--cpu-steps', type=int, default=3, help='build(1, m) steps of the cpu_baseline / parity sample')
     ap.add_argument('--ref-rows', type=int, default=16384, help='rows per step of the --impl reference arm')
-    ap.add_argument('--ref-opt-itrs', type=int, default=4)
+    ap.add_argument('--ref-opt-itrs', type=int, default=None, help='optimiser steps per build step of the reference arm (default: --opt-itrs)')
+    ap.add_argument('--ref-sampler', default='newton', choices=['newton', 'bfgs'],
+                    help="mode finder of the reference arm's Laplace sampler: 'newton' (default: the same algebra as the product arm, faster, "
+                         "so the ratio is conservative) or 'bfgs' (the reference's stock scipy call, util/opt.py:10-33)")
+    ap.add_argument('--digits', type=int, default=None, choices=[5, 6, 7], help='precision tier of the tensor-core contraction (default: the library default)')
+    ap.add_argument('--configs', action='store_true', help='instead of the north-star workload: time BASELINE configs 1-4 (build seconds, CPU port beside)')
     ap.add_argument('--sampler', default='hybrid', choices=['newton', 'hybrid', 'device', 'bfgs'],
                     help="product arm's Laplace sampler: 'hybrid' (default) = mode and Cholesky factor on the host, the S x D x D affine map "
                          "of the normals on the device; 'newton' = all on the host (what the reference arm runs); 'device' = all on the "
@@ -102,13 +108,13 @@ def new_sampler(D, seed, method=None):
     return s
 
 
-def run_oracle_build(Z, S, beta, opt_itrs, steps, warmup, seed=1):
+def run_oracle_build(Z, S, beta, opt_itrs, steps, warmup, seed=1, method=None):
     """time `steps` build(1, m) iterations of the numpy restatement of the reference on rows Z"""
     import numpy as np
     import model_lr
     from oracle import np_models as om, np_coresets as oc
     D = Z.shape[1]
-    o = oc.GreedyVI(Z, new_sampler(D, seed), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
+    o = oc.GreedyVI(Z, new_sampler(D, seed, method), S, lambda p, t: om.lr_betalik(p, t, beta), opt_itrs=opt_itrs, sched=sched)
     for m in range(1, warmup+1):
         o.build(1, m)
     evals = 0
@@ -127,18 +133,24 @@ def reference_arm(a):
         return
     import numpy as np
     import model_lr
+    ref_itrs = a.ref_opt_itrs if a.ref_opt_itrs is not None else a.opt_itrs
     Z, _, _, _ = model_lr.gen_synthetic_outliers(a.ref_rows, a.d, seed=a.seed)
-    _, evals, dt = run_oracle_build(Z, a.s, a.beta, a.ref_opt_itrs, a.steps, a.warmup)
+    _, evals, dt = run_oracle_build(Z, a.s, a.beta, ref_itrs, a.steps, a.warmup, method=a.ref_sampler)
     v = evals/dt
     cores = blas_threads()
     sample = ('numpy restatement of the reference (oracle/, pinned bit-for-bit to /root/reference): %d build(1,m) steps on '
-              '%d rows x D=%d x S=%d, opt_itrs=%d; dgemm on %d BLAS threads, elementwise numpy single-threaded as in the reference'
-              % (a.steps, a.ref_rows, a.d, a.s, a.ref_opt_itrs, cores))
+              '%d rows x D=%d x S=%d, opt_itrs=%d, %s Laplace sampler; dgemm on %d BLAS threads, elementwise numpy single-threaded as in '
+              'the reference.  The reference cannot hold N=%d (its N x S matrix alone is %.0f GB): evaluations per second on this bounded '
+              'sample stand for its rate (SURVEY 8d)' % (a.steps, a.ref_rows, a.d, a.s, ref_itrs, a.ref_sampler, cores, a.n, a.n*a.s*8/1e9))
+    cfg = workload_config(a, world=1)
+    # what this arm actually ran: a bounded row sample of the workload above (same D, S, beta, opt_itrs per step)
+    cfg['ran'] = {'rows': a.ref_rows, 'opt_itrs': ref_itrs, 'sampler': a.ref_sampler, 'extrapolated': True,
+                  'note': 'rate measured on %d of the %d rows; a full-size reference build does not fit host memory' % (a.ref_rows, a.n)}
     print(json.dumps({
         'impl': 'reference', 'metric': 'beta_likelihood_evals_per_s', 'value': v, 'unit': 'evals/s', 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': 1e3*dt/a.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(a, world=1),
+        'config': cfg,
         'cpu_baseline': {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'host': {'cpu_count': os.cpu_count()},
@@ -256,6 +268,9 @@ def b200_arm(a):
     from bayesiancoresets._shard import partition_rows
 
     N, D, S, beta, K, W = a.n, a.d, a.s, a.beta, a.steps, a.warmup
+    if a.digits is not None:
+        _fused.set_contraction_digits(a.digits)
+    digits = _fused.DIGITS
     # the host side of this arm is the sampler's D x D algebra: BLAS thread pools only thrash on it
     blas_default = blas_threads()
     try:
@@ -345,12 +360,16 @@ def b200_arm(a):
     if route == 'q':
         kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
                  'column sums, fused)')
-        digit_pairs, fp64_inst = 28, 65          # kept digit pairs (d <= 6); FP64-pipe instructions per evaluation (SASS count)
+        digit_pairs, fp64_inst = digits*(digits+1)//2, 65   # kept digit pairs (diagonals d < digits); FP64-pipe instructions per evaluation (SASS count)
         int8_ops = digit_pairs*2.*n_local*S*128
         # measured on this pool (tools/mma_i8_rate.cu, profiles/r01_mma_i8_rate.txt): 8192 int8 MACs per cycle per SM from N = 128 up
         int8_peak = eng.sms*8192*2.*1965e6/1e12
         extra = {
-            'route': 'q',
+            'route': 'q', 'contraction_digits': digits,
+            'precision': ('operands contracted to their leading %d int8 digits (%d bits below the row / sample maximum; 7 digits = the '
+                          'accuracy of an fp64 dgemm, the north star allows 3xTF32 = about 30 bits); every tier keeps the reference\'s '
+                          'index sequences on all golden builds (tests/test_gpu_parity.py::test_precision_tiers_keep_reference_selections)'
+                          % (digits, 8*digits-2)),
             'int8_tensor': {'ops_per_launch': int8_ops, 'achieved_tops': int8_ops/(col_mean*1e-3)/1e12, 'peak_tops': int8_peak,
                             'frac': int8_ops/(col_mean*1e-3)/1e12/int8_peak,
                             'peak_source': 'tcgen05.mma.kind::i8 rate measured on this pool: 8192 MACs/cycle/SM x SMs x 1965 MHz '
@@ -367,9 +386,11 @@ def b200_arm(a):
         'kernel': kname,
         'bound': 'tensor', 'achieved': achieved, 'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved/FP64_DMMA_PEAK_TFLOPS,
         'traffic': None,
-        'peak_source': 'algorithmic fp64 flops 2*N*S*D against the FP64 tensor (DMMA mma.sync m16n8k4 f64) peak measured on this pool, '
-                       'profiles/r01_fp64_peaks.jsonl -- the fastest NATIVE fp64 contraction rate of the chip; MEASURED_PEAKS.json '
-                       'holds no fp64 figure and tcgen05 has no f64 kind (the q route emulates fp64 exactly on int8 tensor cores)',
+        'peak_source': 'algorithmic fp64 flops 2*N*S*D against the FP64 tensor (DMMA mma.sync m16n8k4 f64) peak: 36.9 TFLOP/s MEASURED on '
+                       'this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.jsonl), 40 TFLOP/s nominal -- the fastest NATIVE fp64 '
+                       'contraction rate of the chip; MEASURED_PEAKS.json holds no fp64 figure and tcgen05 has no f64 kind (the q route '
+                       'contracts on int8 tensor cores, so it can exceed this figure: see int8_tensor and fp64_pipe for the pipes it runs on)',
+        'peak_nominal': 40.0, 'frac_of_nominal': achieved/40.0,
         'launch_ms': col_mean, 'launches_timed': len(col_ms), 'rows_per_launch': n_local,
         'algorithmic_flops_per_launch': flops, 'evals_per_s_kernel': n_local*S/(col_mean*1e-3),
         'hbm': {'algorithmic_bytes_per_launch': alg_bytes, 'achieved_gbs': alg_bytes/(col_mean*1e-3)/1e9, 'peak_gbs': hbm_peak,
@@ -379,18 +400,39 @@ def b200_arm(a):
     }
     roofline.update(extra)
     if route == 'q':
-        qbytes = ((n_local + 127)//128)*7*128*128 + 8.*n_local + 7.*S*128*((n_local + 127)//128)*0   # image + row scales
+        qbytes = ((n_local + 127)//128)*digits*128*128 + 8.*n_local   # digit planes read + row scales
         roofline['hbm'].update({'algorithmic_bytes_per_launch': qbytes, 'achieved_gbs': qbytes/(col_mean*1e-3)/1e9,
                                 'frac': qbytes/(col_mean*1e-3)/1e9/hbm_peak,
-                                'note': 'int8 digit image of the rows (7 B per feature) + row scales; samples stay in L2'})
+                                'note': 'int8 digit planes of the rows (%d B per feature) + row scales; samples stay in L2' % digits})
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for a
         # 1,000,000-row launch (= the algorithmic 904 MB; the operands are read exactly once); it scales linearly in rows
-        roofline['traffic'] = 911.4*n_local
-        roofline['traffic_source'] = 'ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v4.txt), scaled by rows'
+        per_row = {7: 911.4, 6: 911.4*6/7., 5: 911.4*5/7.}[digits]
+        roofline['traffic'] = per_row*n_local
+        roofline['traffic_source'] = ('ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for the '
+                                      '7-digit image, = its algorithmic bytes), scaled by rows and by the digit planes a launch reads; not '
+                                      'measured in this run (DRAM counters need ncu)')
         roofline['bound_detail'] = ('FP64 pipe of the fused potential epilogue PLUS the tensor time of the int8 digit MMAs: on B200 the FP64 pipe '
                                     'makes no progress while the tensor core is busy (profiles/r01_q_ablation.txt), so the two add up; '
                                     'HBM is at 2 % of its peak')
     idcs_value = [int(i) for i in alg.idcs]
+    if route == 'q':
+        # the other precision tiers of the same pass, timed right here on the resident rows (3 passes each after 2 warm-ups)
+        tg, tiers = alg._tangent, {}
+        for dg in (7, 6, 5):
+            _fused.set_contraction_digits(dg)
+            for _ in range(2):
+                tg.fp.colsum_parts(tg.rows, None, out=tg.parts)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(3):
+                tg.fp.colsum_parts(tg.rows, None, out=tg.parts)
+            t1e.record()
+            torch.cuda.synchronize()
+            ms = max_over_ranks(t0e.elapsed_time(t1e)/3.)
+            tiers['digits_%d' % dg] = {'launch_ms': ms, 'digit_pairs': dg*(dg+1)//2, 'evals_per_s_kernel': n_local*S/(ms*1e-3),
+                                       'fp64_equiv_tflops': flops/(ms*1e-3)/1e12}
+        _fused.set_contraction_digits(digits)
+        roofline['tiers'] = tiers
 
     # ---- stage 2 (materialised n x S matrix: snnls / Hilbert scoring) and stage 3 (coreset-side step), timed on their own ----
     stage2 = stage3 = None
@@ -482,26 +524,32 @@ def b200_arm(a):
         for threads in (blas_default, 1):
             if threadpool_limits is not None:
                 with threadpool_limits(limits=threads, user_api='blas'):
-                    o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, 1, 0)
+                    o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, a.cpu_steps, 0)
             else:
                 if threads == 1:
                     continue
-                o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, 1, 0)
+                o, ev, t = run_oracle_build(Zs, S, beta, a.cpu_opt_itrs, a.cpu_steps, 0)
             used = threads
             if best is None or ev/t > best[0]:
                 best = (ev/t, used, t)
         cpu = {'value': best[0], 'unit': 'evals/s', 'cores': best[1], 'kind': 'port',
-               'sample': 'numpy oracle (restatement of the reference, pinned to it): one build(1,1) step on the first %d rows, '
+               'sample': 'numpy oracle (restatement of the reference, pinned to it): %d build(1,m) steps on the first %d rows, '
                          'D=%d S=%d opt_itrs=%d (%.1f s); faster of default BLAS threads and 1 thread; host has %d cpus'
-                         % (ns, D, S, a.cpu_opt_itrs, best[2], os.cpu_count())}
-        # the same sample through the CUDA path: identical index, weights within 1e-6
+                         % (a.cpu_steps, ns, D, S, a.cpu_opt_itrs, best[2], os.cpu_count())}
+        # the same sample through the CUDA path (tensor-core route): identical index sequence, weights within 1e-6
         prj = bc.BetaBlackBoxProjector(new_sampler(D, 1, a.sampler), S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
         algs = bc.BetaCoreset(Zs, prj, opt_itrs=a.cpu_opt_itrs, step_sched=sched, beta=beta, learn_beta=False)
-        algs.build(1, 1)
+        for m in range(1, a.cpu_steps+1):
+            algs.build(1, m)
         ow, _, oi = o.get()
         gw, _, gi, _ = algs.get()
-        parity = {'rows': ns, 'indices_equal': [int(i) for i in gi] == [int(i) for i in oi], 'indices': [int(i) for i in gi],
-                  'max_rel_weight_diff': float(np.max(np.abs(gw-ow)/np.abs(ow))) if len(ow) == len(gw) and len(ow) else None}
+        same = [int(i) for i in gi] == [int(i) for i in oi]
+        nz = (np.abs(ow) > 0) if same else None
+        parity = {'rows': ns, 'steps': a.cpu_steps, 'opt_itrs': a.cpu_opt_itrs, 'contraction_digits': digits,
+                  'indices_equal': same, 'indices': [int(i) for i in gi], 'oracle_indices': [int(i) for i in oi],
+                  'weights': [float(x) for x in gw], 'oracle_weights': [float(x) for x in ow],
+                  'max_rel_weight_diff': float(np.max(np.abs(gw[nz]-ow[nz])/np.abs(ow[nz]))) if same and nz.any() else None,
+                  'tolerance': 1e-6}
 
     if rank == 0:
         line = {
@@ -526,6 +574,103 @@ def b200_arm(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------- BASELINE configs 1-4 --
+def configs_leg(a):
+    """build seconds of BASELINE.json's configs 1-4 on one GPU with the numpy port of the reference beside each (the CPU
+    arm runs fewer build steps of the same problem and is compared per build step).  One JSON line per config.  The
+    problems are the seeded ones of tests/golden/problems.py (config 1 = examples/zellner_gaussian/main.py restated line
+    by line; config 2 = the tests/test_snnls matrix; configs 3 / 4 = SURVEY 8d's generators at 100K / 1M rows)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    import problems
+    import bayesiancoresets as bc
+    import model_lr, gaussian, model_neurlinr
+    from bayesiancoresets import _native as nv
+    from oracle import np_snnls as osn, np_coresets as oc
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1, user_api='blas')     # D x D samplers: BLAS thread pools only thrash (SURVEY section 6)
+    except Exception:
+        pass
+    torch.cuda.set_device(0)
+
+    def potentials(prob):
+        if prob['model'] == 'lr':
+            return model_lr.beta_likelihood, model_lr.log_likelihood
+        if prob['model'] == 'gauss':
+            return gaussian.gaussian_beta_likelihood.bind(**prob['params']), gaussian.gaussian_loglikelihood.bind(**prob['params'])
+        return model_neurlinr.neurlinr_beta_likelihood.bind(**prob['params']), model_neurlinr.neurlinr_loglikelihood.bind(**prob['params'])
+
+    def greedy(case, gpu_steps, cpu_steps, label):
+        prob = case['make']()
+        problems.reseed(case)
+        bl, ll = potentials(prob)
+        prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
+        alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'],
+                             step_sched=case['sched'], beta=case['beta'], learn_beta=False)
+        alg.build(1, 1)                       # first step: uploads, row image, lazy allocations
+        torch.cuda.synchronize()
+        l0 = nv.lib().bc_launch_count()
+        t0 = time.perf_counter()
+        for m in range(2, gpu_steps+1):
+            alg.build(1, m)
+        torch.cuda.synchronize()
+        g = (time.perf_counter()-t0)/max(gpu_steps-1, 1)
+        launches = nv.lib().bc_launch_count() - l0
+        gi = [int(i) for i in alg.idcs]
+        prob = case['make']()
+        problems.reseed(case)
+        o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], prob['oracle_betalik'](case['beta']), n_sub_select=case['n_sel'],
+                        n_sub_opt=case['n_opt'], opt_itrs=case['opt_itrs'], sched=case['sched'])
+        with np.errstate(all='ignore'):
+            o.build(1, 1)
+            t0 = time.perf_counter()
+            for m in range(2, cpu_steps+1):
+                o.build(1, m)
+        c = (time.perf_counter()-t0)/max(cpu_steps-1, 1)
+        oi = [int(i) for i in o.idcs]
+        n = min(len(gi), len(oi))
+        print(json.dumps({'config': label, 'rows': int(prob['data'].shape[0]), 'D': int(prob['data'].shape[1]), 'S': case['S'],
+                          'opt_itrs': case['opt_itrs'], 'subsample': [case['n_sel'], case['n_opt']],
+                          'b200_s_per_build_step': g, 'b200_build_steps_timed': gpu_steps-1, 'b200_ms_per_optimiser_step': 1e3*g/(1+case['opt_itrs']),
+                          'b200_launches_per_build_step': launches/max(gpu_steps-1, 1),
+                          'cpu_port_s_per_build_step': c, 'cpu_build_steps_timed': cpu_steps-1, 'cpu_threads': 1, 'speedup': c/g,
+                          'indices_equal_on_common_prefix': gi[:n] == oi[:n], 'indices': gi[:12]}), flush=True)
+
+    cases = {c['name']: c for c in problems.coreset_cases(True)}
+    greedy(cases['c1_zellner_gaussian'], 12, 3, 'C1 examples/zellner_gaussian (N=5700 d=100 S=200, 1000 ADAM steps per point, sub-samples 1000/200)')
+    # C2: snnls on the 1000 x 100 matrix of tests/test_snnls
+    V = problems.snnls_matrix()
+    for name, cls in (('giga', bc.snnls.GIGA), ('fw', bc.snnls.FrankWolfe), ('omp', bc.snnls.OrthoPursuit)):
+        alg = cls(V.T, V.sum(axis=0)); alg.build(3); alg.reset()
+        torch.cuda.synchronize(); t0 = time.perf_counter(); alg.build(100); torch.cuda.synchronize(); g = time.perf_counter()-t0
+        o = osn.SOLVERS[name](V.T, V.sum(axis=0)); t0 = time.perf_counter(); o.run(100); c = time.perf_counter()-t0
+        print(json.dumps({'config': 'C2 snnls %s, A = 100 x 1000, build(100)' % name, 'b200_s': g, 'cpu_port_s': c, 'speedup': c/g,
+                          'weights_rel_diff': float(np.abs(alg.weights()-o.w).max()/np.abs(o.w).max()),
+                          'note': 'latency-bound at this size: 0.8 MB of data, a handful of launches and scalar read-backs per iteration'}), flush=True)
+    greedy(cases['c3_logreg_100k'], 5, 3, 'C3 examples/zellner_logreg (N=100K D=20 S=100 beta=0.1, full data, Laplace sampler)')
+    c4 = dict(cases['c4_neurlin_100k'], make=problems.make_neurlin(1_000_000, 64, 42))
+    c4cpu = cases['c4_neurlin_100k']
+    # config 4 at its stated 1M rows on the GPU; the CPU port is timed on 100K rows and scaled by 10 (its cost is linear in rows)
+    prob = c4['make']()
+    problems.reseed(c4)
+    bl, ll = potentials(prob)
+    prj = bc.BetaBlackBoxProjector(prob['sampler'], c4['S'], bl, ll, None)
+    alg = bc.BetaCoreset(prob['data'], prj, opt_itrs=c4['opt_itrs'], step_sched=c4['sched'], beta=c4['beta'], learn_beta=False)
+    alg.build(1, 1); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for m in range(2, 6):
+        alg.build(1, m)
+    torch.cuda.synchronize(); g = (time.perf_counter()-t0)/4.
+    prob = c4cpu['make'](); problems.reseed(c4cpu)
+    o = oc.GreedyVI(prob['data'], prob['sampler'], c4cpu['S'], prob['oracle_betalik'](c4cpu['beta']), opt_itrs=c4cpu['opt_itrs'], sched=c4cpu['sched'])
+    o.build(1, 1); t0 = time.perf_counter(); o.build(1, 2); c = (time.perf_counter()-t0)
+    print(json.dumps({'config': 'C4 examples/zellner_neural_linear (N=1M D=64 S=256 beta=0.2, conjugate sampler)', 'rows': 1_000_000,
+                      'b200_s_per_build_step': g, 'b200_ms_per_optimiser_step': 1e3*g/(1+c4['opt_itrs']),
+                      'cpu_port_s_per_build_step_100k_rows': c, 'cpu_port_s_per_build_step_scaled_to_1M': 10*c, 'speedup': 10*c/g,
+                      'indices': [int(i) for i in alg.idcs]}), flush=True)
+
+
 def _quiet_stdout():
     """libraries (NCCL's version banner, ...) write to fd 1: point it at stderr while the bench runs so that stdout carries
     exactly one JSON line; returns a file object on the real stdout"""
@@ -538,7 +683,9 @@ def _quiet_stdout():
 if __name__ == '__main__':
     args = parse()
     sys.stdout = _quiet_stdout()
-    if args.impl == 'reference':
+    if args.configs:
+        configs_leg(args)
+    elif args.impl == 'reference':
         reference_arm(args)
     else:
         b200_arm(args)

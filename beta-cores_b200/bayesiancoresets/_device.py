@@ -17,7 +17,13 @@ def _require_cuda():
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """raw handle of torch's current stream on the current device.  torch.cuda.current_stream() builds a Stream object
+    through several Python layers (16 us per call, measured: it was 0.13 ms of a 0.87 ms optimiser step of the Gaussian
+    example); the private accessor below returns the same handle in a fraction of a microsecond."""
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:      # pragma: no cover  (a torch build without the private accessors)
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def ptr(t):

@@ -59,6 +59,7 @@ class FusedProjection(object):
         self.S = None
         self.Sld = None
         self._theta = None
+        self._gather = None        # scratch (image, rowscale, rowaux, capacity in rows) of gathered passes
 
     # ---- configuration ----
     # The bc_ctx workspace behind `ctx_name` is shared by every FusedProjection of the engine (one potential and one
@@ -112,13 +113,14 @@ class FusedProjection(object):
         return rows.rowaux
 
     def _q_operands(self, rows, sub):
-        """(image, rowscale, rowaux) when the tensor-core route applies to this pass, else None"""
-        if ROUTE != 'q' or sub is not None or self.D > nv.lib().bc_q_max_features():
+        """(image, rowscale, rowaux) when the tensor-core route applies to this pass, else None.  `sub` (a gather list of local
+        row numbers): the listed rows of the dataset's image are re-packed into a compact scratch image first (bc_q_gather_rows)."""
+        if ROUTE != 'q' or self.D > nv.lib().bc_q_max_features():
             return None
         aux_col = self.D if self.pot.model == 'neurlin' else None
         # in a sharded job the first call exchanges the feature exponents: every rank comes through here, rows or not
         img, rs, aux, fexp = rows.quantised(self.ctx, self.D, aux_col)
-        if rows.n_local == 0:
+        if rows.n_local == 0 or (sub is not None and int(sub.numel()) == 0):
             return None
         if self.eng.fexp_applied.get(self.ctx_name) is not fexp:     # the ctx's sample image must match this row image
             nv.call('bc_set_feature_exponents', self.ctx, ptr(fexp), self.D, stream_ptr())
@@ -127,7 +129,18 @@ class FusedProjection(object):
             nv.call('bc_set_contraction_digits', self.ctx, DIGITS)
             self._applied()['digits'] = DIGITS
         ra = self._rowaux(rows) if self.pot.model == 'gaussian' else aux
-        return img, rs, ra
+        if sub is None:
+            return img, rs, ra
+        n = int(sub.numel())
+        if self._gather is None or self._gather[3] < n:
+            cap = max(2*n, 1024)
+            nb = nv.c_i64()
+            nv.call('bc_q_image_bytes', cap, ctypes.byref(nb))
+            self._gather = (torch.empty(nb.value, dtype=torch.uint8, device=self.eng.device), self.eng.empty(cap), self.eng.empty(cap), cap)
+        gimg, grs, gaux, _ = self._gather
+        nv.call('bc_q_gather_rows', self.ctx, ptr(img), ptr(rs), ptr(ra), ptr(sub), n, ptr(gimg), ptr(grs), ptr(gaux) if ra is not None else None,
+                stream_ptr())
+        return gimg, grs, (gaux if ra is not None else None)
 
     def _check(self, rows):
         if self.S is None or self._applied()['samples_of'] is not self:

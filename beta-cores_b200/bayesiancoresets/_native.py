@@ -24,6 +24,7 @@ SIGNATURES = {
     'bc_project_materialise': [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp],
     'bc_q_image_bytes': [c_i64, ctypes.POINTER(c_i64)],
     'bc_quantise_rows': [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'bc_q_gather_rows': [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     'bc_feature_exponents': [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp],
     'bc_set_feature_exponents': [c_vp, c_vp, c_int, c_vp],
     'bc_set_contraction_digits': [c_vp, c_int],
@@ -37,6 +38,7 @@ SIGNATURES = {
     'bc_core_pgrad': [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp],
     'bc_dense_pgrad': [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp],
     'bc_laplace_logistic': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
+    'bc_sample_solve': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_sample_affine': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
     'bc_dense_rownorms': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp],

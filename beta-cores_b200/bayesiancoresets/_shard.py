@@ -88,11 +88,18 @@ class Comm(object):
             pass
         return cls(None)
 
+    def _staged(self, t):
+        """gloo moves host memory only: CUDA tensors are staged through the host (two ranks sharing one GPU in the tests;
+        NCCL, the production backend, takes device tensors directly)"""
+        return t.is_cuda and self.dist.get_backend() == 'gloo'
+
     def allgather(self, t):
         """(world, *t.shape) tensor of every rank's `t` (same device/dtype), rank-ordered"""
         if self.world == 1:
             return t.unsqueeze(0)
         import torch
+        if self._staged(t):
+            return self.allgather(t.cpu()).to(t.device)
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         if t.is_cuda:
             self.dist.all_gather_into_tensor(out, t.contiguous())
@@ -103,7 +110,24 @@ class Comm(object):
                 out[r].copy_(p)
         return out
 
+    def allgather_var(self, t):
+        """list of every rank's 1-d tensor `t`, rank-ordered; the lengths may differ"""
+        if self.world == 1:
+            return [t]
+        import torch
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+        sizes = [int(v) for v in self.allgather(n).cpu().numpy()[:, 0]]
+        pad = torch.zeros(max(max(sizes), 1), dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t
+        allp = self.allgather(pad)
+        return [allp[r, :sizes[r]] for r in range(self.world)]
+
     def broadcast(self, t, src):
         if self.world > 1:
-            self.dist.broadcast(t, src=src)
+            if self._staged(t):
+                h = t.cpu()
+                self.dist.broadcast(h, src=src)
+                t.copy_(h)
+            else:
+                self.dist.broadcast(t, src=src)
         return t

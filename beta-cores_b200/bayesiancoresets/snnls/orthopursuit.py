@@ -17,11 +17,11 @@ class OrthoPursuit(SparseNNLS):
     def _setup(self):
         self._require_nonzero_columns()
         if self._N:
-            self._active_dev = self._eng.zeros(self._N, dtype=torch.uint8)
+            self._active_dev = self._eng.zeros(max(self._nl, 1), dtype=torch.uint8)     # this rank's block of datapoints
 
     def _sync_active(self):
         self._active_dev.zero_()
-        nz = [i for i, x in zip(self._act, self._aw) if x > 0]
+        nz = [i-self._row0 for i, x in zip(self._act, self._aw) if x > 0 and self._row0 <= i < self._row0+self._nl]
         if nz:
             self._active_dev[torch.as_tensor(nz, dtype=torch.int64, device=self._eng.device)] = 1
 
@@ -37,14 +37,6 @@ class OrthoPursuit(SparseNNLS):
 
     def _reweight(self, f):
         # orthopursuit.py:37-42
-        f = int(f)
-        if f in self._act:
-            self._aw[self._act.index(f)] = 1.
-        else:
-            self._act.append(f)
-            self._aw.append(1.)
+        self._aw[self._activate(int(f))] = 1.
         nz = sorted(i for i, x in zip(self._act, self._aw) if x > 0)
-        sol = self._nnls_on(nz)
-        lut = dict(zip(nz, sol))
-        self._aw = [float(lut.get(i, x)) for i, x in zip(self._act, self._aw)]
-        self._xw_valid = False
+        self._assign(nz, self._nnls_on(nz))

@@ -4,10 +4,24 @@ one retry, numeric-limit latch, optimize()).
 
 Device layout: the reference's A is (S, N) with one column per datapoint; here the matrix lives in HBM
 datapoint-major, V = A^T (N x S, row n contiguous), so that the per-iteration score pass streams each
-datapoint's S values with coalesced 16-byte loads (bc_dense_score).  The iterate A w is formed from the
-active rows only (bc_dense_combine); the S-length line-search algebra is one single-CTA kernel per step
-(bc_vec_step); the host sees a handful of scalars per iteration and applies the reference's guards to them.
+datapoint's S values with coalesced 16-byte loads (bc_dense_score).
+
+What an iteration touches:
+  * the score pass reads V once (8 N S bytes, the HBM-bound part);
+  * the rows that ever received weight are CACHED in a small replicated matrix (m x S): the iterate A w is
+    re-formed from those m rows on the device (bc_dense_combine) -- exact, so the reference's strict error-monotone
+    check (snnls.py:56-62) sees the errors it would see, at O(m S) instead of the reference's three N x S products per
+    iteration (SURVEY 3.3); the weights go up through a pinned buffer without a synchronisation;
+  * the S-length line-search algebra is one single-CTA kernel per step (bc_vec_step);
+  * the host reads three small results per iteration (selection, step scalars, new error) and applies the
+    reference's guards to them; the error of the current weights is remembered, not recomputed.
+
+Datapoints (the rows of V) may be sharded over torch.distributed ranks (last sentence): every rank scores
+its own block, the ranks exchange one (score, global index) pair per iteration (two for OrthoPursuit) and merge them
+with numpy's arg-max rule; a newly selected row is broadcast once by its owner into every rank's cache, after which
+the iterate, the line search and the error are computed redundantly and identically everywhere.
 """
+import bisect
 import logging
 import secrets
 import numpy as np
@@ -17,6 +31,7 @@ from scipy.optimize import nnls
 from .. import util
 from .. import _native as nv
 from .._device import Engine, ptr, stream_ptr
+from .._shard import Comm, merge_best, partition_rows
 from ..util.errors import NumericalPrecisionError
 
 
@@ -30,20 +45,25 @@ class SparseNNLS(object):
         self.check_error_monotone = check_error_monotone
         self._eng = Engine.get()
         self._ctx = self._eng.ctx()
+        self._comm = Comm.current()
         A = np.asarray(A, dtype=np.float64)
         self._S, self._N = (A.shape[0], A.shape[1]) if A.ndim == 2 else (0, 0)
+        self._nl, self._row0 = self._N, 0
         if A.size:
-            At = self._eng.upload(A)                                   # (S, N) as the caller laid it out
-            V = self._eng.empty(self._N, self._S)
-            nv.call('bc_transpose', self._ctx, ptr(At), self._S, self._N, int(At.stride(0)), ptr(V), self._S, stream_ptr())
-            del At
-            self._attach(V, None)
+            # in a multi-rank job every rank is handed the same host matrix and keeps its own block of columns (= datapoints)
+            r0, nl = partition_rows(self._N, self._comm.world, self._comm.rank) if self._comm.world > 1 else (0, self._N)
+            V = self._eng.empty(max(nl, 1), self._S)
+            if nl:
+                At = self._eng.upload(np.ascontiguousarray(A[:, r0:r0+nl]))          # (S, nl) as the caller laid it out
+                nv.call('bc_transpose', self._ctx, ptr(At), self._S, nl, int(At.stride(0)), ptr(V), self._S, stream_ptr())
+                del At
+            self._attach(V[:nl], None, r0, self._N)
         self._reset_weights()
 
     @classmethod
-    def from_device(cls, V, norms, b_host):
-        """build a solver directly on a device-resident datapoint-major matrix V (n x S), e.g. the output of
-        the materialise pass (HilbertCoreset); `A` is exposed lazily as V^T on the host."""
+    def from_device(cls, V, norms, b_host, row0=0, n_total=None):
+        """build a solver directly on a device-resident datapoint-major matrix V (n_local x S), e.g. the output of the
+        materialise pass (HilbertCoreset); rows [row0, row0 + n_local) of n_total in a sharded job."""
         self = cls.__new__(cls)
         self.alg_name = '%s-%s' % (cls.__name__, secrets.token_hex(3))
         self.log = logging.LoggerAdapter(logging.getLogger(), {'id': self.alg_name})
@@ -53,26 +73,45 @@ class SparseNNLS(object):
         self.check_error_monotone = True
         self._eng = Engine.get()
         self._ctx = self._eng.ctx()
-        self._N, self._S = int(V.shape[0]), int(V.shape[1])
+        self._comm = Comm.current()
+        self._S = int(V.shape[1])
+        self._N = int(n_total) if n_total is not None else int(V.shape[0])
+        self._nl, self._row0 = int(V.shape[0]), int(row0)
         if self._N:
-            self._attach(V, norms)
+            self._attach(V, norms, row0, self._N)
         self._reset_weights()
         self._setup()
         return self
 
-    def _attach(self, V, norms):
+    def _attach(self, V, norms, row0, n_total):
         self._V = V
-        self._ldv = int(V.stride(0))
+        self._nl, self._row0 = int(V.shape[0]), int(row0)
+        self._ldv = int(V.stride(0)) if self._nl else self._S
         if norms is None:
-            norms = self._eng.empty(self._N)
-            nv.call('bc_dense_rownorms', self._ctx, ptr(V), self._N, self._S, self._ldv, ptr(norms), stream_ptr())
+            norms = self._eng.empty(max(self._nl, 1))
+            if self._nl:
+                nv.call('bc_dense_rownorms', self._ctx, ptr(V), self._nl, self._S, self._ldv, ptr(norms), stream_ptr())
         self._norms = norms
-        self._norms_host = norms.cpu().numpy()                        # N doubles, once: zero-column check, FW's norm sum
+        # all N norms on every host, once: the zero-column check and Frank-Wolfe's sum of norms (frankwolfe.py:10)
+        if self._comm.world > 1:
+            parts = self._comm.allgather_var(norms[:self._nl])
+            self._starts = list(np.cumsum([0] + [int(p.numel()) for p in parts])[:-1])
+            self._norms_host = torch.cat(parts).cpu().numpy()
+            if self._starts[self._comm.rank] != self._row0 or self._norms_host.shape[0] != n_total:
+                raise ValueError('row blocks of the ranks do not tile [0, %d)' % n_total)
+        else:
+            self._starts = [0]
+            self._norms_host = norms[:self._nl].cpu().numpy()
         self._b_dev = self._eng.upload(self.b)
         self._xw = self._eng.zeros(self._S)
         self._u = self._eng.zeros(2*self._S)
         self._out = self._eng.zeros(8)
-        self._xw_valid = False
+        self._cache_cap = 0
+        self._Vact = None
+        self._aw_dev = None
+        self._seq_dev = None
+        self._pin = [torch.empty(1, dtype=torch.float64).pin_memory(), torch.empty(1, dtype=torch.float64).pin_memory()]
+        self._pin_k = 0
 
     def _setup(self):
         pass
@@ -83,9 +122,11 @@ class SparseNNLS(object):
 
     # ---- weights: sparse on the inside, the reference's dense `w` on the outside ----
     def _reset_weights(self):
-        self._act = []            # indices that ever received weight, in order of first selection
+        self._act = []            # global indices that ever received weight, in order of first selection
+        self._pos = {}            # index -> position in _act (= row of the cache)
         self._aw = []             # their weights
         self._xw_valid = False
+        self._err = None          # error() of the current weights, once computed
 
     @property
     def w(self):
@@ -97,29 +138,59 @@ class SparseNNLS(object):
     @w.setter
     def w(self, w):
         w = np.asarray(w, dtype=np.float64)
-        nz = np.nonzero(w)[0]
-        self._act = [int(i) for i in nz]
-        self._aw = [float(w[i]) for i in nz]
+        self._reset_weights()
+        for i in np.nonzero(w)[0]:
+            self._activate(int(i))
+            self._aw[self._pos[int(i)]] = float(w[i])
+        self._touch()
+
+    def _touch(self):
         self._xw_valid = False
+        self._err = None
+
+    def _owner(self, f):
+        return bisect.bisect_right(self._starts, f) - 1
+
+    def _activate(self, f):
+        """make sure datapoint f has a row in the replicated cache (fetched once from its owner) and a weight slot"""
+        f = int(f)
+        if f in self._pos:
+            return self._pos[f]
+        k = len(self._act)
+        if k >= self._cache_cap:
+            cap = max(64, 2*self._cache_cap)
+            Vn = self._eng.empty(cap, self._S)
+            if self._Vact is not None and k:
+                Vn[:k].copy_(self._Vact[:k])
+            self._Vact, self._cache_cap = Vn, cap
+            self._aw_dev = self._eng.zeros(cap)
+            self._seq_dev = torch.arange(cap, dtype=torch.int64, device=self._eng.device)
+            self._pin = [torch.empty(cap, dtype=torch.float64).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory()]
+        own = self._owner(f) if self._comm.world > 1 else self._comm.rank
+        if own == self._comm.rank:
+            self._Vact[k].copy_(self._V[f-self._row0])
+        if self._comm.world > 1:
+            self._comm.broadcast(self._Vact[k], own)
+        self._act.append(f)
+        self._pos[f] = k
+        self._aw.append(0.)
+        return k
 
     def _scale_and_add(self, alpha, f, beta):
         """w = alpha*w ; w[f] = max(0, w[f] + beta)      (giga.py:63-64, frankwolfe.py:39-40)"""
+        k = self._activate(f)
         self._aw = [alpha*x for x in self._aw]
-        f = int(f)
-        if f in self._act:
-            k = self._act.index(f)
-            self._aw[k] = max(0., self._aw[k]+beta)
-        else:
-            self._act.append(f)
-            self._aw.append(max(0., 0.*alpha+beta))
-        self._xw_valid = False
+        self._aw[k] = max(0., self._aw[k]+beta)
+        self._touch()
 
     def _snapshot(self):
-        return (list(self._act), list(self._aw))
+        return (list(self._aw), self._err)
 
     def _restore(self, snap):
-        self._act, self._aw = list(snap[0]), list(snap[1])
-        self._xw_valid = False
+        # rows selected since the snapshot stay cached (with weight 0, exactly the reference's w after `self.w = prev_w`)
+        self._aw = list(snap[0]) + [0.]*(len(self._act)-len(snap[0]))
+        self._touch()
+        self._err = snap[1]
 
     def reset(self):
         self._reset_weights()
@@ -133,12 +204,18 @@ class SparseNNLS(object):
 
     # ---- device steps ----
     def _iterate(self):
-        """xw = A w on the device, from the active rows only"""
+        """xw = A w on the device, re-formed exactly from the cached active rows"""
         if not self._xw_valid:
             m = len(self._act)
-            idx = self._eng.upload(np.asarray(self._act, dtype=np.int64), dtype=torch.int64) if m else None
-            aw = self._eng.upload(np.asarray(self._aw, dtype=np.float64)) if m else None
-            nv.call('bc_dense_combine', self._ctx, ptr(self._V), self._ldv, self._S, ptr(idx), ptr(aw), m, ptr(self._xw), stream_ptr())
+            if m:
+                self._pin_k ^= 1
+                pin = self._pin[self._pin_k]
+                pin[:m] = torch.from_numpy(np.asarray(self._aw, dtype=np.float64))
+                self._aw_dev[:m].copy_(pin[:m], non_blocking=True)
+                nv.call('bc_dense_combine', self._ctx, ptr(self._Vact), self._S, self._S, ptr(self._seq_dev), ptr(self._aw_dev), m,
+                        ptr(self._xw), stream_ptr())
+            else:
+                self._xw.zero_()
             self._xw_valid = True
         return self._xw
 
@@ -147,17 +224,24 @@ class SparseNNLS(object):
                 ptr(u), ptr(self._out if out is None else out), stream_ptr())
 
     def _score(self, mode, u, active=None):
-        nv.call('bc_dense_score', self._ctx, mode, ptr(self._V), self._N, self._S, self._ldv, ptr(self._norms), ptr(u), ptr(active), 0,
-                ptr(self._out[4:]), None, stream_ptr())
+        if self._nl:
+            nv.call('bc_dense_score', self._ctx, mode, ptr(self._V), self._nl, self._S, self._ldv, ptr(self._norms), ptr(u), ptr(active),
+                    self._row0, ptr(self._out[4:]), None, stream_ptr())
+        else:       # a rank without datapoints offers no candidate (index -1 loses every merge)
+            empty = np.zeros(4)
+            empty[1::2] = np.array([-1, -1], dtype=np.int64).view(np.float64)
+            self._out[4:].copy_(torch.from_numpy(empty))
 
     def _row(self, f):
-        return self._V[int(f)]
+        return self._Vact[self._activate(f)]
 
     def error(self):
         if self._N == 0:
             return float(np.sqrt((self.b**2).sum()))
-        self._vec(nv.VEC_RESID)
-        return float(self._out[:1].cpu().numpy()[0])
+        if self._err is None:
+            self._vec(nv.VEC_RESID)
+            self._err = float(self._out[:1].cpu().numpy()[0])
+        return self._err
 
     # ---- the reference's build loop (snnls.py:31-78) ----
     def build(self, itrs):
@@ -199,16 +283,21 @@ class SparseNNLS(object):
                              % (self.size(), self.error()))
 
     def _active_columns(self, idx):
-        """host (S, m) matrix of the columns idx (Lawson-Hanson runs on the host: S x m, tiny)"""
-        idx = np.asarray(idx, dtype=np.int64)
-        d_idx = self._eng.upload(idx, dtype=torch.int64)
-        out = self._eng.empty(max(len(idx), 1), self._S)
-        nv.call('bc_dense_gather', self._ctx, ptr(self._V), self._ldv, self._S, ptr(d_idx), len(idx), ptr(out), self._S, stream_ptr())
-        return np.ascontiguousarray(out[:len(idx)].cpu().numpy().T)
+        """host (S, m) matrix of the columns idx, from the replicated cache (Lawson-Hanson runs on the host: S x m, tiny)"""
+        ks = [self._activate(int(i)) for i in idx]
+        if not ks:
+            return np.zeros((self._S, 0))
+        sel = self._Vact[torch.as_tensor(ks, dtype=torch.int64, device=self._eng.device)]
+        return np.ascontiguousarray(sel.cpu().numpy().T)
 
     def _nnls_on(self, idx):
         res = nnls(self._active_columns(idx), self.b, maxiter=100*self._N)
         return res[0]
+
+    def _assign(self, idx, sol):
+        lut = dict(zip(idx, sol))
+        self._aw = [float(lut.get(i, x)) for i, x in zip(self._act, self._aw)]
+        self._touch()
 
     # snnls.py:82-97
     def optimize(self):
@@ -216,10 +305,7 @@ class SparseNNLS(object):
             prev_cost = self.error()
             prev_w = self._snapshot()
             nz = sorted(i for i, x in zip(self._act, self._aw) if x > 0)
-            sol = self._nnls_on(nz)
-            lut = dict(zip(nz, sol))
-            self._aw = [float(lut.get(i, x)) for i, x in zip(self._act, self._aw)]
-            self._xw_valid = False
+            self._assign(nz, self._nnls_on(nz))
             new_cost = self.error()
             if new_cost > prev_cost*(1.+util.TOL):
                 raise NumericalPrecisionError(
@@ -242,6 +328,16 @@ class SparseNNLS(object):
         raise NotImplementedError
 
     def _best(self):
-        """(score, index) of the last score pass; plus the negative-direction pair for OrthoPursuit"""
-        o = self._out.cpu().numpy()
+        """(out, score, index, neg-score, neg-index) of the last score pass, merged over the ranks with numpy's arg-max rule;
+        out[0:4] = the scalars of the last bc_vec_step (identical on every rank)"""
+        if self._comm.world == 1:
+            o = self._out.cpu().numpy()
+        else:
+            allo = self._comm.allgather(self._out).cpu().numpy()
+            o = allo[self._comm.rank].copy()
+            bi = allo[:, 5:6].copy().view(np.int64)[:, 0]
+            ni = allo[:, 7:8].copy().view(np.int64)[:, 0]
+            bv, bidx = merge_best((allo[r, 4], int(bi[r])) for r in range(allo.shape[0]))
+            nvv, nidx = merge_best((allo[r, 6], int(ni[r])) for r in range(allo.shape[0]))
+            return o, float(bv), int(bidx), float(nvv), int(nidx)
         return o, float(o[4]), int(o[5:6].view(np.int64)[0]), float(o[6]), int(o[7:8].view(np.int64)[0])

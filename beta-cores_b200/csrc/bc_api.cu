@@ -418,6 +418,18 @@ int bc_quantise_rows(bc_ctx* c, const double* d_X, int64_t ldx, int64_t n, int D
   return BC_OK;
 }
 
+int bc_q_gather_rows(bc_ctx* c, const void* d_image, const double* d_rowscale, const double* d_rowaux, const int64_t* d_idx, int64_t n,
+                     void* d_image_out, double* d_rowscale_out, double* d_rowaux_out, void* stream) {
+  if (!c || !d_image || !d_rowscale || !d_image_out || !d_rowscale_out || n < 0 || (n > 0 && !d_idx)) return BC_ERR_ARG;
+  if ((d_rowaux_out != nullptr) != (d_rowaux != nullptr)) return BC_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_image) & 15) || (reinterpret_cast<uintptr_t>(d_image_out) & 15)) return BC_ERR_ALIGN;
+  if (n == 0) return BC_OK;
+  BC_CUDA(launch_gather_image(reinterpret_cast<const unsigned char*>(d_image), d_rowscale, d_rowaux, reinterpret_cast<const long long*>(d_idx), n,
+                              reinterpret_cast<unsigned char*>(d_image_out), d_rowscale_out, d_rowaux_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
 static int q_common(bc_ctx* c, const void* d_image, const double* d_rowscale, int64_t n, const double* d_rowaux, QProjArgs& P,
                     int* grid) {
   if (!c || !d_image || !d_rowscale || n < 0) return BC_ERR_ARG;
@@ -572,6 +584,14 @@ int bc_sample_affine(bc_ctx* c, const double* d_mu, const double* d_L, const dou
                      void* stream) {
   if (!c || !d_mu || !d_L || !d_R || !d_theta || S < 0 || D < 1 || ldt < D) return BC_ERR_ARG;
   BC_CUDA(launch_sample_affine(d_mu, d_L, d_R, S, D, d_theta, ldt, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
+int bc_sample_solve(bc_ctx* c, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
+                    void* stream) {
+  if (!c || !d_mu || !d_C || !d_R || !d_theta || S < 0 || D < 1 || D > 160 || ldt < D) return BC_ERR_ARG;
+  BC_CUDA(launch_sample_solve(d_mu, d_C, d_R, S, D, d_theta, ldt, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

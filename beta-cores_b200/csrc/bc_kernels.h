@@ -105,6 +105,8 @@ cudaError_t launch_feature_exponents(const double* X, long long ldx, long long n
                                      cudaStream_t st);
 cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, int D, unsigned char* image, double* rowscale,
                                  double* aux_out, int aux_col, const int* fexp, cudaStream_t st);
+cudaError_t launch_gather_image(const unsigned char* src, const double* src_scale, const double* src_aux, const long long* idx, long long n,
+                                unsigned char* dst, double* dst_scale, double* dst_aux, cudaStream_t st);
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
                                     const int* fexp, unsigned long long* scratch2, cudaStream_t st);
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st);
@@ -131,6 +133,7 @@ cudaError_t launch_pgrad_dense(const double* G, int M, int S, int D, const doubl
 // ---- bc_sampler.cu: device-side posterior samplers ----
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
                                     double tol, int* info, cudaStream_t st);
+cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 
 // ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----

@@ -206,6 +206,48 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
   return cudaGetLastError();
 }
 
+// Gathered row image: rows idx[0..n) of a quantised image (duplicates allowed, the reference sub-samples WITH replacement,
+// bcores.py:53) re-packed into a compact image of ceil(n / 128) tiles, each row moved to the swizzle slot of its new
+// position, with its scale (and optional per-row auxiliary value).  One warp per output row, lane l moves the 4 bytes of
+// contraction indices 4l..4l+3 of every digit plane: 7 coalesced 128-byte reads and writes per row.  This is what puts
+// sub-sampled passes (n_subsample_select / n_subsample_opt) and group passes on the tensor-core route.
+__global__ void __launch_bounds__(256) k_gather_image(const unsigned char* __restrict__ src, const double* __restrict__ src_scale,
+                                                      const double* __restrict__ src_aux, const long long* __restrict__ idx, long long n,
+                                                      unsigned char* __restrict__ dst, double* __restrict__ dst_scale,
+                                                      double* __restrict__ dst_aux) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows_padded = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
+  for (long long r = warp; r < rows_padded; r += nwarps) {
+    unsigned char* out = dst + (size_t)(r / kQTileRows) * kQTileBytes + q_swizzle_off((uint32_t)(r % kQTileRows), (uint32_t)lane * 4u);
+    if (r < n) {
+      const long long g = __ldg(idx + r);
+      const unsigned char* in = src + (size_t)(g / kQTileRows) * kQTileBytes + q_swizzle_off((uint32_t)(g % kQTileRows), (uint32_t)lane * 4u);
+#pragma unroll
+      for (int sl = 0; sl < kQSlices; ++sl)
+        *reinterpret_cast<uint32_t*>(out + (size_t)sl * kQSliceA) = __ldg(reinterpret_cast<const uint32_t*>(in + (size_t)sl * kQSliceA));
+      if (lane == 0) {
+        dst_scale[r] = __ldg(src_scale + g);
+        if (dst_aux) dst_aux[r] = __ldg(src_aux + g);
+      }
+    } else {
+#pragma unroll
+      for (int sl = 0; sl < kQSlices; ++sl) *reinterpret_cast<uint32_t*>(out + (size_t)sl * kQSliceA) = 0u;
+    }
+  }
+}
+
+cudaError_t launch_gather_image(const unsigned char* src, const double* src_scale, const double* src_aux, const long long* idx, long long n,
+                                unsigned char* dst, double* dst_scale, double* dst_aux, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long rows_padded = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
+  long long blocks = (rows_padded + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_gather_image<<<(int)blocks, 256, 0, st>>>(src, src_scale, src_aux, idx, n, dst, dst_scale, dst_aux);
+  return cudaGetLastError();
+}
+
 // exponent shared by all S samples: ilogb(max |B'|) + 3 over the feature-scaled samples B'[s][k] = B[s][k] 2^fexp[k], and
 // the matching scale 2^(e - 32) (NaN if any entry is not finite: the reference's own result is NaN in every quantity
 // downstream of such a sample set).  Two steps: a grid-wide max of the bit patterns (|x| orders like its bits; a

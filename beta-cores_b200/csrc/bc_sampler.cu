@@ -297,6 +297,41 @@ __global__ void __launch_bounds__(128) k_sample_affine(const double* __restrict_
   }
 }
 
+// Theta[s][:] = mu + C^-1 R[s][:]  for the LOWER Cholesky factor C of the negative Hessian: the same samples as
+// `mu + randn(S, D).dot(LSig.T)` with LSig = C^-1 (get_laplace, util/opt.py:27-33), without forming the inverse -- the
+// host then only factors (dpotrf) and never inverts (dtrtri is the slower of the two at D = 128).  One thread per sample,
+// forward substitution with the solution held in shared memory ([D][32], conflict-free); every lane reads the same C
+// entry (broadcast from L1).  Four partial sums break the DFMA dependency chain.
+__global__ void __launch_bounds__(32) k_sample_solve(const double* __restrict__ mu, const double* __restrict__ C, const double* __restrict__ R,
+                                                     int S, int D, double* __restrict__ out, int ldo) {
+  extern __shared__ double xs[];   // [D][32]
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x * 32 + lane;
+  const bool valid = s < S;
+  const double* r = R + (size_t)(valid ? s : 0) * D;
+  for (int i = 0; i < D; ++i) {
+    const double* ci = C + (size_t)i * D;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 4 <= i; j += 4) {
+      a0 = fma(__ldg(ci + j), xs[(j + 0) * 32 + lane], a0);
+      a1 = fma(__ldg(ci + j + 1), xs[(j + 1) * 32 + lane], a1);
+      a2 = fma(__ldg(ci + j + 2), xs[(j + 2) * 32 + lane], a2);
+      a3 = fma(__ldg(ci + j + 3), xs[(j + 3) * 32 + lane], a3);
+    }
+    for (; j < i; ++j) a0 = fma(__ldg(ci + j), xs[j * 32 + lane], a0);
+    const double x = (r[i] - ((a0 + a1) + (a2 + a3))) / __ldg(ci + i);
+    xs[i * 32 + lane] = x;
+    if (valid) out[(size_t)s * ldo + i] = __ldg(mu + i) + x;
+  }
+}
+
+cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st) {
+  if (S <= 0) return cudaSuccess;
+  k_sample_solve<<<(S + 31) / 32, 32, (size_t)D * 32 * sizeof(double), st>>>(mu, C, R, S, D, out, ldo);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
                                     double tol, int* info, cudaStream_t st) {
   const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);

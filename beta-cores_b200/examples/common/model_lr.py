@@ -103,13 +103,30 @@ def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200, want_margins=False):
     th = np.array(mu0, dtype=np.float64)
     m = -Zw.dot(th)
     f = _log_joint_from_margins(m, th, ww)
+    # Few coreset points (M < D/2, the usual case while a coreset is being built): the negative Hessian I + Z^T diag(d) Z is
+    # a rank-M update of the identity, so the Newton step comes from an M x M system (Woodbury),
+    #   H^-1 g = g - Z^T r (I + r K r)^-1 r Z g,   r = sqrt(d),  K = Z Z^T (formed once per call),
+    # instead of a D x D factorisation per iteration.  Same iteration, same stopping rule; the iterates agree to rounding.
+    M, D = Zw.shape
+    dual = 0 < 2*M < D
+    K = Zw.dot(Zw.T) if dual else None
     for _ in range(maxit):
         s, c = _margin_terms(m)
         g = -th + Zw.T.dot(ww*s)
-        L, info = sl.lapack.dpotrf(_neg_hessian(Zw, ww, c), lower=1, overwrite_a=1)
-        if info != 0:
-            raise np.linalg.LinAlgError('negative Hessian not positive definite (dpotrf info %d)' % info)
-        step, _ = sl.lapack.dpotrs(L, g, lower=1)
+        if dual:
+            r = np.sqrt(ww*c)
+            A = K*r[:, np.newaxis]*r[np.newaxis, :]
+            A[np.diag_indices_from(A)] += 1.
+            La, info = sl.lapack.dpotrf(A, lower=1, overwrite_a=1)
+            if info != 0:
+                raise np.linalg.LinAlgError('negative Hessian not positive definite (dual dpotrf info %d)' % info)
+            v, _ = sl.lapack.dpotrs(La, r*Zw.dot(g), lower=1)
+            step = g - Zw.T.dot(r*v)
+        else:
+            L, info = sl.lapack.dpotrf(_neg_hessian(Zw, ww, c), lower=1, overwrite_a=1)
+            if info != 0:
+                raise np.linalg.LinAlgError('negative Hessian not positive definite (dpotrf info %d)' % info)
+            step, _ = sl.lapack.dpotrs(L, g, lower=1)
         t = 1.
         while True:
             th_new = th + t*step
@@ -127,7 +144,7 @@ def _newton_mode(Zw, ww, mu0, tol=1e-13, maxit=200, want_margins=False):
     return (th, m) if want_margins else th
 
 
-def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
+def get_laplace(wts, Z, mu0, diag=False, method='bfgs', want_inverse=True):
     """N(mu, L L^T) Laplace approximation of the weighted posterior; returns (mu, L, Linv^T-factor)
     like bayesiancoresets/util/opt.py:10-33.  method='bfgs': the reference's optimiser (scipy BFGS with analytic
     gradient, up to 10 restarts from a jittered start); method='newton': the same mode by damped Newton steps."""
@@ -142,6 +159,8 @@ def get_laplace(wts, Z, mu0, diag=False, method='bfgs'):
                 raise np.linalg.LinAlgError('negative Hessian not positive definite (dpotrf info %d)' % info)
             mask = _lower_mask(L.shape[0])         # dpotrf / dtrtri leave the other triangle untouched
             LSigInv = L*mask
+            if not want_inverse:                   # the caller solves against the factor itself (bc_sample_solve)
+                return mu, None, LSigInv
             LSig, info = sl.lapack.dtrtri(LSigInv, lower=1)
             return mu, LSig*mask, LSigInv
     else:
@@ -221,9 +240,11 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
     """method='device' / 'hybrid': the S x D samples are formed on the GPU and returned as a device tensor (the projector's
     fused path takes it without a host round trip).  The standard normals still come from numpy's global stream, so the
     sampler consumes it exactly like the host one.
-      'hybrid': mode, Cholesky factor and its inverse on the host (`get_laplace(method='newton')`, warm-started), only the
-                S x D x D affine map mu + R L^T on the device (csrc/bc_sampler.cu::k_sample_affine) -- it takes the GEMM and
-                the 8 S D-byte sample upload off the host's critical path (the normals go up instead, and do not wait for the weights);
+      'hybrid': mode and Cholesky factor C of the negative Hessian on the host (`get_laplace(method='newton')`, warm-started;
+                the Newton steps come from an M x M system while the coreset is small), the samples mu + C^-1 R^T on the device
+                by forward substitution (csrc/bc_sampler.cu::k_sample_solve) -- the host neither inverts the factor (dtrtri is
+                the slower LAPACK call of the two) nor multiplies, and the 8 S D-byte sample upload leaves its critical path
+                (the normals go up instead, and do not wait for the weights);
       'device': the Newton mode search and the factorisations too (k_laplace_logistic, one CTA; D <= 160).  Same iteration and
                 tolerance as `_newton_mode`; the two agree to rounding.  At D = 128 the single-CTA factorisations are
                 latency-bound and no faster than the host's LAPACK, so 'hybrid' is the quicker of the two."""
@@ -255,19 +276,24 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
             st['ml_pin'] = torch.empty(D*D + D, dtype=torch.float64).pin_memory()
         theta = eng.empty(S, D)
         keep = wts > 0
+        st['factor'] = False
         if pts.shape[0] == 0 or not keep.any():           # empty coreset: the N(0, I) prior
             st['mu'].zero_()
             st['L'].copy_(torch.eye(D, dtype=torch.float64, device=eng.device))
             st['mu_host'] = None
         elif host_factor:
             start = st['mu_host'] if st['mu_host'] is not None else mu0
-            mu, LSig, _ = get_laplace(wts, pts, start, method='newton')
+            solve = D <= 160                               # bc_sample_solve's limit; beyond it: invert on the host as before
+            mu, LSig, LSigInv = get_laplace(wts, pts, start, method='newton', want_inverse=not solve)
             st['mu_host'] = mu
+            st['factor'] = solve                           # st['L'] holds the Cholesky factor, not its inverse
+            if not solve:
+                LSigInv = LSig
             if st.get('ml_ev') is not None:
                 st['ml_ev'].synchronize()
             buf = st['ml_pin'].numpy()
             buf[:D] = mu
-            buf[D:] = LSig.ravel()
+            buf[D:] = LSigInv.ravel()
             st['ml'].copy_(st['ml_pin'], non_blocking=True)
             st['ml_ev'] = torch.cuda.Event()
             st['ml_ev'].record()
@@ -281,7 +307,8 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
         Rd = pin.to(eng.device, non_blocking=True)
         st['ev'][k] = torch.cuda.Event()
         st['ev'][k].record()
-        nv.call('bc_sample_affine', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        nv.call('bc_sample_solve' if st['factor'] else 'bc_sample_affine', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta),
+                int(theta.stride(0)), stream_ptr())
         return theta
 
     def status():

@@ -85,7 +85,7 @@ int bc_project_materialise(bc_ctx* ctx, const double* d_X, int64_t ldx, const in
  * Same results as bc_project_colsum / bc_project_score (same reference lines), with the contraction on the
  * 5th-generation tensor cores: rows and samples are split error-free into 7 signed base-256 digits and multiplied
  * exactly in int8 x int8 -> int32 (tcgen05.mma.kind::i8, accumulators in TMEM); see csrc/bc_project_q.cu.
- * Feature count D <= bc_q_max_features() (128); full row blocks only (no gather list).
+ * Feature count D <= bc_q_max_features() (128).  Gather lists: through bc_q_gather_rows.
  * The row image is built ONCE per dataset; bc_set_samples() builds the sample image. */
 int bc_q_max_features(void);
 /* Precision tier of the tensor-core contraction.  The images always hold 7 digits (55 bits + sign below the row / sample
@@ -97,6 +97,12 @@ int bc_q_max_features(void);
 int bc_set_contraction_digits(bc_ctx* ctx, int digits);   /* 5, 6 or 7 */
 int bc_contraction_digits(const bc_ctx* ctx);
 int bc_q_image_bytes(int64_t n, int64_t* bytes);     /* device bytes of the quantised image of n rows */
+/* Sub-sampled / group passes on the tensor-core route (bcores.py:52-55 `np.random.randint(N, size=n)` rows, :46-51 group rows):
+ * rows d_idx[0..n) of a quantised image (local row numbers, duplicates allowed) are re-packed, with their scales and optional
+ * per-row auxiliary values, into a compact image of bc_q_image_bytes(n) bytes that bc_project_colsum_q / _score_q take like
+ * any other.  d_rowaux / d_rowaux_out: both NULL or both given. */
+int bc_q_gather_rows(bc_ctx* ctx, const void* d_image, const double* d_rowscale, const double* d_rowaux, const int64_t* d_idx, int64_t n,
+                     void* d_image_out, double* d_rowscale_out, double* d_rowaux_out, void* stream);
 /* Feature exponents (optional, recommended for data whose columns differ much in magnitude).  The digit split keeps 56
  * bits below the largest entry of a row; with x_k 2^-c_k in the row image and theta_k 2^+c_k in the sample image
  * (c_k = ilogb max_n |x_nk|, powers of two: the products are unchanged) every feature is O(1) in its row and the
@@ -158,6 +164,11 @@ int bc_laplace_logistic(bc_ctx* ctx, const double* d_Z, int64_t ldz, const doubl
                         int maxit, double tol, int* d_info, void* stream);
 int bc_sample_affine(bc_ctx* ctx, const double* d_mu, const double* d_L, const double* d_R, int S, int D, double* d_theta, int ldt,
                      void* stream);
+/* bc_sample_solve: the same samples from the Cholesky factor itself, d_theta[s][:] = d_mu + C^-1 d_R[s][:] (d_C: D x D lower
+ *   factor of the negative Hessian, row-major, get_laplace's LSigInv; util/opt.py:27-33 inverts it and multiplies) -- the
+ *   host side then only factors.  D <= 160. */
+int bc_sample_solve(bc_ctx* ctx, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
+                    void* stream);
 
 /* ---- stage 2 on a materialised n x S matrix (snnls solvers, black-box projections) --------- */
 int bc_dense_rownorms(bc_ctx* ctx, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream);

@@ -1,0 +1,25 @@
+"""host-side profile of BASELINE config 1 (examples/zellner_gaussian: N=5700 d=100 S=200, 1000 ADAM steps per point, sub-samples
+1000/200): where a 0.87 ms optimiser step goes.  cProfile over two build steps after one warm-up step."""
+import os, sys, time, cProfile, pstats
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'beta-cores_b200'), os.path.join(ROOT, 'beta-cores_b200', 'examples', 'common'), os.path.join(ROOT, 'tests', 'golden')):
+    sys.path.insert(0, p)
+import numpy as np, torch
+from threadpoolctl import threadpool_limits
+threadpool_limits(limits=1, user_api='blas')
+import problems, bayesiancoresets as bc, gaussian
+case = [c for c in problems.coreset_cases(True) if c['name'] == 'c1_zellner_gaussian'][0]
+prob = case['make']()
+bl = gaussian.gaussian_beta_likelihood.bind(**prob['params']); ll = gaussian.gaussian_loglikelihood.bind(**prob['params'])
+prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
+alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'],
+                     step_sched=case['sched'], beta=case['beta'], learn_beta=False)
+alg.build(1, 1)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+pr = cProfile.Profile(); pr.enable()
+alg.build(1, 2); alg.build(1, 3)
+torch.cuda.synchronize()
+pr.disable()
+print('2 build steps: %.3f s (%.3f ms per optimiser step incl. profiler overhead)' % (time.perf_counter()-t0, 1e3*(time.perf_counter()-t0)/2002))
+pstats.Stats(pr).sort_stats('tottime').print_stats(28)
