@@ -602,11 +602,22 @@ def configs_leg(a):
             return gaussian.gaussian_beta_likelihood.bind(**prob['params']), gaussian.gaussian_loglikelihood.bind(**prob['params'])
         return model_neurlinr.neurlinr_beta_likelihood.bind(**prob['params']), model_neurlinr.neurlinr_loglikelihood.bind(**prob['params'])
 
+    def product_sampler(prob):
+        """the sampler as a user of this package writes it: same algebra and same numpy stream as the plain host callback
+        the CPU arm runs (so both arms draw the same samples), formed on the device with the normals drawn a call ahead"""
+        from bayesiancoresets.util import rng
+        rng.drain()
+        if prob['model'] == 'gauss':
+            return gaussian.make_conjugate_sampler(prob['prior']['mu0'], prob['prior']['Sig0inv'], prob['params']['Siginv'], device=True, prefetch=True)
+        if prob['model'] == 'nl':
+            return model_neurlinr.make_conjugate_sampler(prob['prior']['mu0'], prob['prior']['Sig0inv'], prob['params']['sigsq'], device=True, prefetch=True)
+        return model_lr.make_laplace_sampler(prob['data'].shape[1], method='hybrid', prefetch=True)
+
     def greedy(case, gpu_steps, cpu_steps, label):
         prob = case['make']()
         problems.reseed(case)
         bl, ll = potentials(prob)
-        prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
+        prj = bc.BetaBlackBoxProjector(product_sampler(prob), case['S'], bl, ll, None)
         alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'],
                              step_sched=case['sched'], beta=case['beta'], learn_beta=False)
         alg.build(1, 1)                       # first step: uploads, row image, lazy allocations
@@ -619,6 +630,7 @@ def configs_leg(a):
         g = (time.perf_counter()-t0)/max(gpu_steps-1, 1)
         launches = nv.lib().bc_launch_count() - l0
         gi = [int(i) for i in alg.idcs]
+        prj.sampler.drain()
         prob = case['make']()
         problems.reseed(case)
         o = oc.GreedyVI(prob['data'], prob['sampler'], case['S'], prob['oracle_betalik'](case['beta']), n_sub_select=case['n_sel'],
@@ -656,12 +668,13 @@ def configs_leg(a):
     prob = c4['make']()
     problems.reseed(c4)
     bl, ll = potentials(prob)
-    prj = bc.BetaBlackBoxProjector(prob['sampler'], c4['S'], bl, ll, None)
+    prj = bc.BetaBlackBoxProjector(product_sampler(prob), c4['S'], bl, ll, None)
     alg = bc.BetaCoreset(prob['data'], prj, opt_itrs=c4['opt_itrs'], step_sched=c4['sched'], beta=c4['beta'], learn_beta=False)
     alg.build(1, 1); torch.cuda.synchronize(); t0 = time.perf_counter()
     for m in range(2, 6):
         alg.build(1, m)
     torch.cuda.synchronize(); g = (time.perf_counter()-t0)/4.
+    prj.sampler.drain()
     prob = c4cpu['make'](); problems.reseed(c4cpu)
     o = oc.GreedyVI(prob['data'], prob['sampler'], c4cpu['S'], prob['oracle_betalik'](c4cpu['beta']), opt_itrs=c4cpu['opt_itrs'], sched=c4cpu['sched'])
     o.build(1, 1); t0 = time.perf_counter(); o.build(1, 2); c = (time.perf_counter()-t0)

@@ -101,6 +101,26 @@ class FusedProjection(object):
         nv.call('bc_set_samples', self.ctx, ptr(t), self.S, int(t.stride(0)), stream_ptr())
         st['samples_of'] = self
 
+    def note_samples(self, theta):
+        """bookkeeping of set_samples() for a caller that hands `theta` to the library itself (bc_greedy_opt_step runs
+        bc_set_samples as its first stage)"""
+        st = self._applied()
+        if st['potential'] is None or st['potential'][0] != id(self):
+            raise nv.NativeError('set_samples() must follow configure()')
+        self._theta = theta
+        self.S = int(theta.shape[0])
+        self.Sld = nv.lib().bc_colsum_ld(self.S)
+        st['samples_of'] = self
+
+    def gather_scratch(self, n):
+        """scratch image / scales / aux for a gathered pass of n rows on the tensor-core route"""
+        if self._gather is None or self._gather[3] < n:
+            cap = max(2*n, 1024)
+            nb = nv.c_i64()
+            nv.call('bc_q_image_bytes', cap, ctypes.byref(nb))
+            self._gather = (torch.empty(nb.value, dtype=torch.uint8, device=self.eng.device), self.eng.empty(cap), self.eng.empty(cap), cap)
+        return self._gather
+
     # ---- helpers ----
     def _rowaux(self, rows):
         if self.pot.model != 'gaussian':
@@ -132,12 +152,7 @@ class FusedProjection(object):
         if sub is None:
             return img, rs, ra
         n = int(sub.numel())
-        if self._gather is None or self._gather[3] < n:
-            cap = max(2*n, 1024)
-            nb = nv.c_i64()
-            nv.call('bc_q_image_bytes', cap, ctypes.byref(nb))
-            self._gather = (torch.empty(nb.value, dtype=torch.uint8, device=self.eng.device), self.eng.empty(cap), self.eng.empty(cap), cap)
-        gimg, grs, gaux, _ = self._gather
+        gimg, grs, gaux, _ = self.gather_scratch(n)
         nv.call('bc_q_gather_rows', self.ctx, ptr(img), ptr(rs), ptr(ra), ptr(sub), n, ptr(gimg), ptr(grs), ptr(gaux) if ra is not None else None,
                 stream_ptr())
         return gimg, grs, (gaux if ra is not None else None)

@@ -55,6 +55,25 @@ SIGNATURES = {
 PLAIN = {'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
+
+
+class StepArgs(ctypes.Structure):
+    """bc_step_args of include/betacores.h"""
+    _fields_ = [('d_theta', c_vp), ('S', c_int), ('ldt', c_int),
+                ('d_image', c_vp), ('d_rowscale', c_vp), ('d_rowaux_q', c_vp),
+                ('d_gimage', c_vp), ('d_growscale', c_vp), ('d_growaux', c_vp),
+                ('d_X', c_vp), ('ldx', c_i64), ('d_rowaux', c_vp),
+                ('d_rows', c_vp), ('n', c_i64), ('scaling', c_dbl),
+                ('d_pts', c_vp), ('ldp', c_i64), ('M', c_int), ('d_pts_rowaux', c_vp),
+                ('d_Vc', c_vp), ('ldv', c_i64),
+                ('d_parts', c_vp), ('d_colsum', c_vp), ('d_resid', c_vp), ('d_grad', c_vp),
+                ('d_w', c_vp), ('d_m1', c_vp), ('d_m2', c_vp),
+                ('lr', c_dbl), ('b1', c_dbl), ('b2', c_dbl), ('c1', c_dbl), ('c2', c_dbl), ('eps', c_dbl), ('d_nn_mask', c_vp),
+                ('ev_pass_begin', c_vp), ('ev_pass_end', c_vp)]
+
+
+SIGNATURES['bc_greedy_opt_step'] = [c_vp, ctypes.POINTER(StepArgs), c_vp]
+
 MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2
 KIND_LOGLIK, KIND_BETALIK, KIND_BETAGRAD = 0, 1, 2
 SCORE_FW, SCORE_GIGA, SCORE_CORR, SCORE_OMP = 0, 1, 2, 3

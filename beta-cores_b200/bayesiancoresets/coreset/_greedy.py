@@ -22,11 +22,17 @@ from .. import _native as nv
 from .._device import Engine, DeviceRows, ptr, stream_ptr, padded_ld
 from .._shard import Comm, local_subsample, merge_best, owner_of
 from ..util.opt import nn_opt, partial_nn_opt
+from ..util import rng
 from .coreset import Coreset
 
 
 def _as_f64_2d(a):
     return np.atleast_2d(np.asarray(a, dtype=np.float64))
+
+
+# one library call per optimiser step (bc_greedy_opt_step) instead of one per kernel; BC_FUSED_STEP=0 keeps the call-by-call loop
+import os
+FUSED_STEP_CALL = os.environ.get('BC_FUSED_STEP', '1') != '0'
 
 
 class _Tangent(object):
@@ -326,7 +332,7 @@ class GreedyVICoreset(Coreset):
         if self.n_subsample_select is None:
             gi, scaling = list(range(G)), 1.
         else:
-            gi = np.random.randint(G, size=self.n_subsample_select)                       # bcores.py:57
+            gi = rng.randint(G, self.n_subsample_select)                       # bcores.py:57
             scaling = G/self.n_subsample_select
         gv = t.group_rows(self.groups, gi)
         colsum = t.group_colsum(gv)
@@ -370,7 +376,7 @@ class GreedyVICoreset(Coreset):
         if self.n_subsample_select is None:
             sub_idcs, scaling = None, 1.
         else:
-            sub_idcs = np.random.randint(self._n_total, size=self.n_subsample_select)      # bcores.py:53
+            sub_idcs = rng.randint(self._n_total, self.n_subsample_select)      # bcores.py:53
             scaling = self._n_total/self.n_subsample_select
         colsum = t.colsum(sub_idcs)
         if self.pts.size > 0:
@@ -405,17 +411,20 @@ class GreedyVICoreset(Coreset):
             for i in range(self.opt_itrs):
                 self.ll_projector.update(self.wts, self.pts)
                 if self.n_subsample_opt is not None:
-                    np.random.randint(self._n_total, size=self.n_subsample_opt)
+                    rng.randint(self._n_total, self.n_subsample_opt)
             return
         core = self._core_operand(t)
         g = t.eng.empty(M)
         beta = self._beta()
         scaling = 1. if self.n_subsample_opt is None else self._n_total/self.n_subsample_opt
+        if isinstance(t, _FusedTangent) and t.comm.world == 1 and FUSED_STEP_CALL:
+            self.wts = self._optimize_fused_steps(t, core, beta, scaling)
+            return
 
         def grd(w_host, w_dev):
             t.begin(w_host, self.pts, beta)
             if self.n_subsample_opt is not None:
-                sub_idcs = np.random.randint(self._n_total, size=self.n_subsample_opt)
+                sub_idcs = rng.randint(self._n_total, self.n_subsample_opt)
             elif self.groups is not None and not self._groups_cover:
                 sub_idcs = self._groups_flat        # bcores.py:46-51: the data term is the sum over the grouped rows
             else:
@@ -426,6 +435,79 @@ class GreedyVICoreset(Coreset):
             return t.grad(Vc, resid, g)
         grd.wants_device_iterate = True
         self.wts = nn_opt(self.wts, grd, opt_itrs=self.opt_itrs, step_sched=self.step_sched)
+
+    def _optimize_fused_steps(self, t, core, beta, scaling):
+        """the loop above with ONE library call per optimiser step (bc_greedy_opt_step: the same kernels in the same order,
+        launched back to back from C instead of through a dozen Python -> ctypes crossings).  Single rank, device potential."""
+        from .. import _fused
+        eng, fp, rows = t.eng, t.fp, t.rows
+        M = self.wts.shape[0]
+        b1, b2, eps = 0.9, 0.999, 1e-8                     # util/opt.py:36 defaults (nn_opt is called with them)
+        x = eng.upload(np.asarray(self.wts, dtype=np.float64))
+        m1, m2, g = eng.zeros(M), eng.zeros(M), eng.empty(M)
+        xh = np.asarray(self.wts, dtype=np.float64).copy()
+        prj = self.ll_projector
+        if self.n_subsample_opt is not None:
+            n_pass, fixed_sub = int(self.n_subsample_opt), None
+        elif self.groups is not None and not self._groups_cover:
+            fixed_sub = eng.upload(np.asarray(self._groups_flat, dtype=np.int64), dtype=torch.int64)
+            n_pass = int(fixed_sub.numel())
+        else:
+            n_pass, fixed_sub = rows.n_local, None
+        a = nv.StepArgs()
+        bufs = None
+        idx_dev = eng.empty(max(n_pass, 1), dtype=torch.int64) if self.n_subsample_opt is not None else fixed_sub
+        idx_pin = [torch.empty(max(n_pass, 1), dtype=torch.int64).pin_memory() for _ in range(2)] if self.n_subsample_opt is not None else None
+        for i in range(self.opt_itrs):
+            prj.update(xh, self.pts)                           # host sampler: consumes np.random exactly like the reference
+            th = prj.samples
+            if isinstance(th, torch.Tensor):
+                th = th.to(device=eng.device, dtype=torch.float64)
+                if not th.is_contiguous():
+                    th = th.contiguous()
+            else:
+                th = eng.upload(np.ascontiguousarray(np.atleast_2d(np.asarray(th, dtype=np.float64))))
+            fp.configure(beta)
+            fp.note_samples(th)
+            S = fp.S
+            if bufs is None or bufs['S'] != S:
+                q = fp._q_operands(rows, None)                 # row image of the whole block (built once), exponents / digits applied
+                bufs = dict(S=S, Vc=eng.empty(M, S), parts=eng.empty(2*fp.Sld), colsum=eng.empty(S), resid=eng.empty(S+1), q=q)
+                a.S, a.ldt = S, int(th.stride(0))
+                if q is not None:
+                    a.d_image, a.d_rowscale, a.d_rowaux_q = q[0].data_ptr(), q[1].data_ptr(), (q[2].data_ptr() if q[2] is not None else None)
+                    if idx_dev is not None:
+                        gs = fp.gather_scratch(n_pass)
+                        a.d_gimage, a.d_growscale, a.d_growaux = gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr()
+                else:
+                    a.d_image = None
+                    ra = fp._rowaux(rows)
+                    a.d_X, a.ldx, a.d_rowaux = rows.t.data_ptr(), rows.ld, (ra.data_ptr() if ra is not None else None)
+                cra = fp._rowaux(core)
+                a.d_pts, a.ldp, a.M, a.d_pts_rowaux = core.t.data_ptr(), core.ld, M, (cra.data_ptr() if cra is not None else None)
+                a.d_Vc, a.ldv = bufs['Vc'].data_ptr(), S
+                a.d_parts, a.d_colsum, a.d_resid, a.d_grad = bufs['parts'].data_ptr(), bufs['colsum'].data_ptr(), bufs['resid'].data_ptr(), g.data_ptr()
+                a.d_w, a.d_m1, a.d_m2, a.b1, a.b2, a.eps, a.d_nn_mask = x.data_ptr(), m1.data_ptr(), m2.data_ptr(), b1, b2, eps, None
+                a.scaling, a.n = float(scaling), n_pass
+                a.d_rows = idx_dev.data_ptr() if idx_dev is not None else None
+            a.d_theta = th.data_ptr()
+            if self.n_subsample_opt is not None:
+                sub = rng.randint(self._n_total, self.n_subsample_opt)                    # bcores.py:53, after the sampler call
+                pin = idx_pin[i & 1]
+                pin.numpy()[...] = sub
+                idx_dev.copy_(pin, non_blocking=True)
+            a.lr, a.c1, a.c2 = float(self.step_sched(i)), 1.-b1**(i+1), 1.-b2**(i+1)
+            if _fused.PASS_TIMERS is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                e1.record()                                    # creates the CUDA events; the library re-records them around the pass
+                a.ev_pass_begin, a.ev_pass_end = e0.cuda_event, e1.cuda_event
+                _fused.PASS_TIMERS.append(('colsum', n_pass, e0, e1))
+            else:
+                a.ev_pass_begin = a.ev_pass_end = None
+            nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+            xh = x.cpu().numpy()                               # one D2H + sync per step: the next sampler call needs the weights
+        return xh
 
     def error(self):
         return 0.       # the reference has no KL estimate either (bcores.py:152-153)

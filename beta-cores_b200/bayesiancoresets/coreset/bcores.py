@@ -2,6 +2,7 @@
 Greedy selection + projected-ADAM reweighting on the beta-likelihood tangent space; the loop itself is in
 _greedy.py, shared with SparseVICoreset."""
 import numpy as np
+from ..util import rng
 from ._greedy import GreedyVICoreset
 
 
@@ -38,7 +39,7 @@ class BetaCoreset(GreedyVICoreset):
             for i in range(self.opt_itrs):             # gradient of nothing: the sampler and the subsample draw still run
                 self.ll_projector.update(self.wts, self.pts)
                 if self.n_subsample_opt is not None:
-                    np.random.randint(self._n_total, size=self.n_subsample_opt)
+                    rng.randint(self._n_total, self.n_subsample_opt)
             return
         core = self._core_operand(t)
         gw, gb = t.eng.empty(M), t.eng.empty(M)
@@ -49,7 +50,7 @@ class BetaCoreset(GreedyVICoreset):
             self.beta = beta                           # opaque callbacks read it through _host_project
             t.begin(w, self.pts, beta)
             if self.n_subsample_opt is not None:
-                sub_idcs = np.random.randint(self._n_total, size=self.n_subsample_opt)
+                sub_idcs = rng.randint(self._n_total, self.n_subsample_opt)
             elif self.groups is not None and not self._groups_cover:
                 sub_idcs = self._groups_flat
             else:

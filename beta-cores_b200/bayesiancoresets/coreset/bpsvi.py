@@ -10,6 +10,7 @@ gradient tensor (bpsvi.py:39,54) is never formed for the built-in models.
 DiffPrivBatchPSVICoreset: the reference imports coreset/dpbpsvi.py (coreset/__init__.py:6) but does not ship it; the
 name is exported so that `import bayesiancoresets` keeps the reference's surface."""
 import numpy as np
+from ..util import rng
 import torch
 
 from .. import _native as nv
@@ -32,6 +33,7 @@ class BatchPSVICoreset(GreedyVICoreset):
 
     # bpsvi.py:17-24 (itrs is ignored, like in the reference)
     def _build(self, itrs, sz):
+        rng.drain()      # np.random.choice draws on its own: no look-ahead in flight
         init_idcs = np.random.choice(self._n_total, size=sz, replace=False)
         if self.rows is not None and not isinstance(self.data, np.ndarray):
             self.pts = np.vstack([np.asarray(self.data[int(i)], dtype=np.float64).reshape(1, -1) for i in init_idcs])
@@ -61,7 +63,7 @@ class BatchPSVICoreset(GreedyVICoreset):
             w_host = x_host[:sz]
             p_host = x_host[sz:].reshape((sz, d))
             t.begin(w_host, p_host, None)                                  # sampler first (bpsvi.py:28)
-            sub_idcs = None if self.n_subsample_opt is None else np.random.randint(self._n_total, size=self.n_subsample_opt)
+            sub_idcs = None if self.n_subsample_opt is None else rng.randint(self._n_total, self.n_subsample_opt)
             colsum = t.colsum(sub_idcs)
             core = DeviceRows(t.eng, p_host) if isinstance(t, _FusedTangent) else p_host
             Vc = t.core_rows(core)

@@ -11,6 +11,7 @@ import torch
 from .. import _native as nv
 from .._device import Engine, DeviceRows, ptr, stream_ptr
 from .._shard import Comm, partition_rows
+from ..util import rng
 from ..snnls.giga import GIGA
 from ..snnls.snnls import SparseNNLS
 from .coreset import Coreset
@@ -22,7 +23,7 @@ class HilbertCoreset(Coreset):
             sub_idcs = None
         else:
             n_subsample = min(data.shape[0], n_subsample)
-            sub_idcs = np.random.randint(data.shape[0], size=n_subsample)          # hilbert.py:14
+            sub_idcs = rng.randint(data.shape[0], n_subsample)          # hilbert.py:14
         fused = ll_projector.fused(data.shape[1]) if hasattr(ll_projector, 'fused') else None
         device_solver = isinstance(snnls, type) and issubclass(snnls, SparseNNLS)
         if fused is not None and device_solver:

@@ -5,6 +5,7 @@ the hot path, pure host RNG bookkeeping -- kept so the baselines in the drivers 
 Counts: every draw of an already-held point (or group) bumps its count; the weights are the counts rescaled to
 sum to N.  A coreset warm-started through `wts=` starts with one count per initial point (sampling.py:9-11)."""
 import numpy as np
+from ..util import rng
 from .coreset import Coreset
 
 
@@ -53,6 +54,7 @@ class UniformSamplingCoreset(Coreset):
         if self.size()+itrs > sz:
             raise ValueError('%s._build(): # itrs + current size cannot exceed total desired size sz. # itr = %s cur sz: %s '
                              'desired sz: %s' % (self.alg_name, itrs, self.size(), sz))
+        rng.drain()      # plain np.random draws below: no sampler look-ahead may be in flight
         if self.groups is not None:
             for _ in range(itrs):
                 self._draw_group()

@@ -233,7 +233,8 @@ class SparseNNLS(object):
             self._out[4:].copy_(torch.from_numpy(empty))
 
     def _row(self, f):
-        return self._Vact[self._activate(f)]
+        k = self._activate(f)          # may (re)allocate the cache: look the tensor up afterwards
+        return self._Vact[k]
 
     def error(self):
         if self._N == 0:

@@ -28,3 +28,70 @@ def affine_samples(mu, L, R):
     out = eng.empty(S, D)
     nv.call('bc_sample_affine', eng.ctx('sampler'), ptr(d_mu), ptr(d_L), ptr(d_R), S, D, ptr(out), int(out.stride(0)), stream_ptr())
     return out
+
+
+class ConjugateDeviceSampler(object):
+    """The device form of a conjugate sampler, built for the optimiser loop (one call per ADAM step):
+        precision(wts, pts) -> (H, v)   the D x D posterior precision and the linear term (host, tiny)
+        samples = mu + C^-1 R^T,  C = chol(H) (LAPACK dpotrf on the host), mu = C^-1 C^-T v (two dtrtrs), R = randn(S, D)
+    -- the same distribution AND the same samples as the reference's `mu + randn(S, D).dot(LSigp.T)` with
+    LSigp = C^-1 (gaussian.py:28-32, model_neurlinr.py:115-122), without forming the inverse: the triangular solve
+    against the S normal vectors runs on the GPU (csrc/bc_sampler.cu::k_sample_solve).  [mu | C] goes up in one copy from
+    pinned memory, the normals in another; with `ahead` (util/rng.py) they are drawn one call ahead on a helper thread,
+    already into pinned memory."""
+
+    def __init__(self, D, precision, ahead=None):
+        self.D, self.precision, self.ahead = int(D), precision, ahead
+        self.st = None
+
+    def _stage(self, r):
+        st = self.st
+        k = st['k'] = st['k'] ^ 1
+        if st['pin'][k] is None or tuple(st['pin'][k].shape) != r.shape:
+            st['pin'][k] = torch.empty(*r.shape, dtype=torch.float64).pin_memory()
+        if st['ev'][k] is not None:
+            st['ev'][k].synchronize()                  # the upload that last used this buffer has left it
+        st['pin'][k].numpy()[...] = r
+        return k, st['pin'][k]
+
+    def __call__(self, S, wts, pts):
+        import scipy.linalg as sl
+        if self.ahead is not None:
+            self.ahead.begin_cycle()
+        eng = Engine.get()
+        D = self.D
+        if self.st is None:
+            self.st = {'k': 0, 'pin': [None, None], 'ev': [None, None], 'ml': eng.empty(D*D + D),
+                       'ml_pin': torch.empty(D*D + D, dtype=torch.float64).pin_memory(), 'ml_ev': None}
+        st = self.st
+        H, v = self.precision(np.asarray(wts, dtype=np.float64), pts)
+        C, info = sl.lapack.dpotrf(H, lower=1, overwrite_a=0)
+        if info != 0:
+            raise np.linalg.LinAlgError('posterior precision not positive definite (dpotrf info %d)' % info)
+        # the reference's mean is LSigp LSigp^T v with LSigp = C^-1, i.e. C^-1 (C^-T v) = (C^T C)^-1 v -- NOT H^-1 v = (C C^T)^-1 v
+        # (gaussian.py:31, model_neurlinr.py:121 multiply by the inverse FACTOR's Gram matrix); two triangular solves
+        y, info = sl.lapack.dtrtrs(C, v, lower=1, trans=1)
+        mu, info = sl.lapack.dtrtrs(C, y, lower=1, trans=0)
+        if st['ml_ev'] is not None:
+            st['ml_ev'].synchronize()
+        buf = st['ml_pin'].numpy()
+        buf[:D] = mu
+        buf[D:] = np.tril(C).ravel()
+        st['ml'].copy_(st['ml_pin'], non_blocking=True)
+        st['ml_ev'] = torch.cuda.Event()
+        st['ml_ev'].record()
+        if self.ahead is not None:
+            k, pin = self.ahead.randn(S, D, self._stage)
+        else:
+            k, pin = self._stage(np.random.randn(S, D))
+        Rd = pin.to(eng.device, non_blocking=True)
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
+        theta = eng.empty(S, D)
+        nv.call('bc_sample_solve', eng.ctx('sampler'), ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)),
+                stream_ptr())
+        return theta
+
+    def drain(self):
+        if self.ahead is not None:
+            self.ahead.drain()

@@ -549,6 +549,38 @@ int bc_adam_step(bc_ctx* c, const double* d_g, double* d_x, double* d_m1, double
   return BC_OK;
 }
 
+int bc_greedy_opt_step(bc_ctx* c, const bc_step_args* a, void* stream) {
+  if (!c || !a || !a->d_theta || a->M <= 0 || !a->d_pts || !a->d_Vc || !a->d_parts || !a->d_colsum || !a->d_resid || !a->d_grad || !a->d_w ||
+      !a->d_m1 || !a->d_m2 || a->n < 0)
+    return BC_ERR_ARG;
+  int rc;
+  if ((rc = bc_set_samples(c, a->d_theta, a->S, a->ldt, stream))) return rc;
+  if (a->ev_pass_begin) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_begin, (cudaStream_t)stream));
+  if (a->d_image && a->n > 0) {
+    const void* img = a->d_image;
+    const double* rs = a->d_rowscale;
+    const double* ra = a->d_rowaux_q;
+    if (a->d_rows) {
+      if (!a->d_gimage || !a->d_growscale) return BC_ERR_ARG;
+      if ((rc = bc_q_gather_rows(c, a->d_image, a->d_rowscale, a->d_rowaux_q, a->d_rows, a->n, a->d_gimage, a->d_growscale,
+                                 a->d_rowaux_q ? a->d_growaux : nullptr, stream)))
+        return rc;
+      img = a->d_gimage;
+      rs = a->d_growscale;
+      ra = a->d_rowaux_q ? a->d_growaux : nullptr;
+    }
+    if ((rc = bc_project_colsum_q(c, img, rs, a->n, ra, a->d_parts, stream))) return rc;
+  } else {
+    if ((rc = bc_project_colsum(c, a->d_X, a->ldx, a->d_rows, a->n, a->d_rowaux, a->d_parts, stream))) return rc;
+  }
+  if (a->ev_pass_end) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_end, (cudaStream_t)stream));
+  if ((rc = bc_colsum_combine(c, a->d_parts, 1, a->S, a->d_colsum, stream))) return rc;
+  if ((rc = bc_project_materialise(c, a->d_pts, a->ldp, nullptr, a->M, a->d_pts_rowaux, a->d_Vc, a->ldv, nullptr, nullptr, 0, stream))) return rc;
+  if ((rc = bc_core_resid(c, a->d_colsum, a->scaling, a->d_Vc, a->M, a->S, a->ldv, a->d_w, a->d_resid, stream))) return rc;
+  if ((rc = bc_core_grad(c, a->d_Vc, a->M, a->S, a->ldv, a->d_resid, a->d_grad, stream))) return rc;
+  return bc_adam_step(c, a->d_grad, a->d_w, a->d_m1, a->d_m2, a->M, a->lr, a->b1, a->b2, a->c1, a->c2, a->eps, a->d_nn_mask, stream);
+}
+
 int bc_core_pgrad(bc_ctx* c, const double* d_P, int M, int64_t ldp, const double* d_w, const double* d_resid, double* d_out,
                   int64_t ldo, void* stream) {
   if (!c || !d_P || !d_w || !d_resid || !d_out || M < 0 || ldp < 1 || ldo < 1) return BC_ERR_ARG;

@@ -36,10 +36,23 @@ def gaussian_KL(mu0, Sig0, mu1, Sig1inv):
     return 0.5*(t1+t2+t3-mu0.shape[0])
 
 
-def make_conjugate_sampler(mu0, Sig0inv, Siginv, device=False):
-    """sampler(S, wts, pts) as in examples/zellner_gaussian/main.py:87-92.  device=True: the S x d x d product of the last
-    line runs on the GPU and the samples stay there (bayesiancoresets/util/samplers.py); same numpy stream, same (mu, L)."""
+def make_conjugate_sampler(mu0, Sig0inv, Siginv, device=False, prefetch=False):
+    """sampler(S, wts, pts) as in examples/zellner_gaussian/main.py:87-92.
+    device=True: the samples are formed on the GPU and stay there (bayesiancoresets/util/samplers.py): the host factors the
+    d x d posterior precision, the triangular solve against the S normal vectors runs on the device; same numpy stream, same
+    samples.  prefetch=True (device form): the normals -- and the coreset class's sub-sample indices -- are drawn one call
+    ahead on a helper thread (bayesiancoresets/util/rng.py); the global stream is consumed in the same order."""
     d = mu0.shape[0]
+    if device and d <= 160:
+        from bayesiancoresets.util import rng
+        from bayesiancoresets.util.samplers import ConjugateDeviceSampler
+        Sig0inv_mu0 = np.dot(Sig0inv, mu0)
+
+        def precision(wts, pts):
+            if pts.shape[0] == 0:
+                return Sig0inv + 0.*Siginv, Sig0inv_mu0 + 0.
+            return Sig0inv + wts.sum()*Siginv, Sig0inv_mu0 + np.dot(Siginv, (wts[:, np.newaxis]*pts).sum(axis=0))
+        return ConjugateDeviceSampler(d, precision, rng.activate() if prefetch else None)
 
     def sampler(S, wts, pts):
         if pts.shape[0] == 0:

@@ -189,33 +189,30 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
 
     method='hybrid' / 'device' form the samples on the GPU and return a device tensor (see `_device_laplace_sampler`).
     method='newton' additionally warm-starts each mode search at the previous mode (consecutive optimiser steps move the
-    weights a little).  prefetch=True draws the NEXT call's S x D standard normals on a helper thread while the caller is
-    busy (the draw does not depend on the weights); the global numpy stream is consumed in exactly the same order and
-    amounts as without it, provided nothing else draws from it between two sampler calls (true for full-data builds)."""
+    weights a little).  prefetch=True draws the NEXT call's S x D standard normals -- and whatever the coreset class draws
+    between two calls, the sub-sample indices of bcores.py:53 -- on a helper thread while the caller is busy (the draws do
+    not depend on the weights); the global numpy stream is consumed in exactly the same order and amounts as without it
+    (bayesiancoresets/util/rng.py)."""
     mu0 = np.zeros(D) if mu0 is None else mu0
-    state = {'mu': None, 'fut': None, 'shape': None}
-    pool = None
+    state = {'mu': None}
+    ahead = None
     if prefetch:
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=1)
+        from bayesiancoresets.util import rng
+        ahead = rng.activate()
 
     def normals(S, d, stage=None):
         """S x d standard normals from numpy's global stream; `stage` (optional) post-processes a draw on the thread that made it"""
-        def draw():
-            r = np.random.randn(S, d)
-            return r if stage is None else stage(r)
-        if pool is None:
-            return draw()
-        if state['fut'] is not None and state['shape'] == (S, d):
-            out = state['fut'].result()
-        else:
-            if state['fut'] is not None:
-                state['fut'].result()       # a draw of another shape was in flight: it has consumed the stream; keep order
-            out = draw()
-        state['fut'], state['shape'] = pool.submit(draw), (S, d)
-        return out
+        if ahead is not None:
+            return ahead.randn(S, d, stage)
+        r = np.random.randn(S, d)
+        return r if stage is None else stage(r)
+
+    def new_call():
+        if ahead is not None:
+            ahead.begin_cycle()
 
     def sampler(S, wts, pts):
+        new_call()
         if pts.shape[0] == 0:
             wts = np.zeros(1)
             pts = np.zeros((1, D))
@@ -225,18 +222,18 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
         return mu + normals(S, mu.shape[0]).dot(LSig.T)
 
     def drain():
-        """wait for the draw in flight (call before re-seeding numpy's global stream)"""
-        if state['fut'] is not None:
-            state['fut'].result()
-            state['fut'] = None
+        """stop the look-ahead and leave numpy's global stream where this sampler's own draws have left it (call before
+        re-seeding it, or before drawing from it directly)"""
+        if ahead is not None:
+            ahead.drain()
 
     if method in ('device', 'hybrid'):
-        sampler = _device_laplace_sampler(D, mu0, normals, host_factor=(method == 'hybrid'))
+        sampler = _device_laplace_sampler(D, mu0, normals, host_factor=(method == 'hybrid'), new_call=new_call)
     sampler.drain = drain
     return sampler
 
 
-def _device_laplace_sampler(D, mu0, normals, host_factor):
+def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None):
     """method='device' / 'hybrid': the S x D samples are formed on the GPU and returned as a device tensor (the projector's
     fused path takes it without a host round trip).  The standard normals still come from numpy's global stream, so the
     sampler consumes it exactly like the host one.
@@ -264,6 +261,7 @@ def _device_laplace_sampler(D, mu0, normals, host_factor):
         return k, st['pin'][k]
 
     def sampler(S, wts, pts):
+        new_call()
         eng = Engine.get()
         ctx = eng.ctx('sampler')
         wts = np.asarray(wts, dtype=np.float64)

@@ -24,10 +24,23 @@ def weighted_post(th0, Sig0inv, sigsq, z, w):
     return mup, LSigp, LSigpInv
 
 
-def make_conjugate_sampler(mu0, Sig0inv, sigsq, device=False):
+def make_conjugate_sampler(mu0, Sig0inv, sigsq, device=False, prefetch=False):
     """sampler(S, wts, pts) with the conjugate posterior of the linear head (model_neurlinr.py:115-122).  device=True: the
-    S x D x D product of the last line runs on the GPU and the samples stay there (bayesiancoresets/util/samplers.py)."""
+    host factors the D x D posterior precision, the samples are formed on the GPU by a triangular solve against the normals
+    and stay there (bayesiancoresets/util/samplers.py); prefetch=True: normals drawn one call ahead (util/rng.py)."""
     D = mu0.shape[0]
+    if device and D <= 160:
+        from bayesiancoresets.util import rng
+        from bayesiancoresets.util.samplers import ConjugateDeviceSampler
+        Sig0inv_mu0 = np.dot(Sig0inv, mu0)
+
+        def precision(wts, pts):
+            if pts.shape[0] == 0:
+                return Sig0inv + 0., Sig0inv_mu0 + 0.
+            z = np.atleast_2d(pts)
+            X, Y = z[:, :-1], z[:, -1]
+            return Sig0inv + (wts[:, np.newaxis]*X).T.dot(X)/sigsq, Sig0inv_mu0 + (wts[:, np.newaxis]*Y[:, np.newaxis]*X).sum(axis=0)/sigsq
+        return ConjugateDeviceSampler(D, precision, rng.activate() if prefetch else None)
 
     def sampler(S, wts, pts):
         if pts.shape[0] == 0:

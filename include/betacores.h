@@ -152,6 +152,34 @@ int bc_dense_pgrad(bc_ctx* ctx, const double* d_G, int M, int S, int D, const do
 int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, double* d_m2, int n, double lr, double b1, double b2,
                  double c1, double c2, double eps, const unsigned char* d_nn_mask, void* stream);
 
+/* ---- one optimiser step in one call ------------------------------------------------------------------------------
+ * bc_greedy_opt_step enqueues, on `stream`, everything one projected-ADAM step of BetaCoreset._optimize / SparseVICoreset._optimize
+ * does after the sampler has produced Theta (bcores.py:142-146, util/opt.py:45-52):
+ *     bc_set_samples -> [bc_q_gather_rows] -> bc_project_colsum(_q) -> bc_colsum_combine -> bc_project_materialise (the M coreset
+ *     rows) -> bc_core_resid -> bc_core_grad -> bc_adam_step
+ * -- the same kernels in the same order as the individual entry points, so the results are bit-identical; what it saves is the
+ * host's per-call overhead (a dozen FFI crossings per step matter when a step is a few hundred microseconds: the sub-sampled
+ * Gaussian example runs 1000 of them per coreset point).  Single-rank jobs only (a sharded job exchanges the column-sum parts
+ * between the pass and the combine).  All pointers are device pointers unless named h_. */
+typedef struct bc_step_args {
+  const double* d_theta; int S; int ldt;                         /* posterior samples of this step (S x ldt) */
+  /* data rows: the tensor-core route when d_image is set (with its scratch image for gathered passes), else the FP64 route */
+  const void* d_image; const double* d_rowscale; const double* d_rowaux_q;
+  void* d_gimage; double* d_growscale; double* d_growaux;
+  const double* d_X; int64_t ldx; const double* d_rowaux;
+  const int64_t* d_rows; int64_t n;                              /* gather list (NULL: the first n rows) and row count */
+  double scaling;                                                /* N / n for a sub-sampled pass, 1 otherwise (bcores.py:55) */
+  /* coreset side */
+  const double* d_pts; int64_t ldp; int M; const double* d_pts_rowaux;
+  double* d_Vc; int64_t ldv;                                     /* M x S workspace: the centred projection of the coreset points */
+  double* d_parts; double* d_colsum; double* d_resid; double* d_grad;   /* 2 (S+1), S, S+1, M doubles */
+  /* projected ADAM (util/opt.py:45-52) */
+  double* d_w; double* d_m1; double* d_m2; double lr, b1, b2, c1, c2, eps; const unsigned char* d_nn_mask;
+  /* optional instrumentation: two cudaEvent_t recorded on `stream` right before / after the data-row pass (NULL: none) */
+  void* ev_pass_begin; void* ev_pass_end;
+} bc_step_args;
+int bc_greedy_opt_step(bc_ctx* ctx, const bc_step_args* args, void* stream);
+
 /* ---- device-side posterior samplers (the reference's samplers are host callbacks) ----------------
  * bc_laplace_logistic: Laplace approximation of the weighted logistic posterior with N(0, I) prior -- what
  *   bayesiancoresets/util/opt.py:10-33 get_laplace / examples/zellner_logreg/main.py:86-111 compute on the host: d_mu holds

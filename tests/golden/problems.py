@@ -111,7 +111,7 @@ def make_gaussian(N, d, seed):
                 pts = np.zeros((1, d))
             mu, Lp, _ = om.gauss_weighted_post(mu0, Sig0inv, Siginv, pts, w)
             return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
-        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig),
+        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig), prior=dict(mu0=mu0, Sig0inv=Sig0inv),
                     ref_betalik=lambda lr, ga, nl: (lambda x, th, beta: ga.gaussian_beta_likelihood(x, th, beta, Siginv, logdetSig)),
                     ref_loglik=lambda lr, ga, nl: (lambda x, th: ga.gaussian_loglikelihood(x, th, Siginv, logdetSig)),
                     ref_gradll=lambda lr, ga, nl: (lambda x, th: ga.gaussian_grad_x_loglikelihood(x, th, Siginv)),
@@ -144,7 +144,7 @@ def make_neurlin(N, D, seed):
                 pts = np.zeros((1, D+1))
             mu, Lp, _ = om.nl_weighted_post(mu0, Sig0inv, sigsq, pts, w)
             return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
-        return dict(model='nl', data=Z, sampler=sampler, params=dict(sigsq=sigsq),
+        return dict(model='nl', data=Z, sampler=sampler, params=dict(sigsq=sigsq), prior=dict(mu0=mu0, Sig0inv=Sig0inv),
                     ref_betalik=lambda lr, ga, nl: (lambda z, th, beta: nl.neurlinr_beta_likelihood(z, th, beta, sigsq)),
                     ref_loglik=lambda lr, ga, nl: (lambda z, th: nl.neurlinr_loglikelihood(z, th, sigsq)),
                     oracle_betalik=lambda beta: (lambda pts, th: om.nl_betalik(pts, th, beta, sigsq)),
@@ -189,7 +189,7 @@ def make_c1_zellner_gaussian():
                 pts = np.zeros((1, d))
             mu, Lp, _ = om.gauss_weighted_post(mu0, Sig0inv, Siginv, pts, w)
             return mu + np.random.randn(S, mu.shape[0]).dot(Lp.T)
-        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig),
+        return dict(model='gauss', data=data, sampler=sampler, params=dict(Siginv=Siginv, logdetSig=logdetSig), prior=dict(mu0=mu0, Sig0inv=Sig0inv),
                     ref_betalik=lambda lr, ga, nl: (lambda x, th, beta: ga.gaussian_beta_likelihood(x, th, beta, Siginv, logdetSig)),
                     ref_loglik=lambda lr, ga, nl: (lambda x, th: ga.gaussian_loglikelihood(x, th, Siginv, logdetSig)),
                     ref_gradll=lambda lr, ga, nl: (lambda x, th: ga.gaussian_grad_x_loglikelihood(x, th, Siginv)),

@@ -95,3 +95,41 @@ def test_affine_samples_rejects_a_full_matrix():
     from bayesiancoresets.util.samplers import affine_samples
     with pytest.raises(ValueError):
         affine_samples(np.zeros(3), np.ones((3, 3)), np.zeros((4, 3)))
+
+
+@pytest.mark.parametrize('name', ['gauss_beta_sub', 'nl_beta_small', 'gauss_svi_full'])
+def test_golden_builds_with_device_samplers_and_look_ahead_rng(name):
+    """the package's conjugate samplers in their optimiser-loop form (host factors the D x D precision, samples formed on the
+    device by a triangular solve, normals AND the sub-sample indices drawn one call ahead on a helper thread): the builds
+    must reproduce the golden coresets the unmodified reference produced with its plain host sampler on the same seeds --
+    i.e. the global numpy stream is consumed in exactly the reference's order (util/rng.py) and the samples agree"""
+    import os
+    import bayesiancoresets as bc
+    import gaussian, model_neurlinr
+    import problems
+    from bayesiancoresets.util import rng
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'g3_coresets.npz'))
+    case = [c for c in problems.coreset_cases(False) if c['name'] == name][0]
+    prob = case['make']()
+    rng.drain()
+    problems.reseed(case)
+    if prob['model'] == 'gauss':
+        sampler = gaussian.make_conjugate_sampler(prob['prior']['mu0'], prob['prior']['Sig0inv'], prob['params']['Siginv'], device=True, prefetch=True)
+        bl, ll = gaussian.gaussian_beta_likelihood.bind(**prob['params']), gaussian.gaussian_loglikelihood.bind(**prob['params'])
+    else:
+        sampler = model_neurlinr.make_conjugate_sampler(prob['prior']['mu0'], prob['prior']['Sig0inv'], prob['params']['sigsq'], device=True, prefetch=True)
+        bl, ll = model_neurlinr.neurlinr_beta_likelihood.bind(**prob['params']), model_neurlinr.neurlinr_loglikelihood.bind(**prob['params'])
+    if case['alg'] == 'beta':
+        alg = bc.BetaCoreset(prob['data'], bc.BetaBlackBoxProjector(sampler, case['S'], bl, ll, None), n_subsample_select=case['n_sel'],
+                             n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'], step_sched=case['sched'], beta=case['beta'], learn_beta=False)
+    else:
+        alg = bc.SparseVICoreset(prob['data'], bc.BlackBoxProjector(sampler, case['S'], ll, None), n_subsample_select=case['n_sel'],
+                                 n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'], step_sched=case['sched'])
+    for m in range(1, case['M']+1):
+        alg.build(1, m)
+    sampler.drain()
+    w, _, i = alg.get()[:3]
+    np.testing.assert_array_equal(i, g[name+'_idcs'])
+    np.testing.assert_allclose(w, g[name+'_wts'], rtol=1e-6, atol=1e-9)
+    ahead = rng.active()
+    assert ahead is not None and ahead.hits > case['M']*case['opt_itrs']//2       # the look-ahead did serve most draws

@@ -282,3 +282,44 @@ def test_fused_projection_reapplies_its_potential_after_another_owner(monkeypatc
     assert calls.count('bc_set_potential') == 3 and A.S == 3
     with pytest.raises(nv.NativeError):
         B.set_samples(th)                    # B never re-configured: the workspace holds A's potential
+
+
+def test_stream_ahead_consumes_the_global_stream_like_direct_draws():
+    """util/rng.py: draws made one sampler call ahead on a helper thread, with pattern changes (selection vs optimiser
+    sub-sample sizes, cycles that end early or run long) and a drain in between, return exactly the numbers direct
+    np.random calls return -- and leave the global stream in the same state."""
+    from bayesiancoresets.util.rng import StreamAhead
+    S, D, N = 7, 5, 1000
+    # a script of cycles: each = the draws between two sampler calls
+    script = ([[('randn', S, D)]]*3 + [[('randn', S, D), ('randint', N, 20)]]*5 + [[('randn', S, D), ('randint', N, 50)]]
+              + [[('randn', S, D), ('randint', N, 20)]]*4 + [[('randn', S, D)]] + [[('randn', S, D), ('randint', N, 20), ('randint', N, 3)]]*3
+              + [[('randn', S+1, D)]]*2)
+
+    def play(ahead):
+        out = []
+        for c, cycle in enumerate(script):
+            if ahead is not None:
+                ahead.begin_cycle()
+            for op in cycle:
+                if op[0] == 'randn':
+                    out.append(ahead.randn(op[1], op[2]) if ahead is not None else np.random.randn(op[1], op[2]))
+                else:
+                    out.append(ahead.randint(op[1], op[2]) if ahead is not None else np.random.randint(op[1], size=op[2]))
+            if c == 12 and ahead is not None:
+                ahead.drain()
+                out.append(np.random.rand(3))        # someone else draws directly after a drain
+            elif c == 12:
+                out.append(np.random.rand(3))
+        if ahead is not None:
+            ahead.drain()
+        out.append(np.random.rand(4))                # the stream ends up in the same place
+        return out
+    np.random.seed(123)
+    ref = play(None)
+    np.random.seed(123)
+    a = StreamAhead()
+    got = play(a)
+    assert len(ref) == len(got)
+    for x, y in zip(ref, got):
+        np.testing.assert_array_equal(x, y)
+    assert a.hits > 20 and a.rewinds >= 4          # it did speculate, and it did have to rewind at the pattern changes

@@ -11,7 +11,8 @@ import problems, bayesiancoresets as bc, gaussian
 case = [c for c in problems.coreset_cases(True) if c['name'] == 'c1_zellner_gaussian'][0]
 prob = case['make']()
 bl = gaussian.gaussian_beta_likelihood.bind(**prob['params']); ll = gaussian.gaussian_loglikelihood.bind(**prob['params'])
-prj = bc.BetaBlackBoxProjector(prob['sampler'], case['S'], bl, ll, None)
+sampler = gaussian.make_conjugate_sampler(prob['prior']['mu0'], prob['prior']['Sig0inv'], prob['params']['Siginv'], device=True, prefetch=True)
+prj = bc.BetaBlackBoxProjector(sampler, case['S'], bl, ll, None)
 alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subsample_opt=case['n_opt'], opt_itrs=case['opt_itrs'],
                      step_sched=case['sched'], beta=case['beta'], learn_beta=False)
 alg.build(1, 1)
