@@ -162,10 +162,12 @@ def workload_config(a, world):
                         % (a.n, a.d, a.s, a.beta),
             'N': a.n, 'D': a.d, 'S': a.s, 'beta': a.beta, 'opt_itrs': a.opt_itrs,
             'step': 'one BetaCoreset.build(1, m): 1 selection + opt_itrs ADAM steps = (1+opt_itrs) N x S projections',
-            'sampler': {'hybrid': 'Laplace approximation of the weighted coreset posterior: mode (warm-started damped Newton steps) and D x D '
-                                  'Cholesky factor / inverse on the host, samples mu + R L^T formed on the device (k_sample_affine) from S x D '
-                                  'normals drawn from the global numpy stream one call ahead on a helper thread; called every optimiser '
-                                  'step.  The reference arm runs the same algebra entirely on the host (same random numbers)',
+            'sampler': {'hybrid': 'Laplace approximation of the weighted coreset posterior, called every optimiser step.  Selection steps: mode '
+                                  '(warm-started damped Newton steps) and D x D Cholesky factor on the host, samples mu + C^-1 R^T formed on the '
+                                  'device (k_sample_solve).  Optimiser steps: the sampler\'s device_step protocol -- mode (dual-space Newton), '
+                                  'factor and samples all by kernels from the device-resident weights, no host round trip.  The S x D normals '
+                                  'come from the global numpy stream, drawn one call ahead on a helper thread, in the reference\'s order.  The '
+                                  'reference arm runs the same algebra entirely on the host (same random numbers)',
                         'device': 'Laplace approximation of the weighted coreset posterior on the device (csrc/bc_sampler.cu: warm-started '
                                   'damped Newton mode search, D x D Cholesky factor and inverse, affine map of S x D normals drawn from '
                                   'the global numpy stream one call ahead on a helper thread), called every optimiser step; the reference '
@@ -298,12 +300,25 @@ def b200_arm(a):
     sampler_clock = [0, 0.]
 
     def timed_sampler(fn):
+        """counts the sampler calls and the HOST time spent in them; forwards the device-step protocol (there the host time is
+        what it takes to queue the kernels and fetch the pre-drawn normals -- the sampler's algebra runs on the GPU)"""
         def sampler(Sn, w, pts):
             t = time.perf_counter()
             out = fn(Sn, w, pts)
             sampler_clock[0] += 1
             sampler_clock[1] += time.perf_counter() - t
             return out
+        if hasattr(fn, 'device_step'):
+            def device_step(Sn, w_dev, core):
+                t = time.perf_counter()
+                out = fn.device_step(Sn, w_dev, core)
+                sampler_clock[0] += 1
+                sampler_clock[1] += time.perf_counter() - t
+                return out
+            sampler.device_step = device_step
+            sampler.supports_device_step = fn.supports_device_step
+        if hasattr(fn, 'drain'):
+            sampler.drain = fn.drain
         return sampler
 
     def make_alg(rows):

@@ -38,6 +38,8 @@ SIGNATURES = {
     'bc_core_pgrad': [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp],
     'bc_dense_pgrad': [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp],
     'bc_laplace_logistic': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
+    'bc_laplace_logistic_factor': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
+    'bc_conjugate_factor': [c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp],
     'bc_sample_solve': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_sample_affine': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
@@ -69,7 +71,7 @@ class StepArgs(ctypes.Structure):
                 ('d_parts', c_vp), ('d_colsum', c_vp), ('d_resid', c_vp), ('d_grad', c_vp),
                 ('d_w', c_vp), ('d_m1', c_vp), ('d_m2', c_vp),
                 ('lr', c_dbl), ('b1', c_dbl), ('b2', c_dbl), ('c1', c_dbl), ('c2', c_dbl), ('eps', c_dbl), ('d_nn_mask', c_vp),
-                ('ev_pass_begin', c_vp), ('ev_pass_end', c_vp)]
+                ('ev_pass_begin', c_vp), ('ev_pass_end', c_vp), ('phase', c_int), ('nparts', c_int), ('d_parts_all', c_vp)]
 
 
 SIGNATURES['bc_greedy_opt_step'] = [c_vp, ctypes.POINTER(StepArgs), c_vp]

@@ -33,6 +33,9 @@ def _as_f64_2d(a):
 # one library call per optimiser step (bc_greedy_opt_step) instead of one per kernel; BC_FUSED_STEP=0 keeps the call-by-call loop
 import os
 FUSED_STEP_CALL = os.environ.get('BC_FUSED_STEP', '1') != '0'
+# samplers that offer device_step() run the optimiser loop without any host synchronisation; BC_DEVICE_SAMPLER_LOOP=0 keeps
+# calling them through the reference's host protocol sampler(S, wts, pts)
+DEVICE_SAMPLER_LOOP = os.environ.get('BC_DEVICE_SAMPLER_LOOP', '1') != '0'
 
 
 class _Tangent(object):
@@ -417,7 +420,7 @@ class GreedyVICoreset(Coreset):
         g = t.eng.empty(M)
         beta = self._beta()
         scaling = 1. if self.n_subsample_opt is None else self._n_total/self.n_subsample_opt
-        if isinstance(t, _FusedTangent) and t.comm.world == 1 and FUSED_STEP_CALL:
+        if isinstance(t, _FusedTangent) and FUSED_STEP_CALL:
             self.wts = self._optimize_fused_steps(t, core, beta, scaling)
             return
 
@@ -437,41 +440,63 @@ class GreedyVICoreset(Coreset):
         self.wts = nn_opt(self.wts, grd, opt_itrs=self.opt_itrs, step_sched=self.step_sched)
 
     def _optimize_fused_steps(self, t, core, beta, scaling):
-        """the loop above with ONE library call per optimiser step (bc_greedy_opt_step: the same kernels in the same order,
-        launched back to back from C instead of through a dozen Python -> ctypes crossings).  Single rank, device potential."""
+        """the optimiser loop with ONE library call per step (bc_greedy_opt_step: the same kernels in the same order as the
+        call-by-call loop, launched back to back from C; a row-sharded job calls its two halves around the exchange of the
+        column-sum parts).
+
+        Sampler protocol.  The reference's sampler is a host callback `sampler(S, wts, pts)` and stays one: the weights come
+        back to the host every step for it.  A sampler that also offers `device_step(S, w_dev, core)` (this package's
+        Laplace / conjugate samplers) forms the posterior and the samples from the device-resident iterate instead; the loop
+        then has NO host synchronisation at all -- the host queues step after step (and draws the normals a call ahead,
+        util/rng.py), the weights are read back once at the end."""
         from .. import _fused
-        eng, fp, rows = t.eng, t.fp, t.rows
+        eng, fp, rows, comm = t.eng, t.fp, t.rows, t.comm
         M = self.wts.shape[0]
         b1, b2, eps = 0.9, 0.999, 1e-8                     # util/opt.py:36 defaults (nn_opt is called with them)
         x = eng.upload(np.asarray(self.wts, dtype=np.float64))
         m1, m2, g = eng.zeros(M), eng.zeros(M), eng.empty(M)
         xh = np.asarray(self.wts, dtype=np.float64).copy()
         prj = self.ll_projector
-        if self.n_subsample_opt is not None:
+        smp = getattr(prj, 'sampler', None)
+        on_device = DEVICE_SAMPLER_LOOP and hasattr(smp, 'device_step') and smp.supports_device_step() and not getattr(prj, 'encoder', None)
+        sub_mode = self.n_subsample_opt is not None
+        if sub_mode:
             n_pass, fixed_sub = int(self.n_subsample_opt), None
         elif self.groups is not None and not self._groups_cover:
-            fixed_sub = eng.upload(np.asarray(self._groups_flat, dtype=np.int64), dtype=torch.int64)
+            _, loc = local_subsample(self._groups_flat, rows.row0, rows.n_local)
+            fixed_sub = eng.upload(np.asarray(loc, dtype=np.int64), dtype=torch.int64)
             n_pass = int(fixed_sub.numel())
         else:
             n_pass, fixed_sub = rows.n_local, None
         a = nv.StepArgs()
         bufs = None
-        idx_dev = eng.empty(max(n_pass, 1), dtype=torch.int64) if self.n_subsample_opt is not None else fixed_sub
-        idx_pin = [torch.empty(max(n_pass, 1), dtype=torch.int64).pin_memory() for _ in range(2)] if self.n_subsample_opt is not None else None
+        idx_dev = eng.empty(max(n_pass, 1), dtype=torch.int64) if sub_mode else fixed_sub
+        idx_pin = [torch.empty(max(n_pass, 1), dtype=torch.int64).pin_memory() for _ in range(2)] if sub_mode else None
+        idx_ev = [None, None]
+        world = comm.world
+        th = None
         for i in range(self.opt_itrs):
-            prj.update(xh, self.pts)                           # host sampler: consumes np.random exactly like the reference
-            th = prj.samples
-            if isinstance(th, torch.Tensor):
-                th = th.to(device=eng.device, dtype=torch.float64)
-                if not th.is_contiguous():
-                    th = th.contiguous()
+            if on_device:
+                th = smp.device_step(prj.projection_dimension, x, core)
             else:
-                th = eng.upload(np.ascontiguousarray(np.atleast_2d(np.asarray(th, dtype=np.float64))))
+                prj.update(xh, self.pts)                       # host sampler: consumes np.random exactly like the reference
+                th = prj.samples
+                if isinstance(th, torch.Tensor):
+                    th = th.to(device=eng.device, dtype=torch.float64)
+                    if not th.is_contiguous():
+                        th = th.contiguous()
+                else:
+                    th = eng.upload(np.ascontiguousarray(np.atleast_2d(np.asarray(th, dtype=np.float64))))
+            if world > 1 and (i == 0 or not on_device):
+                t._theta_buf = th
+                t._replicate_samples()                         # checked, not assumed: see _FusedTangent._replicate_samples
             fp.configure(beta)
             fp.note_samples(th)
             S = fp.S
             if bufs is None or bufs['S'] != S:
                 q = fp._q_operands(rows, None)                 # row image of the whole block (built once), exponents / digits applied
+                if q is None and rows.n_local > 0 and _fused.ROUTE == 'q' and fp.D <= nv.lib().bc_q_max_features():
+                    raise nv.NativeError('row image unavailable')
                 bufs = dict(S=S, Vc=eng.empty(M, S), parts=eng.empty(2*fp.Sld), colsum=eng.empty(S), resid=eng.empty(S+1), q=q)
                 a.S, a.ldt = S, int(th.stride(0))
                 if q is not None:
@@ -481,8 +506,8 @@ class GreedyVICoreset(Coreset):
                         a.d_gimage, a.d_growscale, a.d_growaux = gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr()
                 else:
                     a.d_image = None
-                    ra = fp._rowaux(rows)
-                    a.d_X, a.ldx, a.d_rowaux = rows.t.data_ptr(), rows.ld, (ra.data_ptr() if ra is not None else None)
+                    ra = fp._rowaux(rows) if rows.n_local else None
+                    a.d_X, a.ldx, a.d_rowaux = (rows.t.data_ptr() if rows.n_local else None), rows.ld, (ra.data_ptr() if ra is not None else None)
                 cra = fp._rowaux(core)
                 a.d_pts, a.ldp, a.M, a.d_pts_rowaux = core.t.data_ptr(), core.ld, M, (cra.data_ptr() if cra is not None else None)
                 a.d_Vc, a.ldv = bufs['Vc'].data_ptr(), S
@@ -491,22 +516,42 @@ class GreedyVICoreset(Coreset):
                 a.scaling, a.n = float(scaling), n_pass
                 a.d_rows = idx_dev.data_ptr() if idx_dev is not None else None
             a.d_theta = th.data_ptr()
-            if self.n_subsample_opt is not None:
+            if sub_mode:
                 sub = rng.randint(self._n_total, self.n_subsample_opt)                    # bcores.py:53, after the sampler call
-                pin = idx_pin[i & 1]
-                pin.numpy()[...] = sub
-                idx_dev.copy_(pin, non_blocking=True)
+                if world > 1 or rows.row0 != 0 or rows.n_local != self._n_total:
+                    _, sub = local_subsample(sub, rows.row0, rows.n_local)                # the sub-sampled rows this rank owns
+                k = i & 1
+                if idx_ev[k] is not None:
+                    idx_ev[k].synchronize()                    # the upload that last used this pinned buffer has left it
+                pin = idx_pin[k]
+                pin.numpy()[:len(sub)] = sub
+                idx_dev[:len(sub)].copy_(pin[:len(sub)], non_blocking=True)
+                idx_ev[k] = torch.cuda.Event()
+                idx_ev[k].record()
+                a.n = len(sub)
             a.lr, a.c1, a.c2 = float(self.step_sched(i)), 1.-b1**(i+1), 1.-b2**(i+1)
             if _fused.PASS_TIMERS is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 e1.record()                                    # creates the CUDA events; the library re-records them around the pass
                 a.ev_pass_begin, a.ev_pass_end = e0.cuda_event, e1.cuda_event
-                _fused.PASS_TIMERS.append(('colsum', n_pass, e0, e1))
+                _fused.PASS_TIMERS.append(('colsum', int(a.n), e0, e1))
             else:
                 a.ev_pass_begin = a.ev_pass_end = None
-            nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
-            xh = x.cpu().numpy()                               # one D2H + sync per step: the next sampler call needs the weights
+            if world == 1:
+                a.phase = 0
+                nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+            else:
+                a.phase = 1
+                nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+                allparts = comm.allgather(bufs['parts'])       # (world, 2 Sld): one double-double part per rank, rank order
+                a.phase, a.nparts, a.d_parts_all = 2, world, allparts.data_ptr()
+                nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+            if not on_device:
+                xh = x.cpu().numpy()                           # one D2H + sync per step: the next sampler call needs the weights
+        if on_device:
+            xh = x.cpu().numpy()
+            prj.samples = th
         return xh
 
     def error(self):

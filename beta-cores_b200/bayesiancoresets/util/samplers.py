@@ -40,9 +40,58 @@ class ConjugateDeviceSampler(object):
     pinned memory, the normals in another; with `ahead` (util/rng.py) they are drawn one call ahead on a helper thread,
     already into pinned memory."""
 
-    def __init__(self, D, precision, ahead=None):
+    def __init__(self, D, precision, ahead=None, device_model=None):
         self.D, self.precision, self.ahead = int(D), precision, ahead
         self.st = None
+        # (model id, A0 = Sig0inv, A1 = Siginv or None, v0 = Sig0inv mu0, sigsq): lets the optimiser loop form the posterior on the
+        # device from device-resident weights (device_step), with no host round trip per step
+        self.device_model = device_model
+        self._dm = None
+
+    def _state(self, eng):
+        D = self.D
+        if self.st is None:
+            self.st = {'k': 0, 'pin': [None, None], 'ev': [None, None], 'ml': eng.empty(D*D + D),
+                       'ml_pin': torch.empty(D*D + D, dtype=torch.float64).pin_memory(), 'ml_ev': None,
+                       'info': torch.zeros(2, dtype=torch.int32, device=eng.device)}
+        return self.st
+
+    def _normals_to_device(self, eng, S):
+        st = self.st
+        if self.ahead is not None:
+            k, pin = self.ahead.randn(S, self.D, self._stage)
+        else:
+            k, pin = self._stage(np.random.randn(S, self.D))
+        Rd = pin.to(eng.device, non_blocking=True)
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
+        return Rd
+
+    def device_step(self, S, w_dev, core):
+        """the sampler call of one optimiser step with the weights ALREADY on the device (`w_dev`, M doubles) and the coreset
+        points as resident rows (`core`, a DeviceRows): posterior factor, mean and samples are formed by kernels
+        (bc_conjugate_factor, bc_sample_solve), nothing is read back -- the host only queues work and draws the normals."""
+        if self.ahead is not None:
+            self.ahead.begin_cycle()
+        eng = Engine.get()
+        st = self._state(eng)
+        D = self.D
+        if self._dm is None:
+            model, A0, A1, v0, sigsq = self.device_model
+            self._dm = (model, eng.upload(np.ascontiguousarray(A0, dtype=np.float64)),
+                        eng.upload(np.ascontiguousarray(A1, dtype=np.float64)) if A1 is not None else None,
+                        eng.upload(np.ascontiguousarray(v0, dtype=np.float64)), float(sigsq) if sigsq is not None else 1.0)
+        model, A0, A1, v0, sigsq = self._dm
+        ctx = eng.ctx('sampler')
+        nv.call('bc_conjugate_factor', ctx, model, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(A0), ptr(A1), ptr(v0), sigsq,
+                ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(st['info']), stream_ptr())
+        Rd = self._normals_to_device(eng, S)
+        theta = eng.empty(S, D)
+        nv.call('bc_sample_solve', ctx, ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        return theta
+
+    def supports_device_step(self):
+        return self.device_model is not None and self.D <= 160
 
     def _stage(self, r):
         st = self.st
@@ -60,10 +109,7 @@ class ConjugateDeviceSampler(object):
             self.ahead.begin_cycle()
         eng = Engine.get()
         D = self.D
-        if self.st is None:
-            self.st = {'k': 0, 'pin': [None, None], 'ev': [None, None], 'ml': eng.empty(D*D + D),
-                       'ml_pin': torch.empty(D*D + D, dtype=torch.float64).pin_memory(), 'ml_ev': None}
-        st = self.st
+        st = self._state(eng)
         H, v = self.precision(np.asarray(wts, dtype=np.float64), pts)
         C, info = sl.lapack.dpotrf(H, lower=1, overwrite_a=0)
         if info != 0:
@@ -80,13 +126,7 @@ class ConjugateDeviceSampler(object):
         st['ml'].copy_(st['ml_pin'], non_blocking=True)
         st['ml_ev'] = torch.cuda.Event()
         st['ml_ev'].record()
-        if self.ahead is not None:
-            k, pin = self.ahead.randn(S, D, self._stage)
-        else:
-            k, pin = self._stage(np.random.randn(S, D))
-        Rd = pin.to(eng.device, non_blocking=True)
-        st['ev'][k] = torch.cuda.Event()
-        st['ev'][k].record()
+        Rd = self._normals_to_device(eng, S)
         theta = eng.empty(S, D)
         nv.call('bc_sample_solve', eng.ctx('sampler'), ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)),
                 stream_ptr())

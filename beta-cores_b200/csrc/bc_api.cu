@@ -550,31 +550,42 @@ int bc_adam_step(bc_ctx* c, const double* d_g, double* d_x, double* d_m1, double
 }
 
 int bc_greedy_opt_step(bc_ctx* c, const bc_step_args* a, void* stream) {
-  if (!c || !a || !a->d_theta || a->M <= 0 || !a->d_pts || !a->d_Vc || !a->d_parts || !a->d_colsum || !a->d_resid || !a->d_grad || !a->d_w ||
+  if (!c || !a || a->phase < 0 || a->phase > 2) return BC_ERR_ARG;
+  if (!a->d_theta || a->M <= 0 || !a->d_pts || !a->d_Vc || !a->d_parts || !a->d_colsum || !a->d_resid || !a->d_grad || !a->d_w ||
       !a->d_m1 || !a->d_m2 || a->n < 0)
     return BC_ERR_ARG;
+  if (a->phase == 2 && (!a->d_parts_all || a->nparts < 1)) return BC_ERR_ARG;
   int rc;
-  if ((rc = bc_set_samples(c, a->d_theta, a->S, a->ldt, stream))) return rc;
-  if (a->ev_pass_begin) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_begin, (cudaStream_t)stream));
-  if (a->d_image && a->n > 0) {
-    const void* img = a->d_image;
-    const double* rs = a->d_rowscale;
-    const double* ra = a->d_rowaux_q;
-    if (a->d_rows) {
-      if (!a->d_gimage || !a->d_growscale) return BC_ERR_ARG;
-      if ((rc = bc_q_gather_rows(c, a->d_image, a->d_rowscale, a->d_rowaux_q, a->d_rows, a->n, a->d_gimage, a->d_growscale,
-                                 a->d_rowaux_q ? a->d_growaux : nullptr, stream)))
+  if (a->phase != 2) {
+    if ((rc = bc_set_samples(c, a->d_theta, a->S, a->ldt, stream))) return rc;
+    if (a->ev_pass_begin) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_begin, (cudaStream_t)stream));
+    if (a->d_image && a->n > 0) {
+      const void* img = a->d_image;
+      const double* rs = a->d_rowscale;
+      const double* ra = a->d_rowaux_q;
+      if (a->d_rows) {
+        if (!a->d_gimage || !a->d_growscale) return BC_ERR_ARG;
+        if ((rc = bc_q_gather_rows(c, a->d_image, a->d_rowscale, a->d_rowaux_q, a->d_rows, a->n, a->d_gimage, a->d_growscale,
+                                   a->d_rowaux_q ? a->d_growaux : nullptr, stream)))
+          return rc;
+        img = a->d_gimage;
+        rs = a->d_growscale;
+        ra = a->d_rowaux_q ? a->d_growaux : nullptr;
+      }
+      if ((rc = bc_project_colsum_q(c, img, rs, a->n, ra, a->d_parts, stream))) return rc;
+    } else {
+      if (a->n > 0 && !a->d_X) return BC_ERR_ARG;
+      if ((rc = bc_project_colsum(c, a->d_X ? a->d_X : a->d_pts, a->d_X ? a->ldx : a->ldp, a->d_rows, a->n, a->d_rowaux, a->d_parts, stream)))
         return rc;
-      img = a->d_gimage;
-      rs = a->d_growscale;
-      ra = a->d_rowaux_q ? a->d_growaux : nullptr;
     }
-    if ((rc = bc_project_colsum_q(c, img, rs, a->n, ra, a->d_parts, stream))) return rc;
-  } else {
-    if ((rc = bc_project_colsum(c, a->d_X, a->ldx, a->d_rows, a->n, a->d_rowaux, a->d_parts, stream))) return rc;
+    if (a->ev_pass_end) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_end, (cudaStream_t)stream));
+    if (a->phase == 1) return BC_OK;
   }
-  if (a->ev_pass_end) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_end, (cudaStream_t)stream));
-  if ((rc = bc_colsum_combine(c, a->d_parts, 1, a->S, a->d_colsum, stream))) return rc;
+  if (a->phase == 2) {
+    if ((rc = bc_colsum_combine(c, a->d_parts_all, a->nparts, a->S, a->d_colsum, stream))) return rc;
+  } else {
+    if ((rc = bc_colsum_combine(c, a->d_parts, 1, a->S, a->d_colsum, stream))) return rc;
+  }
   if ((rc = bc_project_materialise(c, a->d_pts, a->ldp, nullptr, a->M, a->d_pts_rowaux, a->d_Vc, a->ldv, nullptr, nullptr, 0, stream))) return rc;
   if ((rc = bc_core_resid(c, a->d_colsum, a->scaling, a->d_Vc, a->M, a->S, a->ldv, a->d_w, a->d_resid, stream))) return rc;
   if ((rc = bc_core_grad(c, a->d_Vc, a->M, a->S, a->ldv, a->d_resid, a->d_grad, stream))) return rc;
@@ -603,11 +614,36 @@ int bc_dense_pgrad(bc_ctx* c, const double* d_G, int M, int S, int D, const doub
   return BC_OK;
 }
 
+static int laplace_common(bc_ctx* c, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_L, int maxit,
+                          double tol, int* d_info, int flags, void* stream) {
+  if (!c || !d_Z || !d_w || !d_mu || !d_L || !d_info || M < 1 || D < 1 || D > 160 || ldz < D || maxit < 1) return BC_ERR_ARG;
+  if (((size_t)D * (D + 1) + 4 * (size_t)D + 5 * (size_t)M + 80) * sizeof(double) > kMaxSmem - 1024) return BC_ERR_UNSUPPORTED;
+  BC_CUDA(launch_laplace_logistic(d_Z, ldz, d_w, M, D, d_mu, d_L, maxit, tol, d_info, flags, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
 int bc_laplace_logistic(bc_ctx* c, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_L, int maxit,
                         double tol, int* d_info, void* stream) {
-  if (!c || !d_Z || !d_w || !d_mu || !d_L || !d_info || M < 1 || D < 1 || D > 160 || ldz < D || maxit < 1) return BC_ERR_ARG;
-  if (((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)M + 70) * sizeof(double) > kMaxSmem - 1024) return BC_ERR_UNSUPPORTED;
-  BC_CUDA(launch_laplace_logistic(d_Z, ldz, d_w, M, D, d_mu, d_L, maxit, tol, d_info, (cudaStream_t)stream));
+  return laplace_common(c, d_Z, ldz, d_w, M, D, d_mu, d_L, maxit, tol, d_info, 0, stream);
+}
+
+int bc_laplace_logistic_factor(bc_ctx* c, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_C, int maxit,
+                               double tol, int* d_info, void* stream) {
+  return laplace_common(c, d_Z, ldz, d_w, M, D, d_mu, d_C, maxit, tol, d_info, 3, stream);
+}
+
+int bc_conjugate_factor(bc_ctx* c, int model, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, const double* d_A0,
+                        const double* d_A1, const double* d_v0, double sigsq, double* d_mu, double* d_C, int* d_info, void* stream) {
+  if (!c || !d_Z || !d_w || !d_A0 || !d_v0 || !d_mu || !d_C || !d_info || M < 1 || D < 1 || D > 160) return BC_ERR_ARG;
+  if (model == BC_MODEL_GAUSSIAN) {
+    if (!d_A1 || ldz < D) return BC_ERR_ARG;
+  } else if (model == BC_MODEL_NEURLIN) {
+    if (!(sigsq > 0.0) || ldz < D + 1) return BC_ERR_ARG;
+  } else {
+    return BC_ERR_UNSUPPORTED;
+  }
+  BC_CUDA(launch_conjugate_factor(model, d_Z, ldz, d_w, M, D, d_A0, d_A1, d_v0, sigsq, d_mu, d_C, d_info, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

@@ -10,6 +10,25 @@
 
 namespace bc {
 
+// ------------------------------------------------------------- debug build --
+// -DBC_DEBUG (tools/build_variants.py debug="-DBC_DEBUG"; the GPU suite is run against that library once per round, since
+// compute-sanitizer is not available on this pool): device-side checks of the invariants a racy or mis-phased pipeline would
+// break -- ring-slot and TMEM addressing bounds, tile bounds of the bulk copies -- and a watchdog on every mbarrier wait
+// (a lost arrival becomes a printed trap instead of a hang).
+#if defined(BC_DEBUG)
+#include <stdio.h>
+#define BC_DASSERT(cond)                                                                                      \
+  do {                                                                                                        \
+    if (!(cond)) {                                                                                            \
+      printf("BC_DEBUG assert failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)threadIdx.x);                                                                               \
+      __trap();                                                                                               \
+    }                                                                                                         \
+  } while (0)
+#else
+#define BC_DASSERT(cond) ((void)0)
+#endif
+
 // ---------------------------------------------------------------- mbarrier --
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -28,6 +47,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if defined(BC_DEBUG)
+  // watchdog form: ~2^26 polls (seconds) without the phase flipping = a lost arrival / wrong parity somewhere in the pipeline
+  unsigned long long spins = 0;
+  while (true) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > (1ull << 26)) {
+      printf("BC_DEBUG mbarrier watchdog: block %d thread %d waits on barrier at smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
@@ -37,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+#endif
 }
 // 1-D bulk copy global -> shared through the TMA engine; completes `bytes` on `bar`.
 // Requirements: dst, src 16-byte aligned, bytes a multiple of 16.

@@ -132,7 +132,9 @@ cudaError_t launch_pgrad_dense(const double* G, int M, int S, int D, const doubl
 
 // ---- bc_sampler.cu: device-side posterior samplers ----
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
-                                    double tol, int* info, cudaStream_t st);
+                                    double tol, int* info, int flags, cudaStream_t st);
+cudaError_t launch_conjugate_factor(int model, const double* Z, long long ldz, const double* w, int M, int D, const double* A0, const double* A1,
+                                    const double* v0, double sigsq, double* mu, double* C, int* info, cudaStream_t st);
 cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 

@@ -73,6 +73,9 @@ static_assert(QSmem::total <= kMaxSmem, "shared memory budget");
 // spinning try_wait loop would steal issue slots from the epilogue warps that share their SM sub-partition.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
+#if defined(BC_DEBUG)
+  unsigned long long spins = 0;
+#endif
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -83,6 +86,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "memory");
     if (done) break;
     __nanosleep(64);
+#if defined(BC_DEBUG)
+    if (++spins > (1ull << 24)) {
+      printf("BC_DEBUG mbarrier watchdog (service warp): block %d thread %d, barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
   }
 }
 
@@ -377,11 +387,14 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         mbar_wait_relaxed(empty_a, (tcount & 1) ^ 1);
         mbar_arrive_expect_tx(full_a, (uint32_t)(NS * kQSliceA));
         const unsigned char* srcA = P.imgA + (size_t)tile * kQTileBytes;
+        BC_DASSERT(tile >= 0 && tile < ntiles);
+        BC_DASSERT((reinterpret_cast<uintptr_t>(srcA) & 15) == 0 && (smem_u32(As) & 1023) == 0);
 #pragma unroll
         for (int s = 0; s < NS; ++s) bulk_g2s(As + (size_t)s * kQSliceA, srcA + (size_t)s * kQSliceA, kQSliceA, full_a);
         for (int c = 0; c < nchunks; ++c, ++itb) {
           const uint32_t st = itb % kQStagesB, ph = (itb / kQStagesB) & 1;
           mbar_wait_relaxed(empty_b + st, ph ^ 1);
+          BC_DASSERT(st < (uint32_t)kQStagesB && c < nchunks);
           mbar_arrive_expect_tx(full_b + st, (uint32_t)(NS * kQSliceB));
           bulk_g2s(Bs + (size_t)st * kQChunkBytes, P.imgB + (size_t)c * kQChunkBytes, NS * kQSliceB, full_b + st);
         }
@@ -412,6 +425,8 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           tc_fence_after();
           const uint64_t bdesc0 = umma_desc_sw128(smem_u32(Bs + (size_t)st * kQChunkBytes));
           const uint32_t d0 = tmem_base + (uint32_t)(buf * kQDiagCols);
+          BC_DASSERT((tmem_base & 0xffffu) + (uint32_t)(buf * kQDiagCols + NS * kQChunk) <= 512u);   // accumulator columns inside the allocation
+          BC_DASSERT(P.ksteps >= 1 && P.ksteps <= 4);
           if (elect_one()) {
             // K blocks beyond the feature count hold only zero digits: not multiplied (D = 20 issues 7 MMAs per chunk
             // instead of 28).  Fully unrolled per block count: the issue rate of this one thread is on the critical path.
@@ -499,6 +514,9 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         tc_fence_after();
         int dg[4][NS];   // [column of the batch][diagonal]
         auto fetch = [&](int batch) {
+          // this warp's lane quarter, this group's half of the chunk, inside the buffer the MMA warp has just filled
+          BC_DASSERT(((tlane >> 16) & 0x7fu) == (uint32_t)(q * 32) + ((tmem_base >> 16) & 0x7fu));
+          BC_DASSERT((tlane & 0xffffu) + (uint32_t)((NS - 1) * kQChunk + batch * 4 + 4) <= (tmem_base & 0xffffu) + (uint32_t)((buf + 1) * kQDiagCols));
 #pragma unroll
           for (int d = 0; d < NS; ++d) {
             uint32_t v[4];
@@ -623,6 +641,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 2);
             fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 1);
             if (b == 1) mbar_wait(ring_empty + slot, rph ^ 1);
+            BC_DASSERT(slot < (uint32_t)kQSlots && off >= 0 && off < 8);
             if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + (b >> 1) * 8 + off] = fv[0];
           }
         }

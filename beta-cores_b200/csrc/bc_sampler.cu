@@ -158,10 +158,15 @@ __device__ double log_joint(const double* w, const double* mrg, int M, int D, co
 
 __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* __restrict__ Z, long long ldz, const double* __restrict__ w,
                                                                   int M, int D, double* __restrict__ mu_io, double* __restrict__ Lsig,
-                                                                  int maxit, double tol, int* __restrict__ info) {
+                                                                  int maxit, double tol, int* __restrict__ info, int flags) {
+  // flags bit 0: write the lower Cholesky factor C of the negative Hessian itself (get_laplace's LSigInv) instead of its inverse
+  //       bit 1: Newton steps from the M x M dual system (Woodbury; needs M <= D): H = I + Z^T diag(d) Z is a rank-M update of
+  //              the identity, H^-1 g = g - Z^T r (I + r K r)^-1 r Z g with r = sqrt(d), K = Z Z^T -- the same step as
+  //              examples/common/model_lr.py::_newton_mode takes while the coreset is small, at M^3 instead of D^3 per iteration
   extern __shared__ double sm[];
   const int ld = D + 1, Mp = (M + 1) & ~1;
-  double* H = sm;                 // [D*ld]
+  const bool dual = (flags & 2) && M <= D;
+  double* H = sm;                 // [D*ld]  (the dual system A, M x (M+1), lives here during the mode search)
   double* th = H + D * ld;        // [D]
   double* tn = th + D;            // [D] trial point
   double* g = tn + D;             // [D] gradient, then Newton step
@@ -170,6 +175,8 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
   double* mtr = mrg + Mp;         // [Mp] margins at the trial point
   double* red = mtr + Mp;         // [64]
   double* rd = red + 64;          // [D] reciprocal diagonal of the Cholesky factor
+  double* rr = rd + D;            // [Mp] r_i = sqrt(w_i c_i)            (dual steps)
+  double* rhs = rr + Mp;          // [Mp] r_i z_i.g, then the dual solution (dual steps)
   __shared__ int flag;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   for (int k = tid; k < D; k += nt) th[k] = mu_io[k];
@@ -220,12 +227,60 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
       g[k] = acc;
     }
     __syncthreads();
-    hessian();
-    if (!chol_lower(H, D, ld, rd, &flag)) {
-      status = 2;
-      break;
+    if (dual) {
+      const int lda = M + 1;
+      for (int i = tid; i < M; i += nt) {
+        const double m = mrg[i];
+        double c = 0.0;
+        if (m < 100.0) {
+          const double e = exp(m), sg = e / (1.0 + e);
+          c = sg * (1.0 - sg);
+        }
+        rr[i] = sqrt(w[i] * c);
+      }
+      __syncthreads();
+      // A = I + r_i r_j z_i.z_j (lower triangle), one warp per entry; rhs_i = r_i z_i.g
+      const int npairs = M * (M + 1) / 2;
+      for (int p = wid; p < npairs + M; p += nw) {
+        if (p < npairs) {
+          int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+          while (i * (i + 1) / 2 > p) --i;
+          while ((i + 1) * (i + 2) / 2 <= p) ++i;
+          const int j = p - i * (i + 1) / 2;
+          double a = 0.0;
+          for (int k = lane; k < D; k += 32) a = fma(Z[i * ldz + k], Z[j * ldz + k], a);
+          a = warp_sum(a);
+          if (lane == 0) H[i * lda + j] = ((i == j) ? 1.0 : 0.0) + rr[i] * rr[j] * a;
+        } else {
+          const int i = p - npairs;
+          double a = 0.0;
+          for (int k = lane; k < D; k += 32) a = fma(Z[i * ldz + k], g[k], a);
+          a = warp_sum(a);
+          if (lane == 0) rhs[i] = rr[i] * a;
+        }
+      }
+      __syncthreads();
+      if (!chol_lower(H, M, lda, rd, &flag)) {
+        status = 2;
+        break;
+      }
+      chol_solve(H, rd, M, lda, rhs);
+      for (int i = tid; i < M; i += nt) rhs[i] *= rr[i];
+      __syncthreads();
+      for (int k = tid; k < D; k += nt) {
+        double acc = g[k];
+        for (int i = 0; i < M; ++i) acc = fma(-rhs[i], Z[i * ldz + k], acc);
+        g[k] = acc;                // g <- Newton step
+      }
+      __syncthreads();
+    } else {
+      hessian();
+      if (!chol_lower(H, D, ld, rd, &flag)) {
+        status = 2;
+        break;
+      }
+      chol_solve(H, rd, D, ld, g);   // g <- Newton step
     }
-    chol_solve(H, rd, D, ld, g);   // g <- Newton step
     // damped step: halve until the log-joint does not decrease (it is strictly concave)
     double t = 1.0, fn = f;
     for (;;) {
@@ -274,13 +329,119 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
     if (!chol_lower(H, D, ld, rd, &flag)) status = 2;
   }
   if (status == 0) {
-    tri_inverse_lower(H, rd, D, ld, Lsig);   // get_laplace's LSig
+    if (flags & 1) {
+      for (int q = tid; q < D * D; q += nt) {
+        const int i = q / D, j = q - i * D;
+        Lsig[q] = (j <= i) ? H[i * ld + j] : 0.0;   // get_laplace's LSigInv
+      }
+    } else {
+      tri_inverse_lower(H, rd, D, ld, Lsig);   // get_laplace's LSig
+    }
     for (int k = tid; k < D; k += nt) mu_io[k] = th[k];
   }
   if (tid == 0) {
     info[0] = status;
     info[1] = it;
   }
+}
+
+// Conjugate weighted posteriors on the device (the host-free optimiser loop): precision H, its lower Cholesky factor C and
+// the mean AS THE REFERENCE COMPUTES IT, mu = LSigp LSigp^T v with LSigp = C^-1, i.e. C^-1 (C^-T v) (gaussian.py:28-32,
+// model_neurlinr.py:115-122 -- the Gram matrix of the inverse FACTOR, not H^-1).
+//   model 1 (Gaussian mean, known covariance): H = A0 + (sum_i w_i) A1,            v = v0 + A1 (sum_i w_i x_i)
+//   model 2 (neural-linear head):              H = A0 + X^T diag(w) X / sigsq,     v = v0 + X^T (w y) / sigsq   (rows z = [x, y])
+// with A0 = Sig0inv, A1 = Siginv, v0 = Sig0inv mu0.  One CTA.
+__global__ void __launch_bounds__(kLapThreads) k_conjugate_factor(int model, const double* __restrict__ Z, long long ldz,
+                                                                  const double* __restrict__ w, int M, int D, const double* __restrict__ A0,
+                                                                  const double* __restrict__ A1, const double* __restrict__ v0, double sigsq,
+                                                                  double* __restrict__ mu_out, double* __restrict__ C_out, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int ld = D + 1;
+  double* H = sm;            // [D*ld]
+  double* v = H + D * ld;    // [D]
+  double* xs = v + D;        // [D] weighted row sum
+  double* rd = xs + D;       // [D]
+  double* red = rd + D;      // [64]
+  __shared__ int flag;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  if (model == 1) {
+    double part = 0.0;
+    for (int i = tid; i < M; i += nt) part += w[i];
+    const double sw = blk_sum(part, red);
+    for (int k = tid; k < D; k += nt) {
+      double acc = 0.0;
+      for (int i = 0; i < M; ++i) acc = fma(w[i], Z[i * ldz + k], acc);
+      xs[k] = acc;
+    }
+    __syncthreads();
+    for (int q = tid; q < D * D; q += nt) {
+      const int a = q / D, b = q - a * D;
+      if (b <= a) H[a * ld + b] = fma(sw, A1[q], A0[q]);
+    }
+    for (int a = wid; a < D; a += nw) {
+      double acc = 0.0;
+      for (int k = lane; k < D; k += 32) acc = fma(A1[a * D + k], xs[k], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) v[a] = v0[a] + acc;
+    }
+  } else {
+    const double is2 = 1.0 / sigsq;
+    for (int a = wid; a < D; a += nw) {
+      for (int b = lane; b <= a; b += 32) {
+        double acc = 0.0;
+        for (int i = 0; i < M; ++i) acc = fma(w[i] * Z[i * ldz + a], Z[i * ldz + b], acc);
+        H[a * ld + b] = fma(acc, is2, A0[a * D + b]);
+      }
+    }
+    for (int k = tid; k < D; k += nt) {
+      double acc = 0.0;
+      for (int i = 0; i < M; ++i) acc = fma(w[i] * Z[i * ldz + D], Z[i * ldz + k], acc);
+      v[k] = fma(acc, is2, v0[k]);
+    }
+  }
+  __syncthreads();
+  if (!chol_lower(H, D, ld, rd, &flag)) {
+    if (tid == 0) info[0] = 2;
+    return;
+  }
+  if (tid < 32) {
+    for (int j = D - 1; j >= 0; --j) {     // C^T y = v
+      const double xj = v[j] * rd[j];
+      __syncwarp();
+      if (lane == 0) v[j] = xj;
+      for (int i = lane; i < j; i += 32) v[i] = fma(-H[j * ld + i], xj, v[i]);
+      __syncwarp();
+    }
+    for (int j = 0; j < D; ++j) {          // C mu = y
+      const double xj = v[j] * rd[j];
+      __syncwarp();
+      if (lane == 0) v[j] = xj;
+      for (int i = j + 1 + lane; i < D; i += 32) v[i] = fma(-H[i * ld + j], xj, v[i]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < D; k += nt) mu_out[k] = v[k];
+  for (int q = tid; q < D * D; q += nt) {
+    const int i = q / D, j = q - i * D;
+    C_out[q] = (j <= i) ? H[i * ld + j] : 0.0;
+  }
+  if (tid == 0) {
+    info[0] = 0;
+    info[1] = 0;
+  }
+}
+
+cudaError_t launch_conjugate_factor(int model, const double* Z, long long ldz, const double* w, int M, int D, const double* A0, const double* A1,
+                                    const double* v0, double sigsq, double* mu, double* C, int* info, cudaStream_t st) {
+  const size_t smem = ((size_t)D * (D + 1) + 3 * (size_t)D + 64) * sizeof(double);
+  const size_t cap = kMaxSmem - 1024;
+  static DeviceOnce once;
+  cudaError_t e = raise_dynamic_smem(k_conjugate_factor, cap, once);
+  if (e != cudaSuccess) return e;
+  if (smem > cap) return cudaErrorInvalidValue;
+  k_conjugate_factor<<<1, kLapThreads, smem, st>>>(model, Z, ldz, w, M, D, A0, A1, v0, sigsq, mu, C, info);
+  return cudaGetLastError();
 }
 
 // Theta[s][d] = mu[d] + sum_k R[s][k] L[d][k]      (mu + randn(S, D).dot(L.T))
@@ -333,14 +494,14 @@ cudaError_t launch_sample_solve(const double* mu, const double* C, const double*
 }
 
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
-                                    double tol, int* info, cudaStream_t st) {
-  const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 3 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
+                                    double tol, int* info, int flags, cudaStream_t st) {
+  const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 5 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
   const size_t cap = kMaxSmem - 1024;   // the kernel also has a few bytes of static shared memory
   static DeviceOnce once;
   cudaError_t e = raise_dynamic_smem(k_laplace_logistic, cap, once);
   if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
-  k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info);
+  k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info, flags);
   return cudaGetLastError();
 }
 

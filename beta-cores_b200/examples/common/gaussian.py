@@ -52,7 +52,8 @@ def make_conjugate_sampler(mu0, Sig0inv, Siginv, device=False, prefetch=False):
             if pts.shape[0] == 0:
                 return Sig0inv + 0.*Siginv, Sig0inv_mu0 + 0.
             return Sig0inv + wts.sum()*Siginv, Sig0inv_mu0 + np.dot(Siginv, (wts[:, np.newaxis]*pts).sum(axis=0))
-        return ConjugateDeviceSampler(d, precision, rng.activate() if prefetch else None)
+        return ConjugateDeviceSampler(d, precision, rng.activate() if prefetch else None,
+                                      device_model=(1, Sig0inv, Siginv, Sig0inv_mu0, None))
 
     def sampler(S, wts, pts):
         if pts.shape[0] == 0:

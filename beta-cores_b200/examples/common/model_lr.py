@@ -280,6 +280,9 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
             st['L'].copy_(torch.eye(D, dtype=torch.float64, device=eng.device))
             st['mu_host'] = None
         elif host_factor:
+            if st.get('device_mode'):                      # the optimiser loop has moved the mode on the device: resume from it
+                st['mu_host'] = st['mu'].cpu().numpy().copy()
+                st['device_mode'] = False
             start = st['mu_host'] if st['mu_host'] is not None else mu0
             solve = D <= 160                               # bc_sample_solve's limit; beyond it: invert on the host as before
             mu, LSig, LSigInv = get_laplace(wts, pts, start, method='newton', want_inverse=not solve)
@@ -309,9 +312,39 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
                 int(theta.stride(0)), stream_ptr())
         return theta
 
+    def device_step(S, w_dev, core):
+        """the sampler call of one optimiser step with the weights already on the device (`w_dev`) and the coreset points as
+        resident rows (`core`, a DeviceRows): mode (warm-started dual Newton steps), Cholesky factor and samples are formed by
+        kernels (bc_laplace_logistic_factor, bc_sample_solve); nothing is read back, the host only queues work and draws the
+        normals.  Rows with weight 0 do not contribute, exactly like `keep = wts > 0` on the host."""
+        new_call()
+        eng = Engine.get()
+        ctx = eng.ctx('sampler')
+        if st['mu'] is None:
+            st['ml'] = eng.empty(D*D + D)
+            st['mu'], st['L'] = st['ml'][:D], st['ml'][D:].view(D, D)
+            st['mu'].copy_(torch.from_numpy(np.asarray(mu0, dtype=np.float64)))
+            st['info'] = torch.zeros(2, dtype=torch.int32, device=eng.device)
+            st['ml_pin'] = torch.empty(D*D + D, dtype=torch.float64).pin_memory()
+        if st.get('mu_host') is not None:              # a host-side call came in between: warm-start from its mode
+            st['mu'].copy_(torch.from_numpy(st['mu_host']))
+            st['mu_host'] = None
+        theta = eng.empty(S, D)
+        nv.call('bc_laplace_logistic_factor', ctx, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(st['mu']), ptr(st['L']), 200, 1e-13,
+                ptr(st['info']), stream_ptr())
+        st['device_mode'] = True
+        k, pin = normals(S, D, stage)
+        Rd = pin.to(eng.device, non_blocking=True)
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
+        nv.call('bc_sample_solve', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        return theta
+
     def status():
         """(status, newton steps) of the last device mode search: 0 = converged"""
         return tuple(int(v) for v in st['info'].cpu()) if st['info'] is not None else (0, 0)
     sampler.status = status
     sampler.state = st
+    sampler.device_step = device_step
+    sampler.supports_device_step = lambda: D <= 160
     return sampler

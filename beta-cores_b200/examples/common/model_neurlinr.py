@@ -40,7 +40,8 @@ def make_conjugate_sampler(mu0, Sig0inv, sigsq, device=False, prefetch=False):
             z = np.atleast_2d(pts)
             X, Y = z[:, :-1], z[:, -1]
             return Sig0inv + (wts[:, np.newaxis]*X).T.dot(X)/sigsq, Sig0inv_mu0 + (wts[:, np.newaxis]*Y[:, np.newaxis]*X).sum(axis=0)/sigsq
-        return ConjugateDeviceSampler(D, precision, rng.activate() if prefetch else None)
+        return ConjugateDeviceSampler(D, precision, rng.activate() if prefetch else None,
+                                      device_model=(2, Sig0inv, None, Sig0inv_mu0, sigsq))
 
     def sampler(S, wts, pts):
         if pts.shape[0] == 0:

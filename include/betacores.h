@@ -159,8 +159,8 @@ int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, doub
  *     rows) -> bc_core_resid -> bc_core_grad -> bc_adam_step
  * -- the same kernels in the same order as the individual entry points, so the results are bit-identical; what it saves is the
  * host's per-call overhead (a dozen FFI crossings per step matter when a step is a few hundred microseconds: the sub-sampled
- * Gaussian example runs 1000 of them per coreset point).  Single-rank jobs only (a sharded job exchanges the column-sum parts
- * between the pass and the combine).  All pointers are device pointers unless named h_. */
+ * Gaussian example runs 1000 of them per coreset point).  A sharded job exchanges the column-sum parts between the pass and the
+ * combine: it calls the two halves (`phase`).  All pointers are device pointers. */
 typedef struct bc_step_args {
   const double* d_theta; int S; int ldt;                         /* posterior samples of this step (S x ldt) */
   /* data rows: the tensor-core route when d_image is set (with its scratch image for gathered passes), else the FP64 route */
@@ -177,6 +177,10 @@ typedef struct bc_step_args {
   double* d_w; double* d_m1; double* d_m2; double lr, b1, b2, c1, c2, eps; const unsigned char* d_nn_mask;
   /* optional instrumentation: two cudaEvent_t recorded on `stream` right before / after the data-row pass (NULL: none) */
   void* ev_pass_begin; void* ev_pass_end;
+  /* row-sharded jobs run the step in two halves around their exchange of the column-sum parts:
+   * phase 0 = the whole step (single rank); 1 = samples .. this rank's part in d_parts; 2 = combine the nparts parts at
+   * d_parts_all (rank order) .. ADAM */
+  int phase; int nparts; const double* d_parts_all;
 } bc_step_args;
 int bc_greedy_opt_step(bc_ctx* ctx, const bc_step_args* args, void* stream);
 
@@ -190,6 +194,18 @@ int bc_greedy_opt_step(bc_ctx* ctx, const bc_step_args* args, void* stream);
  *   `mu + np.random.randn(S, D).dot(LSig.T)` (main.py:144), with the normals drawn by the caller's own stream. */
 int bc_laplace_logistic(bc_ctx* ctx, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_L,
                         int maxit, double tol, int* d_info, void* stream);
+/* Host-free forms for the optimiser loop (weights and coreset rows already on the device, nothing returns to the host):
+ * bc_laplace_logistic_factor: as bc_laplace_logistic, with the Newton steps taken from the M x M dual system while M <= D
+ *   (Woodbury: the negative Hessian is a rank-M update of the identity) and d_C = the lower Cholesky FACTOR of the negative
+ *   Hessian at the mode (get_laplace's LSigInv), to be used with bc_sample_solve.
+ * bc_conjugate_factor: the conjugate weighted posteriors of examples/common/gaussian.py:28-32 (model = BC_MODEL_GAUSSIAN:
+ *   H = A0 + (sum w) A1, v = v0 + A1 sum_i w_i x_i) and model_neurlinr.py:115-122 (BC_MODEL_NEURLIN: H = A0 + X^T diag(w) X / sigsq,
+ *   v = v0 + X^T (w y) / sigsq, rows [x, y]); A0 = Sig0inv, A1 = Siginv, v0 = Sig0inv mu0 (D x D row-major / D).  d_C = chol(H),
+ *   d_mu = C^-1 C^-T v -- the reference's `LSigp.dot(LSigp.T)` applied to v.  D <= 160. */
+int bc_laplace_logistic_factor(bc_ctx* ctx, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_C,
+                               int maxit, double tol, int* d_info, void* stream);
+int bc_conjugate_factor(bc_ctx* ctx, int model, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, const double* d_A0,
+                        const double* d_A1, const double* d_v0, double sigsq, double* d_mu, double* d_C, int* d_info, void* stream);
 int bc_sample_affine(bc_ctx* ctx, const double* d_mu, const double* d_L, const double* d_R, int S, int D, double* d_theta, int ldt,
                      void* stream);
 /* bc_sample_solve: the same samples from the Cholesky factor itself, d_theta[s][:] = d_mu + C^-1 d_R[s][:] (d_C: D x D lower

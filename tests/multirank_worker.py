@@ -53,6 +53,15 @@ alg = bc.BetaCoreset(Z, bc.BetaBlackBoxProjector(sampler, S, model_lr.beta_likel
 for m in range(1, 6):
     alg.build(1, m)
 record('beta_sub', alg)
+# 2b. the host-free optimiser loop: a sampler with the device_step protocol (two-phase steps around the exchange when sharded)
+np.random.seed(7)
+smp = model_lr.make_laplace_sampler(7, method='hybrid', prefetch=True)
+alg = bc.BetaCoreset(Z, bc.BetaBlackBoxProjector(smp, S, model_lr.beta_likelihood, model_lr.log_likelihood, None), opt_itrs=8,
+                     n_subsample_opt=700, step_sched=sched, beta=0.2, learn_beta=False)
+for m in range(1, 6):
+    alg.build(1, m)
+smp.drain()
+record('beta_device_loop', alg)
 # 3. group-wise selection
 np.random.seed(5)
 groups = problems.ragged_groups(3001, 9)

@@ -133,3 +133,85 @@ def test_golden_builds_with_device_samplers_and_look_ahead_rng(name):
     np.testing.assert_allclose(w, g[name+'_wts'], rtol=1e-6, atol=1e-9)
     ahead = rng.active()
     assert ahead is not None and ahead.hits > case['M']*case['opt_itrs']//2       # the look-ahead did serve most draws
+
+
+@pytest.mark.parametrize('M,D', [(1, 3), (7, 10), (40, 128), (128, 128), (150, 100)])
+def test_laplace_factor_kernel_matches_host(M, D):
+    """bc_laplace_logistic_factor (dual-space Newton steps while M <= D, Cholesky FACTOR out) against the host get_laplace"""
+    import torch
+    import model_lr
+    from bayesiancoresets import _native as nv
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    eng = Engine.get()
+    Z, w = _problem(M, D, 11)
+    mu, _, C = model_lr.get_laplace(w, Z, np.zeros(D), method='newton', want_inverse=False)
+    core = DeviceRows(eng, Z)
+    d_mu, d_C = eng.zeros(D), eng.empty(D, D)
+    info = torch.zeros(2, dtype=torch.int32, device=eng.device)
+    d_w = eng.upload(w)
+    nv.call('bc_laplace_logistic_factor', eng.ctx('sampler'), ptr(core.t), core.ld, ptr(d_w), M, D, ptr(d_mu), ptr(d_C), 200, 1e-13,
+            ptr(info), stream_ptr())
+    assert int(info.cpu()[0]) == 0
+    np.testing.assert_allclose(d_mu.cpu().numpy(), mu, rtol=0, atol=1e-10*max(1., np.abs(mu).max()))
+    np.testing.assert_allclose(d_C.cpu().numpy(), C, rtol=0, atol=1e-9*np.abs(C).max())
+
+
+@pytest.mark.parametrize('model', ['gaussian', 'neurlin'])
+def test_conjugate_factor_kernel_matches_host(model):
+    """bc_conjugate_factor: precision factor and the reference's mean C^-1 C^-T v (gaussian.py:28-32, model_neurlinr.py:115-122)"""
+    import torch
+    import gaussian, model_neurlinr
+    from bayesiancoresets import _native as nv
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    eng = Engine.get()
+    r = np.random.RandomState(4)
+    D, M = 23, 57
+    A = r.randn(D, D)
+    Sig0inv = np.eye(D) + 0.1*A.dot(A.T)
+    mu0 = r.randn(D)
+    w = r.rand(M)*3
+    w[::7] = 0.
+    if model == 'gaussian':
+        B = r.randn(D, D)
+        Siginv = np.linalg.inv(np.eye(D)*4 + B.dot(B.T))
+        pts = r.randn(M, D)
+        mu, _, C = gaussian.weighted_post(mu0, Sig0inv, Siginv, pts, w)
+        args = (nv.MODEL_GAUSSIAN, Sig0inv, Siginv, 1.0)
+    else:
+        pts = np.hstack((np.maximum(r.randn(M, D), 0), r.randn(M, 1)))
+        mu, _, C = model_neurlinr.weighted_post(mu0, Sig0inv, 0.6, pts, w)
+        args = (nv.MODEL_NEURLIN, Sig0inv, None, 0.6)
+    core = DeviceRows(eng, pts)
+    d_mu, d_C = eng.empty(D), eng.empty(D, D)
+    info = torch.zeros(2, dtype=torch.int32, device=eng.device)
+    A1 = eng.upload(args[2]) if args[2] is not None else None
+    d_w, A0, v0 = eng.upload(w), eng.upload(args[1]), eng.upload(Sig0inv.dot(mu0))      # named: the buffers must outlive the call
+    nv.call('bc_conjugate_factor', eng.ctx('sampler'), args[0], ptr(core.t), core.ld, ptr(d_w), M, D, ptr(A0), ptr(A1),
+            ptr(v0), args[3], ptr(d_mu), ptr(d_C), ptr(info), stream_ptr())
+    assert int(info.cpu()[0]) == 0
+    np.testing.assert_allclose(d_C.cpu().numpy(), C, rtol=0, atol=1e-12*np.abs(C).max())
+    np.testing.assert_allclose(d_mu.cpu().numpy(), mu, rtol=0, atol=1e-11*max(1., np.abs(mu).max()))
+
+
+def test_device_sampler_loop_matches_host_protocol_loop(monkeypatch):
+    """the optimiser loop with the sampler's device_step (no host round trip per step) builds the coreset the loop builds
+    when the same sampler is called through the reference's host protocol sampler(S, wts, pts)"""
+    import bayesiancoresets as bc
+    import model_lr
+    from bayesiancoresets.coreset import _greedy
+    r = np.random.RandomState(0)
+    N, D, S = 4000, 24, 96
+    Z = r.randn(N, D)
+    out = []
+    for loop in (True, False):
+        monkeypatch.setattr(_greedy, 'DEVICE_SAMPLER_LOOP', loop)
+        np.random.seed(2)
+        smp = model_lr.make_laplace_sampler(D, method='hybrid', prefetch=True)
+        prj = bc.BetaBlackBoxProjector(smp, S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+        alg = bc.BetaCoreset(Z, prj, opt_itrs=12, n_subsample_opt=1500, step_sched=lambda i: 1./(1.+i), beta=0.3, learn_beta=False)
+        for m in range(1, 7):
+            alg.build(1, m)
+        smp.drain()
+        out.append((alg.idcs.copy(), alg.wts.copy()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-7, atol=1e-10)

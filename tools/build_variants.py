@@ -1,6 +1,9 @@
-"""Build experiment variants of libbetacores.so (only bc_project_q.cu differs) into beta-cores_b200/lib/variants/.
-    python tools/build_variants.py NAME="-DFLAG ..." [NAME2="..."]
-Select one at run time with BC_LIB_PATH=beta-cores_b200/lib/variants/libbetacores_NAME.so"""
+"""Build experiment / debug variants of libbetacores.so into beta-cores_b200/lib/variants/.
+    python tools/build_variants.py NAME="-DFLAG ..." [NAME2="..."]          every unit recompiled with the flags
+    python tools/build_variants.py q:NAME="-DFLAG"                          only bc_project_q.cu differs (quick kernel experiments)
+Select one at run time with BC_LIB_PATH=beta-cores_b200/lib/variants/libbetacores_NAME.so
+    debug="-DBC_DEBUG"   device-side invariant checks + mbarrier watchdogs (csrc/bc_common.cuh); the GPU suite is run against it
+                         once per round (compute-sanitizer is closed on this pool)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, 'beta-cores_b200')
@@ -9,14 +12,28 @@ import build as B
 B.build()
 out = os.path.join(B.LIB, 'variants')
 os.makedirs(out, exist_ok=True)
-procs = []
+jobs = []
 for spec in sys.argv[1:]:
     name, flags = spec.split('=', 1)
-    obj = os.path.join(out, 'bc_project_q_%s.o' % name)
-    procs.append((name, obj, subprocess.Popen([B.NVCC] + B.FLAGS + flags.split() + ['-c', os.path.join(B.CSRC, 'bc_project_q.cu'), '-o', obj])))
-for name, obj, p in procs:
-    assert p.wait() == 0, name
-    objs = [obj if u == 'bc_project_q.cu' else os.path.join(B.LIB, u.replace('.cu', '.o')) for u in B.UNITS]
+    only_q = name.startswith('q:')
+    name = name[2:] if only_q else name
+    units = ['bc_project_q.cu'] if only_q else B.UNITS
+    objs = []
+    for u in B.UNITS:
+        if u in units:
+            obj = os.path.join(out, '%s_%s.o' % (u[:-3], name))
+            jobs.append((name, subprocess.Popen([B.NVCC] + B.FLAGS + flags.split() + ['-c', os.path.join(B.CSRC, u), '-o', obj])))
+        else:
+            obj = os.path.join(B.LIB, u.replace('.cu', '.o'))
+        objs.append(obj)
+    jobs.append((name, objs))
+links = {}
+for name, j in jobs:
+    if isinstance(j, list):
+        links[name] = j
+    else:
+        assert j.wait() == 0, name
+for name, objs in links.items():
     so = os.path.join(out, 'libbetacores_%s.so' % name)
     subprocess.run([B.NVCC, '-shared', '-o', so] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'], check=True)
     print(so)
