@@ -572,8 +572,11 @@ def b200_arm(a):
             'ms_per_step': 1e3*dt/K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(a, world), 'build_seconds_per_point': dt/K,
             'selected_indices': idcs_value, 'roofline': roofline, 'gpu_launches': int(launches), 'clocks': clk,
-            'host': {'cpu_count': os.cpu_count(), 'sampler_calls': sampler_calls, 'sampler_ms_per_call': 1e3*sampler_s/max(sampler_calls, 1),
-                     'sampler_share_of_step': sampler_s/dt},
+            'host': {'cpu_count': os.cpu_count(), 'sampler_calls': sampler_calls, 'sampler_host_ms_per_call': 1e3*sampler_s/max(sampler_calls, 1),
+                     'sampler_note': ('optimiser steps call the sampler through its device_step protocol: its algebra runs in kernels on the '
+                                      'device-resident weights and the host only queues work -- it runs ahead of the GPU and then BLOCKS on it '
+                                      '(launch queue, pinned normal buffers), so the host time per call is waiting, not work')
+                                     if a.sampler in ('hybrid', 'device') else 'host sampler: the time per call is on the critical path of a step'},
         }
         if stage2 is not None:
             line['stage2'] = stage2
