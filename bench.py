@@ -66,6 +66,10 @@ def parse():
                          "so the ratio is conservative) or 'bfgs' (the reference's stock scipy call, util/opt.py:10-33)")
     ap.add_argument('--digits', type=int, default=None, choices=[5, 6, 7], help='precision tier of the tensor-core contraction (default: the library default)')
     ap.add_argument('--configs', action='store_true', help='instead of the north-star workload: time BASELINE configs 1-4 (build seconds, CPU port beside)')
+    ap.add_argument('--sweep', default=None, metavar='N1,N2,...|default',
+                    help="BASELINE config 5, the scale sweep: one value-leg line per N (default list 1M,3M,10M,30M,100M) at this GPU count, "
+                         "appended to --sweep-out; points whose row shard + row image do not fit one GPU's HBM are reported as skipped")
+    ap.add_argument('--sweep-out', default=None, help='file the sweep lines are appended to (default profiles/r02_sweep_n<gpus>.jsonl)')
     ap.add_argument('--sampler', default='hybrid', choices=['newton', 'hybrid', 'device', 'bfgs'],
                     help="product arm's Laplace sampler: 'hybrid' (default) = mode and Cholesky factor on the host, the S x D x D affine map "
                          "of the normals on the device; 'newton' = all on the host (what the reference arm runs); 'device' = all on the "
@@ -250,7 +254,7 @@ class ClockSampler(object):
         return out
 
 
-def b200_arm(a):
+def b200_arm(a, emit=True):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -261,7 +265,7 @@ def b200_arm(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=dev)
     import bayesiancoresets as bc
     import model_lr
@@ -430,7 +434,7 @@ def b200_arm(a):
                                     'makes no progress while the tensor core is busy (profiles/r01_q_ablation.txt), so the two add up; '
                                     'HBM is at 2 % of its peak')
     idcs_value = [int(i) for i in alg.idcs]
-    if route == 'q':
+    if route == 'q' and not getattr(a, 'lean', False):
         # the other precision tiers of the same pass, timed right here on the resident rows (3 passes each after 2 warm-ups)
         tg, tiers = alg._tangent, {}
         for dg in (7, 6, 5):
@@ -451,7 +455,7 @@ def b200_arm(a):
 
     # ---- stage 2 (materialised n x S matrix: snnls / Hilbert scoring) and stage 3 (coreset-side step), timed on their own ----
     stage2 = stage3 = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not getattr(a, 'lean', False):
         from bayesiancoresets._device import ptr, stream_ptr
         ctx2 = eng.ctx('bench-stage2')
         n2 = min(1_000_000, N)
@@ -587,9 +591,47 @@ def b200_arm(a):
             line['cpu_baseline'] = cpu
         if parity is not None:
             line['parity'] = parity
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        if emit:
+            print(json.dumps(line))
+        return line
+    return None
+
+
+def sweep_leg(a):
+    """BASELINE config 5: N = 1M .. 100M rows of the north-star problem at this GPU count, one value-leg line per
+    point (rows resident, same step, same timing rules as the default arm).  A point needs its fp64 row shard (8 D bytes per
+    row) and the 7-plane int8 row image (7 D bytes per row) in HBM at once; one that does not fit is listed as skipped."""
+    import copy
+    import torch
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    ns = [1_000_000, 3_000_000, 10_000_000, 30_000_000, 100_000_000] if a.sweep == 'default' else [int(float(x)) for x in a.sweep.split(',')]
+    out = a.sweep_out or os.path.join(ROOT, 'profiles', 'r02_sweep_n%d.jsonl' % world)
+    free, total = torch.cuda.mem_get_info()
+    rows = []
+    for n in ns:
+        need = (n/world)*a.d*(8 + 7) + (2 << 30)
+        if need > total*0.97:
+            line = {'N': n, 'n_gpus': world, 'skipped': 'row shard + row image need %.0f GB of the %.0f GB HBM of one GPU' % (need/1e9, total/1e9)}
+        else:
+            b = copy.copy(a)
+            b.n, b.no_e2e, b.no_cpu_baseline, b.lean = n, True, True, True
+            full = b200_arm(b, emit=False)
+            torch.cuda.empty_cache()
+            if rank != 0:
+                continue
+            r = full['roofline']
+            line = {'N': n, 'n_gpus': world, 'D': a.d, 'S': a.s, 'opt_itrs': a.opt_itrs, 'steps': a.steps, 'warmup': a.warmup,
+                    'evals_per_s': full['value'], 'build_seconds_per_point': full['build_seconds_per_point'],
+                    'pass_ms': r['launch_ms'], 'kernel_evals_per_s': r['evals_per_s_kernel'], 'fp64_equiv_tflops': r['achieved'],
+                    'share_of_step_in_passes': r['share_of_step'], 'contraction_digits': r.get('contraction_digits'),
+                    'selected_indices': full['selected_indices'], 'clocks': full['clocks']}
+        if rank == 0:
+            rows.append(line)
+            with open(out, 'a') as f:
+                f.write(json.dumps(line) + '\n')
+            print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------- BASELINE configs 1-4 --
@@ -718,5 +760,13 @@ if __name__ == '__main__':
         configs_leg(args)
     elif args.impl == 'reference':
         reference_arm(args)
+    elif args.sweep:
+        sweep_leg(args)
     else:
         b200_arm(args)
+    try:
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()
+    except Exception:
+        pass
