@@ -76,6 +76,15 @@ class StepArgs(ctypes.Structure):
 
 SIGNATURES['bc_greedy_opt_step'] = [c_vp, ctypes.POINTER(StepArgs), c_vp]
 
+
+class MTState(ctypes.Structure):
+    """bc_mt_state of include/betacores.h: numpy's legacy RandomState in its own representation"""
+    _fields_ = [('key', ctypes.c_uint32*624), ('pos', ctypes.c_int32), ('has_gauss', ctypes.c_int32), ('gauss', c_dbl)]
+
+
+SIGNATURES['bc_mt_randn'] = [ctypes.POINTER(MTState), c_vp, c_i64, c_int]
+SIGNATURES['bc_mt_randint'] = [ctypes.POINTER(MTState), c_i64, c_vp, c_i64]
+
 MODEL_LOGISTIC, MODEL_GAUSSIAN, MODEL_NEURLIN = 0, 1, 2
 KIND_LOGLIK, KIND_BETALIK, KIND_BETAGRAD = 0, 1, 2
 SCORE_FW, SCORE_GIGA, SCORE_CORR, SCORE_OMP = 0, 1, 2, 3

@@ -30,6 +30,23 @@ def affine_samples(mu, L, R):
     return out
 
 
+class _PinnedStage(object):
+    """where a draw of normals goes: one of the owner's two pinned staging buffers.  Called with a finished draw it copies;
+    through `into` the native generator of util/rng.py writes the draw there directly (runs on the thread that draws)."""
+
+    def __init__(self, owner):
+        self.o = owner
+
+    def __call__(self, r):
+        k, pin = self.o._stage_buf(r.shape)
+        pin.numpy()[...] = r
+        return k, pin
+
+    def into(self, shape):
+        k, pin = self.o._stage_buf(shape)
+        return (k, pin), pin.numpy()
+
+
 class ConjugateDeviceSampler(object):
     """The device form of a conjugate sampler, built for the optimiser loop (one call per ADAM step):
         precision(wts, pts) -> (H, v)   the D x D posterior precision and the linear term (host, tiny)
@@ -47,6 +64,7 @@ class ConjugateDeviceSampler(object):
         # device from device-resident weights (device_step), with no host round trip per step
         self.device_model = device_model
         self._dm = None
+        self._stage = _PinnedStage(self)
 
     def _state(self, eng):
         D = self.D
@@ -93,14 +111,14 @@ class ConjugateDeviceSampler(object):
     def supports_device_step(self):
         return self.device_model is not None and self.D <= 160
 
-    def _stage(self, r):
+    def _stage_buf(self, shape):
+        """the next of two pinned staging buffers, free again (the upload that last used it has left it)"""
         st = self.st
         k = st['k'] = st['k'] ^ 1
-        if st['pin'][k] is None or tuple(st['pin'][k].shape) != r.shape:
-            st['pin'][k] = torch.empty(*r.shape, dtype=torch.float64).pin_memory()
+        if st['pin'][k] is None or tuple(st['pin'][k].shape) != tuple(shape):
+            st['pin'][k] = torch.empty(*shape, dtype=torch.float64).pin_memory()
         if st['ev'][k] is not None:
-            st['ev'][k].synchronize()                  # the upload that last used this buffer has left it
-        st['pin'][k].numpy()[...] = r
+            st['ev'][k].synchronize()
         return k, st['pin'][k]
 
     def __call__(self, S, wts, pts):

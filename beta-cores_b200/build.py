@@ -11,7 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib')
 OUT = os.path.join(LIB, 'libbetacores.so')
-UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_sampler.cu', 'bc_dense.cu', 'bc_api.cu']
+UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_sampler.cu', 'bc_dense.cu', 'bc_api.cu', 'bc_hostrng.cu']
+# bc_hostrng.cu is host code that must reproduce numpy's floating-point results bit for bit: no FMA contraction
+UNIT_FLAGS = {'bc_hostrng.cu': ['-Xcompiler', '-ffp-contract=off']}
 HEADERS = ['bc_common.cuh', 'bc_npmean.h', 'bc_umma.cuh', 'bc_fastmath.cuh', 'bc_models.cuh', 'bc_kernels.h', os.path.join('..', '..', 'include', 'betacores.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
@@ -33,7 +35,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(LIB, u.replace('.cu', '.o'))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            jobs.append([NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj])
+            jobs.append([NVCC] + FLAGS + UNIT_FLAGS.get(u, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj])
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

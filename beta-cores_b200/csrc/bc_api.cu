@@ -21,6 +21,9 @@ struct bc_ctx {
   size_t smem = 0;
   ModelParams mp{};
   const double* d_siginv = nullptr;
+  double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
+  size_t cap_sT = 0;
+  bool siginvT_ready = false;
   // samples
   bool samples_set = false;
   int S = 0;
@@ -152,6 +155,7 @@ int bc_create(int device, bc_ctx** out) {
 int bc_destroy(bc_ctx* c) {
   if (!c) return BC_OK;
   cudaFree(c->B);
+  cudaFree(c->siginvT);
   cudaFree(c->colaux);
   cudaFree(c->bbar);
   cudaFree(c->part_colsum);
@@ -208,6 +212,7 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
     }
   }
   c->d_siginv = d_siginv;
+  c->siginvT_ready = false;
   c->potential_set = true;
   c->samples_set = false;
   return BC_OK;
@@ -222,8 +227,14 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
   if ((rc = grow(&c->bbar, &c->capD, (size_t)c->Dpad + 1))) return rc;
   if ((rc = grow(&c->part_colsum, &c->cap_part, (size_t)c->sms * 2 * bc_colsum_ld(S)))) return rc;
   c->S = S;
-  BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->B, c->Dpad, c->colaux, c->bbar,
-                                 (cudaStream_t)stream));
+  if (c->model == BC_MODEL_GAUSSIAN && !c->siginvT_ready) {
+    if ((rc = grow(&c->siginvT, &c->cap_sT, (size_t)c->Dk * c->Dk))) return rc;
+    BC_CUDA(launch_transpose(c->d_siginv, c->Dk, c->Dk, c->Dk, c->siginvT, c->Dk, (cudaStream_t)stream));
+    BC_LAUNCHED(1);
+    c->siginvT_ready = true;
+  }
+  BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->model == BC_MODEL_GAUSSIAN ? c->siginvT : nullptr, c->B,
+                                 c->Dpad, c->colaux, c->bbar, (cudaStream_t)stream));
   BC_LAUNCHED(2);
   c->q_ready = false;
   if (c->Dk <= kQK) {

@@ -112,8 +112,8 @@ cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsi
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----
-cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,
-                                   double* colaux, double* bbar, cudaStream_t st);
+cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
+                                   double* B, int ldb, double* colaux, double* bbar, cudaStream_t st);
 cudaError_t launch_rowquad(const double* X, long long n, int D, long long ldx, const double* siginv, double* out, cudaStream_t st);
 cudaError_t launch_colsum_combine(const double* parts, int nparts, int S, int Sld, double* out, cudaStream_t st);
 cudaError_t launch_core_resid(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, const double* w,

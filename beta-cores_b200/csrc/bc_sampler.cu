@@ -15,7 +15,7 @@
 
 namespace bc {
 
-constexpr int kLapThreads = 1024;   // one CTA; every phase is latency-bound, so as many warps as a CTA can hold
+constexpr int kLapThreads = 512;    // one CTA; every phase is latency-bound; 512 threads leave 128 registers each for the register-tiled Cholesky
 
 __device__ __forceinline__ double blk_sum(double x, double* red) {  // all threads get the result
   x = warp_sum(x);
@@ -28,11 +28,17 @@ __device__ __forceinline__ double blk_sum(double x, double* red) {  // all threa
   return y;
 }
 
-// In-place lower Cholesky of the D x D matrix H (row-major, leading dimension ld = D + 1 so that column walks are free of
-// shared-memory bank conflicts) in shared memory, blocked: warp 0 factorises a panel of kPanel columns with warp-level
-// synchronisation only, then every warp applies the rank-kPanel update to the trailing block.  2 CTA barriers per panel
-// instead of 3 per column: at D = 128 the unblocked form spent most of its time in barriers.  rd[j] = 1 / L[j][j].
-// Returns false if H is not positive definite.
+// In-place lower Cholesky of the D x D matrix H (row-major, leading dimension ld = D + 1, odd, so that walks down a column
+// are free of shared-memory bank conflicts) in shared memory.  Blocked in panels of kPanel columns, three phases per panel:
+//   A  warp 0 factorises the kPanel x kPanel diagonal block in REGISTERS (lane = row, shuffles broadcast the pivot row):
+//      the serial part of the algorithm costs one sqrt + one reciprocal + two shuffle rounds per column and never touches
+//      shared memory;
+//   B  one thread per row below the block: x L11^T = A21 by forward substitution with the 16 row entries in registers;
+//   C  every warp updates 32 x 8 blocks of the trailing triangle with 4 x 2 register tiles (0.75 shared-memory loads per FMA
+//      instead of 2 for an entry-per-thread update).
+// Every entry sees exactly the operations of the unblocked right-looking algorithm in the same order (subtract the
+// contributions of columns 0, 1, ... in turn, then scale by the reciprocal pivot), so the factor does not depend on the
+// blocking.  rd[j] = 1 / L[j][j].  Returns false if H is not positive definite.
 constexpr int kPanel = 16;
 __device__ bool chol_lower(double* H, int D, int ld, double* rd, int* flag) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -40,36 +46,92 @@ __device__ bool chol_lower(double* H, int D, int ld, double* rd, int* flag) {
   __syncthreads();
   for (int j0 = 0; j0 < D; j0 += kPanel) {
     const int nb = min(kPanel, D - j0);
-    if (wid == 0) {
-      for (int c = 0; c < nb; ++c) {
-        const int j = j0 + c;
-        const double d = H[j * ld + j];
-        if (!(d > 0.0)) {
-          if (lane == 0) *flag = 1;
-          break;
-        }
+    if (wid == 0) {                                   // ---- A
+      double a[kPanel];
+      const int r = lane;
+#pragma unroll
+      for (int c = 0; c < kPanel; ++c)                // rows / columns beyond the matrix: identity (factorises to itself)
+        a[c] = (r < nb && c <= r) ? H[(j0 + r) * ld + j0 + c] : ((c == r) ? 1.0 : 0.0);
+      bool bad = false;
+      double myinv = 0.0;
+#pragma unroll
+      for (int c = 0; c < kPanel; ++c) {
+        const double d = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(d > 0.0)) bad = true;
         const double s = sqrt(d), inv = 1.0 / s;
-        __syncwarp();
-        for (int i = j + lane; i < D; i += 32) H[i * ld + j] = (i == j) ? s : H[i * ld + j] * inv;
-        if (lane == 0) rd[j] = inv;
-        __syncwarp();
-        for (int i = j + 1 + lane; i < D; i += 32) {   // the panel's remaining columns
-          const double lij = H[i * ld + j];
-          for (int k = j + 1; k < j0 + nb; ++k)
-            if (i >= k) H[i * ld + k] = fma(-lij, H[k * ld + j], H[i * ld + k]);
+        a[c] = (r == c) ? s : a[c] * inv;
+        if (r == c) myinv = inv;
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k) {
+          if (k <= c) continue;                      // (constant trip counts: the loops unroll completely, a[] stays in registers)
+          const double lkc = __shfl_sync(0xffffffffu, a[c], k);
+          if (r >= k) a[k] = fma(-a[c], lkc, a[k]);
         }
-        __syncwarp();
+      }
+      if (bad && lane == 0) *flag = 1;
+      if (r < nb) {
+#pragma unroll
+        for (int c = 0; c < kPanel; ++c)
+          if (c <= r) H[(j0 + r) * ld + j0 + c] = a[c];
+        rd[j0 + r] = myinv;
       }
     }
     __syncthreads();
     if (*flag) return false;
-    // trailing block: H[i][k] -= sum_c L[i][j0+c] L[k][j0+c], j0+nb <= k <= i; one warp per row, lanes over k
     const int r0 = j0 + nb;
-    for (int i = r0 + wid; i < D; i += nw) {
-      for (int k = r0 + lane; k <= i; k += 32) {
-        double a = H[i * ld + k];
-        for (int c = 0; c < nb; ++c) a = fma(-H[i * ld + j0 + c], H[k * ld + j0 + c], a);
-        H[i * ld + k] = a;
+    if (r0 >= D) break;                               // (nb == kPanel from here on)
+    if (tid < D - r0) {                               // ---- B
+      const int i = r0 + tid;
+      double x[kPanel];
+#pragma unroll
+      for (int c = 0; c < kPanel; ++c) x[c] = H[i * ld + j0 + c];
+#pragma unroll
+      for (int c = 0; c < kPanel; ++c) {
+        x[c] *= rd[j0 + c];
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k)
+          if (k > c) x[k] = fma(-x[c], H[(j0 + k) * ld + j0 + c], x[k]);
+      }
+#pragma unroll
+      for (int c = 0; c < kPanel; ++c) H[i * ld + j0 + c] = x[c];
+    }
+    __syncthreads();
+    {                                                 // ---- C
+      const int n = D - r0, li = lane >> 2, lk = lane & 3;
+      int cnt = 0;
+      for (int bi = 0; bi * 32 < n; ++bi) {
+        for (int bk = 0; bk * 8 <= bi * 32 + 31 && bk * 8 < n; ++bk, ++cnt) {
+          if (cnt % nw != wid) continue;
+          int ia[4], kb[2];
+          double acc[4][2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ia[q] = r0 + bi * 32 + q * 8 + li;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) kb[q] = r0 + bk * 8 + q * 4 + lk;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) acc[q][p] = (ia[q] < D && kb[p] <= ia[q]) ? H[ia[q] * ld + kb[p]] : 0.0;
+          const int il[4] = {min(ia[0], D - 1), min(ia[1], D - 1), min(ia[2], D - 1), min(ia[3], D - 1)};
+          const int kl[2] = {min(kb[0], D - 1), min(kb[1], D - 1)};
+#pragma unroll 4
+          for (int c = 0; c < kPanel; ++c) {
+            double Li[4], Lk[2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Li[q] = H[il[q] * ld + j0 + c];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) Lk[p] = H[kl[p] * ld + j0 + c];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int p = 0; p < 2; ++p) acc[q][p] = fma(-Li[q], Lk[p], acc[q][p]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+              if (ia[q] < D && kb[p] <= ia[q]) H[ia[q] * ld + kb[p]] = acc[q][p];
+        }
       }
     }
     __syncthreads();
@@ -77,31 +139,72 @@ __device__ bool chol_lower(double* H, int D, int ld, double* rd, int* flag) {
   return true;
 }
 
-// x <- (L L^T)^-1 x by warp 0 alone (warp-level synchronisation; the other warps wait at the closing barrier)
-__device__ void chol_solve(const double* L, const double* rd, int D, int ld, double* x) {
+// Triangular solves by ONE warp with the vector in registers (lane owns entries 32 q + lane): per column one shuffle, one
+// multiply by the reciprocal pivot and one FMA per owned entry; the factor is read down a column (forward, conflict-free
+// with the odd leading dimension) or along a row (backward).
+constexpr int kMaxQ = 6;   // D <= 192 (the shared-memory budget already limits D to 168)
+__device__ __forceinline__ void tri_forward(const double* L, const double* rd, int D, int ld, double (&r)[kMaxQ]) {   // L y = x
   const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q0 = 0; q0 < kMaxQ; ++q0) {
+    if (q0 * 32 >= D) continue;
+    for (int l = 0; l < 32; ++l) {
+      const int j = q0 * 32 + l;
+      if (j >= D) break;
+      const double xj = __shfl_sync(0xffffffffu, r[q0], l) * rd[j];
+      if (lane == l) r[q0] = xj;
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q) {
+        const int i = q * 32 + lane;
+        if (q >= q0 && i > j && i < D) r[q] = fma(-L[i * ld + j], xj, r[q]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tri_backward(const double* L, const double* rd, int D, int ld, double (&r)[kMaxQ]) {  // L^T z = y
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q0 = kMaxQ - 1; q0 >= 0; --q0) {
+    if (q0 * 32 >= D) continue;
+    for (int l = 31; l >= 0; --l) {
+      const int j = q0 * 32 + l;
+      if (j >= D) continue;
+      const double xj = __shfl_sync(0xffffffffu, r[q0], l) * rd[j];
+      if (lane == l) r[q0] = xj;
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q) {
+        const int i = q * 32 + lane;
+        if (q <= q0 && i < j) r[q] = fma(-L[j * ld + i], xj, r[q]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tri_load(const double* x, int D, double (&r)[kMaxQ]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) r[q] = (q * 32 + lane < D) ? x[q * 32 + lane] : 0.0;
+}
+__device__ __forceinline__ void tri_store(double* x, int D, const double (&r)[kMaxQ]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q)
+    if (q * 32 + lane < D) x[q * 32 + lane] = r[q];
+}
+
+// x <- (L L^T)^-1 x by warp 0 alone (the other warps wait at the closing barrier)
+__device__ void chol_solve(const double* L, const double* rd, int D, int ld, double* x) {
   if (threadIdx.x < 32) {
-    for (int j = 0; j < D; ++j) {          // L y = x, column-oriented
-      const double xj = x[j] * rd[j];
-      __syncwarp();
-      if (lane == 0) x[j] = xj;
-      for (int i = j + 1 + lane; i < D; i += 32) x[i] = fma(-L[i * ld + j], xj, x[i]);
-      __syncwarp();
-    }
-    for (int j = D - 1; j >= 0; --j) {     // L^T z = y
-      const double xj = x[j] * rd[j];
-      __syncwarp();
-      if (lane == 0) x[j] = xj;
-      for (int i = lane; i < j; i += 32) x[i] = fma(-L[j * ld + i], xj, x[i]);
-      __syncwarp();
-    }
+    double r[kMaxQ];
+    tri_load(x, D, r);
+    tri_forward(L, rd, D, ld, r);
+    tri_backward(L, rd, D, ld, r);
+    tri_store(x, D, r);
   }
   __syncthreads();
 }
 
 // out (D x D, row-major, global) = L^-1 for the lower-triangular L in shared memory: one warp per column c solves
 // L x = e_c by column-oriented forward substitution with the residuals of rows 32 q + lane in registers.
-constexpr int kMaxQ = 6;   // D <= 192 (the shared-memory budget already limits D to 168)
 __device__ void tri_inverse_lower(const double* L, const double* rd, int D, int ld, double* out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c = wid; c < D; c += nw) {
@@ -405,20 +508,11 @@ __global__ void __launch_bounds__(kLapThreads) k_conjugate_factor(int model, con
     return;
   }
   if (tid < 32) {
-    for (int j = D - 1; j >= 0; --j) {     // C^T y = v
-      const double xj = v[j] * rd[j];
-      __syncwarp();
-      if (lane == 0) v[j] = xj;
-      for (int i = lane; i < j; i += 32) v[i] = fma(-H[j * ld + i], xj, v[i]);
-      __syncwarp();
-    }
-    for (int j = 0; j < D; ++j) {          // C mu = y
-      const double xj = v[j] * rd[j];
-      __syncwarp();
-      if (lane == 0) v[j] = xj;
-      for (int i = j + 1 + lane; i < D; i += 32) v[i] = fma(-H[i * ld + j], xj, v[i]);
-      __syncwarp();
-    }
+    double r[kMaxQ];
+    tri_load(v, D, r);
+    tri_backward(H, rd, D, ld, r);         // C^T y = v
+    tri_forward(H, rd, D, ld, r);          // C mu = y
+    tri_store(v, D, r);
   }
   __syncthreads();
   for (int k = tid; k < D; k += nt) mu_out[k] = v[k];
@@ -460,36 +554,45 @@ __global__ void __launch_bounds__(128) k_sample_affine(const double* __restrict_
 
 // Theta[s][:] = mu + C^-1 R[s][:]  for the LOWER Cholesky factor C of the negative Hessian: the same samples as
 // `mu + randn(S, D).dot(LSig.T)` with LSig = C^-1 (get_laplace, util/opt.py:27-33), without forming the inverse -- the
-// host then only factors (dpotrf) and never inverts (dtrtri is the slower of the two at D = 128).  One thread per sample,
-// forward substitution with the solution held in shared memory ([D][32], conflict-free); every lane reads the same C
-// entry (broadcast from L1).  Four partial sums break the DFMA dependency chain.
-__global__ void __launch_bounds__(32) k_sample_solve(const double* __restrict__ mu, const double* __restrict__ C, const double* __restrict__ R,
-                                                     int S, int D, double* __restrict__ out, int ldo) {
-  extern __shared__ double xs[];   // [D][32]
-  const int lane = threadIdx.x;
-  const int s = blockIdx.x * 32 + lane;
-  const bool valid = s < S;
-  const double* r = R + (size_t)(valid ? s : 0) * D;
-  for (int i = 0; i < D; ++i) {
-    const double* ci = C + (size_t)i * D;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int j = 0;
-    for (; j + 4 <= i; j += 4) {
-      a0 = fma(__ldg(ci + j), xs[(j + 0) * 32 + lane], a0);
-      a1 = fma(__ldg(ci + j + 1), xs[(j + 1) * 32 + lane], a1);
-      a2 = fma(__ldg(ci + j + 2), xs[(j + 2) * 32 + lane], a2);
-      a3 = fma(__ldg(ci + j + 3), xs[(j + 3) * 32 + lane], a3);
-    }
-    for (; j < i; ++j) a0 = fma(__ldg(ci + j), xs[j * 32 + lane], a0);
-    const double x = (r[i] - ((a0 + a1) + (a2 + a3))) / __ldg(ci + i);
-    xs[i * 32 + lane] = x;
-    if (valid) out[(size_t)s * ldo + i] = __ldg(mu + i) + x;
+// host then only factors (dpotrf) and never inverts (dtrtri is the slower of the two at D = 128).  One WARP per sample:
+// column-oriented forward substitution with the right-hand side in registers (tri_forward); the CTA first stages the lower
+// triangle of C into shared memory (row-major, odd leading dimension: walks down a column are conflict-free) with the
+// reciprocal pivots.  A step costs a shuffle, a multiply and one FMA per owned entry: 2 us per sample at D = 128, all
+// samples in parallel (the thread-per-sample form it replaces took 225 us at D = 100).
+constexpr int kSolveWarps = 16;
+__global__ void __launch_bounds__(kSolveWarps * 32) k_sample_solve(const double* __restrict__ mu, const double* __restrict__ C,
+                                                                   const double* __restrict__ R, int S, int D, double* __restrict__ out,
+                                                                   int ldo) {
+  extern __shared__ double sm[];
+  const int ld = D | 1;
+  double* L = sm;              // [D][ld]
+  double* rd = L + D * ld;     // [D]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int q = tid; q < D * D; q += blockDim.x) {
+    const int i = q / D, j = q - i * D;
+    if (j <= i) L[i * ld + j] = __ldg(C + q);
   }
+  for (int i = tid; i < D; i += blockDim.x) rd[i] = 1.0 / __ldg(C + (size_t)i * D + i);
+  __syncthreads();
+  const int s = blockIdx.x * kSolveWarps + wid;
+  if (s >= S) return;
+  double r[kMaxQ];
+  tri_load(R + (size_t)s * D, D, r);
+  tri_forward(L, rd, D, ld, r);
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q)
+    if (q * 32 + lane < D) out[(size_t)s * ldo + q * 32 + lane] = __ldg(mu + q * 32 + lane) + r[q];
 }
 
 cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st) {
   if (S <= 0) return cudaSuccess;
-  k_sample_solve<<<(S + 31) / 32, 32, (size_t)D * 32 * sizeof(double), st>>>(mu, C, R, S, D, out, ldo);
+  const size_t smem = ((size_t)D * (D | 1) + D) * sizeof(double);
+  const size_t cap = kMaxSmem - 1024;
+  static DeviceOnce once;
+  cudaError_t e = raise_dynamic_smem(k_sample_solve, cap, once);
+  if (e != cudaSuccess) return e;
+  if (smem > cap) return cudaErrorInvalidValue;
+  k_sample_solve<<<(S + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, smem, st>>>(mu, C, R, S, D, out, ldo);
   return cudaGetLastError();
 }
 

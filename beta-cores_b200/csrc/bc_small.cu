@@ -27,12 +27,21 @@ __device__ __forceinline__ double block_sum(double x, double* red /* >= 33 doubl
 }
 
 // ------------------------------------------------------- sample preparation --
-// one block per sample s.
-__global__ void k_prepare_rows(int model, const double* __restrict__ theta, int S, int D, int ldt,
-                               const double* __restrict__ siginv, double* __restrict__ B, int ldb, double* __restrict__ colaux) {
+// one block per sample s.  Gaussian: B[s][:] = Siginv theta_s and colaux[s] = theta_s Siginv theta_s -- two D-long dot
+// products per thread, both summed over j in increasing order; the first walks a ROW of Siginv, so it reads the
+// transposed copy siginvT (made once per bc_set_potential) to keep a warp's loads coalesced (the row walk of the original
+// cost 32 sectors per load: 41 us per call at D = 100, now 3).
+__global__ void __launch_bounds__(128) k_prepare_rows(int model, const double* __restrict__ theta, int S, int D, int ldt,
+                                                      const double* __restrict__ siginv, const double* __restrict__ siginvT,
+                                                      double* __restrict__ B, int ldb, double* __restrict__ colaux) {
   __shared__ double red[33];
+  extern __shared__ double ths[];   // [D] this sample
   const int s = blockIdx.x;
   const double* th = theta + (size_t)s * ldt;
+  if (model == MODEL_GAUSSIAN) {
+    for (int k = threadIdx.x; k < D; k += blockDim.x) ths[k] = th[k];
+    __syncthreads();
+  }
   double part = 0.0;
   for (int k = threadIdx.x; k < ldb; k += blockDim.x) {
     double b = 0.0;
@@ -40,12 +49,26 @@ __global__ void k_prepare_rows(int model, const double* __restrict__ theta, int 
       if (model == MODEL_GAUSSIAN) {
         // B[s][k] = (Siginv theta_s)[k]      gaussian.py:12  x.dot(Siginv.dot(th.T))
         double acc = 0.0, acc2 = 0.0;
-        for (int j = 0; j < D; ++j) {
-          acc = fma(siginv[(size_t)k * D + j], th[j], acc);
-          acc2 = fma(th[j], siginv[(size_t)j * D + k], acc2);  // (th.dot(Siginv))[k]   gaussian.py:11
+        int j = 0;
+        for (; j + 4 <= D; j += 4) {
+          double u[4], v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            u[q] = siginvT ? __ldg(siginvT + (size_t)(j + q) * D + k) : __ldg(siginv + (size_t)k * D + j + q);
+            v[q] = __ldg(siginv + (size_t)(j + q) * D + k);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc = fma(u[q], ths[j + q], acc);
+            acc2 = fma(ths[j + q], v[q], acc2);  // (th.dot(Siginv))[k]   gaussian.py:11
+          }
+        }
+        for (; j < D; ++j) {
+          acc = fma(siginvT ? __ldg(siginvT + (size_t)j * D + k) : __ldg(siginv + (size_t)k * D + j), ths[j], acc);
+          acc2 = fma(ths[j], __ldg(siginv + (size_t)j * D + k), acc2);
         }
         b = acc;
-        part = fma(th[k], acc2, part);
+        part = fma(ths[k], acc2, part);
       } else {
         b = th[k];
       }
@@ -58,47 +81,41 @@ __global__ void k_prepare_rows(int model, const double* __restrict__ theta, int 
   }
 }
 
-// bbar[k] = mean_s B[s][k] for k < ldb; bbar[ldb] = mean_s colaux[s] (0 if no colaux)
-__global__ void k_prepare_mean(const double* __restrict__ B, int S, int ldb, const double* __restrict__ colaux,
-                               double* __restrict__ bbar) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  // sequential sum over the samples (the order is part of the result); the loads of 8 samples are issued together so that
-  // the chain is bound by the adds, not by 8 x the L2 latency
-  if (k < ldb) {
-    double acc = 0.0;
-    for (int s = 0; s < S; s += 8) {
-      double v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (s + j < S) ? B[(size_t)(s + j) * ldb + k] : 0.0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (s + j < S) acc += v[j];
+// bbar[k] = mean_s B[s][k] for k < ldb; bbar[ldb] = mean_s colaux[s] (0 if no colaux).
+// The sum over the samples is SEQUENTIAL per column (its order is part of the result), so a column costs one dependent
+// DADD per sample; what can be hidden is the memory latency: a CTA owns 32 columns, all its threads stage a tile of
+// kMeanTile samples into shared memory (coalesced, every load in flight at once) and one warp then adds it up.
+constexpr int kMeanCols = 32, kMeanTile = 128, kMeanThreads = 256;
+__global__ void __launch_bounds__(kMeanThreads) k_prepare_mean(const double* __restrict__ B, int S, int ldb, const double* __restrict__ colaux,
+                                                               double* __restrict__ bbar) {
+  __shared__ double tile[kMeanTile][kMeanCols + 1];
+  const int k0 = blockIdx.x * kMeanCols, tid = threadIdx.x;
+  const int kk = tid & (kMeanCols - 1), k = k0 + kk;
+  double acc = 0.0;
+  for (int s0 = 0; s0 < S; s0 += kMeanTile) {
+    const int ns = min(kMeanTile, S - s0);
+    for (int r = tid / kMeanCols; r < ns; r += kMeanThreads / kMeanCols) {
+      double v = 0.0;
+      if (k < ldb) v = B[(size_t)(s0 + r) * ldb + k];
+      else if (k == ldb && colaux) v = colaux[s0 + r];
+      tile[r][kk] = v;
     }
-    bbar[k] = acc / (double)S;
-  } else if (k == ldb) {
-    double acc = 0.0;
-    if (colaux) {
-      for (int s = 0; s < S; s += 8) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (s + j < S) ? colaux[s + j] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (s + j < S) acc += v[j];
-      }
+    __syncthreads();
+    if (tid < kMeanCols) {
+#pragma unroll 8
+      for (int r = 0; r < ns; ++r) acc += tile[r][kk];
     }
-    bbar[ldb] = acc / (double)S;
+    __syncthreads();
   }
+  if (tid < kMeanCols && k <= ldb) bbar[k] = acc / (double)S;
 }
 
-cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, double* B, int ldb,
-                                   double* colaux, double* bbar, cudaStream_t st) {
-  k_prepare_rows<<<S, 128, 0, st>>>(model, theta, S, D, ldt, siginv, B, ldb, colaux);
+cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
+                                   double* B, int ldb, double* colaux, double* bbar, cudaStream_t st) {
+  k_prepare_rows<<<S, 128, (size_t)D * sizeof(double), st>>>(model, theta, S, D, ldt, siginv, siginvT, B, ldb, colaux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int threads = 128;
-  k_prepare_mean<<<(ldb + 1 + threads - 1) / threads, threads, 0, st>>>(B, S, ldb, model == MODEL_GAUSSIAN ? colaux : nullptr,
-                                                                          bbar);
+  k_prepare_mean<<<(ldb + 1 + kMeanCols - 1) / kMeanCols, kMeanThreads, 0, st>>>(B, S, ldb, model == MODEL_GAUSSIAN ? colaux : nullptr, bbar);
   return cudaGetLastError();
 }
 

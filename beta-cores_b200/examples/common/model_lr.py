@@ -250,15 +250,26 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
     from bayesiancoresets._device import Engine, ptr, stream_ptr
     st = {'mu': None, 'L': None, 'info': None, 'pin': [None, None], 'ev': [None, None], 'k': 0, 'mu_host': None, 'ml': None}
 
-    def stage(r):
-        """copy a draw into one of two pinned staging buffers (runs on the thread that drew it)"""
+    def stage_buf(shape):
+        """the next of two pinned staging buffers, free again (the upload that last used it has left it)"""
         k = st['k'] = st['k'] ^ 1
-        if st['pin'][k] is None or tuple(st['pin'][k].shape) != r.shape:
-            st['pin'][k] = torch.empty(*r.shape, dtype=torch.float64).pin_memory()
+        if st['pin'][k] is None or tuple(st['pin'][k].shape) != tuple(shape):
+            st['pin'][k] = torch.empty(*shape, dtype=torch.float64).pin_memory()
         if st['ev'][k] is not None:
-            st['ev'][k].synchronize()                      # the upload that last used this buffer has left it
-        st['pin'][k].numpy()[...] = r
+            st['ev'][k].synchronize()
         return k, st['pin'][k]
+
+    def stage(r):
+        """copy a draw into a pinned staging buffer (runs on the thread that drew it)"""
+        k, pin = stage_buf(r.shape)
+        pin.numpy()[...] = r
+        return k, pin
+
+    def stage_into(shape):
+        """... or have the native generator write the draw there directly (bayesiancoresets/util/rng.py)"""
+        k, pin = stage_buf(shape)
+        return (k, pin), pin.numpy()
+    stage.into = stage_into
 
     def sampler(S, wts, pts):
         new_call()

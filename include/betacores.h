@@ -52,8 +52,8 @@ int bc_colsum_ld(int S);                /* leading dimension of the (hi, lo) pla
 /* ---- stage 1: potentials and posterior samples ------------------------------------------- */
 /* Select the potential f(x_n, theta_s).  D = contraction length (feature count; the neural-linear
  * target y is column D of each data row).  h_params: 8 host doubles, see bc_models.cuh / the
- * Python model modules (they hold beta, sigma^2, normalisers ...).  d_siginv: device D x D
- * (Gaussian only).  Replaces the likelihood callbacks of
+ * Python model modules (they hold beta, sigma^2, normalisers ...).  d_siginv: device D x D (Gaussian
+ * only); it must stay allocated and UNCHANGED until the next bc_set_potential (later calls read it and a transposed copy).  Replaces the likelihood callbacks of
  * examples/common/model_lr.py:72-86, gaussian.py:7-15,34-62, model_neurlinr.py:90-110. */
 int bc_set_potential(bc_ctx* ctx, int model, int kind, int D, const double* h_params, const double* d_siginv);
 /* Install the S current posterior samples (device, S x ldt): what Projector.update() stores in
@@ -242,6 +242,17 @@ int bc_vec_step(bc_ctx* ctx, int op, const double* d_xw, const double* d_xf, con
  * centred = 0 returns the un-centred potential (the likelihood callback's own return value). */
 int bc_host_project(int device, int model, int kind, int D, const double* h_params, const double* h_siginv, const double* h_X,
                     int64_t n, int64_t ldx_h, const double* h_theta, int S, double* h_V, int centred);
+
+/* ---- host side: numpy's legacy global random stream, natively (csrc/bc_hostrng.cu) ----------------------------------
+ * The reference's samplers end in `np.random.randn(S, D)` (examples/zellner_gaussian/main.py:87-92, zellner_logreg/main.py:
+ * 139-144) and its sub-sampled modes draw `np.random.randint(N, size=n)` (bayesiancoresets/coreset/bcores.py:53), all from
+ * numpy's one global RandomState.  These two functions continue that stream bit for bit (MT19937 words, polar Box-Muller
+ * with the cached second value, masked-rejection bounded integers) from a state in numpy's own representation
+ * (`np.random.get_state()` -> key, pos, has_gauss, cached_gaussian), several times faster than numpy's generator; `threads`
+ * worker threads share the per-pair log / sqrt.  No device work.  randint: high - 1 < 2^32. */
+typedef struct bc_mt_state { uint32_t key[624]; int32_t pos; int32_t has_gauss; double gauss; } bc_mt_state;
+int bc_mt_randn(bc_mt_state* st, double* h_out, int64_t n, int threads);
+int bc_mt_randint(bc_mt_state* st, int64_t high, int64_t* h_out, int64_t n);
 
 #ifdef __cplusplus
 }

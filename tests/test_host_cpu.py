@@ -284,6 +284,36 @@ def test_fused_projection_reapplies_its_potential_after_another_owner(monkeypatc
         B.set_samples(th)                    # B never re-configured: the workspace holds A's potential
 
 
+def test_native_legacy_stream_is_bit_identical_to_numpy():
+    """csrc/bc_hostrng.cu (bc_mt_randn / bc_mt_randint): numpy's legacy RandomState continued natively from its own state --
+    same normals bit for bit (odd counts, the cached second value, several worker threads), same bounded integers, and
+    the state handed back is the state numpy itself ends in (numpy/random/src/legacy/legacy-distributions.c::legacy_gauss,
+    mt19937.c, _bounded_integers.pyx masked rejection)."""
+    import ctypes
+    from bayesiancoresets import _native as nv
+    from bayesiancoresets.util import rng
+    np.random.seed(20260101)
+    np.random.randn(3)                      # leaves a cached gaussian behind
+    for n, threads, high, k in [(1, 1, 5700, 13), (7, 1, 1, 4), (20000, 4, 10_000_000, 200), (3, 2, 2**32, 9), (131073, 3, 1000, 50),
+                                (4096, 2, 3, 7), (20001, 4, 5700, 1000), (2, 1, 2**31, 3)]:
+        st = np.random.get_state()
+        ref = np.random.randn(n)
+        ri = np.random.randint(high, size=k)
+        after = np.random.get_state()
+        np.random.set_state(st)
+        m = rng._checkout()
+        out = np.empty(n)
+        nv.call('bc_mt_randn', ctypes.byref(m), out.ctypes.data, n, threads)
+        oi = np.empty(k, dtype=np.int64)
+        nv.call('bc_mt_randint', ctypes.byref(m), high, oi.ctypes.data, k)
+        rng._checkin(m)
+        np.testing.assert_array_equal(out.view(np.int64), ref.view(np.int64))
+        np.testing.assert_array_equal(oi, ri)
+        s2 = np.random.get_state()
+        np.testing.assert_array_equal(s2[1], after[1])
+        assert tuple(s2[2:]) == tuple(after[2:])
+
+
 def test_stream_ahead_consumes_the_global_stream_like_direct_draws():
     """util/rng.py: draws made one sampler call ahead on a helper thread, with pattern changes (selection vs optimiser
     sub-sample sizes, cycles that end early or run long) and a drain in between, return exactly the numbers direct

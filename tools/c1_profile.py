@@ -18,8 +18,28 @@ alg = bc.BetaCoreset(prob['data'], prj, n_subsample_select=case['n_sel'], n_subs
 alg.build(1, 1)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-pr = cProfile.Profile(); pr.enable()
 alg.build(1, 2); alg.build(1, 3)
+torch.cuda.synchronize()
+print('2 build steps, no profiler: %.3f ms per optimiser step' % (1e3*(time.perf_counter()-t0)/2002))
+# the native legacy generator against numpy's on this host (one optimiser step draws S x D = 200 x 100 normals)
+import ctypes
+from bayesiancoresets import _native as nv
+from bayesiancoresets.util import rng as _rng
+sampler.drain()
+m = _rng._checkout(); buf = np.empty(20000)
+for thr in (1, 2, 4, 8):
+    nv.call('bc_mt_randn', ctypes.byref(m), buf.ctypes.data, 20000, thr)
+    t = time.perf_counter()
+    for _ in range(200):
+        nv.call('bc_mt_randn', ctypes.byref(m), buf.ctypes.data, 20000, thr)
+    print('bc_mt_randn(20000) %d thread(s): %.1f us' % (thr, (time.perf_counter()-t)/200*1e6))
+t = time.perf_counter()
+for _ in range(200):
+    np.random.randn(200, 100)
+print('np.random.randn(200, 100): %.1f us   (RNG_THREADS in use: %d)' % ((time.perf_counter()-t)/200*1e6, _rng.RNG_THREADS))
+t0 = time.perf_counter()
+pr = cProfile.Profile(); pr.enable()
+alg.build(1, 4); alg.build(1, 5)
 torch.cuda.synchronize()
 pr.disable()
 print('2 build steps: %.3f s (%.3f ms per optimiser step incl. profiler overhead)' % (time.perf_counter()-t0, 1e3*(time.perf_counter()-t0)/2002))
