@@ -41,6 +41,7 @@ SIGNATURES = {
     'bc_laplace_logistic_factor': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
     'bc_conjugate_factor': [c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp],
     'bc_sample_solve': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
+    'bc_sample_solve_hinted': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp],
     'bc_sample_affine': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
     'bc_dense_rownorms': [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp],

@@ -13,7 +13,7 @@ is consumed exactly as without this class.
 
 The helper does not call numpy's generator: while a speculation is in flight the global stream is CHECKED OUT of numpy
 (`np.random.get_state()` -> a native bc_mt_state) and continued by libbetacores' own implementation of the legacy generator
-(csrc/bc_hostrng.cu: the same MT19937 words, the same polar Box-Muller arithmetic, the process's libm -- bit-identical
+(csrc/bc_hostrng.cpp: the same MT19937 words, the same polar Box-Muller arithmetic, the process's libm -- bit-identical
 output, tests/test_host_cpu.py), which is several times faster than numpy's per-call path and splits the log/sqrt part
 over a few threads: at 25-30 ns per normal numpy's generator alone took longer than all the kernels of an optimiser step
 of the Gaussian example.  Rewinding restores a native snapshot; the state goes back into numpy (`np.random.set_state`)

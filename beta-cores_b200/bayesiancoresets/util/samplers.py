@@ -105,7 +105,8 @@ class ConjugateDeviceSampler(object):
                 ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(st['info']), stream_ptr())
         Rd = self._normals_to_device(eng, S)
         theta = eng.empty(S, D)
-        nv.call('bc_sample_solve', ctx, ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        nv.call('bc_sample_solve_hinted', ctx, ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)),
+                ptr(st['info']), stream_ptr())
         return theta
 
     def supports_device_step(self):

@@ -11,9 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib')
 OUT = os.path.join(LIB, 'libbetacores.so')
-UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_sampler.cu', 'bc_dense.cu', 'bc_api.cu', 'bc_hostrng.cu']
-# bc_hostrng.cu is host code that must reproduce numpy's floating-point results bit for bit: no FMA contraction
-UNIT_FLAGS = {'bc_hostrng.cu': ['-Xcompiler', '-ffp-contract=off']}
+UNITS = ['bc_project.cu', 'bc_project_q.cu', 'bc_small.cu', 'bc_sampler.cu', 'bc_dense.cu', 'bc_api.cu', 'bc_hostrng.cpp']
+# bc_hostrng.cpp is host-only code (g++ directly) that must reproduce numpy's floating-point results bit for bit: no FMA contraction
+CXX = os.environ.get('CXX', 'g++')
+CXXFLAGS = ['-O3', '-std=c++17', '-fPIC', '-ffp-contract=off', '-pthread']
 HEADERS = ['bc_common.cuh', 'bc_npmean.h', 'bc_umma.cuh', 'bc_fastmath.cuh', 'bc_models.cuh', 'bc_kernels.h', os.path.join('..', '..', 'include', 'betacores.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
@@ -32,10 +33,13 @@ def build(force=False, verbose=False):
     objs, jobs = [], []
     for u in UNITS:
         src = os.path.join(CSRC, u)
-        obj = os.path.join(LIB, u.replace('.cu', '.o'))
+        obj = os.path.join(LIB, os.path.splitext(u)[0] + '.o')
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            jobs.append([NVCC] + FLAGS + UNIT_FLAGS.get(u, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj])
+            if u.endswith('.cpp'):
+                jobs.append([CXX] + CXXFLAGS + ['-c', src, '-o', obj])
+            else:
+                jobs.append([NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj])
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

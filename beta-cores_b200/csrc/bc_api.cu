@@ -24,6 +24,7 @@ struct bc_ctx {
   double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
   size_t cap_sT = 0;
   bool siginvT_ready = false;
+  int* siginv_diag = nullptr;  // device flag: d_siginv is a diagonal matrix (k_prepare_rows then takes one term per dot product)
   // samples
   bool samples_set = false;
   int S = 0;
@@ -47,8 +48,12 @@ struct bc_ctx {
   bool fexp_on = false;
   int* fexp = nullptr;                     // kQK ints
   unsigned long long* fscratch = nullptr;  // kQK column maxima (bc_feature_exponents)
-  unsigned long long* sscratch = nullptr;  // 2 words: max bits / non-finite flag of the samples, zero between calls
+  unsigned long long* sscratch = nullptr;  // two slots of 2 words: max bits / non-finite flag of a sample set; a call uses slot
+  int sslot = 0;                           // `sslot` and its quantise kernel clears the other one for the next call
   int q_digits = 6;                        // leading digits of the 7-digit images a launch contracts (bc_set_contraction_digits)
+  // bc_greedy_opt_step, single-part jobs: where the next column-sum pass also leaves the centred column sum (its finalize
+  // kernel then does the work of bc_colsum_combine); consumed by that pass
+  double* fuse_colsum_out = nullptr;
 };
 
 static int cuda_fail(cudaError_t e) {
@@ -146,8 +151,8 @@ int bc_create(int device, bc_ctx** out) {
   BC_CUDA(cudaMalloc((void**)&c->fexp, kQK * sizeof(int)));
   BC_CUDA(cudaMemset(c->fexp, 0, kQK * sizeof(int)));
   BC_CUDA(cudaMalloc((void**)&c->fscratch, kQK * sizeof(unsigned long long)));
-  BC_CUDA(cudaMalloc((void**)&c->sscratch, 2 * sizeof(unsigned long long)));
-  BC_CUDA(cudaMemset(c->sscratch, 0, 2 * sizeof(unsigned long long)));
+  BC_CUDA(cudaMalloc((void**)&c->sscratch, 4 * sizeof(unsigned long long)));
+  BC_CUDA(cudaMemset(c->sscratch, 0, 4 * sizeof(unsigned long long)));
   *out = c;
   return BC_OK;
 }
@@ -156,6 +161,7 @@ int bc_destroy(bc_ctx* c) {
   if (!c) return BC_OK;
   cudaFree(c->B);
   cudaFree(c->siginvT);
+  cudaFree(c->siginv_diag);
   cudaFree(c->colaux);
   cudaFree(c->bbar);
   cudaFree(c->part_colsum);
@@ -230,11 +236,16 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
   if (c->model == BC_MODEL_GAUSSIAN && !c->siginvT_ready) {
     if ((rc = grow(&c->siginvT, &c->cap_sT, (size_t)c->Dk * c->Dk))) return rc;
     BC_CUDA(launch_transpose(c->d_siginv, c->Dk, c->Dk, c->Dk, c->siginvT, c->Dk, (cudaStream_t)stream));
-    BC_LAUNCHED(1);
+    if (!c->siginv_diag) BC_CUDA(cudaMalloc((void**)&c->siginv_diag, sizeof(int)));
+    BC_CUDA(launch_offdiag_test(c->d_siginv, c->Dk, c->siginv_diag, (cudaStream_t)stream));
+    BC_LAUNCHED(2);
     c->siginvT_ready = true;
   }
+  const bool q_route = c->Dk <= kQK;
+  if (q_route) c->sslot ^= 1;
   BC_CUDA(launch_prepare_samples(c->model, d_theta, S, c->Dk, ldt, c->d_siginv, c->model == BC_MODEL_GAUSSIAN ? c->siginvT : nullptr, c->B,
-                                 c->Dpad, c->colaux, c->bbar, (cudaStream_t)stream));
+                                 c->Dpad, c->colaux, c->bbar, c->fexp_on ? c->fexp : nullptr, q_route ? c->sscratch + 2 * c->sslot : nullptr,
+                                 c->model == BC_MODEL_GAUSSIAN ? c->siginv_diag : nullptr, (cudaStream_t)stream));
   BC_LAUNCHED(2);
   c->q_ready = false;
   if (c->Dk <= kQK) {
@@ -242,8 +253,9 @@ int bc_set_samples(bc_ctx* c, const double* d_theta, int S, int ldt, void* strea
     if ((rc = grow(&c->qB, &c->cap_qB, chunks * kQChunkBytes / sizeof(double)))) return rc;
     if ((rc = grow(&c->colscale, &c->cap_cs, 2))) return rc;   // [0] = scale, [1] = the shared exponent (int)
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, (cudaStream_t)stream));
-    BC_LAUNCHED(3);
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, c->sslot, true,
+                                    (cudaStream_t)stream));
+    BC_LAUNCHED(1);
     c->q_ready = true;
   }
   c->samples_set = true;
@@ -265,9 +277,10 @@ int bc_set_feature_exponents(bc_ctx* c, const int32_t* d_fexp, int D, void* stre
   if (d_fexp) BC_CUDA(cudaMemcpyAsync(c->fexp, d_fexp, (size_t)D * sizeof(int), cudaMemcpyDeviceToDevice, st));
   c->fexp_on = d_fexp != nullptr;
   if (c->samples_set && c->q_ready) {   // the sample image in place was built for other exponents
+    c->sslot ^= 1;
     BC_CUDA(launch_quantise_samples(c->B, c->Dpad, c->S, c->Dk, reinterpret_cast<unsigned char*>(c->qB), c->colscale,
-                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, st));
-    BC_LAUNCHED(3);
+                                    reinterpret_cast<int*>(c->colscale + 1), c->fexp_on ? c->fexp : nullptr, c->sscratch, c->sslot, false, st));
+    BC_LAUNCHED(2);
   }
   return BC_OK;
 }
@@ -333,7 +346,9 @@ int bc_project_colsum(bc_ctx* c, const double* d_X, int64_t ldx, const int64_t* 
     return BC_OK;
   }
   BC_CUDA(launch_project(P, c->model, c->kind, c->poly, MODE_COLSUM, cfg, grid, smem, st));
-  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
+  double* fused = c->fuse_colsum_out;
+  c->fuse_colsum_out = nullptr;
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st, fused));
   BC_LAUNCHED(2);
   return BC_OK;
 }
@@ -484,7 +499,9 @@ int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale
     return BC_OK;
   }
   BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_COLSUM, c->q_digits, grid, st));
-  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st));
+  double* fused = c->fuse_colsum_out;
+  c->fuse_colsum_out = nullptr;
+  BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st, fused));
   BC_LAUNCHED(2);
   return BC_OK;
 }
@@ -567,9 +584,13 @@ int bc_greedy_opt_step(bc_ctx* c, const bc_step_args* a, void* stream) {
     return BC_ERR_ARG;
   if (a->phase == 2 && (!a->d_parts_all || a->nparts < 1)) return BC_ERR_ARG;
   int rc;
+  bool combined = false;
   if (a->phase != 2) {
     if ((rc = bc_set_samples(c, a->d_theta, a->S, a->ldt, stream))) return rc;
     if (a->ev_pass_begin) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_begin, (cudaStream_t)stream));
+    // a single-part job (phase 0) with rows to pass over: the pass's finalize kernel also writes the centred column sum
+    c->fuse_colsum_out = (a->phase == 0 && a->n > 0) ? a->d_colsum : nullptr;
+    combined = c->fuse_colsum_out != nullptr;
     if (a->d_image && a->n > 0) {
       const void* img = a->d_image;
       const double* rs = a->d_rowscale;
@@ -583,24 +604,28 @@ int bc_greedy_opt_step(bc_ctx* c, const bc_step_args* a, void* stream) {
         rs = a->d_growscale;
         ra = a->d_rowaux_q ? a->d_growaux : nullptr;
       }
-      if ((rc = bc_project_colsum_q(c, img, rs, a->n, ra, a->d_parts, stream))) return rc;
+      rc = bc_project_colsum_q(c, img, rs, a->n, ra, a->d_parts, stream);
     } else {
       if (a->n > 0 && !a->d_X) return BC_ERR_ARG;
-      if ((rc = bc_project_colsum(c, a->d_X ? a->d_X : a->d_pts, a->d_X ? a->ldx : a->ldp, a->d_rows, a->n, a->d_rowaux, a->d_parts, stream)))
-        return rc;
+      rc = bc_project_colsum(c, a->d_X ? a->d_X : a->d_pts, a->d_X ? a->ldx : a->ldp, a->d_rows, a->n, a->d_rowaux, a->d_parts, stream);
     }
+    c->fuse_colsum_out = nullptr;
+    if (rc) return rc;
     if (a->ev_pass_end) BC_CUDA(cudaEventRecord((cudaEvent_t)a->ev_pass_end, (cudaStream_t)stream));
     if (a->phase == 1) return BC_OK;
   }
   if (a->phase == 2) {
     if ((rc = bc_colsum_combine(c, a->d_parts_all, a->nparts, a->S, a->d_colsum, stream))) return rc;
-  } else {
+  } else if (!combined) {
     if ((rc = bc_colsum_combine(c, a->d_parts, 1, a->S, a->d_colsum, stream))) return rc;
   }
   if ((rc = bc_project_materialise(c, a->d_pts, a->ldp, nullptr, a->M, a->d_pts_rowaux, a->d_Vc, a->ldv, nullptr, nullptr, 0, stream))) return rc;
-  if ((rc = bc_core_resid(c, a->d_colsum, a->scaling, a->d_Vc, a->M, a->S, a->ldv, a->d_w, a->d_resid, stream))) return rc;
-  if ((rc = bc_core_grad(c, a->d_Vc, a->M, a->S, a->ldv, a->d_resid, a->d_grad, stream))) return rc;
-  return bc_adam_step(c, a->d_grad, a->d_w, a->d_m1, a->d_m2, a->M, a->lr, a->b1, a->b2, a->c1, a->c2, a->eps, a->d_nn_mask, stream);
+  // residual, gradient and the projected ADAM update in one launch (the kernels of bc_core_resid / bc_core_grad / bc_adam_step
+  // back to back in one CTA)
+  BC_CUDA(launch_core_step(a->d_colsum, a->scaling, a->d_Vc, a->M, a->S, a->ldv, a->d_w, a->d_resid, a->d_grad, a->d_m1, a->d_m2, a->lr,
+                           a->b1, a->b2, a->c1, a->c2, a->eps, a->d_nn_mask, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
 }
 
 int bc_core_pgrad(bc_ctx* c, const double* d_P, int M, int64_t ldp, const double* d_w, const double* d_resid, double* d_out,
@@ -667,12 +692,17 @@ int bc_sample_affine(bc_ctx* c, const double* d_mu, const double* d_L, const dou
   return BC_OK;
 }
 
-int bc_sample_solve(bc_ctx* c, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
-                    void* stream) {
+int bc_sample_solve_hinted(bc_ctx* c, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
+                           const int* d_factor_info, void* stream) {
   if (!c || !d_mu || !d_C || !d_R || !d_theta || S < 0 || D < 1 || D > 160 || ldt < D) return BC_ERR_ARG;
-  BC_CUDA(launch_sample_solve(d_mu, d_C, d_R, S, D, d_theta, ldt, (cudaStream_t)stream));
+  BC_CUDA(launch_sample_solve(d_mu, d_C, d_R, S, D, d_theta, ldt, d_factor_info ? d_factor_info + 1 : nullptr, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
+}
+
+int bc_sample_solve(bc_ctx* c, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
+                    void* stream) {
+  return bc_sample_solve_hinted(c, d_mu, d_C, d_R, S, D, d_theta, ldt, nullptr, stream);
 }
 
 int bc_dense_rownorms(bc_ctx* c, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream) {

@@ -36,11 +36,20 @@ namespace {
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
 
+// The three bulk loops (state regeneration, tempering, word -> attempt conversion) are compiled twice, for the x86-64
+// baseline and for AVX2, and picked at load time (GCC function multi-versioning).  Neither version may fuse a multiply
+// with an add: the unit is built with -ffp-contract=off, and "avx2" does not include FMA.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define BC_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define BC_CLONES
+#endif
+
 #define BC_MT_TWIST(u, v) ((((u) & kUpper) | ((v) & kLower)) >> 1) ^ ((uint32_t)(-(int32_t)((v) & 1)) & kMatrixA)
 // mt19937_gen: key[i] = key[(i + M) mod N] ^ twist(key[i], key[(i + 1) mod N]).  Written as ranges inside which no
 // iteration reads a word another iteration of the same range writes (word i + M - N was finished a whole range earlier),
 // so that each range vectorises.
-inline void mt_gen(uint32_t* key) {
+BC_CLONES void mt_gen(uint32_t* key) {
   int i;
 #pragma GCC ivdep
   for (i = 0; i < kN - kM; ++i) key[i] = key[i + kM] ^ BC_MT_TWIST(key[i], key[i + 1]);                 // 0 .. 226 reads 397 .. 623 (old)
@@ -57,6 +66,20 @@ inline uint32_t temper(uint32_t y) {
   y ^= (y << 15) & 0xefc60000u;
   y ^= (y >> 18);
   return y;
+}
+BC_CLONES void temper_block(const uint32_t* __restrict__ k, uint32_t* __restrict__ o, int n) {
+  for (int i = 0; i < n; ++i) o[i] = temper(k[i]);
+}
+// `na` attempts of the polar method from 4 na words: x1, x2 and r2 = x1^2 + x2^2 (legacy_gauss with mt19937_next_double)
+BC_CLONES void attempts(const uint32_t* __restrict__ b, int na, double* __restrict__ tx1, double* __restrict__ tx2, double* __restrict__ tr2) {
+  for (int a = 0; a < na; ++a) {
+    const double d1 = ((double)(int32_t)(b[4 * a] >> 5) * 67108864.0 + (double)(int32_t)(b[4 * a + 1] >> 6)) / 9007199254740992.0;
+    const double d2 = ((double)(int32_t)(b[4 * a + 2] >> 5) * 67108864.0 + (double)(int32_t)(b[4 * a + 3] >> 6)) / 9007199254740992.0;
+    const double x1 = 2.0 * d1 - 1.0, x2 = 2.0 * d2 - 1.0;
+    tx1[a] = x1;
+    tx2[a] = x2;
+    tr2[a] = x1 * x1 + x2 * x2;
+  }
 }
 
 // A window of tempered words in stream order, refilled one state block at a time (at most 3 unconsumed words are carried
@@ -77,7 +100,7 @@ struct Words {
     const int take = kN - st->pos;
     const uint32_t* k = st->key + st->pos;
     uint32_t* o = buf + left;
-    for (int i = 0; i < take; ++i) o[i] = temper(k[i]);
+    temper_block(k, o, take);
     st->pos = kN;
     at = 0;
     end = left + take;
@@ -195,14 +218,7 @@ extern "C" int bc_mt_randn(bc_mt_state* st, double* h_out, int64_t n, int thread
     const uint32_t* b = w.buf + w.at;
     const int na = (w.end - w.at) / 4;
     double tx1[(kN + 4) / 4], tx2[(kN + 4) / 4], tr2[(kN + 4) / 4];
-    for (int a = 0; a < na; ++a) {
-      const double d1 = ((double)(int32_t)(b[4 * a] >> 5) * 67108864.0 + (double)(int32_t)(b[4 * a + 1] >> 6)) / 9007199254740992.0;
-      const double d2 = ((double)(int32_t)(b[4 * a + 2] >> 5) * 67108864.0 + (double)(int32_t)(b[4 * a + 3] >> 6)) / 9007199254740992.0;
-      const double x1 = 2.0 * d1 - 1.0, x2 = 2.0 * d2 - 1.0;
-      tx1[a] = x1;
-      tx2[a] = x2;
-      tr2[a] = x1 * x1 + x2 * x2;
-    }
+    attempts(b, na, tx1, tx2, tr2);
     int a = 0;
     for (; a < na && got < npairs; ++a) {
       const double r2 = tr2[a];

@@ -76,7 +76,7 @@ int project_tile_rows(int cfg);
 cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int mode, int tile_cfg, int grid, size_t smem, cudaStream_t st, int csplit = 1);
 int project_chunks(int S);
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld, double* out_dd,
-                                    double* out_best, int mode, cudaStream_t st);
+                                    double* out_best, int mode, cudaStream_t st, double* colsum_out = nullptr);
 
 
 // ---- bc_project_q.cu: tensor-core (tcgen05 int8 Ozaki) route of the fused projection ----
@@ -108,16 +108,21 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
 cudaError_t launch_gather_image(const unsigned char* src, const double* src_scale, const double* src_aux, const long long* idx, long long n,
                                 unsigned char* dst, double* dst_scale, double* dst_aux, cudaStream_t st);
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    const int* fexp, unsigned long long* scratch2, cudaStream_t st);
+                                    const int* fexp, unsigned long long* scratch4, int slot, bool have_max, cudaStream_t st);
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st);
 
 // ---- bc_small.cu: sample preparation, coreset-side step, ADAM ----
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
-                                   double* B, int ldb, double* colaux, double* bbar, cudaStream_t st);
+                                   double* B, int ldb, double* colaux, double* bbar, const int* fexp, unsigned long long* absmax_slot,
+                                   const int* siginv_diag, cudaStream_t st);
+cudaError_t launch_offdiag_test(const double* A, int D, int* flag, cudaStream_t st);
 cudaError_t launch_rowquad(const double* X, long long n, int D, long long ldx, const double* siginv, double* out, cudaStream_t st);
 cudaError_t launch_colsum_combine(const double* parts, int nparts, int S, int Sld, double* out, cudaStream_t st);
 cudaError_t launch_core_resid(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, const double* w,
                               double* resid, cudaStream_t st);
+cudaError_t launch_core_step(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, double* x, double* resid,
+                             double* grad, double* m1, double* m2, double lr, double b1, double b2, double c1, double c2, double eps,
+                             const unsigned char* nn_mask, cudaStream_t st);
 cudaError_t launch_core_maxcorr(const double* Vc, int M, int S, long long ldv, const double* resid, int skip, double* out,
                                 cudaStream_t st);
 cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, const double* resid, double* grad, cudaStream_t st);
@@ -135,7 +140,8 @@ cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double
                                     double tol, int* info, int flags, cudaStream_t st);
 cudaError_t launch_conjugate_factor(int model, const double* Z, long long ldz, const double* w, int M, int D, const double* A0, const double* A1,
                                     const double* v0, double sigsq, double* mu, double* C, int* info, cudaStream_t st);
-cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
+cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, const int* diag_hint,
+                                cudaStream_t st);
 cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 
 // ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----

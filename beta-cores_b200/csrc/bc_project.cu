@@ -402,7 +402,7 @@ __global__ void __launch_bounds__((BM / 16 + 2) * 32, 1) k_project(const ProjArg
 //   out_best: {score, index-as-double-bits}
 __global__ void __launch_bounds__(1024) k_project_finalize(const double* __restrict__ part_colsum, const double* __restrict__ part_misc,
                                                             int nctas, int S, int Sld, double* __restrict__ out_dd,
-                                                            double* __restrict__ out_best, int mode) {
+                                                            double* __restrict__ out_best, int mode, double* __restrict__ colsum_out) {
   __shared__ double sh[1024], sl[1024];
   __shared__ long long si[32];
   const int tid = threadIdx.x;
@@ -439,6 +439,20 @@ __global__ void __launch_bounds__(1024) k_project_finalize(const double* __restr
       const double h = qh + ql;
       out_dd[S] = h;
       out_dd[Sld + S] = ql - (h - qh);
+    }
+    if (colsum_out) {
+      // single-part jobs: the centred column sum right here, operation for operation what k_colsum_combine computes from
+      // one part (bc_greedy_opt_step; saves the launch)
+      __syncthreads();
+      const dd om = {-out_dd[S], -out_dd[Sld + S]};
+      for (int col = tid; col < S; col += blockDim.x) {
+        dd a = {0.0, 0.0}, m = {0.0, 0.0};
+        const dd o = {out_dd[col], out_dd[Sld + col]};
+        a = dd_add(a, o);
+        m = dd_add(m, om);
+        a = dd_add(a, m);
+        colsum_out[col] = a.hi;
+      }
     }
   } else {
     Best b = {0.0, -1};
@@ -539,9 +553,9 @@ cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int
 }
 
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld,
-                                    double* out_dd, double* out_best, int mode, cudaStream_t st) {
+                                    double* out_dd, double* out_best, int mode, cudaStream_t st, double* colsum_out) {
   const int threads = (mode == MODE_SCORE) ? 256 : (S >= 1024 ? 1024 : (S > 256 ? 512 : 256));
-  k_project_finalize<<<1, threads, 0, st>>>(part_colsum, part_misc, nctas, S, Sld, out_dd, out_best, mode);
+  k_project_finalize<<<1, threads, 0, st>>>(part_colsum, part_misc, nctas, S, Sld, out_dd, out_best, mode, colsum_out);
   return cudaGetLastError();
 }
 

@@ -104,9 +104,27 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 template <int R>
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src, long long ld, long long n, int D,
                                                    unsigned char* __restrict__ image, double* __restrict__ scale_out,
-                                                   double* __restrict__ aux_out, int aux_col, const int* __restrict__ common_e,
+                                                   double* __restrict__ aux_out, int aux_col, const unsigned long long* common_sc,
+                                                   unsigned long long* common_sc_next, int* common_e_out, double* common_scale_out,
                                                    const int* __restrict__ fexp, int fsign) {
   const int lane = threadIdx.x & 31;
+  // common_sc (the samples): every row shares ONE exponent, ilogb(max |x|) + 3 over the whole matrix -- their magnitudes are
+  // alike, and a single scale keeps the projection epilogue free of per-column loads.  common_sc[0] = the bit pattern of
+  // that maximum, common_sc[1] != 0 if any entry is not finite (gathered by k_prepare_rows / k_sample_absmax); block 0
+  // publishes (exponent, scale = 2^(e - 32), NaN for a non-finite sample set: the reference's own result is NaN in every
+  // quantity downstream of it) for the projection kernels and clears the OTHER scratch slot for the next sample set.
+  int ce = 0;
+  if (common_sc) {
+    const double cmax = __longlong_as_double((long long)common_sc[0]);
+    const bool cbad = common_sc[1] != 0;
+    ce = (cmax > 0.0 && !cbad) ? ilogb(cmax) + 3 : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *common_e_out = ce;
+      *common_scale_out = cbad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, ce - 32);
+      common_sc_next[0] = 0;
+      common_sc_next[1] = 0;
+    }
+  }
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long rows_padded = ((n + R - 1) / R) * R;
@@ -130,10 +148,7 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ src
       bad = bad || (ob != 0);
     }
     // |x| 2^-e < 1/4  =>  top digit within [-64, 64], the others in [-128, 127]
-    // common_e: every row shares one exponent (the samples: their magnitudes are alike, and a single scale keeps the
-    // projection epilogue free of per-column loads); a non-finite entry anywhere was flagged by k_common_exponent
-    const int e = common_e ? __ldg(common_e) : ((amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0);
-    if (common_e) bad = !(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]) && isfinite(x[3]));
+    const int e = common_sc ? ce : ((amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0);
     uint32_t dig[kQSlices] = {0, 0, 0, 0, 0, 0, 0};
     if (!bad) {
 #pragma unroll
@@ -212,7 +227,7 @@ cudaError_t launch_quantise_rows(const double* X, long long ldx, long long n, in
   long long warps = ((n + kQTileRows - 1) / kQTileRows) * kQTileRows;
   long long blocks = (warps + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col, nullptr, fexp, -1);
+  k_quantise<kQTileRows><<<(int)blocks, 256, 0, st>>>(X, ldx, n, D, image, rowscale, aux_out, aux_col, nullptr, nullptr, nullptr, nullptr, fexp, -1);
   return cudaGetLastError();
 }
 
@@ -258,10 +273,10 @@ cudaError_t launch_gather_image(const unsigned char* src, const double* src_scal
   return cudaGetLastError();
 }
 
-// exponent shared by all S samples: ilogb(max |B'|) + 3 over the feature-scaled samples B'[s][k] = B[s][k] 2^fexp[k], and
-// the matching scale 2^(e - 32) (NaN if any entry is not finite: the reference's own result is NaN in every quantity
-// downstream of such a sample set).  Two steps: a grid-wide max of the bit patterns (|x| orders like its bits; a
-// non-finite entry sets the flag word), then one thread turns it into (e, scale) and clears the scratch for the next call.
+// exponent shared by all S samples: ilogb(max |B'|) + 3 over the feature-scaled samples B'[s][k] = B[s][k] 2^fexp[k].
+// A grid-wide max of the bit patterns (|x| orders like its bits; a non-finite entry sets the flag word) into one of two
+// scratch slots; k_quantise turns it into (e, scale) and clears the other slot, which the next sample set will use.  The
+// max is normally gathered by k_prepare_rows as it writes B (bc_small.cu); this kernel serves the callers that only have B.
 __global__ void __launch_bounds__(256) k_sample_absmax(const double* __restrict__ B, int ldb, int S, int D, const int* __restrict__ fexp,
                                                        unsigned long long* __restrict__ scratch /* [0] max bits, [1] bad */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -286,22 +301,15 @@ __global__ void __launch_bounds__(256) k_sample_absmax(const double* __restrict_
     if (bad) atomicOr(scratch + 1, 1ull);
   }
 }
-__global__ void k_common_exponent(unsigned long long* __restrict__ scratch, int* __restrict__ e_out, double* __restrict__ scale_out) {
-  const double amax = __longlong_as_double((long long)scratch[0]);
-  const bool bad = scratch[1] != 0;
-  const int e = (amax > 0.0 && !bad) ? ilogb(amax) + 3 : 0;
-  *e_out = e;
-  *scale_out = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 32);
-  scratch[0] = 0;
-  scratch[1] = 0;
-}
 
 cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsigned char* image, double* colscale, int* common_e,
-                                    const int* fexp, unsigned long long* scratch2 /* two words, zero between calls */, cudaStream_t st) {
-  k_sample_absmax<<<(S + 7) / 8 < 148 ? (S + 7) / 8 : 148, 256, 0, st>>>(B, ldb, S, D, fexp, scratch2);
-  k_common_exponent<<<1, 1, 0, st>>>(scratch2, common_e, colscale);
+                                    const int* fexp, unsigned long long* scratch4 /* two slots of two words */, int slot, bool have_max,
+                                    cudaStream_t st) {
+  unsigned long long* cur = scratch4 + 2 * (slot & 1);
+  unsigned long long* nxt = scratch4 + 2 * ((slot & 1) ^ 1);
+  if (!have_max) k_sample_absmax<<<(S + 7) / 8 < 148 ? (S + 7) / 8 : 148, 256, 0, st>>>(B, ldb, S, D, fexp, cur);
   const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
-  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, common_e, fexp, +1);
+  k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, cur, nxt, common_e, colscale, fexp, +1);
   return cudaGetLastError();
 }
 

@@ -477,10 +477,8 @@ __global__ void __launch_bounds__(kLapThreads) k_conjugate_factor(int model, con
       xs[k] = acc;
     }
     __syncthreads();
-    for (int q = tid; q < D * D; q += nt) {
-      const int a = q / D, b = q - a * D;
-      if (b <= a) H[a * ld + b] = fma(sw, A1[q], A0[q]);
-    }
+    for (int a = wid; a < D; a += nw)
+      for (int b = lane; b <= a; b += 32) H[a * ld + b] = fma(sw, A1[a * D + b], A0[a * D + b]);
     for (int a = wid; a < D; a += nw) {
       double acc = 0.0;
       for (int k = lane; k < D; k += 32) acc = fma(A1[a * D + k], xs[k], acc);
@@ -502,27 +500,49 @@ __global__ void __launch_bounds__(kLapThreads) k_conjugate_factor(int model, con
       v[k] = fma(acc, is2, v0[k]);
     }
   }
+  // Structure check: a precision whose off-diagonal entries are all exactly zero (isotropic or diagonal prior and noise
+  // covariances: the reference's Gaussian example, Sig0 = I, Sig = 500 I) factorises entry by entry.  The general algorithm
+  // below computes exactly that -- every off-diagonal operation adds a signed zero -- so the shortcut changes no bit, only
+  // the time (D sequential pivots of a sqrt and a reciprocal each are most of this kernel).
   __syncthreads();
-  if (!chol_lower(H, D, ld, rd, &flag)) {
-    if (tid == 0) info[0] = 2;
-    return;
+  int offdiag = 0;
+  for (int a = wid; a < D; a += nw)
+    for (int b = lane; b < a; b += 32) offdiag |= (H[a * ld + b] != 0.0) ? 1 : 0;
+  const int dense = __syncthreads_or(offdiag);
+  if (!dense) {
+    int bad = 0;
+    for (int k = tid; k < D; k += nt) {
+      const double d = H[k * ld + k];
+      if (!(d > 0.0)) bad = 1;
+      const double sq = sqrt(d), inv = 1.0 / sq;
+      H[k * ld + k] = sq;
+      rd[k] = inv;
+      v[k] = (v[k] * inv) * inv;           // C^T y = v, then C mu = y
+    }
+    if (__syncthreads_or(bad)) {
+      if (tid == 0) info[0] = 2;
+      return;
+    }
+  } else {
+    if (!chol_lower(H, D, ld, rd, &flag)) {
+      if (tid == 0) info[0] = 2;
+      return;
+    }
+    if (tid < 32) {
+      double r[kMaxQ];
+      tri_load(v, D, r);
+      tri_backward(H, rd, D, ld, r);         // C^T y = v
+      tri_forward(H, rd, D, ld, r);          // C mu = y
+      tri_store(v, D, r);
+    }
+    __syncthreads();
   }
-  if (tid < 32) {
-    double r[kMaxQ];
-    tri_load(v, D, r);
-    tri_backward(H, rd, D, ld, r);         // C^T y = v
-    tri_forward(H, rd, D, ld, r);          // C mu = y
-    tri_store(v, D, r);
-  }
-  __syncthreads();
   for (int k = tid; k < D; k += nt) mu_out[k] = v[k];
-  for (int q = tid; q < D * D; q += nt) {
-    const int i = q / D, j = q - i * D;
-    C_out[q] = (j <= i) ? H[i * ld + j] : 0.0;
-  }
+  for (int i = wid; i < D; i += nw)
+    for (int j = lane; j < D; j += 32) C_out[i * D + j] = (j <= i) ? H[i * ld + j] : 0.0;
   if (tid == 0) {
     info[0] = 0;
-    info[1] = 0;
+    info[1] = dense ? 0 : 1;               // 1: the factor is diagonal (bc_sample_solve_hinted skips the substitution)
   }
 }
 
@@ -562,15 +582,18 @@ __global__ void __launch_bounds__(128) k_sample_affine(const double* __restrict_
 constexpr int kSolveWarps = 16;
 __global__ void __launch_bounds__(kSolveWarps * 32) k_sample_solve(const double* __restrict__ mu, const double* __restrict__ C,
                                                                    const double* __restrict__ R, int S, int D, double* __restrict__ out,
-                                                                   int ldo) {
+                                                                   int ldo, const int* __restrict__ diag_hint) {
   extern __shared__ double sm[];
   const int ld = D | 1;
   double* L = sm;              // [D][ld]
   double* rd = L + D * ld;     // [D]
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int q = tid; q < D * D; q += blockDim.x) {
-    const int i = q / D, j = q - i * D;
-    if (j <= i) L[i * ld + j] = __ldg(C + q);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  // diag_hint (bc_conjugate_factor's info[1]): the factor is diagonal -- the substitution reduces to its first operation per
+  // entry, x_j = r_j / C_jj (every other one adds a signed zero), and the triangle need not be staged at all
+  const bool diag = diag_hint && *diag_hint == 1;
+  if (!diag) {
+    for (int i = wid; i < D; i += nw)
+      for (int j = lane; j <= i; j += 32) L[i * ld + j] = __ldg(C + (size_t)i * D + j);
   }
   for (int i = tid; i < D; i += blockDim.x) rd[i] = 1.0 / __ldg(C + (size_t)i * D + i);
   __syncthreads();
@@ -578,13 +601,20 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_sample_solve(const double*
   if (s >= S) return;
   double r[kMaxQ];
   tri_load(R + (size_t)s * D, D, r);
-  tri_forward(L, rd, D, ld, r);
+  if (diag) {
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q)
+      if (q * 32 + lane < D) r[q] *= rd[q * 32 + lane];
+  } else {
+    tri_forward(L, rd, D, ld, r);
+  }
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q)
     if (q * 32 + lane < D) out[(size_t)s * ldo + q * 32 + lane] = __ldg(mu + q * 32 + lane) + r[q];
 }
 
-cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, cudaStream_t st) {
+cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, const int* diag_hint,
+                                cudaStream_t st) {
   if (S <= 0) return cudaSuccess;
   const size_t smem = ((size_t)D * (D | 1) + D) * sizeof(double);
   const size_t cap = kMaxSmem - 1024;
@@ -592,7 +622,7 @@ cudaError_t launch_sample_solve(const double* mu, const double* C, const double*
   cudaError_t e = raise_dynamic_smem(k_sample_solve, cap, once);
   if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
-  k_sample_solve<<<(S + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, smem, st>>>(mu, C, R, S, D, out, ldo);
+  k_sample_solve<<<(S + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, smem, st>>>(mu, C, R, S, D, out, ldo, diag_hint);
   return cudaGetLastError();
 }
 

@@ -33,14 +33,25 @@ __device__ __forceinline__ double block_sum(double x, double* red /* >= 33 doubl
 // cost 32 sectors per load: 41 us per call at D = 100, now 3).
 __global__ void __launch_bounds__(128) k_prepare_rows(int model, const double* __restrict__ theta, int S, int D, int ldt,
                                                       const double* __restrict__ siginv, const double* __restrict__ siginvT,
-                                                      double* __restrict__ B, int ldb, double* __restrict__ colaux) {
+                                                      double* __restrict__ B, int ldb, double* __restrict__ colaux,
+                                                      const int* __restrict__ fexp, unsigned long long* __restrict__ absmax_slot,
+                                                      const int* __restrict__ siginv_diag) {
   __shared__ double red[33];
+  __shared__ unsigned long long wm[4], wb[4];
+  unsigned long long mx = 0, bad = 0;   // absmax_slot: max |B' entry| bit pattern / non-finite flag of the feature-scaled samples
   extern __shared__ double ths[];   // [D] this sample
   const int s = blockIdx.x;
   const double* th = theta + (size_t)s * ldt;
+  bool diag = false;
   if (model == MODEL_GAUSSIAN) {
-    for (int k = threadIdx.x; k < D; k += blockDim.x) ths[k] = th[k];
-    __syncthreads();
+    int finite = 1;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+      ths[k] = th[k];
+      finite &= isfinite(th[k]) ? 1 : 0;
+    }
+    // a DIAGONAL Siginv (k_offdiag_test; the reference's Gaussian example uses Sig = 500 I) and a finite sample: each dot
+    // product below has one non-zero term -- the others add a signed zero -- so it is taken alone, bit for bit the same
+    diag = __syncthreads_and(finite) && siginv_diag && *siginv_diag == 1;
   }
   double part = 0.0;
   for (int k = threadIdx.x; k < ldb; k += blockDim.x) {
@@ -50,6 +61,12 @@ __global__ void __launch_bounds__(128) k_prepare_rows(int model, const double* _
         // B[s][k] = (Siginv theta_s)[k]      gaussian.py:12  x.dot(Siginv.dot(th.T))
         double acc = 0.0, acc2 = 0.0;
         int j = 0;
+        if (diag) {
+          const double skk = __ldg(siginv + (size_t)k * D + k);
+          acc = fma(skk, ths[k], acc);
+          acc2 = fma(ths[k], skk, acc2);
+          j = D;
+        }
         for (; j + 4 <= D; j += 4) {
           double u[4], v[4];
 #pragma unroll
@@ -74,11 +91,53 @@ __global__ void __launch_bounds__(128) k_prepare_rows(int model, const double* _
       }
     }
     B[(size_t)s * ldb + k] = b;
+    if (absmax_slot && k < D) {          // what k_sample_absmax (bc_project_q.cu) gathers, while the entry is in a register
+      const double v = fabs(fexp ? scalbn(b, __ldg(fexp + k)) : b);
+      if (!isfinite(v)) bad = 1;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+      if (isfinite(v) && bits > mx) mx = bits;
+    }
+  }
+  if (absmax_slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, o);
+      mx = om > mx ? om : mx;
+      bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      wm[threadIdx.x >> 5] = mx;
+      wb[threadIdx.x >> 5] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        mx = wm[w] > mx ? wm[w] : mx;
+        bad |= wb[w];
+      }
+      if (mx) atomicMax(absmax_slot, mx);
+      if (bad) atomicOr(absmax_slot + 1, 1ull);
+    }
   }
   if (model == MODEL_GAUSSIAN) {
     const double tot = block_sum(part, red);
     if (threadIdx.x == 0) colaux[s] = tot;
   }
+}
+
+// flag[0] = 1 if every off-diagonal entry of the D x D matrix A is (signed) zero, else 0.  One CTA.
+__global__ void __launch_bounds__(256) k_offdiag_test(const double* __restrict__ A, int D, int* __restrict__ flag) {
+  int nz = 0;
+  for (int q = threadIdx.x; q < D * D; q += blockDim.x) {
+    const int i = q / D, j = q - i * D;
+    if (i != j && A[q] != 0.0) nz = 1;
+  }
+  nz = __syncthreads_or(nz);
+  if (threadIdx.x == 0) flag[0] = nz ? 0 : 1;
+}
+cudaError_t launch_offdiag_test(const double* A, int D, int* flag, cudaStream_t st) {
+  k_offdiag_test<<<1, 256, 0, st>>>(A, D, flag);
+  return cudaGetLastError();
 }
 
 // bbar[k] = mean_s B[s][k] for k < ldb; bbar[ldb] = mean_s colaux[s] (0 if no colaux).
@@ -111,8 +170,10 @@ __global__ void __launch_bounds__(kMeanThreads) k_prepare_mean(const double* __r
 }
 
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
-                                   double* B, int ldb, double* colaux, double* bbar, cudaStream_t st) {
-  k_prepare_rows<<<S, 128, (size_t)D * sizeof(double), st>>>(model, theta, S, D, ldt, siginv, siginvT, B, ldb, colaux);
+                                   double* B, int ldb, double* colaux, double* bbar, const int* fexp, unsigned long long* absmax_slot,
+                                   const int* siginv_diag, cudaStream_t st) {
+  k_prepare_rows<<<S, 128, (size_t)D * sizeof(double), st>>>(model, theta, S, D, ldt, siginv, siginvT, B, ldb, colaux, fexp, absmax_slot,
+                                                             siginv_diag);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_prepare_mean<<<(ldb + 1 + kMeanCols - 1) / kMeanCols, kMeanThreads, 0, st>>>(B, S, ldb, model == MODEL_GAUSSIAN ? colaux : nullptr, bbar);
@@ -243,24 +304,71 @@ cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, cons
   return cudaGetLastError();
 }
 
+// resid + grad + ADAM of one optimiser step in ONE launch (bc_greedy_opt_step): the three kernels above back to back in a
+// single CTA of the same shape -- the same loops, the same reduction orders, so the same bits -- separated by CTA barriers
+// instead of launch boundaries (each of them runs for 4 us; the gaps between them cost as much again).
+__device__ __forceinline__ double adam_update(double gi, double x, double* m1, double* m2, int i, double lr, double b1, double b2, double c1,
+                                              double c2, double eps, const unsigned char* nn_mask);
+__global__ void __launch_bounds__(1024) k_core_step(const double* __restrict__ colsum, double scaling, const double* __restrict__ Vc, int M,
+                                                    int S, long long ldv, double* x, double* resid, double* grad, double* m1, double* m2,
+                                                    double lr, double b1, double b2, double c1, double c2, double eps,
+                                                    const unsigned char* __restrict__ nn_mask) {
+  __shared__ double red[33];
+  {   // k_core_resid
+    double tot = 0.0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      double acc = 0.0;
+      for (int m = 0; m < M; ++m) acc = fma(x[m], Vc[(size_t)m * ldv + s], acc);
+      const double r = scaling * colsum[s] - acc;
+      resid[s] = r;
+      tot += r;
+    }
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) resid[S] = tot;
+  }
+  __syncthreads();
+  {   // k_core_rows<true>
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int m = warp; m < M; m += nw) {
+      const double* v = Vc + (size_t)m * ldv;
+      double dot = 0.0;
+      for (int s = lane; s < S; s += 32) dot = fma(v[s], resid[s], dot);
+      dot = warp_sum(dot);
+      if (lane == 0) grad[m] = -dot / (double)S;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) x[i] = adam_update(grad[i], x[i], m1, m2, i, lr, b1, b2, c1, c2, eps, nn_mask);   // k_adam
+}
+
+cudaError_t launch_core_step(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, double* x, double* resid,
+                             double* grad, double* m1, double* m2, double lr, double b1, double b2, double c1, double c2, double eps,
+                             const unsigned char* nn_mask, cudaStream_t st) {
+  k_core_step<<<1, 1024, 0, st>>>(colsum, scaling, Vc, M, S, ldv, x, resid, grad, m1, m2, lr, b1, b2, c1, c2, eps, nn_mask);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------- projected ADAM --
 // util/opt.py:45-52, operation for operation (no FMA contraction: matches numpy's rounding):
 //   m1 = b1*m1 + (1-b1)*g;  m2 = b2*m2 + (1-b2)*g**2
 //   upd = lr*m1/c1/(eps + sqrt(m2/c2));  x -= upd;  x = max(x, 0)   [only where nn_mask, all if null]
 // c1 = 1-b1**(i+1), c2 = 1-b2**(i+1) are computed by the host (python float pow, like the reference).
-__global__ void k_adam(const double* __restrict__ g, double* __restrict__ x, double* __restrict__ m1, double* __restrict__ m2, int n,
-                       double lr, double b1, double b2, double c1, double c2, double eps, const unsigned char* __restrict__ nn_mask) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double gi = g[i];
+__device__ __forceinline__ double adam_update(double gi, double x, double* m1, double* m2, int i, double lr, double b1, double b2, double c1,
+                                              double c2, double eps, const unsigned char* nn_mask) {
   const double a1 = __dadd_rn(__dmul_rn(b1, m1[i]), __dmul_rn(__dsub_rn(1.0, b1), gi));
   const double a2 = __dadd_rn(__dmul_rn(b2, m2[i]), __dmul_rn(__dsub_rn(1.0, b2), __dmul_rn(gi, gi)));
   m1[i] = a1;
   m2[i] = a2;
   const double upd = __ddiv_rn(__ddiv_rn(__dmul_rn(lr, a1), c1), __dadd_rn(eps, __dsqrt_rn(__ddiv_rn(a2, c2))));
-  double xi = __dsub_rn(x[i], upd);
+  double xi = __dsub_rn(x, upd);
   if (!nn_mask || nn_mask[i]) xi = (xi > 0.0 || isnan(xi)) ? xi : 0.0;
-  x[i] = xi;
+  return xi;
+}
+__global__ void k_adam(const double* __restrict__ g, double* __restrict__ x, double* __restrict__ m1, double* __restrict__ m2, int n,
+                       double lr, double b1, double b2, double c1, double c2, double eps, const unsigned char* __restrict__ nn_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = adam_update(g[i], x[i], m1, m2, i, lr, b1, b2, c1, c2, eps, nn_mask);
 }
 
 cudaError_t launch_adam(const double* g, double* x, double* m1, double* m2, int n, double lr, double b1, double b2, double c1,

@@ -157,9 +157,10 @@ int bc_adam_step(bc_ctx* ctx, const double* d_g, double* d_x, double* d_m1, doub
  * does after the sampler has produced Theta (bcores.py:142-146, util/opt.py:45-52):
  *     bc_set_samples -> [bc_q_gather_rows] -> bc_project_colsum(_q) -> bc_colsum_combine -> bc_project_materialise (the M coreset
  *     rows) -> bc_core_resid -> bc_core_grad -> bc_adam_step
- * -- the same kernels in the same order as the individual entry points, so the results are bit-identical; what it saves is the
- * host's per-call overhead (a dozen FFI crossings per step matter when a step is a few hundred microseconds: the sub-sampled
- * Gaussian example runs 1000 of them per coreset point).  A sharded job exchanges the column-sum parts between the pass and the
+ * -- the same arithmetic in the same order as the individual entry points, so the results are bit-identical; what it saves is
+ * the host's per-call overhead (a dozen FFI crossings per step matter when a step is a few hundred microseconds: the sub-sampled
+ * Gaussian example runs 1000 of them per coreset point) and launches: a single-part job's pass leaves the combined column sum
+ * itself, and residual + gradient + ADAM run as one kernel (k_core_step).  A sharded job exchanges the column-sum parts between the pass and the
  * combine: it calls the two halves (`phase`).  All pointers are device pointers. */
 typedef struct bc_step_args {
   const double* d_theta; int S; int ldt;                         /* posterior samples of this step (S x ldt) */
@@ -201,7 +202,8 @@ int bc_laplace_logistic(bc_ctx* ctx, const double* d_Z, int64_t ldz, const doubl
  * bc_conjugate_factor: the conjugate weighted posteriors of examples/common/gaussian.py:28-32 (model = BC_MODEL_GAUSSIAN:
  *   H = A0 + (sum w) A1, v = v0 + A1 sum_i w_i x_i) and model_neurlinr.py:115-122 (BC_MODEL_NEURLIN: H = A0 + X^T diag(w) X / sigsq,
  *   v = v0 + X^T (w y) / sigsq, rows [x, y]); A0 = Sig0inv, A1 = Siginv, v0 = Sig0inv mu0 (D x D row-major / D).  d_C = chol(H),
- *   d_mu = C^-1 C^-T v -- the reference's `LSigp.dot(LSigp.T)` applied to v.  D <= 160. */
+ *   d_mu = C^-1 C^-T v -- the reference's `LSigp.dot(LSigp.T)` applied to v.  D <= 160.  d_info[0] = 0 ok / 2 not positive
+ *   definite; d_info[1] = 1 if H (hence C) is diagonal. */
 int bc_laplace_logistic_factor(bc_ctx* ctx, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, double* d_mu, double* d_C,
                                int maxit, double tol, int* d_info, void* stream);
 int bc_conjugate_factor(bc_ctx* ctx, int model, const double* d_Z, int64_t ldz, const double* d_w, int M, int D, const double* d_A0,
@@ -213,6 +215,12 @@ int bc_sample_affine(bc_ctx* ctx, const double* d_mu, const double* d_L, const d
  *   host side then only factors.  D <= 160. */
 int bc_sample_solve(bc_ctx* ctx, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
                     void* stream);
+/* ... with the d_info words of the bc_conjugate_factor call that produced d_C (device pointer, or NULL): d_info[1] == 1 marks a
+ *   DIAGONAL factor (diagonal prior and noise precisions: examples/zellner_gaussian/main.py:37-38, Sig0 = I, Sig = 500 I), for
+ *   which bc_conjugate_factor skips the D sequential pivots and this call the substitution -- the general code computes the
+ *   same bits there, every off-diagonal operation adding a signed zero. */
+int bc_sample_solve_hinted(bc_ctx* ctx, const double* d_mu, const double* d_C, const double* d_R, int S, int D, double* d_theta, int ldt,
+                           const int* d_factor_info, void* stream);
 
 /* ---- stage 2 on a materialised n x S matrix (snnls solvers, black-box projections) --------- */
 int bc_dense_rownorms(bc_ctx* ctx, const double* d_V, int64_t n, int S, int64_t ldv, double* d_norms, void* stream);
@@ -243,7 +251,7 @@ int bc_vec_step(bc_ctx* ctx, int op, const double* d_xw, const double* d_xf, con
 int bc_host_project(int device, int model, int kind, int D, const double* h_params, const double* h_siginv, const double* h_X,
                     int64_t n, int64_t ldx_h, const double* h_theta, int S, double* h_V, int centred);
 
-/* ---- host side: numpy's legacy global random stream, natively (csrc/bc_hostrng.cu) ----------------------------------
+/* ---- host side: numpy's legacy global random stream, natively (csrc/bc_hostrng.cpp) ----------------------------------
  * The reference's samplers end in `np.random.randn(S, D)` (examples/zellner_gaussian/main.py:87-92, zellner_logreg/main.py:
  * 139-144) and its sub-sampled modes draw `np.random.randint(N, size=n)` (bayesiancoresets/coreset/bcores.py:53), all from
  * numpy's one global RandomState.  These two functions continue that stream bit for bit (MT19937 words, polar Box-Muller

@@ -193,6 +193,56 @@ def test_conjugate_factor_kernel_matches_host(model):
     np.testing.assert_allclose(d_mu.cpu().numpy(), mu, rtol=0, atol=1e-11*max(1., np.abs(mu).max()))
 
 
+@pytest.mark.parametrize('D', [5, 37, 100])
+def test_diagonal_precision_shortcuts_change_no_bit(D):
+    """Diagonal prior and noise precisions (the reference's Gaussian example: Sig0 = I, Sig = 500 I) take shortcuts in three
+    kernels -- bc_conjugate_factor skips the pivoting, bc_sample_solve_hinted the substitution, the sample preparation takes
+    one term per dot product.  Each is checked against the general code path, forced by one denormal off-diagonal entry that
+    cannot change any result: bit-identical output."""
+    import torch
+    import gaussian
+    from bayesiancoresets import _native as nv
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    eng = Engine.get()
+    ctx = eng.ctx('sampler')
+    r = np.random.RandomState(D)
+    M, S = 9, 77
+    Sig0inv = np.diag(0.5 + r.rand(D))
+    Siginv = np.diag(1./(100. + 400.*r.rand(D)))
+    mu0, w, pts = r.randn(D), 3.*r.rand(M), 5.*r.randn(M, D)
+    core, d_w, v0 = DeviceRows(eng, pts), eng.upload(w), eng.upload(Sig0inv.dot(mu0))
+    R = eng.upload(r.randn(S, D))
+    res = []
+    for dense in (False, True):
+        A0h, A1h = Sig0inv.copy(), Siginv.copy()
+        if dense and D > 1:
+            A0h[1, 0] = A0h[0, 1] = 5e-324
+            A1h[D-1, 0] = A1h[0, D-1] = 5e-324
+        A0, A1 = eng.upload(A0h), eng.upload(A1h)
+        d_mu, d_C, th, th2 = eng.empty(D), eng.empty(D, D), eng.empty(S, D), eng.empty(S, D)
+        info = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        nv.call('bc_conjugate_factor', ctx, nv.MODEL_GAUSSIAN, ptr(core.t), core.ld, ptr(d_w), M, D, ptr(A0), ptr(A1), ptr(v0), 1.0,
+                ptr(d_mu), ptr(d_C), ptr(info), stream_ptr())
+        nv.call('bc_sample_solve_hinted', ctx, ptr(d_mu), ptr(d_C), ptr(R), S, D, ptr(th), D, ptr(info), stream_ptr())
+        nv.call('bc_sample_solve', ctx, ptr(d_mu), ptr(d_C), ptr(R), S, D, ptr(th2), D, stream_ptr())
+        inf = info.cpu().numpy()
+        assert inf[0] == 0 and inf[1] == (0 if dense else 1)
+        np.testing.assert_array_equal(th.cpu().numpy(), th2.cpu().numpy())      # hinted == plain on the same factor
+        # the prepared samples / potential under this Siginv
+        pot = gaussian.gaussian_beta_likelihood.bind(Siginv=A1h, logdetSig=float(-np.log(np.diag(Siginv)).sum()))
+        V = pot(pts, th.cpu().numpy(), 0.3)
+        res.append((d_mu.cpu().numpy(), d_C.cpu().numpy(), th.cpu().numpy(), V))
+    (mu_a, C_a, th_a, V_a), (mu_b, C_b, th_b, V_b) = res
+    C_b[1, 0], C_b[D-1, 0] = C_a[1, 0], C_a[D-1, 0]        # the planted denormals' own images
+    np.testing.assert_array_equal(C_a, C_b)
+    np.testing.assert_array_equal(mu_a, mu_b)
+    np.testing.assert_array_equal(th_a, th_b)
+    np.testing.assert_array_equal(V_a, V_b)
+    mu_h, _, C_h = gaussian.weighted_post(mu0, Sig0inv, Siginv, pts, w)
+    np.testing.assert_allclose(C_a, C_h, rtol=0, atol=1e-14*np.abs(C_h).max())
+    np.testing.assert_allclose(mu_a, mu_h, rtol=0, atol=1e-12*max(1., np.abs(mu_h).max()))
+
+
 def test_device_sampler_loop_matches_host_protocol_loop(monkeypatch):
     """the optimiser loop with the sampler's device_step (no host round trip per step) builds the coreset the loop builds
     when the same sampler is called through the reference's host protocol sampler(S, wts, pts)"""

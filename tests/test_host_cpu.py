@@ -285,7 +285,7 @@ def test_fused_projection_reapplies_its_potential_after_another_owner(monkeypatc
 
 
 def test_native_legacy_stream_is_bit_identical_to_numpy():
-    """csrc/bc_hostrng.cu (bc_mt_randn / bc_mt_randint): numpy's legacy RandomState continued natively from its own state --
+    """csrc/bc_hostrng.cpp (bc_mt_randn / bc_mt_randint): numpy's legacy RandomState continued natively from its own state --
     same normals bit for bit (odd counts, the cached second value, several worker threads), same bounded integers, and
     the state handed back is the state numpy itself ends in (numpy/random/src/legacy/legacy-distributions.c::legacy_gauss,
     mt19937.c, _bounded_integers.pyx masked rejection)."""

@@ -20,11 +20,11 @@ for spec in sys.argv[1:]:
     units = ['bc_project_q.cu'] if only_q else B.UNITS
     objs = []
     for u in B.UNITS:
-        if u in units:
+        if u in units and u.endswith('.cu'):
             obj = os.path.join(out, '%s_%s.o' % (u[:-3], name))
             jobs.append((name, subprocess.Popen([B.NVCC] + B.FLAGS + flags.split() + ['-c', os.path.join(B.CSRC, u), '-o', obj])))
         else:
-            obj = os.path.join(B.LIB, u.replace('.cu', '.o'))
+            obj = os.path.join(B.LIB, os.path.splitext(u)[0] + '.o')
         objs.append(obj)
     jobs.append((name, objs))
 links = {}
