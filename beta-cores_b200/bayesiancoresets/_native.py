@@ -41,6 +41,7 @@ SIGNATURES = {
     'bc_laplace_logistic_factor': [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp],
     'bc_conjugate_factor': [c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp],
     'bc_sample_solve': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
+    'bc_set_sample_slot': [c_vp, c_int],
     'bc_sample_solve_hinted': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp],
     'bc_sample_affine': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'bc_adam_step': [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp],
@@ -55,7 +56,7 @@ SIGNATURES = {
     'bc_fit_pow_poly': [c_dbl, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }
-PLAIN = {'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+PLAIN = {'bc_sample_slot': ([c_vp], c_int), 'bc_add_launch_count': ([c_i64], c_i64), 'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
 
@@ -72,7 +73,8 @@ class StepArgs(ctypes.Structure):
                 ('d_parts', c_vp), ('d_colsum', c_vp), ('d_resid', c_vp), ('d_grad', c_vp),
                 ('d_w', c_vp), ('d_m1', c_vp), ('d_m2', c_vp),
                 ('lr', c_dbl), ('b1', c_dbl), ('b2', c_dbl), ('c1', c_dbl), ('c2', c_dbl), ('eps', c_dbl), ('d_nn_mask', c_vp),
-                ('ev_pass_begin', c_vp), ('ev_pass_end', c_vp), ('phase', c_int), ('nparts', c_int), ('d_parts_all', c_vp)]
+                ('ev_pass_begin', c_vp), ('ev_pass_end', c_vp), ('phase', c_int), ('nparts', c_int), ('d_parts_all', c_vp),
+                ('d_sched', c_vp), ('d_step_counter', c_vp)]
 
 
 SIGNATURES['bc_greedy_opt_step'] = [c_vp, ctypes.POINTER(StepArgs), c_vp]

@@ -36,6 +36,12 @@ FUSED_STEP_CALL = os.environ.get('BC_FUSED_STEP', '1') != '0'
 # samplers that offer device_step() run the optimiser loop without any host synchronisation; BC_DEVICE_SAMPLER_LOOP=0 keeps
 # calling them through the reference's host protocol sampler(S, wts, pts)
 DEVICE_SAMPLER_LOOP = os.environ.get('BC_DEVICE_SAMPLER_LOOP', '1') != '0'
+# single-rank host-free loops replay the device work of a step as a CUDA graph (two graphs, one per staging-buffer parity)
+# once the loop is long enough to pay for the two captures (about 3 ms against 30-40 us saved per step: measured on the
+# Gaussian example, 1000 steps per point, 0.157 -> 0.125 ms per step; the 20-step loops of the logistic / neural-linear
+# examples lose); BC_STEP_GRAPH=0 keeps launching kernel by kernel
+STEP_GRAPH = os.environ.get('BC_STEP_GRAPH', '1') != '0'
+STEP_GRAPH_MIN_ITRS = int(os.environ.get('BC_STEP_GRAPH_MIN_ITRS', '200'))
 
 
 class _Tangent(object):
@@ -475,6 +481,39 @@ class GreedyVICoreset(Coreset):
         idx_ev = [None, None]
         world = comm.world
         th = None
+
+        def setup(th):
+            """(first step, or the sample count changed) workspaces and every pointer of the step that does not change"""
+            S = fp.S
+            q = fp._q_operands(rows, None)                 # row image of the whole block (built once), exponents / digits applied
+            if q is None and rows.n_local > 0 and _fused.ROUTE == 'q' and fp.D <= nv.lib().bc_q_max_features():
+                raise nv.NativeError('row image unavailable')
+            b = dict(S=S, Vc=eng.empty(M, S), parts=eng.empty(2*fp.Sld), colsum=eng.empty(S), resid=eng.empty(S+1), q=q)
+            a.S, a.ldt = S, int(th.stride(0))
+            if q is not None:
+                a.d_image, a.d_rowscale, a.d_rowaux_q = q[0].data_ptr(), q[1].data_ptr(), (q[2].data_ptr() if q[2] is not None else None)
+                if idx_dev is not None:
+                    gs = fp.gather_scratch(n_pass)
+                    a.d_gimage, a.d_growscale, a.d_growaux = gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr()
+            else:
+                a.d_image = None
+                ra = fp._rowaux(rows) if rows.n_local else None
+                a.d_X, a.ldx, a.d_rowaux = (rows.t.data_ptr() if rows.n_local else None), rows.ld, (ra.data_ptr() if ra is not None else None)
+            cra = fp._rowaux(core)
+            a.d_pts, a.ldp, a.M, a.d_pts_rowaux = core.t.data_ptr(), core.ld, M, (cra.data_ptr() if cra is not None else None)
+            a.d_Vc, a.ldv = b['Vc'].data_ptr(), S
+            a.d_parts, a.d_colsum, a.d_resid, a.d_grad = b['parts'].data_ptr(), b['colsum'].data_ptr(), b['resid'].data_ptr(), g.data_ptr()
+            a.d_w, a.d_m1, a.d_m2, a.b1, a.b2, a.eps, a.d_nn_mask = x.data_ptr(), m1.data_ptr(), m2.data_ptr(), b1, b2, eps, None
+            a.scaling, a.n = float(scaling), n_pass
+            a.d_rows = idx_dev.data_ptr() if idx_dev is not None else None
+            return b
+
+        # ---- replayed loop: the whole device side of a step as a CUDA graph (single rank, sampler with the graph protocol) ----
+        use_graph = (STEP_GRAPH and on_device and world == 1 and _fused.PASS_TIMERS is None and hasattr(smp, 'graph_enqueue')
+                     and self.opt_itrs >= STEP_GRAPH_MIN_ITRS and (not sub_mode or (rows.row0 == 0 and rows.n_local == self._n_total)))
+        if use_graph:
+            return self._optimize_graph_steps(t, core, beta, smp, prj, a, setup, x, idx_dev, idx_pin, sub_mode)
+
         for i in range(self.opt_itrs):
             if on_device:
                 th = smp.device_step(prj.projection_dimension, x, core)
@@ -492,29 +531,8 @@ class GreedyVICoreset(Coreset):
                 t._replicate_samples()                         # checked, not assumed: see _FusedTangent._replicate_samples
             fp.configure(beta)
             fp.note_samples(th)
-            S = fp.S
-            if bufs is None or bufs['S'] != S:
-                q = fp._q_operands(rows, None)                 # row image of the whole block (built once), exponents / digits applied
-                if q is None and rows.n_local > 0 and _fused.ROUTE == 'q' and fp.D <= nv.lib().bc_q_max_features():
-                    raise nv.NativeError('row image unavailable')
-                bufs = dict(S=S, Vc=eng.empty(M, S), parts=eng.empty(2*fp.Sld), colsum=eng.empty(S), resid=eng.empty(S+1), q=q)
-                a.S, a.ldt = S, int(th.stride(0))
-                if q is not None:
-                    a.d_image, a.d_rowscale, a.d_rowaux_q = q[0].data_ptr(), q[1].data_ptr(), (q[2].data_ptr() if q[2] is not None else None)
-                    if idx_dev is not None:
-                        gs = fp.gather_scratch(n_pass)
-                        a.d_gimage, a.d_growscale, a.d_growaux = gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr()
-                else:
-                    a.d_image = None
-                    ra = fp._rowaux(rows) if rows.n_local else None
-                    a.d_X, a.ldx, a.d_rowaux = (rows.t.data_ptr() if rows.n_local else None), rows.ld, (ra.data_ptr() if ra is not None else None)
-                cra = fp._rowaux(core)
-                a.d_pts, a.ldp, a.M, a.d_pts_rowaux = core.t.data_ptr(), core.ld, M, (cra.data_ptr() if cra is not None else None)
-                a.d_Vc, a.ldv = bufs['Vc'].data_ptr(), S
-                a.d_parts, a.d_colsum, a.d_resid, a.d_grad = bufs['parts'].data_ptr(), bufs['colsum'].data_ptr(), bufs['resid'].data_ptr(), g.data_ptr()
-                a.d_w, a.d_m1, a.d_m2, a.b1, a.b2, a.eps, a.d_nn_mask = x.data_ptr(), m1.data_ptr(), m2.data_ptr(), b1, b2, eps, None
-                a.scaling, a.n = float(scaling), n_pass
-                a.d_rows = idx_dev.data_ptr() if idx_dev is not None else None
+            if bufs is None or bufs['S'] != fp.S:
+                bufs = setup(th)
             a.d_theta = th.data_ptr()
             if sub_mode:
                 sub = rng.randint(self._n_total, self.n_subsample_opt)                    # bcores.py:53, after the sampler call
@@ -552,6 +570,75 @@ class GreedyVICoreset(Coreset):
         if on_device:
             xh = x.cpu().numpy()
             prj.samples = th
+        return xh
+
+    def _optimize_graph_steps(self, t, core, beta, smp, prj, a, setup, x, idx_dev, idx_pin, sub_mode):
+        """The host-free optimiser loop with the device side of a step -- upload of the step's normals and sub-sample indices,
+        the sampler's kernels, sample preparation, the data pass, the coreset rows, residual / gradient / ADAM -- captured once
+        per staging-buffer parity into a CUDA graph and REPLAYED: one graph launch per step instead of a dozen kernel launches
+        and two copies.  What changes from step to step is kept out of the launch parameters: the normals and indices arrive
+        in fixed pinned buffers, the step size and ADAM's bias corrections (util/opt.py:45-52) are read from a device-resident
+        schedule indexed by a device-side step counter.  The first two steps run eagerly (lazy allocations, one-time
+        set-up), so the captured stream work is pure launches.  Same kernels, same order, same bits as the eager loop
+        (tests/test_gpu_parity.py::test_graph_replayed_optimiser_loop_changes_no_bit)."""
+        eng, fp = t.eng, t.fp
+        S = prj.projection_dimension
+        b1, b2 = 0.9, 0.999
+        n = self.opt_itrs
+        sched = np.array([[float(self.step_sched(i)), 1.-b1**(i+1), 1.-b2**(i+1)] for i in range(n)], dtype=np.float64)
+        sched_dev = eng.upload(sched.ravel())
+        counter = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        a.d_sched, a.d_step_counter = sched_dev.data_ptr(), counter.data_ptr()
+        a.ev_pass_begin = a.ev_pass_end = None
+        a.phase = 0
+        idx_ev = [None, None]
+        graphs, slots, nodes = [None, None], [None, None], [0, 0]
+        state = {'bufs': None, 'th': [None, None]}
+        lib = nv.lib()
+
+        def enqueue(k):
+            """everything a step puts on the stream; only fixed buffers are named"""
+            th = smp.graph_enqueue(S, x, core, k)
+            if sub_mode:
+                idx_dev.copy_(idx_pin[k], non_blocking=True)
+            fp.configure(beta)
+            fp.note_samples(th)
+            if state['bufs'] is None:
+                state['bufs'] = setup(th)
+            a.d_theta = th.data_ptr()
+            nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+            state['th'][k] = th
+
+        k_last = None
+        for i in range(n):
+            k = smp.graph_normals(S)                               # host: the step's normals are in pinned staging buffer k
+            if sub_mode:
+                sub = rng.randint(self._n_total, self.n_subsample_opt)     # bcores.py:53, after the sampler's draw
+                if idx_ev[k] is not None:
+                    idx_ev[k].synchronize()                        # the upload that last read this pinned buffer has run
+                idx_pin[k].numpy()[:] = sub
+            if i < 2:
+                enqueue(k)
+            else:
+                if graphs[k] is None:
+                    l0 = lib.bc_launch_count()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, capture_error_mode='thread_local'):
+                        enqueue(k)
+                    graphs[k], slots[k], nodes[k] = gr, lib.bc_sample_slot(t.ctx), int(lib.bc_launch_count() - l0)
+                    lib.bc_add_launch_count(-nodes[k])             # the capture itself ran nothing
+                graphs[k].replay()
+                lib.bc_add_launch_count(nodes[k])
+                k_last = k
+            smp.graph_launched(k)
+            if sub_mode:
+                idx_ev[k] = torch.cuda.Event()
+                idx_ev[k].record()
+        if k_last is not None:
+            nv.call('bc_set_sample_slot', t.ctx, int(slots[k_last]))   # host view of the scratch-slot parity = the device's
+        xh = x.cpu().numpy()
+        prj.samples = state['th'][k].clone()      # (a copy: the replayed buffers belong to the graphs' memory pool)
+        a.d_sched = a.d_step_counter = None
         return xh
 
     def error(self):

@@ -89,8 +89,26 @@ class ConjugateDeviceSampler(object):
         """the sampler call of one optimiser step with the weights ALREADY on the device (`w_dev`, M doubles) and the coreset
         points as resident rows (`core`, a DeviceRows): posterior factor, mean and samples are formed by kernels
         (bc_conjugate_factor, bc_sample_solve), nothing is read back -- the host only queues work and draws the normals."""
+        k = self.graph_normals(S)
+        theta = self.graph_enqueue(S, w_dev, core, k)
+        self.graph_launched(k)
+        return theta
+
+    # The same call in three parts, so that the device work of a step can be CAPTURED into a CUDA graph and replayed
+    # (coreset/_greedy.py): only graph_enqueue touches the stream, and it names nothing but fixed buffers.
+    def graph_normals(self, S):
+        """host part: this step's S x D normals, drawn in the reference's order, are in pinned staging buffer k on return"""
         if self.ahead is not None:
             self.ahead.begin_cycle()
+        self._state(Engine.get())
+        if self.ahead is not None:
+            k, _ = self.ahead.randn(S, self.D, self._stage)
+        else:
+            k, _ = self._stage(np.random.randn(S, self.D))
+        return k
+
+    def graph_enqueue(self, S, w_dev, core, k):
+        """stream part: factor kernel, upload of staging buffer k, solve kernel.  Returns the (S, D) samples."""
         eng = Engine.get()
         st = self._state(eng)
         D = self.D
@@ -103,11 +121,16 @@ class ConjugateDeviceSampler(object):
         ctx = eng.ctx('sampler')
         nv.call('bc_conjugate_factor', ctx, model, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(A0), ptr(A1), ptr(v0), sigsq,
                 ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(st['info']), stream_ptr())
-        Rd = self._normals_to_device(eng, S)
+        Rd = st['pin'][k].to(eng.device, non_blocking=True)
         theta = eng.empty(S, D)
         nv.call('bc_sample_solve_hinted', ctx, ptr(st['ml'][:D]), ptr(st['ml'][D:]), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)),
                 ptr(st['info']), stream_ptr())
         return theta
+
+    def graph_launched(self, k):
+        """after the stream part (or a replay of it) has been queued: staging buffer k is free again once it has run"""
+        self.st['ev'][k] = torch.cuda.Event()
+        self.st['ev'][k].record()
 
     def supports_device_step(self):
         return self.device_model is not None and self.D <= 160

@@ -623,9 +623,21 @@ int bc_greedy_opt_step(bc_ctx* c, const bc_step_args* a, void* stream) {
   // residual, gradient and the projected ADAM update in one launch (the kernels of bc_core_resid / bc_core_grad / bc_adam_step
   // back to back in one CTA)
   BC_CUDA(launch_core_step(a->d_colsum, a->scaling, a->d_Vc, a->M, a->S, a->ldv, a->d_w, a->d_resid, a->d_grad, a->d_m1, a->d_m2, a->lr,
-                           a->b1, a->b2, a->c1, a->c2, a->eps, a->d_nn_mask, (cudaStream_t)stream));
+                           a->b1, a->b2, a->c1, a->c2, a->eps, a->d_nn_mask, a->d_sched, a->d_step_counter, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
+}
+
+// ---- support for replaying an optimiser step as a CUDA graph (coreset/_greedy.py) ----
+int bc_sample_slot(const bc_ctx* c) { return c ? c->sslot : BC_ERR_ARG; }
+int bc_set_sample_slot(bc_ctx* c, int slot) {
+  if (!c || (slot != 0 && slot != 1)) return BC_ERR_ARG;
+  c->sslot = slot;
+  return BC_OK;
+}
+int64_t bc_add_launch_count(int64_t n) {
+  g_launches.fetch_add((long long)n, std::memory_order_relaxed);
+  return (int64_t)g_launches.load(std::memory_order_relaxed);
 }
 
 int bc_core_pgrad(bc_ctx* c, const double* d_P, int M, int64_t ldp, const double* d_w, const double* d_resid, double* d_out,

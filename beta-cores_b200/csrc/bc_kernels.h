@@ -122,7 +122,7 @@ cudaError_t launch_core_resid(const double* colsum, double scaling, const double
                               double* resid, cudaStream_t st);
 cudaError_t launch_core_step(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, double* x, double* resid,
                              double* grad, double* m1, double* m2, double lr, double b1, double b2, double c1, double c2, double eps,
-                             const unsigned char* nn_mask, cudaStream_t st);
+                             const unsigned char* nn_mask, const double* sched, int* step_counter, cudaStream_t st);
 cudaError_t launch_core_maxcorr(const double* Vc, int M, int S, long long ldv, const double* resid, int skip, double* out,
                                 cudaStream_t st);
 cudaError_t launch_core_grad(const double* Vc, int M, int S, long long ldv, const double* resid, double* grad, cudaStream_t st);

@@ -312,8 +312,18 @@ __device__ __forceinline__ double adam_update(double gi, double x, double* m1, d
 __global__ void __launch_bounds__(1024) k_core_step(const double* __restrict__ colsum, double scaling, const double* __restrict__ Vc, int M,
                                                     int S, long long ldv, double* x, double* resid, double* grad, double* m1, double* m2,
                                                     double lr, double b1, double b2, double c1, double c2, double eps,
-                                                    const unsigned char* __restrict__ nn_mask) {
+                                                    const unsigned char* __restrict__ nn_mask, const double* __restrict__ sched,
+                                                    int* step_counter) {
   __shared__ double red[33];
+  // sched / step_counter (CUDA-graph replays: the launch parameters are frozen, so what changes from step to step lives in
+  // device memory): step i = *step_counter takes (lr, c1, c2) = sched[3 i ..] and leaves i + 1 behind
+  int step = 0;
+  if (sched) {
+    step = *step_counter;
+    lr = sched[3 * step];
+    c1 = sched[3 * step + 1];
+    c2 = sched[3 * step + 2];
+  }
   {   // k_core_resid
     double tot = 0.0;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
@@ -339,12 +349,14 @@ __global__ void __launch_bounds__(1024) k_core_step(const double* __restrict__ c
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) x[i] = adam_update(grad[i], x[i], m1, m2, i, lr, b1, b2, c1, c2, eps, nn_mask);   // k_adam
+  if (sched && threadIdx.x == 0) *step_counter = step + 1;   // (every thread read it before the first barrier above)
 }
 
 cudaError_t launch_core_step(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, double* x, double* resid,
                              double* grad, double* m1, double* m2, double lr, double b1, double b2, double c1, double c2, double eps,
-                             const unsigned char* nn_mask, cudaStream_t st) {
-  k_core_step<<<1, 1024, 0, st>>>(colsum, scaling, Vc, M, S, ldv, x, resid, grad, m1, m2, lr, b1, b2, c1, c2, eps, nn_mask);
+                             const unsigned char* nn_mask, const double* sched, int* step_counter, cudaStream_t st) {
+  k_core_step<<<1, 1024, 0, st>>>(colsum, scaling, Vc, M, S, ldv, x, resid, grad, m1, m2, lr, b1, b2, c1, c2, eps, nn_mask, sched,
+                                  step_counter);
   return cudaGetLastError();
 }
 

@@ -328,9 +328,23 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
         resident rows (`core`, a DeviceRows): mode (warm-started dual Newton steps), Cholesky factor and samples are formed by
         kernels (bc_laplace_logistic_factor, bc_sample_solve); nothing is read back, the host only queues work and draws the
         normals.  Rows with weight 0 do not contribute, exactly like `keep = wts > 0` on the host."""
-        new_call()
+        graph_prepare()
         eng = Engine.get()
         ctx = eng.ctx('sampler')
+        theta = eng.empty(S, D)
+        nv.call('bc_laplace_logistic_factor', ctx, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(st['mu']), ptr(st['L']), 200, 1e-13,
+                ptr(st['info']), stream_ptr())
+        k, pin = normals(S, D, stage)          # after the factor kernel is queued: the GPU works while the host waits for the draw
+        Rd = pin.to(eng.device, non_blocking=True)
+        graph_launched(k)
+        nv.call('bc_sample_solve', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+        return theta
+
+    # The same call in parts, so that the device work of a step can be captured into a CUDA graph and replayed
+    # (bayesiancoresets/coreset/_greedy.py): only graph_enqueue touches the stream, and it names nothing but fixed buffers.
+    def graph_prepare():
+        new_call()
+        eng = Engine.get()
         if st['mu'] is None:
             st['ml'] = eng.empty(D*D + D)
             st['mu'], st['L'] = st['ml'][:D], st['ml'][D:].view(D, D)
@@ -340,16 +354,27 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
         if st.get('mu_host') is not None:              # a host-side call came in between: warm-start from its mode
             st['mu'].copy_(torch.from_numpy(st['mu_host']))
             st['mu_host'] = None
+        st['device_mode'] = True
+
+    def graph_normals(S):
+        """host part: this step's S x D normals, drawn in the reference's order, are in pinned staging buffer k on return"""
+        graph_prepare()
+        k, _ = normals(S, D, stage)
+        return k
+
+    def graph_enqueue(S, w_dev, core, k):
+        eng = Engine.get()
+        ctx = eng.ctx('sampler')
         theta = eng.empty(S, D)
         nv.call('bc_laplace_logistic_factor', ctx, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(st['mu']), ptr(st['L']), 200, 1e-13,
                 ptr(st['info']), stream_ptr())
-        st['device_mode'] = True
-        k, pin = normals(S, D, stage)
-        Rd = pin.to(eng.device, non_blocking=True)
-        st['ev'][k] = torch.cuda.Event()
-        st['ev'][k].record()
+        Rd = st['pin'][k].to(eng.device, non_blocking=True)
         nv.call('bc_sample_solve', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
         return theta
+
+    def graph_launched(k):
+        st['ev'][k] = torch.cuda.Event()
+        st['ev'][k].record()
 
     def status():
         """(status, newton steps) of the last device mode search: 0 = converged"""
@@ -357,5 +382,6 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
     sampler.status = status
     sampler.state = st
     sampler.device_step = device_step
+    sampler.graph_normals, sampler.graph_enqueue, sampler.graph_launched = graph_normals, graph_enqueue, graph_launched
     sampler.supports_device_step = lambda: D <= 160
     return sampler

@@ -182,8 +182,18 @@ typedef struct bc_step_args {
    * phase 0 = the whole step (single rank); 1 = samples .. this rank's part in d_parts; 2 = combine the nparts parts at
    * d_parts_all (rank order) .. ADAM */
   int phase; int nparts; const double* d_parts_all;
+  /* CUDA-graph replays (launch parameters frozen at capture): when d_sched is set, step i = *d_step_counter takes
+   * (lr, c1, c2) = d_sched[3 i ..] instead of the values above, and the step leaves i + 1 in *d_step_counter */
+  const double* d_sched; int* d_step_counter;
 } bc_step_args;
 int bc_greedy_opt_step(bc_ctx* ctx, const bc_step_args* args, void* stream);
+/* Replaying captured steps leaves two pieces of HOST state behind the device's: which of the two sample-maximum scratch slots
+ * the last bc_set_samples used (it alternates per call), and the launch counter.  A caller that captures bc_greedy_opt_step /
+ * bc_set_samples into a CUDA graph reads the slot right after capturing (bc_sample_slot), restores the slot of the graph it
+ * replayed last (bc_set_sample_slot) and accounts for the replayed kernels (bc_add_launch_count). */
+int bc_sample_slot(const bc_ctx* ctx);
+int bc_set_sample_slot(bc_ctx* ctx, int slot);
+int64_t bc_add_launch_count(int64_t n);
 
 /* ---- device-side posterior samplers (the reference's samplers are host callbacks) ----------------
  * bc_laplace_logistic: Laplace approximation of the weighted logistic posterior with N(0, I) prior -- what

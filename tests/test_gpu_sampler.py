@@ -243,6 +243,49 @@ def test_diagonal_precision_shortcuts_change_no_bit(D):
     np.testing.assert_allclose(mu_a, mu_h, rtol=0, atol=1e-12*max(1., np.abs(mu_h).max()))
 
 
+@pytest.mark.parametrize('model', ['gaussian_sub', 'logistic_full'])
+def test_graph_replayed_optimiser_loop_changes_no_bit(monkeypatch, model):
+    """coreset/_greedy.py::_optimize_graph_steps: the device side of an optimiser step captured into CUDA graphs and replayed
+    (step size / bias corrections from a device-resident schedule, normals and sub-sample indices through fixed pinned
+    buffers) builds bit for bit the coreset the kernel-by-kernel loop builds, and consumes the numpy stream alike."""
+    import bayesiancoresets as bc
+    import model_lr, gaussian
+    from bayesiancoresets.coreset import _greedy
+    from bayesiancoresets.util import rng
+    r = np.random.RandomState(3)
+    out = []
+    for graph in (True, False):
+        monkeypatch.setattr(_greedy, 'STEP_GRAPH', graph)
+        monkeypatch.setattr(_greedy, 'STEP_GRAPH_MIN_ITRS', 8)
+        rng.drain()
+        np.random.seed(7)
+        if model == 'gaussian_sub':
+            N, D, S = 3000, 20, 64
+            X = r.randn(N, D)*3. if graph else X
+            Siginv = np.eye(D)/9.
+            smp = gaussian.make_conjugate_sampler(np.zeros(D), np.eye(D), Siginv, device=True, prefetch=True)
+            bl = gaussian.gaussian_beta_likelihood.bind(Siginv=Siginv, logdetSig=float(D*np.log(9.)))
+            ll = gaussian.gaussian_loglikelihood.bind(Siginv=Siginv, logdetSig=float(D*np.log(9.)))
+            prj = bc.BetaBlackBoxProjector(smp, S, bl, ll, None)
+            alg = bc.BetaCoreset(X, prj, opt_itrs=45, n_subsample_opt=500, n_subsample_select=800, step_sched=lambda i: .1/(1.+i), beta=0.2,
+                                 learn_beta=False)
+        else:
+            N, D, S = 4000, 24, 96
+            X = r.randn(N, D) if graph else X
+            smp = model_lr.make_laplace_sampler(D, method='hybrid', prefetch=True)
+            prj = bc.BetaBlackBoxProjector(smp, S, model_lr.beta_likelihood, model_lr.log_likelihood, None)
+            alg = bc.BetaCoreset(X, prj, opt_itrs=33, step_sched=lambda i: 1./(1.+i), beta=0.3, learn_beta=False)
+        for m in range(1, 5):
+            alg.build(1, m)
+        smp.drain()
+        w, _, idcs = alg.get()[:3]
+        out.append((np.array(w), np.array(idcs), np.random.rand(3)))
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    assert len(out[0][1]) >= 3 and (out[0][0] > 0).any()
+
+
 def test_device_sampler_loop_matches_host_protocol_loop(monkeypatch):
     """the optimiser loop with the sampler's device_step (no host round trip per step) builds the coreset the loop builds
     when the same sampler is called through the reference's host protocol sampler(S, wts, pts)"""

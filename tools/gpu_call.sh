@@ -1,3 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-./tools/table_eval | tee gpurun_out/r02_table_eval.jsonl
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r02_pytest_13.txt
+timeout 900 python bench.py --configs > gpurun_out/r02_configs_h.jsonl 2> gpurun_out/r02_configs_h.err; echo configs rc=$?
+cut -c1-330 gpurun_out/r02_configs_h.jsonl
