@@ -53,6 +53,8 @@ SIGNATURES = {
     'bc_dense_gather': [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_vp],
     'bc_transpose': [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp],
     'bc_vec_step': [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_dbl, c_vp, c_vp, c_vp],
+    'bc_solver_iterations': [c_vp, c_int, c_int, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                             c_vp, c_vp],
     'bc_fit_pow_poly': [c_dbl, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }

@@ -7,6 +7,11 @@ from .snnls import SparseNNLS
 
 
 class FrankWolfe(SparseNNLS):
+    _device_algo = 1
+
+    def _device_run_operands(self):
+        return self._b_dev, self.Anorms.sum()
+
     def __init__(self, A, b):
         super().__init__(A, b)
         self._setup()

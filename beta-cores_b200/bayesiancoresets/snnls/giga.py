@@ -8,6 +8,11 @@ from .snnls import SparseNNLS
 
 
 class GIGA(SparseNNLS):
+    _device_algo = 0
+
+    def _device_run_operands(self):
+        return self._bn_dev, self.bnorm
+
     def __init__(self, A, b):
         super().__init__(A, b)
         self._setup()

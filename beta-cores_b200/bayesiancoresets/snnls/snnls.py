@@ -244,6 +244,63 @@ class SparseNNLS(object):
             self._err = float(self._out[:1].cpu().numpy()[0])
         return self._err
 
+    # ---- runs of iterations without a host round trip (GIGA, Frank-Wolfe; one rank) ----
+    _device_algo = None            # bc_solver_iterations' algo id; None: this solver iterates on the host path only
+    DEVICE_RUN_MAX = 256           # iterations queued per run (each is four launches; the state comes back once per run)
+
+    def _device_run_operands(self):
+        """(right-hand side of the line search, aux) of bc_solver_iterations for this solver"""
+        raise NotImplementedError
+
+    def _device_iterations(self, want):
+        """queue up to `want` whole iterations on the device (bc_solver_iterations) and adopt the state they leave behind.
+        Returns (iterations completed, a monotone-checked iteration completed, a guard stopped the run)."""
+        import os
+        if (self._device_algo is None or self._comm.world > 1 or self._nl == 0 or os.environ.get('BC_SOLVER_DEVICE_LOOP', '1') == '0'):
+            return 0, False, True
+        want = min(int(want), self.DEVICE_RUN_MAX)
+        eng, S = self._eng, self._S
+        m0 = len(self._act)
+        # room in the row cache for every datapoint the run could add
+        need = m0 + want
+        if need > self._cache_cap:
+            cap = max(64, 2*self._cache_cap, need)
+            Vn = eng.empty(cap, S)
+            if self._Vact is not None and m0:
+                Vn[:m0].copy_(self._Vact[:m0])
+            self._Vact, self._cache_cap = Vn, cap
+            self._aw_dev = eng.zeros(cap)
+            self._seq_dev = torch.arange(cap, dtype=torch.int64, device=eng.device)
+            self._pin = [torch.empty(cap, dtype=torch.float64).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory()]
+        cap = self._cache_cap
+        st = getattr(self, '_run_state', None)
+        if st is None or st['cap'] != cap:
+            st = self._run_state = {'cap': cap, 'dev': eng.empty(8 + 2*cap), 'prev': eng.empty(cap),
+                                    'host': torch.empty(8 + 2*cap, dtype=torch.float64).pin_memory()}
+        size_nonzero = self.size() > 0
+        err = self.error() if size_nonzero else 0.          # (remembered, not recomputed, once an iteration has run)
+        self._iterate()                                     # A w of the current weights in self._xw
+        h = st['host'].numpy()
+        h[:8] = [m0, 0., 0., 0., err, 1. if self.check_error_monotone else 0., cap, 0.]
+        h[8:8+m0] = self._aw
+        h[8+cap:8+cap+m0] = np.asarray(self._act, dtype=np.int64).view(np.float64)
+        st['dev'].copy_(st['host'], non_blocking=True)
+        ctl, aw, act = st['dev'][:8], st['dev'][8:8+cap], st['dev'][8+cap:]
+        rhs, aux = self._device_run_operands()
+        nv.call('bc_solver_iterations', self._ctx, self._device_algo, want, ptr(self._V), self._nl, S, self._ldv, ptr(self._norms),
+                ptr(rhs), ptr(self._b_dev), float(aux), float(util.TOL), ptr(self._Vact), ptr(ctl), ptr(aw), ptr(st['prev']), ptr(act),
+                ptr(self._xw), ptr(self._u), ptr(self._out), stream_ptr())
+        st['host'].copy_(st['dev'])                         # the one read-back of the run (synchronises)
+        m, status, done, checked = int(h[0]), int(h[1]), int(h[2]), h[3] != 0.
+        self._act = [int(v) for v in h[8+cap:8+cap+m].view(np.int64)]
+        self._pos = {f: k for k, f in enumerate(self._act)}
+        self._aw = [float(v) for v in h[8:8+m]]
+        # every exit leaves A w of the adopted weights in self._xw: a guard trips before the weights change, the monotone check
+        # restores them and re-forms A w
+        self._xw_valid = True
+        self._err = float(h[4]) if any(x > 0 for x in self._aw) else None
+        return done, checked, status != 0
+
     # ---- the reference's build loop (snnls.py:31-78) ----
     def build(self, itrs):
         if self.reached_numeric_limit:
@@ -253,7 +310,17 @@ class SparseNNLS(object):
             self.log.warning('there are no data, returning.')
             return
         retried_already = False
-        for i in range(itrs):
+        i = 0
+        while i < itrs:
+            # whole iterations on the device for as long as no guard trips; the iteration that trips one is then taken through
+            # the per-iteration path below, where the reference's error handling lives
+            done, checked, stopped = self._device_iterations(itrs - i)
+            i += done
+            if checked:
+                retried_already = False
+            if not stopped or i >= itrs:
+                continue
+            i += 1
             try:
                 size_nonzero = self.size() > 0
                 if self.check_error_monotone and size_nonzero:

@@ -793,6 +793,30 @@ int bc_vec_step(bc_ctx* c, int op, const double* d_xw, const double* d_xf, const
   return BC_OK;
 }
 
+int bc_solver_iterations(bc_ctx* c, int algo, int iterations, const double* d_V, int64_t n, int S, int64_t ldv, const double* d_norms,
+                         const double* d_b_search, const double* d_b, double aux, double tol, double* d_Vact, double* d_ctl, double* d_aw,
+                         double* d_aw_prev, int64_t* d_act, double* d_xw, double* d_u, double* d_scratch8, void* stream) {
+  if (!c || (algo != 0 && algo != 1) || iterations < 0 || !d_V || n <= 0 || S <= 0 || !d_norms || !d_b_search || !d_b || !d_Vact || !d_ctl ||
+      !d_aw || !d_aw_prev || !d_act || !d_xw || !d_u || !d_scratch8)
+    return BC_ERR_ARG;
+  if ((size_t)S * 2 * sizeof(double) > 200 * 1024) return BC_ERR_UNSUPPORTED;
+  int rc;
+  if ((rc = dense_ws(c, S))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < iterations; ++i) {
+    // _select: GIGA direction / Frank-Wolfe residual, then the score pass with its arg-max (giga.py:20-38, frankwolfe.py:15-17)
+    BC_CUDA(launch_vec_step(algo == 0 ? BC_VEC_GIGA_DIR : BC_VEC_RESID, d_xw, nullptr, algo == 0 ? d_b_search : d_b, S, 0.0, d_u, d_scratch8,
+                            st, d_ctl));
+    BC_CUDA(launch_dense_score(d_V, n, S, ldv, d_norms, d_u, algo == 0 ? BC_SCORE_GIGA : BC_SCORE_FW, nullptr, 0, c->dense_part, c->sms * 8,
+                               d_scratch8 + 4, nullptr, st, d_ctl));
+    // _reweight + error + monotone check
+    BC_CUDA(launch_solver_step(algo, d_V, ldv, S, d_norms, d_b_search, d_b, aux, tol, d_Vact, d_ctl, d_aw, d_aw_prev,
+                               reinterpret_cast<long long*>(d_act), d_xw, d_scratch8, st));
+    BC_LAUNCHED(4);
+  }
+  return BC_OK;
+}
+
 int bc_host_project(int device, int model, int kind, int D, const double* h_params, const double* h_siginv, const double* h_X,
                     int64_t n, int64_t ldx_h, const double* h_theta, int S, double* h_V, int centred) {
   if (!h_X || !h_theta || !h_V || n < 0 || S <= 0 || D <= 0) return BC_ERR_ARG;

@@ -171,8 +171,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_dense_score(const double* __restrict__ V, long long n, int S, long long ldv,
                                                      const double* __restrict__ norms, const double* __restrict__ u,
                                                      const unsigned char* __restrict__ active, long long idx_offset,
-                                                     double* __restrict__ part, double* __restrict__ scores) {
+                                                     double* __restrict__ part, double* __restrict__ scores, const double* stop) {
   extern __shared__ double u_s[];  // NU * S
+  if (stop && stop[1] != 0.0) return;   // a device-resident solver run has stopped (k_solver_step): nothing to score
   constexpr int NU = (MODE == 1) ? 2 : 1;
   __shared__ double bv[8][2];
   __shared__ long long bi[8][2];
@@ -228,9 +229,11 @@ __global__ void __launch_bounds__(256) k_dense_score(const double* __restrict__ 
 // merge of the per-CTA candidates: the order (NaN first, larger value, lower index) is total, so any merge tree gives the
 // sequential result; one block, each thread takes a strided share (a single thread walking several hundred partials cost
 // 0.1 ms per scoring pass)
-__global__ void __launch_bounds__(256) k_dense_score_fin(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_dense_score_fin(const double* __restrict__ part, int nparts, double* __restrict__ out,
+                                                         const double* stop) {
   __shared__ double sv[2][8];
   __shared__ long long si[2][8];
+  if (stop && stop[1] != 0.0) return;
   Best b = {0.0, -1}, nb = {0.0, -1};
   for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
     Best o = {part[p * 4 + 0], __double_as_longlong(part[p * 4 + 1])};
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(256) k_dense_score_fin(const double* __restric
 
 cudaError_t launch_dense_score(const double* V, long long n, int S, long long ldv, const double* norms, const double* u, int mode,
                                const unsigned char* active, long long idx_offset, double* part, int nparts, double* out,
-                               double* scores, cudaStream_t st) {
+                               double* scores, cudaStream_t st, const double* stop) {
   long long want = (n + 7) / 8;
   if (want < 1) want = 1;
   const size_t smem = (size_t)((mode == 1) ? 2 : 1) * S * sizeof(double);
@@ -308,14 +311,14 @@ cudaError_t launch_dense_score(const double* V, long long n, int S, long long ld
   if (resident < nparts) nparts = resident;
   if (want < nparts) nparts = (int)want;
   switch (mode) {
-    case 0: k_dense_score<0><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
-    case 1: k_dense_score<1><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
-    case 2: k_dense_score<2><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
-    default: k_dense_score<3><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores); break;
+    case 0: k_dense_score<0><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores, stop); break;
+    case 1: k_dense_score<1><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores, stop); break;
+    case 2: k_dense_score<2><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores, stop); break;
+    default: k_dense_score<3><<<nparts, 256, smem, st>>>(V, n, S, ldv, norms, u, active, idx_offset, part, scores, stop); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_dense_score_fin<<<1, 256, 0, st>>>(part, nparts, out);
+  k_dense_score_fin<<<1, 256, 0, st>>>(part, nparts, out, stop);
   return cudaGetLastError();
 }
 
@@ -407,10 +410,81 @@ cudaError_t launch_transpose(const double* A, long long rows, long long cols, lo
 //  op 1 GIGA step (giga.py:42-62): in xw (raw), xf, bn, bnorm=aux -> out[0]=gA, out[1]=gB, out[2]=alpha, out[3]=beta
 //  op 2 residual (frankwolfe.py:16, orthopursuit.py:18): u = b - xw; out[0] = sqrt(sum (xw-b)^2)  (snnls.py:28-29)
 //  op 3 FW step (frankwolfe.py:30-31): in xw, xf, b, aux = nsum/nf -> out[0]=gammanum, out[1]=gammadenom
+// The bodies of ops 1-3 as device functions (every thread of the CTA returns the same scalars): k_vec_step and the
+// device-resident solver iteration k_solver_step run exactly the same arithmetic.
+__device__ __forceinline__ void vec_giga_step(const double* xw, const double* xf, const double* b, int S, double aux, double* red, double& gA,
+                                              double& gB, double& alpha, double& beta) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double a = 0.0, f2 = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    a = fma(xw[s], xw[s], a);
+    f2 = fma(xf[s], xf[s], f2);
+  }
+  double nw = sqrt(block_sum_d(a, red));
+  nw = (nw == 0.0) ? 1.0 : nw;
+  const double nf = sqrt(block_sum_d(f2, red));
+  double dbf = 0.0, dbw = 0.0, dwf = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    const double wn = xw[s] / nw, fn = xf[s] / nf;
+    dbf = fma(b[s], fn, dbf);
+    dbw = fma(b[s], wn, dbw);
+    dwf = fma(wn, fn, dwf);
+  }
+  dbf = block_sum_d(dbf, red);
+  dbw = block_sum_d(dbw, red);
+  dwf = block_sum_d(dwf, red);
+  gA = dbf - dbw * dwf;
+  gB = dbw - dbf * dwf;
+  const double ca = gB / (gA + gB) / nw;
+  const double cb = gA / (gA + gB) / nf;
+  double x2 = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    const double x = ca * xw[s] + cb * xf[s];
+    x2 = fma(x, x, x2);
+  }
+  const double nx = sqrt(block_sum_d(x2, red));
+  double xb = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    const double x = ca * xw[s] + cb * xf[s];
+    xb = fma(x / nx, b[s], xb);
+  }
+  xb = block_sum_d(xb, red);
+  const double scale = aux / nx * xb;  // aux = bnorm
+  alpha = ca * scale;
+  beta = cb * scale;
+}
+__device__ __forceinline__ double vec_resid(const double* xw, const double* b, int S, double* u, double* red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double e2 = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    const double d = xw[s] - b[s];
+    if (u) u[s] = b[s] - xw[s];
+    e2 = fma(d, d, e2);
+  }
+  e2 = block_sum_d(e2, red);
+  return sqrt(e2);
+}
+__device__ __forceinline__ void vec_fw_step(const double* xw, const double* xf, const double* b, int S, double aux, double* red, double& num,
+                                            double& den) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  num = 0.0;
+  den = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    const double dlt = aux * xf[s] - xw[s];
+    num = fma(dlt, b[s] - xw[s], num);
+    den = fma(dlt, dlt, den);
+  }
+  num = block_sum_d(num, red);
+  den = block_sum_d(den, red);
+}
+
+// `stop` (optional): the control block of a device-resident solver run (k_solver_step); stop[1] != 0 = a guard has
+// tripped, the speculatively queued iterations behind it do nothing
 __global__ void k_vec_step(int op, const double* __restrict__ xw, const double* __restrict__ xf, const double* __restrict__ b, int S,
-                           double aux, double* __restrict__ u, double* __restrict__ out) {
+                           double aux, double* __restrict__ u, double* __restrict__ out, const double* stop) {
   __shared__ double red[33];
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (stop && stop[1] != 0.0) return;
   if (op == 0) {
     double a = 0.0;
     for (int s = tid; s < S; s += nt) a = fma(xw[s], xw[s], a);
@@ -434,65 +508,20 @@ __global__ void k_vec_step(int op, const double* __restrict__ xw, const double* 
       out[1] = nw;
     }
   } else if (op == 1) {
-    double a = 0.0, f2 = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      a = fma(xw[s], xw[s], a);
-      f2 = fma(xf[s], xf[s], f2);
-    }
-    double nw = sqrt(block_sum_d(a, red));
-    nw = (nw == 0.0) ? 1.0 : nw;
-    const double nf = sqrt(block_sum_d(f2, red));
-    double dbf = 0.0, dbw = 0.0, dwf = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      const double wn = xw[s] / nw, fn = xf[s] / nf;
-      dbf = fma(b[s], fn, dbf);
-      dbw = fma(b[s], wn, dbw);
-      dwf = fma(wn, fn, dwf);
-    }
-    dbf = block_sum_d(dbf, red);
-    dbw = block_sum_d(dbw, red);
-    dwf = block_sum_d(dwf, red);
-    const double gA = dbf - dbw * dwf;
-    const double gB = dbw - dbf * dwf;
-    const double ca = gB / (gA + gB) / nw;
-    const double cb = gA / (gA + gB) / nf;
-    double x2 = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      const double x = ca * xw[s] + cb * xf[s];
-      x2 = fma(x, x, x2);
-    }
-    const double nx = sqrt(block_sum_d(x2, red));
-    double xb = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      const double x = ca * xw[s] + cb * xf[s];
-      xb = fma(x / nx, b[s], xb);
-    }
-    xb = block_sum_d(xb, red);
-    const double scale = aux / nx * xb;  // aux = bnorm
+    double gA, gB, alpha, beta;
+    vec_giga_step(xw, xf, b, S, aux, red, gA, gB, alpha, beta);
     if (tid == 0) {
       out[0] = gA;
       out[1] = gB;
-      out[2] = ca * scale;
-      out[3] = cb * scale;
+      out[2] = alpha;
+      out[3] = beta;
     }
   } else if (op == 2) {
-    double e2 = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      const double d = xw[s] - b[s];
-      if (u) u[s] = b[s] - xw[s];
-      e2 = fma(d, d, e2);
-    }
-    e2 = block_sum_d(e2, red);
-    if (tid == 0) out[0] = sqrt(e2);
+    const double e = vec_resid(xw, b, S, u, red);
+    if (tid == 0) out[0] = e;
   } else {
-    double num = 0.0, den = 0.0;
-    for (int s = tid; s < S; s += nt) {
-      const double dlt = aux * xf[s] - xw[s];
-      num = fma(dlt, b[s] - xw[s], num);
-      den = fma(dlt, dlt, den);
-    }
-    num = block_sum_d(num, red);
-    den = block_sum_d(den, red);
+    double num, den;
+    vec_fw_step(xw, xf, b, S, aux, red, num, den);
     if (tid == 0) {
       out[0] = num;
       out[1] = den;
@@ -501,8 +530,141 @@ __global__ void k_vec_step(int op, const double* __restrict__ xw, const double* 
 }
 
 cudaError_t launch_vec_step(int op, const double* xw, const double* xf, const double* b, int S, double aux, double* u, double* out,
-                            cudaStream_t st) {
-  k_vec_step<<<1, 256, 0, st>>>(op, xw, xf, b, S, aux, u, out);
+                            cudaStream_t st, const double* stop) {
+  k_vec_step<<<1, 256, 0, st>>>(op, xw, xf, b, S, aux, u, out, stop);
+  return cudaGetLastError();
+}
+
+// ---------------------------------- device-resident solver iteration (GIGA / Frank-Wolfe) ----
+// What SparseNNLS.build does on the HOST between the score pass of an iteration and the next one (snnls.py:50-62 with
+// giga.py:40-64 / frankwolfe.py:19-40), as one single-CTA kernel working on device-resident solver state, so that a run of
+// iterations can be queued without a host round trip per iteration:
+//   guards of _select (GIGA: cdirnrm < TOL) -> activation of the selected datapoint f in the row cache -> line search ->
+//   its guards -> w = alpha w, w_f = max(0, w_f + beta) -> A w re-formed from the cached rows -> new error -> the strict
+//   monotone check (error > previous error: restore the weights, stop).
+// Any guard that trips sets ctl[1] and leaves the state as it was BEFORE the iteration; the iterations queued behind it see
+// the flag and do nothing; the host then takes that one iteration through its own code path, which raises and handles the
+// reference's NumericalPrecisionError exactly as before.  The arithmetic is the host path's, operation for operation
+// (same kernels' code, explicit roundings where Python would round twice).
+//   ctl (doubles): [0] m = cached datapoints, [1] status (0 ok, 1 select guard, 2 line-search guard, 3 error not monotone),
+//                  [2] iterations completed, [3] 1 once a completed iteration passed the monotone check (the reference
+//                  resets its retry latch there), [4] error of the current weights (valid whenever some weight is positive),
+//                  [5] check_error_monotone, [6] capacity of the cache
+//   aw[cap], act[cap] (int64 bit patterns), aw_prev[cap]: weights / global indices of the cached datapoints, weight backup
+__global__ void __launch_bounds__(256) k_solver_step(int algo, const double* __restrict__ V, long long ldv, int S,
+                                                     const double* __restrict__ norms, const double* __restrict__ b,
+                                                     const double* __restrict__ b_err, double aux, double tol,
+                                                     double* __restrict__ Vact, double* ctl, double* aw, double* aw_prev, long long* act,
+                                                     double* xw, const double* sel /* [0..3] vec scalars, [4..7] score result */) {
+  // b: the right-hand side of the line search (GIGA: b / |b|, with aux = |b|; Frank-Wolfe: b, with aux = sum of norms);
+  // b_err: the right-hand side of error() -- always the caller's b (snnls.py:28-29)
+  __shared__ double red[33];
+  __shared__ int s_k, s_pos;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (ctl[1] != 0.0) return;
+  int m = (int)ctl[0];
+  const bool check = ctl[5] != 0.0;
+  const long long f = __double_as_longlong(sel[5]);
+  if (algo == 0 && sel[0] < tol) {          // giga.py:28-29  cdirnrm < TOL
+    if (tid == 0) ctl[1] = 1.0;
+    return;
+  }
+  if (f < 0 || m >= (int)ctl[6]) {          // no candidate / cache full: let the host handle it
+    if (tid == 0) ctl[1] = 4.0;
+    return;
+  }
+  // size() > 0 before the step, position of f in the cache
+  if (tid == 0) { s_k = -1; s_pos = 0; }
+  __syncthreads();
+  int pos = 0, k = -1;
+  for (int j = tid; j < m; j += nt) {
+    if (aw[j] > 0.0) pos = 1;
+    if (act[j] == f) k = j;
+  }
+  if (pos) s_pos = 1;
+  if (k >= 0) s_k = k;
+  __syncthreads();
+  const bool size_nonzero = s_pos != 0;
+  k = s_k;
+  const double prev_error = ctl[4];
+  if (k < 0) {                               // first selection of f: its row joins the cache with weight 0
+    k = m;
+    for (int s = tid; s < S; s += nt) Vact[(size_t)k * S + s] = V[f * ldv + s];
+    if (tid == 0) {
+      act[k] = f;
+      aw[k] = 0.0;
+      ctl[0] = (double)(m + 1);
+    }
+    m += 1;
+    __syncthreads();
+  }
+  const double* xf = Vact + (size_t)k * S;
+  double alpha, beta;
+  if (algo == 0) {
+    double gA, gB;
+    vec_giga_step(xw, xf, b, S, aux, red, gA, gB, alpha, beta);
+    if (gA <= 0.0 || gB < 0.0) {             // giga.py:48-49
+      if (tid == 0) ctl[1] = 2.0;
+      return;
+    }
+  } else {
+    const double nf = norms[f];
+    if (!size_nonzero) {                     // frankwolfe.py:21-23
+      alpha = 0.0;
+      beta = __ddiv_rn(aux, nf);
+    } else {
+      double num, den;
+      vec_fw_step(xw, xf, b, S, __ddiv_rn(aux, nf), red, num, den);
+      if (num < 0.0 || den == 0.0 || num > den) {   // frankwolfe.py:32-33
+        if (tid == 0) ctl[1] = 2.0;
+        return;
+      }
+      alpha = __dsub_rn(1.0, __ddiv_rn(num, den));
+      beta = __ddiv_rn(__dmul_rn(__ddiv_rn(aux, nf), num), den);
+    }
+  }
+  // w = alpha w ; w_f = max(0, w_f + beta)      (giga.py:63-64, frankwolfe.py:39-40; two roundings, like the host's floats)
+  for (int j = tid; j < m; j += nt) {
+    const double old = aw[j];
+    aw_prev[j] = old;
+    double v = __dmul_rn(alpha, old);
+    if (j == k) {
+      v = __dadd_rn(v, beta);
+      v = (v > 0.0) ? v : 0.0;
+    }
+    aw[j] = v;
+  }
+  __syncthreads();
+  // A w from the cached rows, in cache order (k_dense_combine), then the error (k_vec_step op 2)
+  for (int s = tid; s < S; s += nt) {
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) acc = fma(aw[j], Vact[(size_t)j * S + s], acc);
+    xw[s] = acc;
+  }
+  __syncthreads();
+  const double err = vec_resid(xw, b_err, S, nullptr, red);
+  if (check && size_nonzero && err > prev_error) {   // snnls.py:56-62
+    for (int j = tid; j < m; j += nt) aw[j] = aw_prev[j];
+    __syncthreads();
+    for (int s = tid; s < S; s += nt) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc = fma(aw[j], Vact[(size_t)j * S + s], acc);
+      xw[s] = acc;
+    }
+    if (tid == 0) ctl[1] = 3.0;
+    return;
+  }
+  if (tid == 0) {
+    ctl[4] = err;
+    ctl[2] += 1.0;
+    if (check && size_nonzero) ctl[3] = 1.0;
+  }
+}
+
+cudaError_t launch_solver_step(int algo, const double* V, long long ldv, int S, const double* norms, const double* b, const double* b_err,
+                               double aux, double tol, double* Vact, double* ctl, double* aw, double* aw_prev, long long* act, double* xw,
+                               const double* sel, cudaStream_t st) {
+  k_solver_step<<<1, 256, 0, st>>>(algo, V, ldv, S, norms, b, b_err, aux, tol, Vact, ctl, aw, aw_prev, act, xw, sel);
   return cudaGetLastError();
 }
 

@@ -151,7 +151,7 @@ cudaError_t launch_dense_colsum(const double* V, long long n, int S, long long l
                                 int Sld, cudaStream_t st);
 cudaError_t launch_dense_score(const double* V, long long n, int S, long long ldv, const double* norms, const double* u, int mode,
                                const unsigned char* active, long long idx_offset, double* part, int nparts, double* out,
-                               double* scores, cudaStream_t st);
+                               double* scores, cudaStream_t st, const double* stop = nullptr);
 cudaError_t launch_dense_combine(const double* V, long long ldv, int S, const long long* idx, const double* w, int m, double* out,
                                  cudaStream_t st);
 cudaError_t launch_dense_center(double* V, long long n, int S, long long ldv, cudaStream_t st);
@@ -160,6 +160,9 @@ cudaError_t launch_dense_gather(const double* V, long long ldv, int S, const lon
 cudaError_t launch_transpose(const double* A, long long rows, long long cols, long long lda, double* out, long long ldo,
                              cudaStream_t st);
 cudaError_t launch_vec_step(int op, const double* xw, const double* xf, const double* b, int S, double aux, double* u, double* out,
-                            cudaStream_t st);
+                            cudaStream_t st, const double* stop = nullptr);
+cudaError_t launch_solver_step(int algo, const double* V, long long ldv, int S, const double* norms, const double* b, const double* b_err,
+                               double aux, double tol, double* Vact, double* ctl, double* aw, double* aw_prev, long long* act, double* xw,
+                               const double* sel, cudaStream_t st);
 
 }  // namespace bc

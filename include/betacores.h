@@ -253,6 +253,24 @@ int bc_transpose(bc_ctx* ctx, const double* d_A, int64_t rows, int64_t cols, int
 int bc_vec_step(bc_ctx* ctx, int op, const double* d_xw, const double* d_xf, const double* d_b, int S, double aux, double* d_u,
                 double* d_out, void* stream);
 
+/* Device-resident solver iterations (GIGA: algo 0, Frank-Wolfe: algo 1).  Queues `iterations` iterations of SparseNNLS.build
+ * (snnls.py:44-62 with giga.py:20-64 / frankwolfe.py:15-40) on `stream` WITHOUT a host round trip between them: per iteration
+ * the direction / residual step, the score pass over the n datapoints with its arg-max, and one single-CTA kernel that does
+ * what the host does between two score passes -- the guards, activation of the selected datapoint in the row cache, the line
+ * search, w = alpha w, w_f = max(0, w_f + beta), A w re-formed from the cached rows, the new error and the strict monotone
+ * check.  A guard that trips (cdirnrm < tol; gA <= 0 or gB < 0; gammanum / gammadenom out of range; error not monotone) sets
+ * d_ctl[1], leaves the state as before that iteration and turns the iterations queued behind it into no-ops; the caller takes
+ * that iteration through the per-iteration entry points, which is where the reference's NumericalPrecisionError handling lives.
+ *   d_ctl (8 doubles): [0] cached datapoints m, [1] status (0 ok, 1 select guard, 2 line-search guard, 3 error not monotone,
+ *     4 cache full / no candidate), [2] iterations completed (in/out), [3] set to 1 once a completed iteration has passed the
+ *     monotone check, [4] error of the current weights (in: valid if any weight is positive), [5] check_error_monotone, [6]
+ *     cache capacity in rows;   d_Vact: capacity x S row cache;  d_aw / d_act / d_aw_prev: capacity weights, global indices, backup;
+ *   d_b_search: b / |b| with aux = |b| (GIGA) or b with aux = sum of the datapoint norms (Frank-Wolfe);  d_b: the caller's b;
+ *   d_xw: A w of the current weights (in/out);  d_u: 2 S scratch;  d_scratch8: 8 doubles. */
+int bc_solver_iterations(bc_ctx* ctx, int algo, int iterations, const double* d_V, int64_t n, int S, int64_t ldv, const double* d_norms,
+                         const double* d_b_search, const double* d_b, double aux, double tol, double* d_Vact, double* d_ctl, double* d_aw,
+                         double* d_aw_prev, int64_t* d_act, double* d_xw, double* d_u, double* d_scratch8, void* stream);
+
 /* ---- host-buffer convenience (what a foreign-language binding would call first) ------------- */
 /* h_V[n x S] = centred potential matrix = BetaBlackBoxProjector.project_f(pts, beta) /
  * BlackBoxProjector.project(pts) (projector.py:51-55, :23-26) for HOST inputs; copies in, runs the

@@ -389,6 +389,34 @@ def test_snnls_fingerprint_matches_reference(bc, name):
     assert alg2.size() == 0 and not alg2.weights().any()
 
 
+@pytest.mark.parametrize('name', ['GIGA', 'FrankWolfe'])
+def test_device_resident_solver_runs_change_no_bit(bc, monkeypatch, name):
+    """bc_solver_iterations: runs of whole GIGA / Frank-Wolfe iterations queued on the device (guards, activation, line search,
+    weight update, error, monotone check in k_solver_step) against the per-iteration host path -- the same weights bit for
+    bit, the same error, the same numeric-limit latch, also when the run crosses into the regime where the strict
+    monotone check fires and the reference's retry / latch logic takes over."""
+    A = problems.snnls_matrix()
+    b = A.sum(axis=0)
+    out = []
+    for dev in ('1', '0'):
+        monkeypatch.setenv('BC_SOLVER_DEVICE_LOOP', dev)
+        res = []
+        for chunks in ([400], [1, 2, 7, 30, 360]):
+            alg = getattr(bc.snnls, name)(A.T, b)
+            for k in chunks:
+                alg.build(k)
+            res.append((alg.weights(), alg.error(), alg.reached_numeric_limit, alg.size()))
+        alg.reset()
+        alg.build(5)
+        res.append((alg.weights(), alg.error(), alg.reached_numeric_limit, alg.size()))
+        out.append(res)
+    for x, y in zip(out[0], out[1]):
+        np.testing.assert_array_equal(x[0], y[0])
+        assert x[1] == y[1] and x[2] == y[2] and x[3] == y[3]
+    np.testing.assert_array_equal(out[0][0][0], out[0][1][0])      # one call or several: the same iterations
+    assert out[0][0][3] > 20
+
+
 def test_snnls_small_cases_and_monotone_error(bc):
     g = np.load(os.path.join(G, 'g2_snnls.npz'))
     for tag, A in problems.snnls_small_cases():
