@@ -1,6 +1,7 @@
 """Orthogonal matching pursuit with non-negative re-solve (drop-in for bayesiancoresets/snnls/orthopursuit.py).
-The signed arg-max over all N datapoints is the device pass; the Lawson-Hanson re-solve on the S x m active
-block stays scipy's on the host, as in the reference (orthopursuit.py:40)."""
+The signed arg-max over all N datapoints is the device pass; the Lawson-Hanson re-solve on the S x m active block runs on
+the device too (bc_nnls on the cached rows, warm-started from the current weights), scipy's routine on the host being the
+fallback for blocks wider than the kernel takes (orthopursuit.py:40)."""
 import numpy as np
 import torch
 
@@ -39,4 +40,4 @@ class OrthoPursuit(SparseNNLS):
         # orthopursuit.py:37-42
         self._aw[self._activate(int(f))] = 1.
         nz = sorted(i for i, x in zip(self._act, self._aw) if x > 0)
-        self._assign(nz, self._nnls_on(nz))
+        self._assign(nz, self._nnls_on(nz, fresh=int(f)))

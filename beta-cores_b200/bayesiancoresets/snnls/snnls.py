@@ -358,7 +358,30 @@ class SparseNNLS(object):
         sel = self._Vact[torch.as_tensor(ks, dtype=torch.int64, device=self._eng.device)]
         return np.ascontiguousarray(sel.cpu().numpy().T)
 
-    def _nnls_on(self, idx):
+    def _nnls_on(self, idx, fresh=None):
+        """argmin |A[:, idx] x - b|, x >= 0 (orthopursuit.py:40, snnls.py:88).  On the device (bc_nnls: Lawson-Hanson on the
+        cached rows, warm-started from the current weights -- `fresh` names an index that has only just been marked for
+        inclusion and starts at 0); scipy's routine on the host when the block is wider than the kernel takes, when the
+        kernel reports numerically dependent columns, or with BC_DEVICE_NNLS=0.  The reference pins no scipy version for this
+        path (DESIGN.md section 4); the two agree to rounding (tests/test_gpu_parity.py::test_device_nnls_matches_scipy)."""
+        import os
+        ks = [self._activate(int(i)) for i in idx]
+        m = len(ks)
+        if m and m <= nv.lib().bc_nnls_max_columns() and os.environ.get('BC_DEVICE_NNLS', '1') != '0':
+            eng = self._eng
+            buf = torch.empty(2*m, dtype=torch.float64).pin_memory()
+            h = buf.numpy()
+            h[:m] = np.asarray(ks, dtype=np.int64).view(np.float64)
+            h[m:] = [0. if (fresh is not None and int(i) == int(fresh)) else max(0., self._aw[k]) for i, k in zip(idx, ks)]
+            d = buf.to(eng.device, non_blocking=True)
+            out = eng.empty(m + 1)
+            info = out[m:].view(torch.int32)
+            nv.call('bc_nnls', self._ctx, ptr(self._Vact), self._S, ptr(d[:m]), m, ptr(self._b_dev), ptr(d[m:]), ptr(out), 0, ptr(info),
+                    stream_ptr())
+            o = out.cpu()
+            if int(o[m:].view(torch.int32)[0]) == 0:
+                return o[:m].numpy().copy()
+            self.log.warning('device nnls did not converge (status %d); solving on the host' % int(o[m:].view(torch.int32)[0]))
         res = nnls(self._active_columns(idx), self.b, maxiter=100*self._N)
         return res[0]
 

@@ -24,6 +24,8 @@ struct bc_ctx {
   double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
   size_t cap_sT = 0;
   bool siginvT_ready = false;
+  double* nnls_rho = nullptr;  // S-length residual scratch of bc_nnls
+  size_t cap_rho = 0;
   int* siginv_diag = nullptr;  // device flag: d_siginv is a diagonal matrix (k_prepare_rows then takes one term per dot product)
   // samples
   bool samples_set = false;
@@ -162,6 +164,7 @@ int bc_destroy(bc_ctx* c) {
   cudaFree(c->B);
   cudaFree(c->siginvT);
   cudaFree(c->siginv_diag);
+  cudaFree(c->nnls_rho);
   cudaFree(c->colaux);
   cudaFree(c->bbar);
   cudaFree(c->part_colsum);
@@ -789,6 +792,20 @@ int bc_vec_step(bc_ctx* c, int op, const double* d_xw, const double* d_xf, const
   if ((op == BC_VEC_GIGA_STEP || op == BC_VEC_FW_STEP) && !d_xf) return BC_ERR_ARG;
   if (op == BC_VEC_GIGA_DIR && !d_u) return BC_ERR_ARG;
   BC_CUDA(launch_vec_step(op, d_xw, d_xf, d_b, S, aux, d_u, d_out, (cudaStream_t)stream));
+  BC_LAUNCHED(1);
+  return BC_OK;
+}
+
+int bc_nnls_max_columns(void) { return 112; }
+
+int bc_nnls(bc_ctx* c, const double* d_rows, int S, const int64_t* d_pos, int m, const double* d_b, const double* d_x0, double* d_x, int maxit,
+            int* d_info, void* stream) {
+  if (!c || !d_rows || !d_pos || !d_b || !d_x || !d_info || S <= 0 || m < 1) return BC_ERR_ARG;
+  if (m > bc_nnls_max_columns()) return BC_ERR_UNSUPPORTED;
+  int rc;
+  if ((rc = grow(&c->nnls_rho, &c->cap_rho, (size_t)S))) return rc;
+  BC_CUDA(launch_nnls_gram(d_rows, S, reinterpret_cast<const long long*>(d_pos), m, d_b, d_x0, d_x, c->nnls_rho, maxit > 0 ? maxit : 3 * m + 10,
+                           d_info, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

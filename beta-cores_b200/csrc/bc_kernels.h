@@ -142,6 +142,8 @@ cudaError_t launch_conjugate_factor(int model, const double* Z, long long ldz, c
                                     const double* v0, double sigsq, double* mu, double* C, int* info, cudaStream_t st);
 cudaError_t launch_sample_solve(const double* mu, const double* C, const double* R, int S, int D, double* out, int ldo, const int* diag_hint,
                                 cudaStream_t st);
+cudaError_t launch_nnls_gram(const double* Vact, int S, const long long* pos, int m, const double* b, const double* x0, double* x_out,
+                             double* rho, int maxit, int* info, cudaStream_t st);
 cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st);
 
 // ---- bc_dense.cu: materialised (n x S) matrix kernels for the snnls solvers ----

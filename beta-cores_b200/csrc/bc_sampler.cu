@@ -626,6 +626,287 @@ cudaError_t launch_sample_solve(const double* mu, const double* C, const double*
   return cudaGetLastError();
 }
 
+// ------------------------------------------------ non-negative least squares --
+// min |A x - b|, x >= 0 for the S x m block of cached datapoint rows (A's column j = row pos[j] of the cache):
+// OrthoPursuit._reweight / SparseNNLS.optimize (orthopursuit.py:37-42, snnls.py:82-97), where the reference calls
+// scipy.optimize.nnls.  Lawson-Hanson active-set iteration, one CTA:
+//   * the least-squares problems on the passive set P are solved through the Cholesky factor of the Gram block G_PP
+//     (G = A^T A, m x m, computed once), appended to row by row as columns enter P and rebuilt when columns leave;
+//   * every solve is refined twice by the corrected semi-normal equations -- residual rho = b - A_P s formed in the data
+//     space, G_PP d = A_P^T rho, s += d -- which brings the normal-equation solve to the accuracy of a QR-based one
+//     (Bjorck) for the conditioning coreset columns have;
+//   * the dual w = A^T (b - A x) is likewise formed from the residual, not from G;
+//   * a WARM start is taken from x0 (the current weights: P starts as their support), so the usual call -- one new column
+//     against an already optimal support -- takes one or two outer iterations instead of m.
+// The minimiser is unique for independent columns, so the result agrees with scipy's to rounding (tests); info[0] = 0 ok,
+// 1 iteration cap, 2 factorisation failed (numerically dependent columns: the caller falls back to the host routine).
+__device__ void tri_forward_only(const double* L, const double* rd, int D, int ld, double* x) {   // L y = x by warp 0
+  if (threadIdx.x < 32) {
+    double r[kMaxQ];
+    tri_load(x, D, r);
+    tri_forward(L, rd, D, ld, r);
+    tri_store(x, D, r);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kLapThreads) k_nnls_gram(const double* __restrict__ Vact, int S, const long long* __restrict__ pos, int m,
+                                                           const double* __restrict__ b, const double* __restrict__ x0,
+                                                           double* __restrict__ x_out, double* __restrict__ rho /* S scratch */,
+                                                           int maxit, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int ldg = m | 1;
+  double* G = sm;                  // [m][ldg]
+  double* L = G + (size_t)m * ldg; // [m][ldg]  factor of G_PP, rows / columns in the order of plist
+  double* c = L + (size_t)m * ldg; // [m] A^T b
+  double* x = c + m;               // [m]
+  double* sv = x + m;              // [m] LS solution, P order
+  double* w = sv + m;              // [m] dual
+  double* gv = w + m;              // [m] right-hand sides, P order
+  double* rd = gv + m;             // [m]
+  double* red = rd + m;            // [64]
+  int* plist = reinterpret_cast<int*>(red + 64);   // [m]
+  int* inP = plist + m;                            // [m]
+  __shared__ int flag, s_p, s_k, s_it;
+  __shared__ double s_val;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+
+  // Gram matrix and A^T b: one warp per entry of the lower triangle
+  const int npairs = m * (m + 1) / 2;
+  for (int q = wid; q < npairs + m; q += nw) {
+    int i, j;
+    const double* vj;
+    if (q < npairs) {
+      i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+      while (i * (i + 1) / 2 > q) --i;
+      while ((i + 1) * (i + 2) / 2 <= q) ++i;
+      j = q - i * (i + 1) / 2;
+      vj = Vact + (size_t)pos[j] * S;
+    } else {
+      i = q - npairs;
+      j = -1;
+      vj = b;
+    }
+    const double* vi = Vact + (size_t)pos[i] * S;
+    double a0 = 0.0, a1 = 0.0;
+    int t = lane;
+    for (; t + 32 < S; t += 64) {
+      a0 = fma(vi[t], vj[t], a0);
+      a1 = fma(vi[t + 32], vj[t + 32], a1);
+    }
+    if (t < S) a0 = fma(vi[t], vj[t], a0);
+    const double d = warp_sum(a0 + a1);
+    if (lane == 0) {
+      if (j >= 0) {
+        G[i * ldg + j] = d;
+        G[j * ldg + i] = d;
+      } else {
+        c[i] = d;
+      }
+    }
+  }
+  for (int j = tid; j < m; j += nt) {
+    const double v = x0 ? x0[j] : 0.0;
+    x[j] = (v > 0.0) ? v : 0.0;
+    inP[j] = (v > 0.0) ? 1 : 0;
+  }
+  if (tid == 0) {
+    int p = 0;
+    for (int j = 0; j < m; ++j)
+      if (x0 && x0[j] > 0.0) plist[p++] = j;
+    s_p = p;
+    s_it = 0;
+  }
+  __syncthreads();
+  double cmax = 0.0;
+  for (int j = 0; j < m; ++j) cmax = fmax(cmax, fabs(c[j]));
+  const double tol = 10.0 * (double)max(S, m) * 2.220446049250313e-16 * cmax;
+
+  // residual rho = b - sum_{a in P} val_a * column(plist[a]) into the global scratch
+  auto residual = [&](const double* val_P, int p) {
+    for (int t = tid; t < S; t += nt) {
+      double acc = b[t];
+      for (int a = 0; a < p; ++a) acc = fma(-val_P[a], Vact[(size_t)pos[plist[a]] * S + t], acc);
+      rho[t] = acc;
+    }
+    __syncthreads();
+  };
+  // out[q] = column(cols ? cols[q] : q) . rho for q < n
+  auto project = [&](double* out, const int* cols, int n) {
+    for (int q = wid; q < n; q += nw) {
+      const double* v = Vact + (size_t)pos[cols ? cols[q] : q] * S;
+      double a0 = 0.0;
+      for (int t = lane; t < S; t += 32) a0 = fma(v[t], rho[t], a0);
+      a0 = warp_sum(a0);
+      if (lane == 0) out[q] = a0;
+    }
+    __syncthreads();
+  };
+  auto rebuild = [&](int p) -> bool {    // L = chol(G_PP) from scratch
+    for (int q = tid; q < p * p; q += nt) {
+      const int a = q / p, bb = q - a * p;
+      if (bb <= a) L[a * ldg + bb] = G[plist[a] * ldg + plist[bb]];
+    }
+    __syncthreads();
+    if (p == 0) return true;
+    return chol_lower(L, p, ldg, rd, &flag);
+  };
+  auto solve = [&](int p) {              // sv = argmin |A_P s - b| with two CSNE refinements
+    for (int a = tid; a < p; a += nt) sv[a] = c[plist[a]];
+    __syncthreads();
+    chol_solve(L, rd, p, ldg, sv);
+    for (int r = 0; r < 2; ++r) {
+      residual(sv, p);
+      project(gv, plist, p);
+      chol_solve(L, rd, p, ldg, gv);
+      for (int a = tid; a < p; a += nt) sv[a] += gv[a];
+      __syncthreads();
+    }
+  };
+
+  int status = 0;
+  if (!rebuild(s_p)) status = 2;
+  bool warm = s_p > 0;
+  while (status == 0) {
+    int p = s_p;
+    if (!warm) {
+      // dual of the current x; stop when no inactive column can still reduce the residual
+      for (int a = tid; a < p; a += nt) gv[a] = x[plist[a]];
+      __syncthreads();
+      residual(gv, p);
+      project(w, nullptr, m);
+      if (tid == 0) {
+        int k = -1;
+        double best = tol;
+        for (int j = 0; j < m; ++j)
+          if (!inP[j] && w[j] > best) {
+            best = w[j];
+            k = j;
+          }
+        s_k = k;
+      }
+      __syncthreads();
+      const int k = s_k;
+      if (k < 0 || p == m) break;
+      // append column k to the factor: L l = G[P, k], d^2 = G_kk - |l|^2
+      for (int a = tid; a < p; a += nt) gv[a] = G[plist[a] * ldg + k];
+      __syncthreads();
+      if (p > 0) tri_forward_only(L, rd, p, ldg, gv);
+      if (tid == 0) {
+        double d2 = G[k * ldg + k];
+        for (int a = 0; a < p; ++a) d2 -= gv[a] * gv[a];
+        s_val = d2;
+      }
+      __syncthreads();
+      const double d2 = s_val;
+      if (!(d2 > 1e-13 * G[k * ldg + k])) {       // numerically dependent on the passive columns: cannot enter (LH's test)
+        if (tid == 0) inP[k] = 2;                  // excluded from the candidates of this call
+        __syncthreads();
+        continue;
+      }
+      for (int a = tid; a < p; a += nt) L[p * ldg + a] = gv[a];
+      if (tid == 0) {
+        const double d = sqrt(d2);
+        L[p * ldg + p] = d;
+        rd[p] = 1.0 / d;
+        plist[p] = k;
+        inP[k] = 1;
+        s_p = p + 1;
+      }
+      __syncthreads();
+      p += 1;
+    }
+    // inner loop: bring the least-squares solution on P back into the positive orthant
+    bool fresh = !warm;                  // the last entry of plist has just entered with x = 0
+    for (;;) {
+      solve(p);
+      if (tid == 0) {
+        int neg = 0;
+        for (int a = 0; a < p; ++a)
+          if (!(sv[a] > 0.0)) neg = 1;
+        s_k = neg;
+        s_it += 1;
+      }
+      __syncthreads();
+      if (fresh && !(sv[p - 1] > 0.0)) {
+        // the column that just entered would leave again at once (Lawson-Hanson's sign test on the new coordinate):
+        // take it out, bar it for this round, and look for another one
+        if (tid == 0) {
+          inP[plist[p - 1]] = 2;
+          s_p = p - 1;
+        }
+        __syncthreads();
+        break;
+      }
+      fresh = false;
+      if (!s_k) {
+        for (int j = tid; j < m; j += nt) {
+          x[j] = 0.0;
+          if (inP[j] == 2) inP[j] = 0;   // x moves: the barred columns may be tried again
+        }
+        __syncthreads();
+        for (int a = tid; a < p; a += nt) x[plist[a]] = sv[a];
+        __syncthreads();
+        break;
+      }
+      if (s_it > maxit) {
+        status = 1;
+        break;
+      }
+      if (tid == 0) {
+        // step from x towards s until the first coordinate reaches zero; the coordinates that block the step leave P
+        double alpha = 1.0;
+        for (int a = 0; a < p; ++a)
+          if (!(sv[a] > 0.0)) {
+            const double xa = x[plist[a]], den = xa - sv[a];
+            const double r = (den > 0.0) ? xa / den : 0.0;
+            if (r < alpha) alpha = r;
+          }
+        int q = 0;
+        for (int a = 0; a < p; ++a) {
+          const int j = plist[a];
+          const double xa = x[j], den = xa - sv[a];
+          const bool blocks = !(sv[a] > 0.0) && (((den > 0.0) ? xa / den : 0.0) <= alpha);
+          const double xn = xa + alpha * (sv[a] - xa);
+          if (!blocks && xn > 0.0) {
+            x[j] = xn;
+            plist[q++] = j;
+          } else {
+            x[j] = 0.0;
+            inP[j] = 0;
+          }
+        }
+        s_p = q;
+      }
+      __syncthreads();
+      p = s_p;
+      if (!rebuild(p)) {
+        status = 2;
+        break;
+      }
+      if (p == 0) break;
+    }
+    warm = false;
+  }
+  for (int j = tid; j < m; j += nt) x_out[j] = x[j];
+  if (tid == 0) {
+    info[0] = status;
+    info[1] = s_it;
+  }
+}
+
+cudaError_t launch_nnls_gram(const double* Vact, int S, const long long* pos, int m, const double* b, const double* x0, double* x_out,
+                             double* rho, int maxit, int* info, cudaStream_t st) {
+  const size_t smem = (2 * (size_t)m * (m | 1) + 6 * (size_t)m + 64) * sizeof(double) + 2 * (size_t)m * sizeof(int);
+  const size_t cap = kMaxSmem - 1024;
+  static DeviceOnce once;
+  cudaError_t e = raise_dynamic_smem(k_nnls_gram, cap, once);
+  if (e != cudaSuccess) return e;
+  if (smem > cap) return cudaErrorInvalidValue;
+  k_nnls_gram<<<1, kLapThreads, smem, st>>>(Vact, S, pos, m, b, x0, x_out, rho, maxit, info);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
                                     double tol, int* info, int flags, cudaStream_t st) {
   const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 5 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);

@@ -253,6 +253,17 @@ int bc_transpose(bc_ctx* ctx, const double* d_A, int64_t rows, int64_t cols, int
 int bc_vec_step(bc_ctx* ctx, int op, const double* d_xw, const double* d_xf, const double* d_b, int S, double aux, double* d_u,
                 double* d_out, void* stream);
 
+/* Non-negative least squares  min |A x - b|, x >= 0  on the device, for OrthoPursuit._reweight / SparseNNLS.optimize
+ * (orthopursuit.py:37-42, snnls.py:82-97: the reference calls scipy.optimize.nnls).  A is S x m, given by its COLUMNS: column j
+ * = row d_pos[j] (S contiguous doubles) of the row-major matrix d_rows (the solvers' cache of selected datapoints).  d_x0
+ * (optional, m doubles >= 0): warm start -- the iteration begins on its support; NULL starts from x = 0 like scipy.
+ * Lawson-Hanson active set on the Gram matrix with corrected-semi-normal-equation refinement, one CTA (csrc/bc_sampler.cu).
+ * d_info[0] = 0 converged / 1 iteration cap / 2 numerically dependent columns (use a host routine); d_info[1] = solves taken.
+ * m <= bc_nnls_max_columns().  The reference pins no version of scipy's routine for this path: agreement is to rounding. */
+int bc_nnls_max_columns(void);
+int bc_nnls(bc_ctx* ctx, const double* d_rows, int S, const int64_t* d_pos, int m, const double* d_b, const double* d_x0, double* d_x,
+            int maxit, int* d_info, void* stream);
+
 /* Device-resident solver iterations (GIGA: algo 0, Frank-Wolfe: algo 1).  Queues `iterations` iterations of SparseNNLS.build
  * (snnls.py:44-62 with giga.py:20-64 / frankwolfe.py:15-40) on `stream` WITHOUT a host round trip between them: per iteration
  * the direction / residual step, the score pass over the n datapoints with its arg-max, and one single-CTA kernel that does

@@ -417,6 +417,65 @@ def test_device_resident_solver_runs_change_no_bit(bc, monkeypatch, name):
     assert out[0][0][3] > 20
 
 
+def test_device_nnls_matches_scipy(bc):
+    """bc_nnls (Lawson-Hanson on the Gram matrix + corrected semi-normal equations, csrc/bc_sampler.cu) against
+    scipy.optimize.nnls: random blocks with clamped coordinates, strongly correlated columns (the regime of coreset
+    columns), warm and cold starts, a single column; then OrthoPursuit built with the device routine against the same build
+    with scipy's (BC_DEVICE_NNLS=0)."""
+    import torch
+    from scipy.optimize import nnls
+    from bayesiancoresets._device import Engine, ptr, stream_ptr
+    from bayesiancoresets import _native as nv
+    eng = Engine.get()
+    ctx = eng.ctx()
+    r = np.random.RandomState(5)
+
+    def solve(A, b, x0=None):
+        S, m = A.shape
+        rows = eng.upload(np.ascontiguousarray(A.T))                 # column j of A = row j of the cache
+        pos = torch.arange(m, dtype=torch.int64, device=eng.device)
+        d_b, out = eng.upload(b), eng.empty(m)
+        d_x0 = eng.upload(x0) if x0 is not None else None
+        info = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        nv.call('bc_nnls', ctx, ptr(rows), S, ptr(pos), m, ptr(d_b), ptr(d_x0), ptr(out), 0, ptr(info), stream_ptr())
+        return out.cpu().numpy(), info.cpu().numpy()
+
+    cases = []
+    for S, m in [(200, 30), (1000, 100), (64, 1), (500, 112), (37, 11)]:
+        A = r.randn(S, m)
+        cases.append((A, A.dot(np.abs(r.randn(m))*(r.rand(m) < .6)) + .3*r.randn(S)))        # some coordinates clamp at 0
+    base = np.abs(r.randn(400, 1)) + 5.
+    A = base + 1e-3*r.randn(400, 40)                                      # columns nearly parallel: condition number ~ 1e5
+    cases.append((A, A.dot(r.rand(40)) + 1e-4*r.randn(400)))
+    for A, b in cases:
+        ref, _ = nnls(A, b, maxiter=100*A.shape[1])
+        for x0 in (None, np.abs(r.randn(A.shape[1]))*(r.rand(A.shape[1]) < .5), ref.copy()):
+            got, info = solve(A, b, x0)
+            assert info[0] == 0, info
+            assert (got >= 0).all()
+            e_ref, e_got = np.linalg.norm(A.dot(ref)-b), np.linalg.norm(A.dot(got)-b)
+            assert e_got <= e_ref*(1+1e-10) + 1e-12*np.linalg.norm(b), (A.shape, e_got, e_ref)
+            scale = np.abs(ref).max() + 1e-300
+            tol = 1e-9 if A.shape[0] != 400 else 1e-5        # the ill-conditioned block: x itself is only defined to cond * eps
+            assert np.abs(got - ref).max() <= tol*scale, (A.shape, np.abs(got-ref).max()/scale)
+        if x0 is not None:
+            assert info[1] <= 3          # started at the solution: nothing to do but confirm it
+
+    A = problems.snnls_matrix()
+    outs = []
+    for dev in ('1', '0'):
+        os.environ['BC_DEVICE_NNLS'] = dev
+        try:
+            alg = bc.snnls.OrthoPursuit(A.T, A.sum(axis=0))
+            alg.build(60)
+            alg.optimize()
+            outs.append((alg.weights(), alg.error()))
+        finally:
+            os.environ.pop('BC_DEVICE_NNLS', None)
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-7, atol=1e-9*np.abs(outs[1][0]).max())
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-9*max(outs[1][1], 1e-300) + 1e-12
+
+
 def test_snnls_small_cases_and_monotone_error(bc):
     g = np.load(os.path.join(G, 'g2_snnls.npz'))
     for tag, A in problems.snnls_small_cases():

@@ -1,5 +1,4 @@
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r02_pytest_14.txt
-timeout 900 python bench.py --configs > gpurun_out/r02_configs_i.jsonl 2> gpurun_out/r02_configs_i.err; echo configs rc=$?
-cut -c1-330 gpurun_out/r02_configs_i.jsonl
+python tools/c1_profile.py > gpurun_out/r02_c1_profile_i.txt 2>&1; echo rc=$?; head -8 gpurun_out/r02_c1_profile_i.txt
+nproc; uptime
