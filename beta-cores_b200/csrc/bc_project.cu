@@ -410,8 +410,24 @@ __global__ void __launch_bounds__(1024) k_project_finalize(const double* __restr
     dd tot = {0.0, 0.0};
     for (int col = tid; col < S; col += blockDim.x) {
       dd a = {0.0, 0.0};
-      for (int c = 0; c < nctas; ++c) {
-        dd o = {part_colsum[(size_t)c * 2 * Sld + col], part_colsum[(size_t)c * 2 * Sld + Sld + col]};
+      // the partials are added in CTA order (the order is part of the result); their loads do not depend on the running
+      // sum, so eight of them are put in flight together -- one L2 round trip per partial made this kernel 53 us at 148 CTAs
+      int c = 0;
+      for (; c + 8 <= nctas; c += 8) {
+        double hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          hi[q] = __ldcg(part_colsum + (size_t)(c + q) * 2 * Sld + col);
+          lo[q] = __ldcg(part_colsum + (size_t)(c + q) * 2 * Sld + Sld + col);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          dd o = {hi[q], lo[q]};
+          a = dd_add(a, o);
+        }
+      }
+      for (; c < nctas; ++c) {
+        dd o = {__ldcg(part_colsum + (size_t)c * 2 * Sld + col), __ldcg(part_colsum + (size_t)c * 2 * Sld + Sld + col)};
         a = dd_add(a, o);
       }
       out_dd[col] = a.hi;

@@ -259,9 +259,9 @@ __device__ double log_joint(const double* w, const double* mrg, int M, int D, co
   return blk_sum(part, red) - 0.5 * (double)D * 1.8378770664093453;   // log(2 pi)
 }
 
-__global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* __restrict__ Z, long long ldz, const double* __restrict__ w,
+__global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* __restrict__ Zg, long long ldzg, const double* __restrict__ w,
                                                                   int M, int D, double* __restrict__ mu_io, double* __restrict__ Lsig,
-                                                                  int maxit, double tol, int* __restrict__ info, int flags) {
+                                                                  int maxit, double tol, int* __restrict__ info, int flags, int stage_rows) {
   // flags bit 0: write the lower Cholesky factor C of the negative Hessian itself (get_laplace's LSigInv) instead of its inverse
   //       bit 1: Newton steps from the M x M dual system (Woodbury; needs M <= D): H = I + Z^T diag(d) Z is a rank-M update of
   //              the identity, H^-1 g = g - Z^T r (I + r K r)^-1 r Z g with r = sqrt(d), K = Z Z^T -- the same step as
@@ -282,6 +282,20 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
   double* rhs = rr + Mp;          // [Mp] r_i z_i.g, then the dual solution (dual steps)
   __shared__ int flag;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  // stage_rows: the M coreset rows are read a dozen times (margins, gradient, Hessian or dual system per Newton step, the
+  // final Hessian) by loops whose trip count is M: from global memory every trip is an L2 round trip.  When they fit beside
+  // the D x D workspace they are copied into shared memory once.
+  const double* Z = Zg;
+  long long ldz = ldzg;
+  if (stage_rows) {
+    double* Zs = rhs + Mp;        // [M][D]
+    for (int q = tid; q < M * D; q += nt) {
+      const int i = q / D, kk = q - i * D;
+      Zs[q] = Zg[i * ldzg + kk];
+    }
+    Z = Zs;
+    ldz = D;
+  }
   for (int k = tid; k < D; k += nt) th[k] = mu_io[k];
   __syncthreads();
   margins(Z, ldz, M, D, th, mrg);
@@ -909,13 +923,16 @@ cudaError_t launch_nnls_gram(const double* Vact, int S, const long long* pos, in
 
 cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double* w, int M, int D, double* mu_io, double* Lsig, int maxit,
                                     double tol, int* info, int flags, cudaStream_t st) {
-  const size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 5 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
+  size_t smem = ((size_t)D * (D + 1) + 4 * (size_t)D + 5 * (size_t)((M + 1) & ~1) + 64) * sizeof(double);
   const size_t cap = kMaxSmem - 1024;   // the kernel also has a few bytes of static shared memory
   static DeviceOnce once;
   cudaError_t e = raise_dynamic_smem(k_laplace_logistic, cap, once);
   if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
-  k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info, flags);
+  const size_t rows = (size_t)M * D * sizeof(double);
+  const int stage_rows = smem + rows <= cap ? 1 : 0;
+  if (stage_rows) smem += rows;
+  k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info, flags, stage_rows);
   return cudaGetLastError();
 }
 

@@ -141,32 +141,41 @@ cudaError_t launch_offdiag_test(const double* A, int D, int* flag, cudaStream_t 
 }
 
 // bbar[k] = mean_s B[s][k] for k < ldb; bbar[ldb] = mean_s colaux[s] (0 if no colaux).
-// The sum over the samples is SEQUENTIAL per column (its order is part of the result), so a column costs one dependent
-// DADD per sample; what can be hidden is the memory latency: a CTA owns 32 columns, all its threads stage a tile of
-// kMeanTile samples into shared memory (coalesced, every load in flight at once) and one warp then adds it up.
-constexpr int kMeanCols = 32, kMeanTile = 128, kMeanThreads = 256;
+// bbar is the PIVOT sample of the FP64 route (its potential is subtracted from a row's before anything is accumulated): any
+// value near the sample mean serves, but it must be the same on every launch configuration, so the summation order is
+// fixed: kMeanChains interleaved chains per column (chain p adds the samples s = p, p + kMeanChains, ... in order), combined
+// in chain order.  A CTA owns 32 columns; thread (chain, column) reads its samples straight from global memory -- the loads
+// are independent of the running sum and coalesced over the columns -- so a column costs S / kMeanChains dependent adds
+// (a single chain per column took 40 us at S = 1024).
+constexpr int kMeanCols = 32, kMeanChains = 8, kMeanThreads = kMeanCols * kMeanChains;
 __global__ void __launch_bounds__(kMeanThreads) k_prepare_mean(const double* __restrict__ B, int S, int ldb, const double* __restrict__ colaux,
                                                                double* __restrict__ bbar) {
-  __shared__ double tile[kMeanTile][kMeanCols + 1];
-  const int k0 = blockIdx.x * kMeanCols, tid = threadIdx.x;
-  const int kk = tid & (kMeanCols - 1), k = k0 + kk;
+  __shared__ double part[kMeanChains][kMeanCols];
+  const int kk = threadIdx.x & (kMeanCols - 1), p = threadIdx.x / kMeanCols;
+  const int k = blockIdx.x * kMeanCols + kk;
   double acc = 0.0;
-  for (int s0 = 0; s0 < S; s0 += kMeanTile) {
-    const int ns = min(kMeanTile, S - s0);
-    for (int r = tid / kMeanCols; r < ns; r += kMeanThreads / kMeanCols) {
-      double v = 0.0;
-      if (k < ldb) v = B[(size_t)(s0 + r) * ldb + k];
-      else if (k == ldb && colaux) v = colaux[s0 + r];
-      tile[r][kk] = v;
+  if (k <= ldb && (k < ldb || colaux)) {
+    const double* src = (k < ldb) ? B + k : colaux;
+    const size_t stride = (k < ldb) ? (size_t)ldb : 1;
+    int s = p;
+    for (; s + 3 * kMeanChains < S; s += 4 * kMeanChains) {
+      const double v0 = src[(size_t)s * stride], v1 = src[(size_t)(s + kMeanChains) * stride];
+      const double v2 = src[(size_t)(s + 2 * kMeanChains) * stride], v3 = src[(size_t)(s + 3 * kMeanChains) * stride];
+      acc += v0;
+      acc += v1;
+      acc += v2;
+      acc += v3;
     }
-    __syncthreads();
-    if (tid < kMeanCols) {
-#pragma unroll 8
-      for (int r = 0; r < ns; ++r) acc += tile[r][kk];
-    }
-    __syncthreads();
+    for (; s < S; s += kMeanChains) acc += src[(size_t)s * stride];
   }
-  if (tid < kMeanCols && k <= ldb) bbar[k] = acc / (double)S;
+  part[p][kk] = acc;
+  __syncthreads();
+  if (p == 0 && k <= ldb) {
+    double tot = part[0][kk];
+#pragma unroll
+    for (int q = 1; q < kMeanChains; ++q) tot += part[q][kk];
+    bbar[k] = tot / (double)S;
+  }
 }
 
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
