@@ -57,9 +57,11 @@ SIGNATURES = {
     'bc_solver_iterations': [c_vp, c_int, c_int, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                              c_vp, c_vp],
     'bc_fit_pow_poly': [c_dbl, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
+    'bc_fit_pow_tab': [c_dbl, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
+    'bc_set_potential_form': [c_vp, c_int],
     'bc_host_project': [c_int, c_int, c_int, c_int, ctypes.POINTER(c_dbl), c_vp, c_vp, c_i64, c_i64, c_vp, c_int, c_vp, c_int],
 }
-PLAIN = {'bc_nnls_max_columns': ([], c_int), 'bc_sample_slot': ([c_vp], c_int), 'bc_add_launch_count': ([c_i64], c_i64), 'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
+PLAIN = {'bc_potential_form': ([c_vp], c_int), 'bc_nnls_max_columns': ([], c_int), 'bc_sample_slot': ([c_vp], c_int), 'bc_add_launch_count': ([c_i64], c_i64), 'bc_version': ([], c_int), 'bc_contraction_digits': ([c_vp], c_int), 'bc_q_max_features': ([], c_int), 'bc_launch_count': ([], c_i64), 'bc_last_cuda_error': ([], c_int), 'bc_sm_count': ([c_vp], c_int),
          'bc_colsum_ld': ([c_int], c_int), 'bc_error_string': ([c_int], ctypes.c_char_p)}
 
 

@@ -1,5 +1,6 @@
 // beta-cores B200: extern "C" entry points (see include/betacores.h for the contract).
 #include <math.h>
+#include <string.h>
 #include <new>
 #include "../../include/betacores.h"
 #include "bc_kernels.h"
@@ -20,6 +21,14 @@ struct bc_ctx {
   int poly = 0;  // logistic beta-likelihood: degree of the (1+t)^-beta polynomial in use (0 = exp/log1p form)
   size_t smem = 0;
   ModelParams mp{};
+  // lane-table form of the logistic beta-likelihood (tensor-core route): 64 doubles per beta, written once into a slot of
+  // `tab_dev` and never modified afterwards (a kernel in flight keeps reading its slot whatever bc_set_potential does next)
+  static constexpr int kTabSlots = 16;
+  double* tab_dev = nullptr;
+  double tab_beta[kTabSlots] = {0};
+  int tab_count = 0;
+  const double* tab_cur = nullptr;   // slot of the current potential, or null: polynomial forms
+  int pot_form = 0;                  // bc_set_potential_form: 0 = fastest form available, 1 = polynomial forms only
   const double* d_siginv = nullptr;
   double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
   size_t cap_sT = 0;
@@ -114,9 +123,63 @@ static double fit_pow_poly(double beta, int deg, double* out) {
   return (double)err;
 }
 
+// Lane-table form of (1+t)^-beta (bc_models.cuh, LogisticF<KIND_BETALIK, kPowTab>): s = 1 + t in [1, 2] is cut into 32
+// intervals with centres s_j = 1 + (j + 1/2)/32;  s^-beta = s_j^-beta (1 + w)^-beta,  w = (s - s_j)/s_j,  |w| <= 1/65,
+// (1 + w)^-beta = 1 + w Q(w).  rs[j] = 1/s_j and us[j] = s_j^-beta correctly rounded; Q = the interpolant of
+// ((1+w)^-beta - 1)/w at kPowTabDeg+1 Chebyshev nodes, monomial coefficients highest degree first; all in long double.
+// Returns max |w Q(w) - ((1+w)^-beta - 1)| over the interval for the ROUNDED coefficients.
+static double fit_pow_tab(double beta, double* w_out, double* rs, double* us) {
+  const long double b = (long double)beta;
+  for (int j = 0; j < 32; ++j) {
+    const long double sj = 1.0L + ((long double)j + 0.5L) / 32.0L;
+    rs[j] = (double)(1.0L / sj);
+    us[j] = (double)powl(sj, -b);
+  }
+  constexpr int n = kPowTabDeg + 1;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  const long double wmax = (1.0L / 65.0L) * 1.0005L;
+  auto Qx = [&](long double w) -> long double {
+    if (fabsl(w) < 1e-9L) return -b + b * (b + 1.0L) * 0.5L * w;
+    return expm1l(-b * log1pl(w)) / w;
+  };
+  long double A[n][n + 1];   // Vandermonde in x = w / wmax
+  for (int i = 0; i < n; ++i) {
+    const long double x = cosl(pi * (i + 0.5L) / n);
+    long double pw = 1.0L;
+    for (int k = 0; k < n; ++k, pw *= x) A[i][k] = pw;
+    A[i][n] = Qx(x * wmax);
+  }
+  for (int col = 0; col < n; ++col) {   // Gauss-Jordan with partial pivoting
+    int piv = col;
+    for (int r = col + 1; r < n; ++r)
+      if (fabsl(A[r][col]) > fabsl(A[piv][col])) piv = r;
+    for (int k = 0; k <= n; ++k) {
+      const long double t = A[col][k];
+      A[col][k] = A[piv][k];
+      A[piv][k] = t;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == col) continue;
+      const long double f = A[r][col] / A[col][col];
+      for (int k = col; k <= n; ++k) A[r][k] -= f * A[col][k];
+    }
+  }
+  long double sc = 1.0L;
+  for (int k = 0; k < n; ++k, sc *= wmax) w_out[kPowTabDeg - k] = (double)(A[k][n] / A[k][k] / sc);
+  long double err = 0.0L;
+  for (int i = 0; i <= 1024; ++i) {
+    const long double w = -wmax + 2.0L * wmax * i / 1024.0L;
+    long double q = 0.0L;
+    for (int k = 0; k < n; ++k) q = q * w + (long double)w_out[k];
+    const long double e = fabsl(w * q - expm1l(-b * log1pl(w)));
+    if (e > err) err = e;
+  }
+  return (double)err;
+}
+
 extern "C" {
 
-int bc_version(void) { return 101; }
+int bc_version(void) { return 102; }
 
 const char* bc_error_string(int code) {
   switch (code) {
@@ -138,6 +201,19 @@ int bc_fit_pow_poly(double beta, int degree, double* h_coef, double* h_err) {
   if (h_err) *h_err = e;
   return BC_OK;
 }
+int bc_fit_pow_tab(double beta, double* h_w, double* h_rs, double* h_us, double* h_err) {
+  if (!(beta > 0.0) || !h_w || !h_rs || !h_us) return BC_ERR_ARG;
+  const double e = fit_pow_tab(beta, h_w, h_rs, h_us);
+  if (h_err) *h_err = e;
+  return BC_OK;
+}
+int bc_set_potential_form(bc_ctx* c, int form) {
+  if (!c || form < 0 || form > 1) return BC_ERR_ARG;
+  c->pot_form = form;
+  c->potential_set = false;   // takes effect with the next bc_set_potential
+  return BC_OK;
+}
+int bc_potential_form(const bc_ctx* c) { return (c && c->tab_cur) ? 2 : 1; }
 int64_t bc_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int bc_create(int device, bc_ctx** out) {
@@ -155,6 +231,7 @@ int bc_create(int device, bc_ctx** out) {
   BC_CUDA(cudaMalloc((void**)&c->fscratch, kQK * sizeof(unsigned long long)));
   BC_CUDA(cudaMalloc((void**)&c->sscratch, 4 * sizeof(unsigned long long)));
   BC_CUDA(cudaMemset(c->sscratch, 0, 4 * sizeof(unsigned long long)));
+  BC_CUDA(cudaMalloc((void**)&c->tab_dev, (size_t)bc_ctx::kTabSlots * 64 * sizeof(double)));
   *out = c;
   return BC_OK;
 }
@@ -175,6 +252,7 @@ int bc_destroy(bc_ctx* c) {
   cudaFree(c->fexp);
   cudaFree(c->fscratch);
   cudaFree(c->sscratch);
+  cudaFree(c->tab_dev);
   delete c;
   return BC_OK;
 }
@@ -210,7 +288,16 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
   if (model == BC_MODEL_LOGISTIC && kind == BC_KIND_BETALIK) {
     const double beta = h_params[0];
     if (!(beta > 0.0)) return BC_ERR_ARG;
-    c->mp.p[2] = 700.0 / (beta > 1.0 ? beta : 1.0);  // clamp of |m| ahead of the exponentials (LogisticF::evalv)
+    // clamps of |m| ahead of the two exponentials (LogisticF::evalv): 700 for e^-a, 700 / beta for e^(-beta a).  The low
+    // words are zero so that the lane-table form can compare high words on the integer pipe.
+    {
+      const double bmax = 700.0 / beta;
+      unsigned long long bits;
+      memcpy(&bits, &bmax, 8);
+      bits &= 0xffffffff00000000ull;
+      memcpy(&c->mp.p[3], &bits, 8);
+      c->mp.p[2] = 700.0;
+    }
     const int degs[2] = {20, kPowPolyMax};
     for (int i = 0; i < 2 && c->poly == 0; ++i) {
       double q[kPowPolyMax + 1];
@@ -219,6 +306,26 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
         c->poly = degs[i];
       }
     }
+    c->tab_cur = nullptr;
+    double w[kPowTabDeg + 1], tabs[64];
+    if (c->pot_form == 0 && fit_pow_tab(beta, w, tabs, tabs + 32) < 5e-17) {   // under half an ulp of (1+t)^-beta in [1/2, 1]: beta up to about 1
+      int slot = -1;
+      for (int i = 0; i < c->tab_count; ++i)
+        if (c->tab_beta[i] == beta) slot = i;
+      if (slot < 0) {
+        if (c->tab_count == bc_ctx::kTabSlots) {   // every slot taken: wait for whatever still reads them, start over
+          BC_CUDA(cudaDeviceSynchronize());
+          c->tab_count = 0;
+        }
+        slot = c->tab_count++;
+        c->tab_beta[slot] = beta;
+        BC_CUDA(cudaMemcpy(c->tab_dev + (size_t)slot * 64, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
+      }
+      for (int k = 0; k <= kPowTabDeg; ++k) c->mp.w[k] = w[k];
+      c->tab_cur = c->tab_dev + (size_t)slot * 64;
+    }
+  } else {
+    c->tab_cur = nullptr;
   }
   c->d_siginv = d_siginv;
   c->siginvT_ready = false;
@@ -477,6 +584,7 @@ static int q_common(bc_ctx* c, const void* d_image, const double* d_rowscale, in
   P.colaux = (c->model == BC_MODEL_GAUSSIAN) ? c->colaux : nullptr;
   P.rowaux = (c->model != BC_MODEL_LOGISTIC) ? d_rowaux : nullptr;
   P.mp = c->mp;
+  P.pot_tabs = c->tab_cur;
   P.part_colsum = c->part_colsum;
   P.part_misc = c->part_misc;
   P.Sld = bc_colsum_ld(c->S);
@@ -501,7 +609,7 @@ int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale
     BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
     return BC_OK;
   }
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_COLSUM, c->q_digits, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_COLSUM, c->q_digits, grid, st));
   double* fused = c->fuse_colsum_out;
   c->fuse_colsum_out = nullptr;
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st, fused));
@@ -520,7 +628,7 @@ int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale,
   P.scores = d_scores;
   P.idx_offset = idx_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_SCORE, c->q_digits, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_SCORE, c->q_digits, grid, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -537,7 +645,7 @@ int bc_contraction_q(bc_ctx* c, const void* d_image, const double* d_rowscale, i
   P.rowaux = nullptr;
   P.V = d_V;
   P.ldv = ldv;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->poly, QMODE_DOT, c->q_digits, grid, (cudaStream_t)stream));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_DOT, c->q_digits, grid, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

@@ -53,6 +53,16 @@ BC_HD double fm_i2d(int k) {
   return (double)k;
 #endif
 }
+BC_HD double fm_hilo2d(int hi, int lo) {
+#if defined(__CUDACC__)
+  return __hiloint2double(hi, lo);
+#else
+  const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint64_t)(uint32_t)lo;
+  double x;
+  memcpy(&x, &u, 8);
+  return x;
+#endif
+}
 BC_HD double fm_add_exponent(double p, int k) {  // p * 2^k for results that stay normal
 #if defined(__CUDACC__)
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
@@ -137,6 +147,108 @@ BC_HD void rcp_1to2_v(const double (&x)[W], double (&r)[W]) {
 #else
   for (int i = 0; i < W; ++i) r[i] = 1.0 / x[i];
 #endif
+}
+
+
+// ------------------------------------------------------------------------------------------------ lane tables --
+// A 32-entry table of doubles held ACROSS THE LANES OF A WARP: lane l keeps entry l in one register pair and a lookup with a
+// per-thread index is one SHFL.IDX pair.  Unlike a gather from shared memory (LDS.64 with a divergent address: 2-3 bank-
+// conflict wavefronts each, tried in round 1 and no faster than the FP64 instructions it replaced) the shuffle has no
+// conflicts and no address arithmetic.  Only for code every lane of the warp executes together (the tensor-core kernel's
+// epilogue).  The host build indexes a plain array.
+struct LaneTab32 {
+#if defined(__CUDACC__)
+  double mine;   // entry [lane]
+  __device__ __forceinline__ double at(int j) const { return __shfl_sync(0xffffffffu, mine, j); }
+#else
+  const double* t;
+  double at(int j) const { return t[j]; }
+#endif
+};
+
+// 2^(j/32), j = 0..31, correctly rounded
+#if defined(__CUDACC__)
+static __constant__
+#else
+static const
+#endif
+    double kExp2Tab32[32] = {1.0,
+                             1.0218971486541166,
+                             1.0442737824274138,
+                             1.0671404006768237,
+                             1.0905077326652577,
+                             1.1143867425958924,
+                             1.1387886347566916,
+                             1.1637248587775775,
+                             1.189207115002721,
+                             1.215247359980469,
+                             1.241857812073484,
+                             1.2690509571917332,
+                             1.2968395546510096,
+                             1.3252366431597413,
+                             1.3542555469368927,
+                             1.383909881963832,
+                             1.4142135623730951,
+                             1.4451808069770467,
+                             1.4768261459394993,
+                             1.5091644275934228,
+                             1.5422108254079407,
+                             1.5759808451078865,
+                             1.6104903319492543,
+                             1.6457554781539649,
+                             1.681792830507429,
+                             1.7186192981224779,
+                             1.7562521603732995,
+                             1.7947090750031072,
+                             1.8340080864093424,
+                             1.8741676341103,
+                             1.9152065613971474,
+                             1.9571441241754002};
+
+// e^x for -700 <= x <= 700 with the table: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, e^x = 2^k T[j] (1 + q(r)),
+// q(r) = r + r^2 P(r) with P of degree 4 (|1 + q - e^r| < 2.3e-19 e^r): 1 + (1 or 2) + 7 FP64 instructions against the
+// 14 of exp_core_v.  Error: the rounding of T[j] and of the final FMA, < 1 ulp together.
+// NLO of the W arguments (the first ones) take the one-step reduction r = x - K fl(ln2/32): its error K 1.7e-18 matters only
+// relative to e^x itself and is for the caller to allow (see LogisticF: t = e^-a enters the result with weight O(t)).
+template <int W, int NLO>
+BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
+  const double kMagic = 6755399441055744.0;
+  const double c[5] = {1.38889253992791387136e-03, 8.33336254165508924507e-03, 4.16666666665591739482e-02, 1.66666666665806706416e-01,
+                       5.00000000000000000000e-01};
+  double kf[W], r[W], r2[W], p[W], t[W];
+  int K[W];
+  BC_UNROLL for (int i = 0; i < W; ++i) kf[i] = fm_fma(x[i], 4.61662413084468283841e+01, kMagic);
+  BC_UNROLL for (int i = 0; i < W; ++i) {
+    K[i] = fm_lo(kf[i]);
+    kf[i] = fm_i2d(K[i]);
+  }
+  BC_UNROLL for (int i = 0; i < W; ++i) t[i] = T.at(K[i] & 31);
+  BC_UNROLL for (int i = 0; i < W; ++i)
+    r[i] = (i < NLO) ? fm_fma(kf[i], -2.16608493924982901946e-02, x[i]) : fm_fma(kf[i], -2.16608493865351192653e-02, x[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) if (i >= NLO) r[i] = fm_fma(kf[i], -5.96317165397058656257e-12, r[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) r2[i] = r[i] * r[i];
+  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = c[0];
+  BC_UNROLL for (int j = 1; j < 5; ++j) {
+    BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], r[i], c[j]);
+  }
+  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(r2[i], p[i], r[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) y[i] = fm_add_exponent(fm_fma(t[i], p[i], t[i]), K[i] >> 5);
+}
+
+// 1/x for x in [1, 2]: the 2^-23 seed of rcp.approx.ftz.f64 and ONE cubic step r (1 + e + e^2), e = 1 - x r: 3 FP64
+// instructions instead of the 4 of two Newton steps, error e^3 < 2^-60 before the final rounding.
+template <int W>
+BC_HD void rcp_1to2_cubic_v(const double (&x)[W], double (&r)[W]) {
+  double e[W];
+#if defined(__CUDACC__)
+  BC_UNROLL for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(x[i]));
+#else
+  // host stand-in for the seed: 1/x cut to the 20 mantissa bits of the high word (coarser than the hardware's 2^-23)
+  for (int i = 0; i < W; ++i) r[i] = fm_hilo2d(fm_hi(1.0 / x[i]), 0);
+#endif
+  BC_UNROLL for (int i = 0; i < W; ++i) e[i] = fm_fma(-x[i], r[i], 1.0);
+  BC_UNROLL for (int i = 0; i < W; ++i) e[i] = fm_fma(e[i], e[i], e[i]);
+  BC_UNROLL for (int i = 0; i < W; ++i) r[i] = fm_fma(r[i], e[i], r[i]);
 }
 
 template <int N, int W>

@@ -93,6 +93,7 @@ struct QProjArgs {
   const double* colaux;  // [S] or null
   const double* rowaux;  // [n] or null
   ModelParams mp;
+  const double* pot_tabs;  // the potential's lane tables (LogisticTabs: 64 doubles) or null
   double* part_colsum;  // [grid][2][Sld]
   double* part_misc;    // [grid][4]
   int Sld;

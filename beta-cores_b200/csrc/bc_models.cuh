@@ -14,10 +14,24 @@ enum : int { MODEL_LOGISTIC = 0, MODEL_GAUSSIAN = 1, MODEL_NEURLIN = 2 };
 enum : int { KIND_LOGLIK = 0, KIND_BETALIK = 1, KIND_BETAGRAD = 2 };
 
 constexpr int kPowPolyMax = 24;  // highest degree of the (1+t)^-beta polynomial
+constexpr int kPowTab = -1;      // POLY value of the lane-table form of (1+t)^-beta (tensor-core kernel only)
+constexpr int kPowTabDeg = 6;    // degree of Q in (1+w)^-beta = 1 + w Q(w)
 struct ModelParams {
   double p[8];
   double q[kPowPolyMax + 1];  // logistic beta-likelihood: (1+t)^-beta on t in [0,1] as a polynomial in 2t-1, highest degree
                               // first, fitted by bc_set_potential for the current beta (bc_api.cu: fit_pow_poly)
+  double w[kPowTabDeg + 1];   // lane-table form: Q's coefficients, highest degree first (bc_api.cu: fit_pow_tab)
+};
+
+// per-thread tables of a potential's lane-table form (bc_fastmath.cuh: LaneTab32); empty for the potentials without one.
+//   dev: the 64 doubles bc_set_potential uploads for the logistic beta-likelihood, [0..32) = 1/s_j, [32..64) = s_j^-beta
+//        with s_j = 1 + (j + 1/2)/32 the centres of the 32 intervals of s = 1 + t in [1, 2]
+struct NoTabs {};
+struct ExpTabs {
+  LaneTab32 e2;
+};
+struct LogisticTabs {
+  LaneTab32 e2, rs, us;
 };
 
 // reference: examples/common/model_lr.py:72-79 (log_likelihood), :81-86 (beta_likelihood).
@@ -33,6 +47,19 @@ struct ModelParams {
 template <int KIND, int POLY = 20>
 struct LogisticF {
   static constexpr bool kRowAux = false, kColAux = false;
+  static constexpr bool kTab = (KIND == KIND_BETALIK && POLY == kPowTab);
+  struct Tabs : LogisticTabs {};
+#if defined(__CUDACC__)
+  __device__ __forceinline__ static Tabs tabs(const double* dev, int lane) {
+    Tabs T = {};
+    if (kTab) {
+      T.e2.mine = kExp2Tab32[lane];
+      T.rs.mine = __ldg(dev + lane);
+      T.us.mine = __ldg(dev + 32 + lane);
+    }
+    return T;
+  }
+#endif
   BC_HD static double eval(double c, double, double, const ModelParams& mp) {
     const double m = -c;
     const double a = fabs(m);
@@ -46,7 +73,7 @@ struct LogisticF {
       const double G = exp_nonpos(-beta * a);
       const double big = rcp_1to2(1.0 + t);
       double E;
-      if (POLY == 0) {
+      if (POLY <= 0) {
         E = exp_nonpos(-beta * log1p_unit(t));
       } else {
         E = horner<(POLY > 0 ? POLY : 1)>(mp.q + (kPowPolyMax - POLY), fm_fma(t, 2.0, -1.0));
@@ -59,12 +86,59 @@ struct LogisticF {
   // W independent elements, stage by stage (instruction-level parallelism for the FP64 pipe).  Same arithmetic as eval()
   // for finite arguments.  Used by the tensor-core kernel, which supplies its own NaN handling (a non-finite row poisons
   // the row's pivot) -- a NaN argument here gives an unspecified result.
-  //   p[2] = largest |m| passed to the exponentials: 700 / max(1, beta)  (one clamp serves e^-a and e^(-beta a); beyond
-  //          it both terms are below 1e-300 of the result)
+  //   p[2] = 700, p[3] = 700 / beta (low word cleared): the largest |m| passed to e^-a and to e^(-beta a); beyond them the
+  //          terms are below 1e-300.  (One clamp at 700 / max(1, beta) for both, as shipped in round 1, froze e^(-beta a) at
+  //          e^(-700 beta) for |m| > 700: wrong by k1 e^-7 at beta = 0.01.)
   template <int W>
-  BC_HD static void evalv(const double (&c)[W], double, const double (&)[W], const ModelParams& mp, double (&out)[W]) {
+  BC_HD static void evalv(const double (&c)[W], double, const double (&)[W], const ModelParams& mp, const Tabs& T, double (&out)[W]) {
     double a[W], x[W], t[W];
-    if (KIND == KIND_LOGLIK) {
+    if (kTab) {
+      // lane-table form: 38 FP64 instructions per element instead of 65.
+      //   |c| and the clamp on the integer pipe (p[2] has a zero low word, so comparing high words is the exact compare);
+      //   t = e^-a, G = e^(-beta a) by exp_tab_v (t with the one-step reduction: its error K 1.7e-18 t is below 1e-17 of the result);
+      //   big = 1/(1+t) by one cubic step;
+      //   E = (1+t)^-beta: s = 1 + t in [1,2] falls into interval j = its top five mantissa bits, s = s_j + d, |d| <= 1/64,
+      //   E = s_j^-beta (1 + w)^-beta with w = d / s_j, (1 + w)^-beta = 1 + w Q(w), Q of degree 6: 10 FP64 instructions
+      //   against the 21 of the degree-20 polynomial.
+      const double beta = mp.p[0], k1 = mp.p[1];
+      const int amax_hi = fm_hi(mp.p[2]), bmax_hi = fm_hi(mp.p[3]);
+      double G[W], big[W], E[W], s[W];
+      {
+        double xx[2 * W], yy[2 * W];
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          const int hi = fm_hi(c[i]) & 0x7fffffff, lo = fm_lo(c[i]);
+          const bool over_a = hi >= amax_hi, over_b = hi >= bmax_hi;
+          a[i] = fm_hilo2d(over_a ? amax_hi : hi, over_a ? 0 : lo);
+          xx[i] = -a[i];
+          xx[W + i] = -beta * fm_hilo2d(over_b ? bmax_hi : hi, over_b ? 0 : lo);
+        }
+        exp_tab_v<2 * W, W>(xx, T.e2, yy);
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          t[i] = yy[i];
+          G[i] = yy[W + i];
+        }
+      }
+      BC_UNROLL for (int i = 0; i < W; ++i) s[i] = 1.0 + t[i];
+      rcp_1to2_cubic_v<W>(s, big);
+      {
+        double d[W], R[W], U[W], w[W], Q[W];
+        BC_UNROLL for (int i = 0; i < W; ++i) {
+          int j = (fm_hi(s[i]) - 0x3ff00000) >> 15;   // s = 2 exactly (t = 1) lands on 32: last interval
+          j = j > 31 ? 31 : j;
+          d[i] = s[i] - fm_hilo2d(0x3ff04000 | (j << 15), 0);
+          R[i] = T.rs.at(j);
+          U[i] = T.us.at(j);
+        }
+        BC_UNROLL for (int i = 0; i < W; ++i) w[i] = d[i] * R[i];
+        horner_v<kPowTabDeg, W>(mp.w, w, Q);
+        BC_UNROLL for (int i = 0; i < W; ++i) Q[i] = w[i] * Q[i];
+        BC_UNROLL for (int i = 0; i < W; ++i) E[i] = fm_fma(U[i], Q[i], U[i]);
+      }
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const double sel = (fm_hi(c[i]) < 0) ? k1 * G[i] : k1;
+        out[i] = E[i] * fm_fma(big[i], fm_fma(G[i], t[i], 1.0), -sel);
+      }
+    } else if (KIND == KIND_LOGLIK) {
       BC_UNROLL for (int i = 0; i < W; ++i) a[i] = fabs(c[i]);
       BC_UNROLL for (int i = 0; i < W; ++i) x[i] = (a[i] > 700.0) ? -700.0 : -a[i];
       exp_core_v<W>(x, t);
@@ -73,18 +147,19 @@ struct LogisticF {
       horner_v<22, W>(kLog1pPoly, u, l);
       BC_UNROLL for (int i = 0; i < W; ++i) out[i] = -(fmax(-c[i], 0.0) + l[i]);
     } else {
-      const double beta = mp.p[0], k1 = mp.p[1], amax = mp.p[2];
-      double G[W], big[W], E[W], u[W];
+      const double beta = mp.p[0], k1 = mp.p[1], amax = mp.p[2], bmax = mp.p[3];
+      double G[W], big[W], E[W], u[W], b[W];
       BC_UNROLL for (int i = 0; i < W; ++i) {
         const double ai = fabs(c[i]);
         a[i] = (ai > amax) ? amax : ai;
+        b[i] = (ai > bmax) ? bmax : ai;
       }
       {
         // both exponentials of all W elements advance together: 2W independent dependency chains
         double xx[2 * W], yy[2 * W];
         BC_UNROLL for (int i = 0; i < W; ++i) {
           xx[i] = -a[i];
-          xx[W + i] = -beta * a[i];
+          xx[W + i] = -beta * b[i];
         }
         exp_core_v<2 * W>(xx, yy);
         BC_UNROLL for (int i = 0; i < W; ++i) {
@@ -94,7 +169,7 @@ struct LogisticF {
       }
       BC_UNROLL for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
       rcp_1to2_v<W>(u, big);
-      if (POLY == 0) {
+      if (POLY <= 0) {
         double l[W];
         BC_UNROLL for (int i = 0; i < W; ++i) u[i] = fm_fma(t[i], 2.0, -1.0);
         horner_v<22, W>(kLog1pPoly, u, l);
@@ -123,6 +198,16 @@ struct LogisticF {
 template <int KIND>
 struct GaussianF {
   static constexpr bool kRowAux = true, kColAux = true;
+  // the kinds with an exponential take it from the 2^(j/32) lane table in the tensor-core kernel (exp_tab_v: 10 FP64
+  // instructions instead of 14); evalv<W>'s last-but-one argument.  The host build passes a plain array.
+  struct Tabs : ExpTabs {};
+#if defined(__CUDACC__)
+  __device__ __forceinline__ static Tabs tabs(const double*, int lane) {
+    Tabs T = {};
+    if (KIND != KIND_LOGLIK) T.e2.mine = kExp2Tab32[lane];
+    return T;
+  }
+#endif
   BC_HD static double eval(double c, double ra, double ca, const ModelParams& mp) {
     const double q = ra + ca - 2.0 * c;
     if (KIND == KIND_LOGLIK) {
@@ -136,7 +221,7 @@ struct GaussianF {
     }
   }
   template <int W>
-  BC_HD static void evalv(const double (&c)[W], double ra, const double (&ca)[W], const ModelParams& mp, double (&out)[W]) {
+  BC_HD static void evalv(const double (&c)[W], double ra, const double (&ca)[W], const ModelParams& mp, const Tabs& T, double (&out)[W]) {
     double q[W];
     BC_UNROLL for (int i = 0; i < W; ++i) q[i] = ra + ca[i] - 2.0 * c[i];
     if (KIND == KIND_LOGLIK) {
@@ -148,7 +233,7 @@ struct GaussianF {
         const double yc = (y < -700.0) ? -700.0 : y;
         x[i] = (yc > 700.0) ? 700.0 : yc;
       }
-      exp_core_v<W>(x, e);
+      exp_tab_v<W, 0>(x, T.e2, e);
       BC_UNROLL for (int i = 0; i < W; ++i) {
         const double y = mp.p[2] * q[i];
         const double ee = (y != y) ? y : e[i];
@@ -172,6 +257,16 @@ struct GaussianF {
 template <int KIND>
 struct NeurlinF {
   static constexpr bool kRowAux = true, kColAux = false;
+  // the kinds with an exponential take it from the 2^(j/32) lane table in the tensor-core kernel (exp_tab_v: 10 FP64
+  // instructions instead of 14); evalv<W>'s last-but-one argument.  The host build passes a plain array.
+  struct Tabs : ExpTabs {};
+#if defined(__CUDACC__)
+  __device__ __forceinline__ static Tabs tabs(const double*, int lane) {
+    Tabs T = {};
+    if (KIND != KIND_LOGLIK) T.e2.mine = kExp2Tab32[lane];
+    return T;
+  }
+#endif
   BC_HD static double eval(double c, double y, double, const ModelParams& mp) {
     const double r2 = y * y - 2.0 * c * y + c * c;
     if (KIND == KIND_LOGLIK) {
@@ -181,7 +276,7 @@ struct NeurlinF {
     }
   }
   template <int W>
-  BC_HD static void evalv(const double (&c)[W], double y, const double (&)[W], const ModelParams& mp, double (&out)[W]) {
+  BC_HD static void evalv(const double (&c)[W], double y, const double (&)[W], const ModelParams& mp, const Tabs& T, double (&out)[W]) {
     double r2[W];
     BC_UNROLL for (int i = 0; i < W; ++i) r2[i] = y * y - 2.0 * c[i] * y + c[i] * c[i];
     if (KIND == KIND_LOGLIK) {
@@ -193,7 +288,7 @@ struct NeurlinF {
         const double zc = (z < -700.0) ? -700.0 : z;
         x[i] = (zc > 700.0) ? 700.0 : zc;
       }
-      exp_core_v<W>(x, e);
+      exp_tab_v<W, 0>(x, T.e2, e);
       BC_UNROLL for (int i = 0; i < W; ++i) {
         const double z = mp.p[4] * r2[i];
         const double ee = (z != z) ? z : e[i];

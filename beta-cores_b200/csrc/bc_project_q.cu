@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     // one scale for all samples; the stored scales are those of the full 7-digit split: 2^-32 each, 256^-(NS+1) is needed
     const double cs = __ldg(P.colscale) * (double)(1ull << (8 * (kQSlices - NS)));
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+    const typename F::Tabs tabs = F::tabs(P.pot_tabs, lane);   // lane-table forms: this lane's entries (bc_fastmath.cuh)
     constexpr int NB = kQHalfCols / 4;     // batches of 4 columns per chunk
     Best best = {0.0, -1};
     uint32_t use = 0, tcount = 0;
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) ca[e] = F::kColAux ? __ldg(P.colaux + min(cb + e, S - 1)) : 0.0;
-            F::template evalv<4>(cval, ra, ca, P.mp, fr);
+            F::template evalv<4>(cval, ra, ca, P.mp, tabs, fr);
             if (grp == 0 && c == 0 && b == 0) {
               // pivot = the potential at the first sample: any per-row constant near the row mean keeps
               // sum f^2 - S mean^2 well conditioned; the other groups read it from shared memory.
@@ -754,6 +755,7 @@ cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, 
   if (mode == QMODE_DOT) return launch_q_digits<LogisticF<KIND_LOGLIK, 0>, QMODE_DOT>(P, digits, grid, st);
   if (model == MODEL_LOGISTIC) {
     if (kind == KIND_LOGLIK) return launch_q_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, digits, grid, st);
+    if (poly == kPowTab) return launch_q_mode<LogisticF<KIND_BETALIK, kPowTab>>(P, mode, digits, grid, st);
     if (poly == 20) return launch_q_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, digits, grid, st);
     if (poly == kPowPolyMax) return launch_q_mode<LogisticF<KIND_BETALIK, kPowPolyMax>>(P, mode, digits, grid, st);
     return launch_q_mode<LogisticF<KIND_BETALIK, 0>>(P, mode, digits, grid, st);

@@ -86,7 +86,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// exact conversion of an integer |t| < 2^53 to fp64 (I2F.F64.S64 on the conversion unit: measured a little faster here than
+// conversion of an int64 to fp64, round to nearest (exact for |t| < 2^53) (I2F.F64.S64 on the conversion unit: measured a little faster here than
 // the integer-add + FP64-add magic-number form, which occupies the contended FP64 pipe)
 __device__ __forceinline__ double exact_ll2d(long long t) { return __ll2double_rn(t); }
 // the NS int32 digit diagonals D_d = sum_{i+j=d} A_i B_j^T  ->  sum_d D_d 256^(NS-1-d)  as an fp64 (one rounding):
@@ -94,6 +94,21 @@ __device__ __forceinline__ double exact_ll2d(long long t) { return __ll2double_r
 template <int NS>
 __device__ __forceinline__ double q_combine_n(const int (&d)[NS]) {
   static_assert(NS >= 4 && NS <= 7, "digit count");
+  if (NS <= 6) {
+    // |D_d| <= (d+1) 2^21, so the whole sum stays below 2^62: one int64 and ONE conversion (same single rounding as the
+    // two-half form below, which the 7-digit split needs)
+    // the four trailing digits by 32 x 32 -> 64 multiply-adds (IMAD.WIDE), the leading ones straight into the high word
+    long long t = (long long)d[NS - 1];
+    t += (long long)d[NS - 2] * 256;
+    t += (long long)d[NS - 3] * 65536;
+    t += (long long)d[NS - 4] * 16777216;
+    if (NS >= 5) {
+      int hi = (int)(t >> 32) + d[NS - 5];
+      if (NS >= 6) hi += d[NS - 6] << 8;
+      t = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)(int)t);
+    }
+    return exact_ll2d(t);
+  }
   long long hi = 0;
 #pragma unroll
   for (int i = 0; i < NS - 3; ++i) hi = (hi << 8) + (long long)d[i];

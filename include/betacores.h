@@ -44,6 +44,16 @@ int64_t bc_launch_count(void);          /* kernels this library has launched in 
  * (1+t)^-beta on t in [0,1] -- the pow() of examples/common/model_lr.py:85 -- and their truncation bound.
  * degree <= 24.  Used by the CPU tests to check the polynomial against a high-precision reference. */
 int bc_fit_pow_poly(double beta, int degree, double* h_coef, double* h_err);
+/* Host-only diagnostic: the lane-table form of the same pow() that the tensor-core kernels use when it is accurate enough
+ * for the given beta (csrc/bc_models.cuh, LogisticF<KIND_BETALIK, kPowTab>):  h_w = the 7 coefficients of Q (highest degree
+ * first) in (1+w)^-beta = 1 + w Q(w), |w| <= 1/65;  h_rs[j] = 1/s_j and h_us[j] = s_j^-beta for the 32 interval centres
+ * s_j = 1 + (j + 1/2)/32 of s = 1 + t;  *h_err = max |w Q(w) - ((1+w)^-beta - 1)|. */
+int bc_fit_pow_tab(double beta, double* h_w, double* h_rs, double* h_us, double* h_err);
+/* Which evaluation form of a potential the tensor-core kernels may use: 0 = the fastest one that meets the quarter-ulp
+ * bound (default), 1 = the polynomial forms only (what the FP64-DMMA kernels always use).  Takes effect with the next
+ * bc_set_potential.  bc_potential_form: 2 if the current potential runs in its lane-table form, else 1. */
+int bc_set_potential_form(bc_ctx* ctx, int form);
+int bc_potential_form(const bc_ctx* ctx);
 int bc_create(int device, bc_ctx** ctx);
 int bc_destroy(bc_ctx* ctx);
 int bc_sm_count(const bc_ctx* ctx);

@@ -123,7 +123,7 @@ def test_logistic_loglik_rewrite(fm):
     assert np.allclose(got, ref, rtol=1e-15, atol=1e-15)
 
 
-@pytest.mark.parametrize('kind,beta,poly', [(1, 0.1, 20), (1, 0.9, 24), (1, 0.1, 0), (1, 3.0, 0), (0, 0.1, 0)])
+@pytest.mark.parametrize('kind,beta,poly', [(1, 0.01, 20), (1, 0.1, 20), (1, 0.9, 24), (1, 0.1, 0), (1, 3.0, 0), (0, 0.1, 0)])
 def test_logistic_vector_forms(fm, kind, beta, poly):
     """evalv<4> -- the stage-interleaved form k_project_q runs (single clamp, integer sign test, no NaN selects) -- against
     60-digit arithmetic"""
@@ -142,3 +142,116 @@ def test_logistic_vector_forms(fm, kind, beta, poly):
             want = _lr_beta_exact(m, beta) if kind == 1 else -mp.log1p(mp.exp(mp.mpf(float(m))))
             worst = max(worst, float(abs(mp.mpf(got)-want)/max(1, abs(want))))
     assert worst < 5e-16*(max(1., (beta+1)/beta) if kind == 1 else 1.), worst
+
+
+# ---- lane-table forms (the tensor-core kernel's default for the logistic beta-likelihood) ----
+def _fit_tab(beta):
+    from bayesiancoresets import _native as nv
+    w, rs, us, err = (ctypes.c_double*7)(), (ctypes.c_double*32)(), (ctypes.c_double*32)(), ctypes.c_double()
+    nv.call('bc_fit_pow_tab', float(beta), w, rs, us, ctypes.byref(err))
+    return w, rs, us, err.value
+
+
+@pytest.fixture(scope='module')
+def fmt(fm):
+    d, i, dp = ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
+    fm.fm_exp_tab.argtypes, fm.fm_exp_tab.restype = [d, i], d
+    fm.fm_logistic_v4_tab.argtypes, fm.fm_logistic_v4_tab.restype = [dp, d, dp, dp, dp, dp], None
+    return fm
+
+
+@pytest.mark.parametrize('lo', [0, 1])
+def test_table_exp_is_one_ulp(fmt, lo):
+    """exp_tab_v: 32-entry 2^(j/32) table + degree-6 expm1 polynomial.  The two-step reduction is within an ulp everywhere; the
+    one-step form adds K * 1.7e-18 (K = 32 x / ln2), i.e. stays within an ulp for |x| < 1 and within 1e-17 ABSOLUTE always"""
+    r = np.random.RandomState(0)
+    xs = np.concatenate([r.uniform(-700, 0, 4000), r.uniform(-2, 0, 4000), -10.**np.linspace(-300, 2.8, 400), [-700., 0., -0.0]])
+    worst_rel, worst_abs = 0., 0.
+    for x in xs:
+        want = mp.exp(mp.mpf(float(x)))
+        got = mp.mpf(fmt.fm_exp_tab(float(x), lo))
+        rel = float(abs(got-want)/want)
+        if lo or abs(x) < 1:
+            worst_rel = max(worst_rel, rel)
+        worst_abs = max(worst_abs, float(abs(got-want)))
+    assert worst_rel < 2.3e-16, worst_rel
+    assert worst_abs < (1.2e-16 if lo else 1.2e-16), worst_abs
+
+
+@pytest.mark.parametrize('beta', [0.01, 0.1, 0.4, 0.5, 0.9])
+def test_pow_table_fit(beta):
+    w, rs, us, err = _fit_tab(beta)
+    assert err < 5e-17, err           # the acceptance bound of bc_set_potential
+    mb = mp.mpf(beta)
+    for j in range(32):
+        sj = 1 + (mp.mpf(j) + mp.mpf(1)/2)/32
+        assert abs(mp.mpf(rs[j]) - 1/sj) <= abs(1/sj)*mp.mpf(2)**-53
+        assert abs(mp.mpf(us[j]) - sj**(-mb)) <= sj**(-mb)*mp.mpf(2)**-53
+    worst = 0
+    for x in np.linspace(-1/65., 1/65., 1001):
+        ww = mp.mpf(float(x))
+        q = mp.mpf(0)
+        for ck in w:
+            q = q*ww + mp.mpf(ck)
+        worst = max(worst, abs(1 + ww*q - (1+ww)**(-mb)))
+    assert worst < 5e-17, worst
+
+
+def test_pow_table_is_refused_where_it_is_not_accurate():
+    assert _fit_tab(3.0)[3] > 5e-17          # bc_set_potential then keeps the polynomial / exp-log forms
+
+
+@pytest.mark.parametrize('beta', [0.01, 0.1, 0.5, 0.9])
+def test_logistic_table_form(fmt, beta):
+    """LogisticF<KIND_BETALIK, kPowTab>::evalv<4> (integer |c| and clamp, table exponentials, cubic reciprocal, table power)
+    against 60-digit arithmetic: the same bound as the polynomial forms"""
+    w, rs, us, err = _fit_tab(beta)
+    r = np.random.RandomState(4)
+    ms = np.concatenate([r.normal(0, 12, 3000), np.linspace(-60, 60, 1201), r.uniform(-1, 1, 800)*1e-3,
+                         [0., -0.0, 700., -700., 745., -745., 5000., -5000., 1e-300, -1e-300]])
+    ms = ms[:4*(len(ms)//4)]
+    worst = 0.
+    out = (ctypes.c_double*4)()
+    for k in range(0, len(ms), 4):
+        c4 = (ctypes.c_double*4)(*[float(-m) for m in ms[k:k+4]])
+        fmt.fm_logistic_v4_tab(c4, beta, w, rs, us, out)
+        for m, got in zip(ms[k:k+4], out):
+            want = _lr_beta_exact(m, beta)
+            worst = max(worst, float(abs(mp.mpf(got)-want)/max(1, abs(want))))
+    assert worst < 5e-16*max(1., (beta+1)/beta), worst
+    # a constant row must give one double: equal arguments, equal results, whatever the lane
+    c4 = (ctypes.c_double*4)(0.3, 0.3, 0.3, 0.3)
+    fmt.fm_logistic_v4_tab(c4, beta, w, rs, us, out)
+    assert len(set(out)) == 1
+
+
+def test_gaussian_and_neural_linear_vector_forms(fmt):
+    """evalv<4> of the Gaussian (gaussian.py:34-62) and neural-linear (model_neurlinr.py:102-110) potentials -- the forms the
+    tensor-core kernel runs, exponential from the lane table -- against 60-digit arithmetic and against the scalar forms"""
+    d, i, dp = ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
+    fmt.fm_gaussian_v.argtypes, fmt.fm_gaussian_v.restype = [i, d, d, d, dp], d
+    fmt.fm_neurlin_v.argtypes, fmt.fm_neurlin_v.restype = [i, d, d, dp], d
+    r = np.random.RandomState(7)
+    beta, dd, s2 = 0.3, 20, 1.7
+    pg = (ctypes.c_double*8)(-3.2, 1/beta, -.5*beta, (1+beta)**(-.5*dd-1), 0.7, 1/beta**2, 1/(2*beta), (1+beta)**(-.5*dd-1)*np.log(1+beta))
+    pn = (ctypes.c_double*8)(-.5*np.log(2*np.pi*s2), 1/(2*s2), (2*np.pi*s2)**(-beta/2), -(beta+1)/beta, -beta/(2*s2), 1/np.sqrt(1+beta), 0, 0)
+    worst = 0.
+    for _ in range(1500):
+        c, ra, ca = r.normal(0, 5), abs(r.normal(0, 30)), abs(r.normal(0, 30))
+        q = mp.mpf(ra) + mp.mpf(ca) - 2*mp.mpf(c)
+        e = mp.exp(mp.mpf(pg[2])*q) if mp.mpf(pg[2])*q > -700 else mp.exp(-700)
+        want = {0: mp.mpf(pg[0]) - q/2, 1: mp.mpf(pg[1])*e - mp.mpf(pg[3]),
+                2: mp.mpf(pg[4])*(mp.mpf(pg[1])*e - mp.mpf(pg[3])) - mp.mpf(pg[5])*e - mp.mpf(pg[6])*q*e - mp.mpf(pg[7])}
+        for kind in (0, 1, 2):
+            got = fmt.fm_gaussian_v(kind, c, ra, ca, pg)
+            scale = max(1, abs(want[kind]), float(abs(q))*float(e)*pg[6] if kind == 2 else 0)
+            worst = max(worst, float(abs(mp.mpf(got) - want[kind])/scale))
+            assert abs(got - fmt.fm_gaussian(kind, c, ra, ca, pg)) <= 4e-15*float(scale)
+        y = r.normal(0, 3)
+        r2 = mp.mpf(y)**2 - 2*mp.mpf(c)*mp.mpf(y) + mp.mpf(c)**2
+        wl = mp.mpf(pn[0]) - mp.mpf(pn[1])*r2
+        wb = mp.mpf(pn[2])*(mp.mpf(pn[3])*mp.exp(mp.mpf(pn[4])*r2) + mp.mpf(pn[5]))
+        worst = max(worst, float(abs(mp.mpf(fmt.fm_neurlin_v(0, c, y, pn)) - wl)/max(1, abs(wl))))
+        worst = max(worst, float(abs(mp.mpf(fmt.fm_neurlin_v(1, c, y, pn)) - wb)/max(1, abs(wb))))
+        assert fmt.fm_neurlin_v(1, c, y, pn) == pytest.approx(fmt.fm_neurlin(1, c, y, pn), rel=1e-14, abs=1e-15)
+    assert worst < 2e-15, worst
