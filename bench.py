@@ -379,7 +379,7 @@ def b200_arm(a, emit=True):
     if route == 'q':
         kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
                  'column sums, fused)')
-        digit_pairs, fp64_inst = digits*(digits+1)//2, 65   # kept digit pairs (diagonals d < digits); FP64-pipe instructions per evaluation (SASS count)
+        digit_pairs, fp64_inst = digits*(digits+1)//2, 42   # kept digit pairs (diagonals d < digits); FP64-pipe instructions per evaluation (SASS count of the lane-table form, profiles/r02_sass_histogram.txt)
         int8_ops = digit_pairs*2.*n_local*S*128
         # measured on this pool (tools/mma_i8_rate.cu, profiles/r01_mma_i8_rate.txt): 8192 int8 MACs per cycle per SM from N = 128 up
         int8_peak = eng.sms*8192*2.*1965e6/1e12
@@ -396,8 +396,20 @@ def b200_arm(a, emit=True):
                                            '= %.0f would be the estimate)' % (2*bf16_peak)},
             'fp64_pipe': {'instructions_per_eval': fp64_inst,
                           'frac_of_issue_peak': n_local*S*fp64_inst/32./(eng.sms*4*0.5*sm_clock_hz*col_mean*1e-3),
-                          'note': 'the potential (two exp, one reciprocal, one degree-20 polynomial per evaluation) runs on the FP64 pipe '
-                                  '(0.5 warp-instructions/cycle/sub-partition, measured tools/fp64_ipc.cu); it, not the tensor pipe, bounds the kernel'}}
+                          'note': 'the potential (two table exponentials, one reciprocal, one table power per evaluation: 42 FP64 instructions, '
+                                  '69 in its polynomial form) runs on the FP64 pipe (0.5 warp-instructions/cycle/sub-partition, measured '
+                                  'tools/fp64_ipc.cu)'}}
+        # FP64 instructions and tcgen05 MMAs issue through ONE pipe of the SM (ncu: sm__pipe_shared_cycles_active = fp64 + tensor, to
+        # the decimal, profiles/r02_ncu_k_project_q_lane_tables.txt): the honest denominator of this kernel is that pipe's time
+        warp_evals_per_subpartition = n_local*S/32./(eng.sms*4)
+        cycles_per_warp_eval = col_mean*1e-3*sm_clock_hz/warp_evals_per_subpartition
+        mma_cycles_per_warp_eval = digit_pairs*128*32*128/8192./32.     # one 128 x 32 chunk = 32 warp-evaluations per sub-partition
+        extra['shared_pipe'] = {'cycles_per_warp_evaluation': cycles_per_warp_eval,
+                                'fp64_cycles': 2.*fp64_inst, 'int8_mma_cycles': mma_cycles_per_warp_eval,
+                                'frac': (2.*fp64_inst + mma_cycles_per_warp_eval)/cycles_per_warp_eval,
+                                'note': 'pipe-time roofline computed live from launch_ms: (FP64 instructions x 2 cycles + int8 MMA cycles at '
+                                        '8192 MACs/cycle/SM) per warp-evaluation per sub-partition over the measured cycles; ncu measured '
+                                        '58.7 % for the same quantity (fp64 38.9 % + tensor 19.8 %)'}
     else:
         kname = 'k_project<LogisticF<BETALIK>, MODE_COLSUM> (FP64 DMMA contraction + beta-likelihood + centring + column sums, fused)'
         extra = {'route': 'dmma'}
@@ -425,14 +437,14 @@ def b200_arm(a, emit=True):
                                 'note': 'int8 digit planes of the rows (%d B per feature) + row scales; samples stay in L2' % digits})
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for a
         # 1,000,000-row launch (= the algorithmic 904 MB; the operands are read exactly once); it scales linearly in rows
-        per_row = {7: 911.4, 6: 911.4*6/7., 5: 911.4*5/7.}[digits]
+        per_row = {7: 911.4, 6: 784.0, 5: 911.4*5/7.}[digits]   # 6 digits: 777.5 + 6.5 MB, profiles/r02_ncu_k_project_q_lane_tables.txt
         roofline['traffic'] = per_row*n_local
-        roofline['traffic_source'] = ('ncu --set full capture at 1M rows per launch (profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for the '
-                                      '7-digit image, = its algorithmic bytes), scaled by rows and by the digit planes a launch reads; not '
+        roofline['traffic_source'] = ('ncu --set full captures at 1M rows per launch (profiles/r02_ncu_k_project_q_lane_tables.txt: 784.0 MB for the 6-digit tier; '
+                                      'profiles/r01_ncu_k_project_q_v4.txt: 911.4 MB for the 7-digit image; = the algorithmic bytes), scaled by rows; not '
                                       'measured in this run (DRAM counters need ncu)')
-        roofline['bound_detail'] = ('FP64 pipe of the fused potential epilogue PLUS the tensor time of the int8 digit MMAs: on B200 the FP64 pipe '
-                                    'makes no progress while the tensor core is busy (profiles/r01_q_ablation.txt), so the two add up; '
-                                    'HBM is at 2 % of its peak')
+        roofline['bound_detail'] = ('FP64 pipe of the fused potential epilogue PLUS the tensor time of the int8 digit MMAs: on B200 both issue through '
+                                    'the same SM pipe (ncu pipe_shared = fp64 + tensor; measured as a stall of the epilogue during the MMA windows in '
+                                    'profiles/r01_q_ablation.txt), so the two add up -- see shared_pipe.frac; HBM is at 2 % of its peak')
     idcs_value = [int(i) for i in alg.idcs]
     if route == 'q' and not getattr(a, 'lean', False):
         # the other precision tiers of the same pass, timed right here on the resident rows (3 passes each after 2 warm-ups)

@@ -1,4 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-python tools/q_time.py > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_project_q -s 3 -c 1 -f -o gpurun_out/r02_q_tab_full python tools/q_time.py > gpurun_out/ncu_q_tab.log 2>&1; echo ncu rc=$?; tail -2 gpurun_out/plain.log
+python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_n1_c.json 2> gpurun_out/r02_bench_n1_c.err; echo bench rc=$?
+python bench.py --configs > gpurun_out/r02_configs_k.jsonl 2> gpurun_out/r02_configs_k.err; echo configs rc=$?
+python bench.py --n 1250000 --no-e2e --no-cpu-baseline --steps 3 --warmup 2 > gpurun_out/r02_bench_shard_d.json 2> gpurun_out/r02_bench_shard_d.err; echo shard rc=$?
