@@ -332,6 +332,57 @@ def test_precision_tiers_keep_reference_selections(bc, models, digits, name):
     np.testing.assert_allclose(w, g[name+'_wts'], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize('beta', [0.01, 0.1, 0.5, 0.9, 3.0])
+def test_lane_table_potential_equals_the_polynomial_form(bc, beta):
+    """bc_set_potential_form: the tensor-core kernels evaluate the logistic beta-likelihood in its lane-table form (table
+    exponentials / table power, 42 FP64 instructions) when the per-beta fit is accurate enough, else (beta = 3) in the
+    polynomial / exp-log forms (69).  Same pass, both forms: column sums agree to the rounding of the potential, the arg-max
+    is the same row, and each agrees with the oracle's materialised matrix."""
+    import torch
+    from bayesiancoresets._device import Engine, DeviceRows, ptr, stream_ptr
+    from bayesiancoresets import _native as nv
+    from oracle import np_models as om
+    eng = Engine.get()
+    ctx = eng.ctx('formtest')
+    n, D, S = 3000, 128, 256
+    r = np.random.RandomState(17)
+    X = r.randn(n, D)
+    X[:40] *= 40.                     # |m| up to a few hundred: the tails of both exponentials
+    Th = r.randn(S, D)/np.sqrt(D)
+    rows, T = DeviceRows(eng, X), eng.upload(Th)
+    ref = om.lr_betalik(X, Th, beta)
+    ref = ref - ref.mean(axis=1)[:, None]
+    resid = np.concatenate([ref.sum(axis=0), [0.]])
+    resid[S] = resid[:S].sum()
+    res = {}
+    try:
+        for form in (1, 0):
+            nv.call('bc_set_potential_form', ctx, form)
+            nv.call('bc_set_potential', ctx, nv.MODEL_LOGISTIC, nv.KIND_BETALIK, D, nv.params8([beta, (beta+1)/beta, 0, 0, 0, 0, 0, 0]), None)
+            assert nv.lib().bc_potential_form(ctx) == (2 if (form == 0 and beta < 1.) else 1)
+            nv.call('bc_set_samples', ctx, ptr(T), S, int(T.stride(0)), stream_ptr())
+            img, rs, _, fexp = rows.quantised(ctx, D)
+            nv.call('bc_set_feature_exponents', ctx, ptr(fexp), D, stream_ptr())
+            Sld = nv.lib().bc_colsum_ld(S)
+            parts, cs = eng.empty(2*Sld), eng.empty(S)
+            nv.call('bc_project_colsum_q', ctx, ptr(img), ptr(rs), n, None, ptr(parts), stream_ptr())
+            nv.call('bc_colsum_combine', ctx, ptr(parts), 1, S, ptr(cs), stream_ptr())
+            best, scores = eng.empty(2), eng.empty(n)
+            rd = eng.upload(resid)
+            nv.call('bc_project_score_q', ctx, ptr(img), ptr(rs), n, None, ptr(rd), 0, ptr(best), ptr(scores), stream_ptr())
+            res[form] = (cs.cpu().numpy(), scores.cpu().numpy(), best.cpu().numpy().copy())
+    finally:
+        nv.call('bc_set_potential_form', ctx, 0)
+    scale = np.abs(ref).sum(axis=0).max()
+    for form in (1, 0):
+        np.testing.assert_allclose(res[form][0], ref.sum(axis=0), rtol=0, atol=2e-12*scale)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=0, atol=1e-13*scale*max(1., (beta+1)/beta/10.))
+    want = ref.dot(resid[:S])/np.sqrt((ref**2).sum(axis=1))/S
+    for form in (1, 0):
+        np.testing.assert_allclose(res[form][1], want, rtol=1e-9, atol=1e-12*np.abs(want).max())
+    assert int(res[0][2].view(np.int64)[1]) == int(res[1][2].view(np.int64)[1]) == int(np.argmax(want))
+
+
 def test_alternating_algorithms_share_the_workspace(bc, models):
     """two coreset objects built ALTERNATELY on one engine (the bc_ctx workspace holds one potential and one sample set
     at a time): a SparseVICoreset (log-likelihood) and a BetaCoreset (beta-likelihood) must each re-apply their own
