@@ -27,7 +27,8 @@ struct bc_ctx {
   double* tab_dev = nullptr;
   double tab_beta[kTabSlots] = {0};
   int tab_count = 0;
-  const double* tab_cur = nullptr;   // slot of the current potential, or null: polynomial forms
+  const double* tab_cur = nullptr;   // slot of the current potential's tables (logistic beta-likelihood), or null
+  bool tab_form = false;             // the tensor-core kernels run the current potential in its lane-table form
   int pot_form = 0;                  // bc_set_potential_form: 0 = fastest form available, 1 = polynomial forms only
   const double* d_siginv = nullptr;
   double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
@@ -213,7 +214,7 @@ int bc_set_potential_form(bc_ctx* c, int form) {
   c->potential_set = false;   // takes effect with the next bc_set_potential
   return BC_OK;
 }
-int bc_potential_form(const bc_ctx* c) { return (c && c->tab_cur) ? 2 : 1; }
+int bc_potential_form(const bc_ctx* c) { return (c && c->tab_form) ? 2 : 1; }
 int64_t bc_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int bc_create(int device, bc_ctx** out) {
@@ -324,8 +325,12 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
       for (int k = 0; k <= kPowTabDeg; ++k) c->mp.w[k] = w[k];
       c->tab_cur = c->tab_dev + (size_t)slot * 64;
     }
+    c->tab_form = c->tab_cur != nullptr;
   } else {
     c->tab_cur = nullptr;
+    // the logistic log-likelihood's tables hold no model constant (bc_fastmath.cuh); Gaussian / neural-linear potentials take
+    // their exponential from the lane table in every form
+    c->tab_form = (model == BC_MODEL_LOGISTIC && kind == BC_KIND_LOGLIK && c->pot_form == 0);
   }
   c->d_siginv = d_siginv;
   c->siginvT_ready = false;
@@ -609,7 +614,7 @@ int bc_project_colsum_q(bc_ctx* c, const void* d_image, const double* d_rowscale
     BC_CUDA(cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 2 * P.Sld, st));
     return BC_OK;
   }
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_COLSUM, c->q_digits, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_form ? kPowTab : c->poly, QMODE_COLSUM, c->q_digits, grid, st));
   double* fused = c->fuse_colsum_out;
   c->fuse_colsum_out = nullptr;
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, d_out_dd, nullptr, MODE_COLSUM, st, fused));
@@ -628,7 +633,7 @@ int bc_project_score_q(bc_ctx* c, const void* d_image, const double* d_rowscale,
   P.scores = d_scores;
   P.idx_offset = idx_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_SCORE, c->q_digits, grid, st));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_form ? kPowTab : c->poly, QMODE_SCORE, c->q_digits, grid, st));
   BC_CUDA(launch_project_finalize(c->part_colsum, c->part_misc, grid, c->S, P.Sld, nullptr, d_best, MODE_SCORE, st));
   BC_LAUNCHED(2);
   return BC_OK;
@@ -645,7 +650,7 @@ int bc_contraction_q(bc_ctx* c, const void* d_image, const double* d_rowscale, i
   P.rowaux = nullptr;
   P.V = d_V;
   P.ldv = ldv;
-  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_cur ? kPowTab : c->poly, QMODE_DOT, c->q_digits, grid, (cudaStream_t)stream));
+  BC_CUDA(launch_project_q(P, c->model, c->kind, c->tab_form ? kPowTab : c->poly, QMODE_DOT, c->q_digits, grid, (cudaStream_t)stream));
   BC_LAUNCHED(1);
   return BC_OK;
 }

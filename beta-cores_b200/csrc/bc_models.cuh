@@ -47,15 +47,20 @@ struct LogisticTabs {
 template <int KIND, int POLY = 20>
 struct LogisticF {
   static constexpr bool kRowAux = false, kColAux = false;
-  static constexpr bool kTab = (KIND == KIND_BETALIK && POLY == kPowTab);
+  static constexpr bool kTab = (POLY == kPowTab);
   struct Tabs : LogisticTabs {};
 #if defined(__CUDACC__)
   __device__ __forceinline__ static Tabs tabs(const double* dev, int lane) {
     Tabs T = {};
     if (kTab) {
       T.e2.mine = kExp2Tab32[lane];
-      T.rs.mine = __ldg(dev + lane);
-      T.us.mine = __ldg(dev + 32 + lane);
+      if (KIND == KIND_BETALIK) {
+        T.rs.mine = __ldg(dev + lane);
+        T.us.mine = __ldg(dev + 32 + lane);
+      } else {               // log-likelihood: 1/s_j and log(s_j), no model constant in them
+        T.rs.mine = kRcpTab32[lane];
+        T.us.mine = kLogTab32[lane];
+      }
     }
     return T;
   }
@@ -92,7 +97,34 @@ struct LogisticF {
   template <int W>
   BC_HD static void evalv(const double (&c)[W], double, const double (&)[W], const ModelParams& mp, const Tabs& T, double (&out)[W]) {
     double a[W], x[W], t[W];
-    if (kTab) {
+    if (kTab && KIND == KIND_LOGLIK) {
+      // lane-table form of -(max(m, 0) + log1p(e^-|m|)), m = -c: t by exp_tab_v, log(1 + t) = log(s_j) + log1p(w) with the
+      // interval tables of bc_fastmath.cuh (T.us holds log(s_j) here): 22 FP64 instructions instead of 42
+      double s[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const int hi = fm_hi(c[i]) & 0x7fffffff;
+        x[i] = -fm_hilo2d(hi < 0x4085e000 ? hi : 0x4085e000, fm_lo(c[i]));   // |c| capped at 700 (and a hair: the low word stays)
+      }
+      exp_tab_v<W, W>(x, T.e2, t);
+      BC_UNROLL for (int i = 0; i < W; ++i) s[i] = 1.0 + t[i];
+      double d[W], R[W], L[W], w[W], w2[W], P[W];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        int j = (fm_hi(s[i]) - 0x3ff00000) >> 15;
+        j = j > 31 ? 31 : j;
+        d[i] = s[i] - fm_hilo2d(0x3ff04000 | (j << 15), 0);
+        R[i] = T.rs.at(j);
+        L[i] = T.us.at(j);
+      }
+      BC_UNROLL for (int i = 0; i < W; ++i) w[i] = d[i] * R[i];
+      BC_UNROLL for (int i = 0; i < W; ++i) w2[i] = w[i] * w[i];
+      horner_v<5, W>(kLog1pTabPoly, w, P);
+      BC_UNROLL for (int i = 0; i < W; ++i) P[i] = fm_fma(w2[i], P[i], w[i]) + L[i];
+      BC_UNROLL for (int i = 0; i < W; ++i) {
+        const int hi = fm_hi(c[i]);
+        const double mx = fm_hilo2d(hi < 0 ? (hi & 0x7fffffff) : 0, hi < 0 ? fm_lo(c[i]) : 0);   // max(-c, 0)
+        out[i] = -(mx + P[i]);
+      }
+    } else if (kTab) {
       // lane-table form: 38 FP64 instructions per element instead of 65.
       //   |c| and the clamp on the integer pipe (p[2] has a zero low word, so comparing high words is the exact compare);
       //   t = e^-a, G = e^(-beta a) by exp_tab_v (t with the one-step reduction: its error K 1.7e-18 t is below 1e-17 of the result);
@@ -106,11 +138,12 @@ struct LogisticF {
       {
         double xx[2 * W], yy[2 * W];
         BC_UNROLL for (int i = 0; i < W; ++i) {
+          // the high word alone is capped (one integer min each): beyond the cap the value keeps its low word, i.e. exceeds
+          // the cap by less than 2^-20 of it -- still inside the range exp_tab_v takes
           const int hi = fm_hi(c[i]) & 0x7fffffff, lo = fm_lo(c[i]);
-          const bool over_a = hi >= amax_hi, over_b = hi >= bmax_hi;
-          a[i] = fm_hilo2d(over_a ? amax_hi : hi, over_a ? 0 : lo);
+          a[i] = fm_hilo2d(hi < amax_hi ? hi : amax_hi, lo);
           xx[i] = -a[i];
-          xx[W + i] = -beta * fm_hilo2d(over_b ? bmax_hi : hi, over_b ? 0 : lo);
+          xx[W + i] = -beta * fm_hilo2d(hi < bmax_hi ? hi : bmax_hi, lo);
         }
         exp_tab_v<2 * W, W>(xx, T.e2, yy);
         BC_UNROLL for (int i = 0; i < W; ++i) {

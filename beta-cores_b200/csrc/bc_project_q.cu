@@ -754,6 +754,7 @@ static cudaError_t launch_q_mode(const QProjArgs& P, int mode, int digits, int g
 cudaError_t launch_project_q(const QProjArgs& P, int model, int kind, int poly, int mode, int digits, int grid, cudaStream_t st) {
   if (mode == QMODE_DOT) return launch_q_digits<LogisticF<KIND_LOGLIK, 0>, QMODE_DOT>(P, digits, grid, st);
   if (model == MODEL_LOGISTIC) {
+    if (kind == KIND_LOGLIK && poly == kPowTab) return launch_q_mode<LogisticF<KIND_LOGLIK, kPowTab>>(P, mode, digits, grid, st);
     if (kind == KIND_LOGLIK) return launch_q_mode<LogisticF<KIND_LOGLIK, 0>>(P, mode, digits, grid, st);
     if (poly == kPowTab) return launch_q_mode<LogisticF<KIND_BETALIK, kPowTab>>(P, mode, digits, grid, st);
     if (poly == 20) return launch_q_mode<LogisticF<KIND_BETALIK, 20>>(P, mode, digits, grid, st);

@@ -28,6 +28,10 @@ __device__ __forceinline__ double blk_sum(double x, double* red) {  // all threa
   return y;
 }
 
+// (Tried in round 2 for coresets of a handful of points, profiles/r02_laplace_parts.txt: H = I + U U^T with U = Z^T diag(r) of rank M
+// factorises by an M x M recurrence, L_kk = sqrt(p), L_ik = u_i . G u_k / sqrt(p), G <- G - (G u_k)(G u_k)^T / p, p = 1 + u_k G u_k,
+// without the D x D Hessian -- one warp, lane = row of G.  Its D sequential steps of shuffles + sqrt + reciprocal took 135 k cycles
+// at D = 128, M = 6 against 19 k (Hessian) + 106 k for the blocked dense factorisation below: not kept.)
 // In-place lower Cholesky of the D x D matrix H (row-major, leading dimension ld = D + 1, odd, so that walks down a column
 // are free of shared-memory bank conflicts) in shared memory.  Blocked in panels of kPanel columns, three phases per panel:
 //   A  warp 0 factorises the kPanel x kPanel diagonal block in REGISTERS (lane = row, shuffles broadcast the pivot row):
@@ -259,6 +263,14 @@ __device__ double log_joint(const double* w, const double* mrg, int M, int D, co
   return blk_sum(part, red) - 0.5 * (double)D * 1.8378770664093453;   // log(2 pi)
 }
 
+
+#if defined(BC_LAP_TRACE)   // phase stamps for tools/laplace_parts.py (tools/build_variants.py laptrace="-DBC_LAP_TRACE")
+__device__ long long g_lap_trace[8];
+extern "C" int bc_lap_trace_read(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_lap_trace, sizeof(g_lap_trace)); }
+#define LAP_TR(i) do { __syncthreads(); if (threadIdx.x == 0) g_lap_trace[i] = clock64(); } while (0)
+#else
+#define LAP_TR(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* __restrict__ Zg, long long ldzg, const double* __restrict__ w,
                                                                   int M, int D, double* __restrict__ mu_io, double* __restrict__ Lsig,
                                                                   int maxit, double tol, int* __restrict__ info, int flags, int stage_rows) {
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
   // stage_rows: the M coreset rows are read a dozen times (margins, gradient, Hessian or dual system per Newton step, the
   // final Hessian) by loops whose trip count is M: from global memory every trip is an L2 round trip.  When they fit beside
   // the D x D workspace they are copied into shared memory once.
+  LAP_TR(0);
   const double* Z = Zg;
   long long ldz = ldzg;
   if (stage_rows) {
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
   __syncthreads();
   margins(Z, ldz, M, D, th, mrg);
   double f = log_joint(w, mrg, M, D, th, red);
+  LAP_TR(1);
   int it = 0, status = 0;
   auto hessian = [&]() {   // H = I + Z^T diag(w c) Z (lower triangle) from the margins at th
     for (int i = tid; i < M; i += nt) {
@@ -441,9 +455,12 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
       break;
     }
   }
+  LAP_TR(2);
   if (status == 0) {
     hessian();
+    LAP_TR(3);
     if (!chol_lower(H, D, ld, rd, &flag)) status = 2;
+    LAP_TR(4);
   }
   if (status == 0) {
     if (flags & 1) {
@@ -456,6 +473,7 @@ __global__ void __launch_bounds__(kLapThreads) k_laplace_logistic(const double* 
     }
     for (int k = tid; k < D; k += nt) mu_io[k] = th[k];
   }
+  LAP_TR(5);
   if (tid == 0) {
     info[0] = status;
     info[1] = it;

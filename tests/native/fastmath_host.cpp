@@ -52,6 +52,19 @@ void fm_logistic_v4_tab(const double* c4, double beta, const double* w, const do
   F::evalv<4>(c, 0, ca, mp, T, o);
   for (int i = 0; i < 4; ++i) out4[i] = o[i];
 }
+// lane-table form of the logistic log-likelihood (static tables)
+void fm_logistic_loglik_v4_tab(const double* c4, double* out4) {
+  bc::ModelParams mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = 0.0;
+  typedef bc::LogisticF<bc::KIND_LOGLIK, bc::kPowTab> F;
+  F::Tabs T;
+  T.e2.t = bc::kExp2Tab32;
+  T.rs.t = bc::kRcpTab32;
+  T.us.t = bc::kLogTab32;
+  double c[4] = {c4[0], c4[1], c4[2], c4[3]}, ca[4] = {0, 0, 0, 0}, o[4];
+  F::evalv<4>(c, 0, ca, mp, T, o);
+  for (int i = 0; i < 4; ++i) out4[i] = o[i];
+}
 // exp_tab_v: e^x for -700 <= x <= 700, one-step (lo = 0) or two-step (lo = 1) reduction
 double fm_exp_tab(double x, int lo) {
   bc::LaneTab32 T;

@@ -255,3 +255,24 @@ def test_gaussian_and_neural_linear_vector_forms(fmt):
         worst = max(worst, float(abs(mp.mpf(fmt.fm_neurlin_v(1, c, y, pn)) - wb)/max(1, abs(wb))))
         assert fmt.fm_neurlin_v(1, c, y, pn) == pytest.approx(fmt.fm_neurlin(1, c, y, pn), rel=1e-14, abs=1e-15)
     assert worst < 2e-15, worst
+
+
+def test_logistic_loglik_table_form(fmt):
+    """LogisticF<KIND_LOGLIK, kPowTab>::evalv<4>: -(max(m,0) + log1p(e^-|m|)) with the table exponential and the interval
+    table of log(1+t), against 60-digit arithmetic (the bound of the polynomial form) and against the numpy oracle"""
+    dp = ctypes.POINTER(ctypes.c_double)
+    fmt.fm_logistic_loglik_v4_tab.argtypes, fmt.fm_logistic_loglik_v4_tab.restype = [dp, dp], None
+    ms = np.concatenate([np.random.RandomState(2).normal(0, 15, 3000), np.linspace(-50, 120, 851), np.linspace(-1e-3, 1e-3, 201),
+                         [0., -0.0, 99.9, 100., 100.1, 700., -700., 745., -745., 1e4, -1e4, 1e-300]])
+    ms = ms[:4*(len(ms)//4)]
+    out = (ctypes.c_double*4)()
+    worst, got_all = 0., []
+    for k in range(0, len(ms), 4):
+        fmt.fm_logistic_loglik_v4_tab((ctypes.c_double*4)(*[float(-m) for m in ms[k:k+4]]), out)
+        for m, got in zip(ms[k:k+4], out):
+            want = -mp.log1p(mp.exp(mp.mpf(float(m))))
+            worst = max(worst, float(abs(mp.mpf(got)-want)/max(1, abs(want))))
+            got_all.append(got)
+    assert worst < 4e-16, worst
+    ref = om.lr_loglik(-ms[:, None], np.ones((1, 1)))[:, 0]
+    assert np.allclose(got_all, ref, rtol=1e-15, atol=1e-15)

@@ -1,5 +1,4 @@
 cd /root/repo
 mkdir -p gpurun_out
-python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_n1_c.json 2> gpurun_out/r02_bench_n1_c.err; echo bench rc=$?
-python bench.py --configs > gpurun_out/r02_configs_k.jsonl 2> gpurun_out/r02_configs_k.err; echo configs rc=$?
-python bench.py --n 1250000 --no-e2e --no-cpu-baseline --steps 3 --warmup 2 > gpurun_out/r02_bench_shard_d.json 2> gpurun_out/r02_bench_shard_d.err; echo shard rc=$?
+BC_LIB_PATH=$PWD/beta-cores_b200/lib/variants/libbetacores_laptrace.so python tools/laplace_parts.py 2>&1 | tail -9 | tee gpurun_out/r02_laplace_parts_b.txt
+python -m pytest tests/test_gpu_sampler.py -m gpu -x -q 2>&1 | tail -5

@@ -21,11 +21,11 @@ def patch(t):
         if old not in t:
             raise SystemExit('make_trace_lib: the kernel source changed, anchor not found:\n' + old)
         t = t.replace(old, new, 1)
-    sub('template <class F, int MODE>\n__global__ void __launch_bounds__(kQThreads, 1) k_project_q(',
+    sub('template <class F, int MODE, int NS>\n__global__ void __launch_bounds__(kQThreads, 1) k_project_q(',
         '__device__ unsigned long long g_trace[24][512];\n'
         '#define TR(kind, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[kind][idx] = clock64(); } while (0)\n'
         'extern "C" int bc_trace_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)); }\n\n'
-        'template <class F, int MODE>\n__global__ void __launch_bounds__(kQThreads, 1) k_project_q(')
+        'template <class F, int MODE, int NS>\n__global__ void __launch_bounds__(kQThreads, 1) k_project_q(')
     sub('          mbar_wait_relaxed(tmem_empty + buf, (use & 1) ^ 1);\n          if (buf) ++use1; else ++use0;\n          mbar_wait_relaxed(full_b + st, ph);\n',
         '          TR(0, itb);\n          mbar_wait_relaxed(tmem_empty + buf, (use & 1) ^ 1);\n          TR(1, itb);\n          if (buf) ++use1; else ++use0;\n'
         '          mbar_wait_relaxed(full_b + st, ph);\n          TR(2, itb);\n')
@@ -53,7 +53,7 @@ def main():
     try:
         obj = os.path.join(LIB, '_trace_q.o')
         subprocess.run([bld.NVCC] + bld.FLAGS + ['-c', src, '-o', obj], check=True)
-        objs = [os.path.join(LIB, u.replace('.cu', '.o')) for u in bld.UNITS if u != 'bc_project_q.cu'] + [obj]
+        objs = [os.path.join(LIB, os.path.splitext(u)[0] + '.o') for u in bld.UNITS if u != 'bc_project_q.cu'] + [obj]
         out = os.path.join(LIB, 'lib_trace.so')
         subprocess.run([bld.NVCC, '-shared', '-o', out] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'], check=True)
         print(out)
