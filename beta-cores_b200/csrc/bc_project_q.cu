@@ -355,8 +355,17 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = P.S;
   const long long n = P.n;
-  const long long ntiles = (n + kQTileRows - 1) / kQTileRows;
-  const int nchunks = (S + kQChunk - 1) / kQChunk;
+  // The loop bounds are formed INSIDE each role (BC_Q_BOUNDS): computed here, ahead of the setmaxnreg branches, ptxas keeps
+  // them in local memory for the 32-register service roles and reloads them once per chunk in every role (2.7 M local
+  // loads per 1M-row launch in profiles/r02_ncu_k_project_q_lane_tables.txt).  The volatile moves pin the computation
+  // behind the role's own register budget.
+#define BC_Q_BOUNDS                                                     \
+  long long n_role;                                                     \
+  int S_role;                                                           \
+  asm volatile("mov.u64 %0, %1;" : "=l"(n_role) : "l"(P.n));            \
+  asm volatile("mov.u32 %0, %1;" : "=r"(S_role) : "r"(P.S));            \
+  const long long ntiles = (n_role + kQTileRows - 1) / kQTileRows;      \
+  const int nchunks = (S_role + kQChunk - 1) / kQChunk;
   const bool want_cols = (MODE == QMODE_COLSUM);
 
   if (tid == 0) {
@@ -383,12 +392,15 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // (the TMEM base address is read from shared memory by each role that needs it -- a value defined here would live in
+  //  local memory across the setmaxnreg branches, like the loop bounds)
+#define BC_Q_TMEM_BASE const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   // setmaxnreg sits at the head of each role's branch: ptxas allocates registers for the code a setmaxnreg dominates
   if (warp == kQEpiWarps) {
     // ======================= producer: TMA-engine bulk copies =======================
     reg_dealloc<kQRegsSvc>();
+    BC_Q_BOUNDS
     if (lane == 0) {
       uint32_t itb = 0, tcount = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -416,6 +428,8 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
     // then feeds tcgen05.mma from uniform registers directly; inside an `if (lane == 0)` region it wraps every MMA in an
     // ELECT / R2UR.BROADCAST loop (89 cycles per MMA measured, more than the MMA takes to execute).  One elected lane issues.
     {
+      BC_Q_BOUNDS
+      BC_Q_TMEM_BASE
       uint32_t idesc[kQSlices];
 #pragma unroll
       for (int i = 0; i < kQSlices; ++i) idesc[i] = umma_idesc_i8(kQChunk * (i < NS ? NS - i : 1));
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   } else if (warp == kQEpiWarps + 2) {
     // ============ reducer: 4 partials per chunk -> double-double column accumulators ============
     reg_dealloc<kQRegsSvc>();
+    BC_Q_BOUNDS
     if (want_cols) {
       double* acc_hi = P.part_colsum + (size_t)blockIdx.x * 2 * P.Sld;
       double* acc_lo = acc_hi + P.Sld;
@@ -490,6 +505,8 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   } else {
     // ================================ epilogue groups ================================
     reg_alloc<kQRegsEpi>();
+    BC_Q_BOUNDS
+    BC_Q_TMEM_BASE
     const int grp = warp >> 2;   // 0..3
     const int buf = grp >> 1;    // accumulator buffer = chunk parity this group serves
     const int half = grp & 1;    // which 16 of the chunk's 32 columns
@@ -720,6 +737,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
   __syncthreads();
   if (warp == kQEpiWarps + 1) {
     tc_fence_after();
+    BC_Q_TMEM_BASE
     tmem_dealloc(tmem_base, 512);
   }
 }
