@@ -538,103 +538,6 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
         mbar_wait(tmem_full + buf, use & 1);
         ++use;
         tc_fence_after();
-#ifdef BC_Q_DRAIN_FIRST
-        // (experiment) drain first: all 16 columns are fetched and recombined to fp64 before the first evaluation, the
-        // accumulator buffer goes back at once, the evaluation loop has no TMEM traffic
-        double cv[kQHalfCols];
-        {
-          int dgA[4][NS];
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int d = 0; d < NS; ++d) {
-              uint32_t v[4];
-              tmem_ld_x4(tlane + (uint32_t)(d * kQChunk + b * 4), v);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) dgA[e][d] = (int)v[e];
-            }
-            tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-#pragma unroll
-              for (int d = 0; d < NS; ++d) asm volatile("" : "+r"(dgA[e][d]));
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) cv[b * 4 + e] = q_combine_n<NS>(dgA[e]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + buf);
-        if (!have_piv) {
-          mbar_wait(piv_full + (tcount & 1), (tcount >> 1) & 1);
-          piv = pivs[(tcount & 1) * 128 + row];
-          have_piv = true;
-        }
-        const uint32_t slot = itb % kQSlots, rph = (itb / kQSlots) & 1;
-        double fv[8];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const int cb = c * kQChunk + half * kQHalfCols + b * 4;
-          double cval[4], ca[4], fr[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) cval[e] = rsc * cv[b * 4 + e];
-          if (MODE == QMODE_DOT) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (rv && cb + e < S) P.V[p * P.ldv + cb + e] = cval[e];
-              fv[(b & 1) * 4 + e] = 0.0;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ca[e] = F::kColAux ? __ldg(P.colaux + min(cb + e, S - 1)) : 0.0;
-            F::template evalv<4>(cval, ra, ca, P.mp, tabs, fr);
-            if (grp == 0 && c == 0 && b == 0) {
-              piv = (rsc != rsc) ? kNaN : fr[0];
-              pivs[(tcount & 1) * 128 + row] = piv;
-              __syncwarp();
-              if (lane == 0) mbar_arrive(piv_full + (tcount & 1));
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) fr[e] = __dsub_rn(fr[e], piv);
-            if (need_mask) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) fr[e] = (rv && cb + e < S) ? fr[e] : 0.0;
-            }
-            if (MODE == QMODE_SCORE) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const double rr = __ldg(P.resid + min(cb + e, S - 1));
-                s1 += fr[e];
-                s2 = fma(fr[e], fr[e], s2);
-                sr = fma(fr[e], rr, sr);
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) fv[(b & 1) * 4 + e] = fr[e];
-          }
-          if (want_cols && (b & 1)) {
-            int off = 0;
-#pragma unroll
-            for (int m = 16, hw = 4; m >= 4; m >>= 1, hw >>= 1) {
-              const bool up = (lane & m) != 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (i < hw) {
-                  const double send = up ? fv[i] : fv[hw + i];
-                  const double keep = up ? fv[hw + i] : fv[i];
-                  fv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                }
-              }
-              if (up) off += hw;
-            }
-            fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 2);
-            fv[0] += __shfl_xor_sync(0xffffffffu, fv[0], 1);
-            if (b == 1) mbar_wait(ring_empty + slot, rph ^ 1);
-            if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + (b >> 1) * 8 + off] = fv[0];
-          }
-        }
-#else
         int dg[4][NS];   // [column of the batch][diagonal]
         auto fetch = [&](int batch) {
           // this warp's lane quarter, this group's half of the chunk, inside the buffer the MMA warp has just filled
@@ -768,7 +671,6 @@ __global__ void __launch_bounds__(kQThreads, 1) k_project_q(const QProjArgs P) {
             if ((lane & 3) == 0) ring[(size_t)slot * 4 * kQChunk + q * kQChunk + half * kQHalfCols + (b >> 1) * 8 + off] = fv[0];
           }
         }
-#endif
         if (want_cols) {
           __syncwarp();
           if (lane == 0) mbar_arrive(ring_full + slot);
