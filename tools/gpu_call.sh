@@ -1,5 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --no-cpu-baseline > gpurun_out/r02_bench_n8_a.json 2> gpurun_out/r02_bench_n8_a.err; echo bench8 rc=$?
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_n4_a.json 2> gpurun_out/r02_bench_n4_a.err; echo bench4 rc=$?
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --sweep default --sweep-out gpurun_out/r02_sweep_n8_b.jsonl > gpurun_out/r02_sweep_n8_b.log 2> gpurun_out/r02_sweep_n8_b.err; echo sweep8 rc=$?
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_20.txt 2>&1; echo pytest rc=$?; tail -4 gpurun_out/r02_pytest_20.txt
+BC_LIB_PATH=$PWD/beta-cores_b200/lib/variants/libbetacores_debug.so python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_debug.txt 2>&1; echo debug pytest rc=$?; tail -4 gpurun_out/r02_pytest_debug.txt
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
