@@ -232,7 +232,11 @@ BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
     BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], r[i], c[j]);
   }
   BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(r2[i], p[i], r[i]);
-  BC_UNROLL for (int i = 0; i < W; ++i) y[i] = fm_add_exponent(fm_fma(t[i], p[i], t[i]), K[i] >> 5);
+  // 2^k: (K >> 5) << 20 added to the high word = ((K & ~31) << 15), one logic + one multiply-add on the integer pipe
+  BC_UNROLL for (int i = 0; i < W; ++i) {
+    const double v = fm_fma(t[i], p[i], t[i]);
+    y[i] = fm_hilo2d(fm_hi(v) + (K[i] & ~31) * 32768, fm_lo(v));
+  }
 }
 
 // 1/x for x in [1, 2]: the 2^-23 seed of rcp.approx.ftz.f64 and ONE cubic step r (1 + e + e^2), e = 1 - x r: 3 FP64

@@ -61,6 +61,9 @@ struct LogisticF {
         T.rs.mine = kRcpTab32[lane];
         T.us.mine = kLogTab32[lane];
       }
+      // keep the entries in registers: without the barrier ptxas re-reads a __constant__ entry at every use, a load with
+      // 32 different addresses per warp (seen as LDC.64 c[0x3][R] once per batch in the SASS of the evaluation loop)
+      asm volatile("" : "+d"(T.e2.mine), "+d"(T.rs.mine), "+d"(T.us.mine));
     }
     return T;
   }
@@ -237,7 +240,10 @@ struct GaussianF {
 #if defined(__CUDACC__)
   __device__ __forceinline__ static Tabs tabs(const double*, int lane) {
     Tabs T = {};
-    if (KIND != KIND_LOGLIK) T.e2.mine = kExp2Tab32[lane];
+    if (KIND != KIND_LOGLIK) {
+      T.e2.mine = kExp2Tab32[lane];
+      asm volatile("" : "+d"(T.e2.mine));   // stays in registers (see LogisticF::tabs)
+    }
     return T;
   }
 #endif
@@ -296,7 +302,10 @@ struct NeurlinF {
 #if defined(__CUDACC__)
   __device__ __forceinline__ static Tabs tabs(const double*, int lane) {
     Tabs T = {};
-    if (KIND != KIND_LOGLIK) T.e2.mine = kExp2Tab32[lane];
+    if (KIND != KIND_LOGLIK) {
+      T.e2.mine = kExp2Tab32[lane];
+      asm volatile("" : "+d"(T.e2.mine));   // stays in registers (see LogisticF::tabs)
+    }
     return T;
   }
 #endif

@@ -1,5 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_20.txt 2>&1; echo pytest rc=$?; tail -4 gpurun_out/r02_pytest_20.txt
-BC_LIB_PATH=$PWD/beta-cores_b200/lib/variants/libbetacores_debug.so python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_debug.txt 2>&1; echo debug pytest rc=$?; tail -4 gpurun_out/r02_pytest_debug.txt
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 120 python tools/q_time.py 2>&1 | tail -1 | tee gpurun_out/r02_q_tab_d.txt
+python tools/potentials_probe.py > gpurun_out/r02_potentials_probe_c.txt 2>&1; tail -8 gpurun_out/r02_potentials_probe_c.txt
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lane_table or tensor_core or precision_tier_contraction or fused_colsum" 2>&1 | tail -3
