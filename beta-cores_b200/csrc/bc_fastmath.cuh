@@ -210,11 +210,14 @@ static const
 // 14 of exp_core_v.  Error: the rounding of T[j] and of the final FMA, < 1 ulp together.
 // NLO of the W arguments (the first ones) take the one-step reduction r = x - K fl(ln2/32): its error K 1.7e-18 matters only
 // relative to e^x itself and is for the caller to allow (see LogisticF: t = e^-a enters the result with weight O(t)).
-template <int W, int NLO>
+template <int W, int NLO, int PDEG = 4>
 BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
   const double kMagic = 6755399441055744.0;
-  const double c[5] = {1.38889253992791387136e-03, 8.33336254165508924507e-03, 4.16666666665591739482e-02, 1.66666666665806706416e-01,
-                       5.00000000000000000000e-01};
+  // q(r) = r + r^2 P(r).  PDEG = 4: interpolant, |1 + q - e^r| < 2.3e-19 e^r.  PDEG = 3: weighted minimax fit (Lawson
+  // iteration on r^2 (P - g) / e^r), < 8.8e-17 e^r -- 0.4 ulp for one FP64 instruction less.
+  const double c4[5] = {1.38889253992791387136e-03, 8.33336254165508924507e-03, 4.16666666665591739482e-02, 1.66666666665806706416e-01,
+                        5.00000000000000000000e-01};
+  const double c3[4] = {8.33332307384487304402e-03, 4.16668942132359595987e-02, 1.66666666669932850287e-01, 4.99999999991721566506e-01};
   double kf[W], r[W], r2[W], p[W], t[W];
   int K[W];
   BC_UNROLL for (int i = 0; i < W; ++i) kf[i] = fm_fma(x[i], 4.61662413084468283841e+01, kMagic);
@@ -227,9 +230,9 @@ BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
     r[i] = (i < NLO) ? fm_fma(kf[i], -2.16608493924982901946e-02, x[i]) : fm_fma(kf[i], -2.16608493865351192653e-02, x[i]);
   BC_UNROLL for (int i = 0; i < W; ++i) if (i >= NLO) r[i] = fm_fma(kf[i], -5.96317165397058656257e-12, r[i]);
   BC_UNROLL for (int i = 0; i < W; ++i) r2[i] = r[i] * r[i];
-  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = c[0];
-  BC_UNROLL for (int j = 1; j < 5; ++j) {
-    BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], r[i], c[j]);
+  BC_UNROLL for (int i = 0; i < W; ++i) p[i] = (PDEG == 4) ? c4[0] : c3[0];
+  BC_UNROLL for (int j = 1; j <= PDEG; ++j) {
+    BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(p[i], r[i], (PDEG == 4) ? c4[j] : c3[j < 4 ? j : 3]);
   }
   BC_UNROLL for (int i = 0; i < W; ++i) p[i] = fm_fma(r2[i], p[i], r[i]);
   // 2^k: (K >> 5) << 20 added to the high word = ((K & ~31) << 15), one logic + one multiply-add on the integer pipe

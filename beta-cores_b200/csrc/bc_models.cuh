@@ -108,7 +108,7 @@ struct LogisticF {
         const int hi = fm_hi(c[i]) & 0x7fffffff;
         x[i] = -fm_hilo2d(hi < 0x4085e000 ? hi : 0x4085e000, fm_lo(c[i]));   // |c| capped at 700 (and a hair: the low word stays)
       }
-      exp_tab_v<W, W>(x, T.e2, t);
+      exp_tab_v<W, W, 3>(x, T.e2, t);   // degree-5 form: t enters through log(1 + t), absolute error below 2e-16
       BC_UNROLL for (int i = 0; i < W; ++i) s[i] = 1.0 + t[i];
       double d[W], R[W], L[W], w[W], w2[W], P[W];
       BC_UNROLL for (int i = 0; i < W; ++i) {
@@ -128,11 +128,12 @@ struct LogisticF {
         out[i] = -(mx + P[i]);
       }
     } else if (kTab) {
-      // lane-table form: 37 FP64 instructions per element instead of 65.
+      // lane-table form: 35 FP64 instructions per element instead of 65.
       //   |c| and the clamp on the integer pipe (p[2] has a zero low word, so comparing high words is the exact compare);
       //   t = e^-a, G = e^(-beta a) by exp_tab_v, both with the one-step reduction: the error K 1.7e-18 e^x (K = 32 x / ln2) is at
       //   most 3e-17 absolute, and G enters the result with weight k1: measured against 50-digit arithmetic the worst error of the
-      //   potential is the same with the two-step reduction (6.5e-16 vs 7.2e-16 at beta = 0.1, 7.5e-16 vs 5.9e-16 at 0.01);
+      //   potential is the same with the two-step reduction (6.5e-16 vs 7.2e-16 at beta = 0.1, 7.5e-16 vs 5.9e-16 at 0.01), and
+      //   6.8e-16 / 9.8e-16 with the degree-5 form of the table exponential used here (test bound: 5e-16 k1, k1 = 11 / 101);
       //   big = 1/(1+t) by one cubic step;
       //   E = (1+t)^-beta: s = 1 + t in [1,2] falls into interval j = its top five mantissa bits, s = s_j + d, |d| <= 1/64,
       //   E = s_j^-beta (1 + w)^-beta with w = d / s_j, (1 + w)^-beta = 1 + w Q(w), Q of degree 6: 10 FP64 instructions
@@ -150,7 +151,7 @@ struct LogisticF {
           xx[i] = -a[i];
           xx[W + i] = -beta * fm_hilo2d(hi < bmax_hi ? hi : bmax_hi, lo);
         }
-        exp_tab_v<2 * W, 2 * W>(xx, T.e2, yy);
+        exp_tab_v<2 * W, 2 * W, 3>(xx, T.e2, yy);
         BC_UNROLL for (int i = 0; i < W; ++i) {
           t[i] = yy[i];
           G[i] = yy[W + i];

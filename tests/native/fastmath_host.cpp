@@ -65,6 +65,16 @@ void fm_logistic_loglik_v4_tab(const double* c4, double* out4) {
   F::evalv<4>(c, 0, ca, mp, T, o);
   for (int i = 0; i < 4; ++i) out4[i] = o[i];
 }
+// the degree-5 form (weighted minimax q)
+double fm_exp_tab5(double x, int lo) {
+  bc::LaneTab32 T;
+  T.t = bc::kExp2Tab32;
+  const double a[1] = {x};
+  double y[1];
+  if (lo) bc::exp_tab_v<1, 0, 3>(a, T, y);
+  else bc::exp_tab_v<1, 1, 3>(a, T, y);
+  return y[0];
+}
 // exp_tab_v: e^x for -700 <= x <= 700, one-step (lo = 0) or two-step (lo = 1) reduction
 double fm_exp_tab(double x, int lo) {
   bc::LaneTab32 T;

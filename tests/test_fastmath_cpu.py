@@ -176,6 +176,14 @@ def test_table_exp_is_one_ulp(fmt, lo):
         worst_abs = max(worst_abs, float(abs(got-want)))
     assert worst_rel < 2.3e-16, worst_rel
     assert worst_abs < (1.2e-16 if lo else 1.2e-16), worst_abs
+    # the degree-5 form the logistic potentials use (weighted minimax polynomial, one FP64 instruction less): 1.3 ulp
+    fmt.fm_exp_tab5.argtypes, fmt.fm_exp_tab5.restype = [ctypes.c_double, ctypes.c_int], ctypes.c_double
+    worst5 = 0.
+    for x in xs:
+        if lo or abs(x) < 1:
+            want = mp.exp(mp.mpf(float(x)))
+            worst5 = max(worst5, float(abs(mp.mpf(fmt.fm_exp_tab5(float(x), lo))-want)/want))
+    assert worst5 < 3.2e-16, worst5
 
 
 @pytest.mark.parametrize('beta', [0.01, 0.1, 0.4, 0.5, 0.9])
