@@ -159,10 +159,11 @@ BC_HD void rcp_1to2_v(const double (&x)[W], double (&r)[W]) {
 struct LaneTab32 {
 #if defined(__CUDACC__)
   double mine;   // entry [lane]
+  // (shfl.idx takes the low five bits of the index: callers pass j unmasked, also a negative one)
   __device__ __forceinline__ double at(int j) const { return __shfl_sync(0xffffffffu, mine, j); }
 #else
   const double* t;
-  double at(int j) const { return t[j]; }
+  double at(int j) const { return t[j & 31]; }
 #endif
 };
 
@@ -225,7 +226,7 @@ BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
     K[i] = fm_lo(kf[i]);
     kf[i] = fm_i2d(K[i]);
   }
-  BC_UNROLL for (int i = 0; i < W; ++i) t[i] = T.at(K[i] & 31);
+  BC_UNROLL for (int i = 0; i < W; ++i) t[i] = T.at(K[i]);   // entry K mod 32
   BC_UNROLL for (int i = 0; i < W; ++i)
     r[i] = (i < NLO) ? fm_fma(kf[i], -2.16608493924982901946e-02, x[i]) : fm_fma(kf[i], -2.16608493865351192653e-02, x[i]);
   BC_UNROLL for (int i = 0; i < W; ++i) if (i >= NLO) r[i] = fm_fma(kf[i], -5.96317165397058656257e-12, r[i]);
@@ -238,7 +239,13 @@ BC_HD void exp_tab_v(const double (&x)[W], const LaneTab32& T, double (&y)[W]) {
   // 2^k: (K >> 5) << 20 added to the high word = ((K & ~31) << 15), one logic + one multiply-add on the integer pipe
   BC_UNROLL for (int i = 0; i < W; ++i) {
     const double v = fm_fma(t[i], p[i], t[i]);
+#if defined(__CUDACC__)
+    int hi;   // one IMAD: left to itself ptxas turns the multiply into a shift and spends a separate add
+    asm("mad.lo.s32 %0, %1, 32768, %2;" : "=r"(hi) : "r"(K[i] & ~31), "r"(fm_hi(v)));
+    y[i] = fm_hilo2d(hi, fm_lo(v));
+#else
     y[i] = fm_hilo2d(fm_hi(v) + (K[i] & ~31) * 32768, fm_lo(v));
+#endif
   }
 }
 

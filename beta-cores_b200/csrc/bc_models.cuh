@@ -112,11 +112,10 @@ struct LogisticF {
       BC_UNROLL for (int i = 0; i < W; ++i) s[i] = 1.0 + t[i];
       double d[W], R[W], L[W], w[W], w2[W], P[W];
       BC_UNROLL for (int i = 0; i < W; ++i) {
-        int j = (fm_hi(s[i]) - 0x3ff00000) >> 15;
-        j = j > 31 ? 31 : j;
-        d[i] = s[i] - fm_hilo2d(0x3ff04000 | (j << 15), 0);
-        R[i] = T.rs.at(j);
-        L[i] = T.us.at(j);
+        const int hs = fm_hi(s[i]) < 0x3fffffff ? fm_hi(s[i]) : 0x3fffffff;     // (as in the beta-likelihood form below)
+        d[i] = s[i] - fm_hilo2d((hs & 0xffff8000) | 0x4000, 0);
+        R[i] = T.rs.at(hs >> 15);
+        L[i] = T.us.at(hs >> 15);
       }
       BC_UNROLL for (int i = 0; i < W; ++i) w[i] = d[i] * R[i];
       BC_UNROLL for (int i = 0; i < W; ++i) w2[i] = w[i] * w[i];
@@ -162,11 +161,12 @@ struct LogisticF {
       {
         double d[W], R[W], U[W], w[W], Q[W];
         BC_UNROLL for (int i = 0; i < W; ++i) {
-          int j = (fm_hi(s[i]) - 0x3ff00000) >> 15;   // s = 2 exactly (t = 1) lands on 32: last interval
-          j = j > 31 ? 31 : j;
-          d[i] = s[i] - fm_hilo2d(0x3ff04000 | (j << 15), 0);
-          R[i] = T.rs.at(j);
-          U[i] = T.us.at(j);
+          // interval = the top five mantissa bits of s; its centre s_j = those bits with a 1 appended.  s = 2 exactly (t = 1) is
+          // capped into the last interval.  The lane tables take the index modulo 32.
+          const int hs = fm_hi(s[i]) < 0x3fffffff ? fm_hi(s[i]) : 0x3fffffff;
+          d[i] = s[i] - fm_hilo2d((hs & 0xffff8000) | 0x4000, 0);
+          R[i] = T.rs.at(hs >> 15);
+          U[i] = T.us.at(hs >> 15);
         }
         BC_UNROLL for (int i = 0; i < W; ++i) w[i] = d[i] * R[i];
         horner_v<kPowTabDeg, W>(mp.w, w, Q);
