@@ -336,6 +336,8 @@ def b200_arm(a, emit=True):
         alg.build(1, m)
     clocks = ClockSampler(local) if rank == 0 else None
     _fused.PASS_TIMERS = []
+    from bayesiancoresets.coreset import _greedy
+    _greedy.STEP_EVENTS = [] if world > 1 else None
     sampler_clock[0], sampler_clock[1] = 0, 0.
     launches0 = nv.lib().bc_launch_count()
     evals = 0
@@ -354,6 +356,41 @@ def b200_arm(a, emit=True):
     launches = nv.lib().bc_launch_count() - launches0
     sampler_calls, sampler_s = sampler_clock[0], sampler_clock[1]
     timers, _fused.PASS_TIMERS = _fused.PASS_TIMERS, None
+    step_events, _greedy.STEP_EVENTS = _greedy.STEP_EVENTS, None
+    step_breakdown = None
+    if step_events:
+        # where an optimiser step of a row-sharded job goes (CUDA events on this rank's stream; mean over the steps, then the
+        # mean and the max over ranks): sampler + sample preparation | data pass | its finalize | all-gather of the parts
+        # (includes waiting for the slowest rank) | second half (combine, coreset rows, residual / gradient / ADAM) | gap to
+        # the next step's first kernel
+        acc = {k: 0. for k in ('sampler_and_prepare', 'sampler', 'pass', 'finalize', 'exchange', 'second_half', 'gap')}
+        host_dt = sorted(b[2][0] - a_[2][0] for a_, b in zip(step_events[:-1], step_events[1:]))
+        import numpy as _np
+        hparts = _np.median(_np.array([[h[k+1] - h[k] for k in range(len(h)-1)] for _, _, h in step_events if len(h) == 5]), axis=0)
+        for j, (sev, pt, _) in enumerate(step_events):
+            pb, pe = (pt[2], pt[3]) if pt is not None else (sev[1], sev[1])
+            acc['sampler_and_prepare'] += sev[0].elapsed_time(pb)
+            if len(sev) > 4:
+                acc['sampler'] = acc.get('sampler', 0.) + sev[0].elapsed_time(sev[4])
+            acc['pass'] += pb.elapsed_time(pe)
+            acc['finalize'] += pe.elapsed_time(sev[1])
+            acc['exchange'] += sev[1].elapsed_time(sev[2])
+            acc['second_half'] += sev[2].elapsed_time(sev[3])
+            if j + 1 < len(step_events):
+                g = sev[3].elapsed_time(step_events[j+1][0][0])
+                acc['gap'] += g if g < 5. else 0.          # (a selection step lies between two build steps' loops)
+        nst = float(len(step_events))
+        mine = torch.tensor([acc[k]/nst for k in sorted(acc)], dtype=torch.float64, device='cuda')
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        step_breakdown = {'unit': 'ms per optimiser step', 'steps': int(nst),
+                          'host_ms_between_steps': {'min': 1e3*host_dt[0], 'median': 1e3*host_dt[len(host_dt)//2],
+                                                    'median_ms_in': dict(zip(('sampler.device_step', 'first_half_call', 'allgather', 'second_half_call'), [1e3*float(v) for v in hparts])),
+                                                    'note': 'wall clock of the host loop on rank 0: a median near the device step time means '
+                                                            'the host is paced by the device (a full launch queue), a small minimum that it queues a step in that time'},
+                          'mean_over_ranks': dict(zip(sorted(acc), [float(v) for v in allr.mean(axis=0)])),
+                          'max_over_ranks': dict(zip(sorted(acc), [float(v) for v in allr.max(axis=0)]))}
     clk = clocks.stop() if clocks else None
     value = evals/dt
     col_ms = [x[2].elapsed_time(x[3]) for x in timers if x[0] == 'colsum']
@@ -587,7 +624,7 @@ def b200_arm(a, emit=True):
             'metric': 'beta_likelihood_evals_per_s', 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': 1e3*dt/K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(a, world), 'build_seconds_per_point': dt/K,
-            'selected_indices': idcs_value, 'roofline': roofline, 'gpu_launches': int(launches), 'clocks': clk,
+            'selected_indices': idcs_value, 'roofline': roofline, 'step_breakdown': step_breakdown, 'gpu_launches': int(launches), 'clocks': clk,
             'host': {'cpu_count': os.cpu_count(), 'sampler_calls': sampler_calls, 'sampler_host_ms_per_call': 1e3*sampler_s/max(sampler_calls, 1),
                      'sampler_note': ('optimiser steps call the sampler through its device_step protocol: its algebra runs in kernels on the '
                                       'device-resident weights and the host only queues work -- it runs ahead of the GPU and then BLOCKS on it '

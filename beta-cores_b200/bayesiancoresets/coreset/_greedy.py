@@ -32,6 +32,7 @@ def _as_f64_2d(a):
 
 # one library call per optimiser step (bc_greedy_opt_step) instead of one per kernel; BC_FUSED_STEP=0 keeps the call-by-call loop
 import os
+import time
 FUSED_STEP_CALL = os.environ.get('BC_FUSED_STEP', '1') != '0'
 # samplers that offer device_step() run the optimiser loop without any host synchronisation; BC_DEVICE_SAMPLER_LOOP=0 keeps
 # calling them through the reference's host protocol sampler(S, wts, pts)
@@ -40,6 +41,9 @@ DEVICE_SAMPLER_LOOP = os.environ.get('BC_DEVICE_SAMPLER_LOOP', '1') != '0'
 # once the loop is long enough to pay for the two captures (about 3 ms against 30-40 us saved per step: measured on the
 # Gaussian example, 1000 steps per point, 0.157 -> 0.125 ms per step; the 20-step loops of the logistic / neural-linear
 # examples lose); BC_STEP_GRAPH=0 keeps launching kernel by kernel
+# instrumentation (bench.py): a list that collects, per optimiser step of a row-sharded job, four CUDA events -- step begin,
+# first half queued, exchange done, second half done -- for the per-step overhead breakdown; None = off
+STEP_EVENTS = None
 STEP_GRAPH = os.environ.get('BC_STEP_GRAPH', '1') != '0'
 STEP_GRAPH_MIN_ITRS = int(os.environ.get('BC_STEP_GRAPH_MIN_ITRS', '200'))
 
@@ -515,8 +519,17 @@ class GreedyVICoreset(Coreset):
             return self._optimize_graph_steps(t, core, beta, smp, prj, a, setup, x, idx_dev, idx_pin, sub_mode)
 
         for i in range(self.opt_itrs):
+            sev = None
+            if STEP_EVENTS is not None and world > 1:
+                sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                sev[0].record()
+                hst = [time.perf_counter()]
             if on_device:
                 th = smp.device_step(prj.projection_dimension, x, core)
+                if sev:
+                    sev.append(torch.cuda.Event(enable_timing=True))
+                    sev[4].record()                            # the sampler's kernels end here, sample preparation follows
+                    hst.append(time.perf_counter())
             else:
                 prj.update(xh, self.pts)                       # host sampler: consumes np.random exactly like the reference
                 th = prj.samples
@@ -562,9 +575,19 @@ class GreedyVICoreset(Coreset):
             else:
                 a.phase = 1
                 nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+                if sev:
+                    sev[1].record()
+                    hst.append(time.perf_counter())
                 allparts = comm.allgather(bufs['parts'])       # (world, 2 Sld): one double-double part per rank, rank order
+                if sev:
+                    sev[2].record()
+                    hst.append(time.perf_counter())
                 a.phase, a.nparts, a.d_parts_all = 2, world, allparts.data_ptr()
                 nv.call('bc_greedy_opt_step', t.ctx, ctypes.byref(a), stream_ptr())
+                if sev:
+                    sev[3].record()
+                    hst.append(time.perf_counter())
+                    STEP_EVENTS.append((sev, _fused.PASS_TIMERS[-1] if _fused.PASS_TIMERS else None, hst))
             if not on_device:
                 xh = x.cpu().numpy()                           # one D2H + sync per step: the next sampler call needs the weights
         if on_device:
