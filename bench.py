@@ -416,7 +416,7 @@ def b200_arm(a, emit=True):
     if route == 'q':
         kname = ('k_project_q<LogisticF<BETALIK>, COLSUM> (tcgen05 int8 Ozaki contraction in TMEM + beta-likelihood + centring + '
                  'column sums, fused)')
-        digit_pairs, fp64_inst = digits*(digits+1)//2, 41   # kept digit pairs (diagonals d < digits); FP64-pipe instructions per evaluation (SASS count of the lane-table form, profiles/r02_sass_histogram.txt)
+        digit_pairs, fp64_inst = digits*(digits+1)//2, 38   # kept digit pairs (diagonals d < digits); FP64-pipe instructions per evaluation (SASS count of the lane-table form, profiles/r02_sass_histogram.txt)
         int8_ops = digit_pairs*2.*n_local*S*128
         # measured on this pool (tools/mma_i8_rate.cu, profiles/r01_mma_i8_rate.txt): 8192 int8 MACs per cycle per SM from N = 128 up
         int8_peak = eng.sms*8192*2.*1965e6/1e12
@@ -433,7 +433,7 @@ def b200_arm(a, emit=True):
                                            '= %.0f would be the estimate)' % (2*bf16_peak)},
             'fp64_pipe': {'instructions_per_eval': fp64_inst,
                           'frac_of_issue_peak': n_local*S*fp64_inst/32./(eng.sms*4*0.5*sm_clock_hz*col_mean*1e-3),
-                          'note': 'the potential (two table exponentials, one reciprocal, one table power per evaluation: 41 FP64 instructions, '
+                          'note': 'the potential (two table exponentials, one reciprocal, one table power per evaluation: 38 FP64 instructions in the loop, '
                                   '69 in its polynomial form) runs on the FP64 pipe (0.5 warp-instructions/cycle/sub-partition, measured '
                                   'tools/fp64_ipc.cu)'}}
         # FP64 instructions and tcgen05 MMAs issue through ONE pipe of the SM (ncu: sm__pipe_shared_cycles_active = fp64 + tensor, to
