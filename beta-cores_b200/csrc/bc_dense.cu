@@ -360,6 +360,7 @@ cudaError_t launch_dense_center(double* V, long long n, int S, long long ldv, cu
   if (n <= 0) return cudaSuccess;
   long long blocks = (n + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  BC_PREFER_MAX_SHARED(k_dense_center);
   k_dense_center<<<(int)blocks, 256, 0, st>>>(V, n, S, ldv);
   return cudaGetLastError();
 }

@@ -33,6 +33,22 @@ inline cudaError_t raise_dynamic_smem(K kern, size_t bytes, DeviceOnce& once) {
   return e;
 }
 
+// The small kernels of an optimiser step run between launches of the projection kernels, which take nearly all of an SM's
+// shared memory.  A kernel that leaves the shared-memory / L1 split at its default makes the SM re-partition on the way in
+// and again on the way out; asking for the maximum carve-out everywhere keeps one configuration for the whole step.
+template <class K>
+inline void prefer_max_shared(K kern, DeviceOnce& once) {
+  const int dev = current_device();
+  if (once.done(dev)) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  once.set(dev);
+}
+#define BC_PREFER_MAX_SHARED(kern)          \
+  do {                                      \
+    static DeviceOnce carve_once__;         \
+    prefer_max_shared(kern, carve_once__);  \
+  } while (0)
+
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 32;  // + one TMA producer warp

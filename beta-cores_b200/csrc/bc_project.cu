@@ -500,6 +500,10 @@ static cudaError_t launch_one(const ProjArgs& P, int grid, size_t smem, cudaStre
   static DeviceOnce once;  // per instantiation, per device
   cudaError_t e = raise_dynamic_smem(kern, kMaxSmem, once);
   if (e != cudaSuccess) return e;
+  {
+    static DeviceOnce carve_once;   // (per instantiation) same shared-memory split as the kernels around it: bc_kernels.h
+    prefer_max_shared(kern, carve_once);
+  }
   kern<<<dim3(grid, MODE == MODE_MATERIALISE ? csplit : 1), (BM / 16 + 2) * 32, smem, st>>>(P);
   return cudaGetLastError();
 }
@@ -571,6 +575,7 @@ cudaError_t launch_project(const ProjArgs& P, int model, int kind, int poly, int
 cudaError_t launch_project_finalize(const double* part_colsum, const double* part_misc, int nctas, int S, int Sld,
                                     double* out_dd, double* out_best, int mode, cudaStream_t st, double* colsum_out) {
   const int threads = (mode == MODE_SCORE) ? 256 : (S >= 1024 ? 1024 : (S > 256 ? 512 : 256));
+  BC_PREFER_MAX_SHARED(k_project_finalize);
   k_project_finalize<<<1, threads, 0, st>>>(part_colsum, part_misc, nctas, S, Sld, out_dd, out_best, mode, colsum_out);
   return cudaGetLastError();
 }

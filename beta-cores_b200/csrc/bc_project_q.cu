@@ -309,6 +309,7 @@ cudaError_t launch_quantise_samples(const double* B, int ldb, int S, int D, unsi
   unsigned long long* nxt = scratch4 + 2 * ((slot & 1) ^ 1);
   if (!have_max) k_sample_absmax<<<(S + 7) / 8 < 148 ? (S + 7) / 8 : 148, 256, 0, st>>>(B, ldb, S, D, fexp, cur);
   const int rows = ((S + kQChunk - 1) / kQChunk) * kQChunk;
+  BC_PREFER_MAX_SHARED(k_quantise<kQChunk>);
   k_quantise<kQChunk><<<(rows + 7) / 8, 256, 0, st>>>(B, ldb, S, D, image, nullptr, nullptr, 0, cur, nxt, common_e, colscale, fexp, +1);
   return cudaGetLastError();
 }

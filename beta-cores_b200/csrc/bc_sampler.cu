@@ -586,6 +586,7 @@ cudaError_t launch_conjugate_factor(int model, const double* Z, long long ldz, c
   cudaError_t e = raise_dynamic_smem(k_conjugate_factor, cap, once);
   if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
+  BC_PREFER_MAX_SHARED(k_conjugate_factor);
   k_conjugate_factor<<<1, kLapThreads, smem, st>>>(model, Z, ldz, w, M, D, A0, A1, v0, sigsq, mu, C, info);
   return cudaGetLastError();
 }
@@ -654,6 +655,7 @@ cudaError_t launch_sample_solve(const double* mu, const double* C, const double*
   cudaError_t e = raise_dynamic_smem(k_sample_solve, cap, once);
   if (e != cudaSuccess) return e;
   if (smem > cap) return cudaErrorInvalidValue;
+  BC_PREFER_MAX_SHARED(k_sample_solve);
   k_sample_solve<<<(S + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, smem, st>>>(mu, C, R, S, D, out, ldo, diag_hint);
   return cudaGetLastError();
 }
@@ -950,12 +952,14 @@ cudaError_t launch_laplace_logistic(const double* Z, long long ldz, const double
   const size_t rows = (size_t)M * D * sizeof(double);
   const int stage_rows = smem + rows <= cap ? 1 : 0;
   if (stage_rows) smem += rows;
+  BC_PREFER_MAX_SHARED(k_laplace_logistic);
   k_laplace_logistic<<<1, kLapThreads, smem, st>>>(Z, ldz, w, M, D, mu_io, Lsig, maxit, tol, info, flags, stage_rows);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sample_affine(const double* mu, const double* L, const double* R, int S, int D, double* out, int ldo, cudaStream_t st) {
   if (S <= 0) return cudaSuccess;
+  BC_PREFER_MAX_SHARED(k_sample_affine);
   k_sample_affine<<<S, 128, (size_t)D * sizeof(double), st>>>(mu, L, R, S, D, out, ldo);
   return cudaGetLastError();
 }

@@ -181,10 +181,12 @@ __global__ void __launch_bounds__(kMeanThreads) k_prepare_mean(const double* __r
 cudaError_t launch_prepare_samples(int model, const double* theta, int S, int D, int ldt, const double* siginv, const double* siginvT,
                                    double* B, int ldb, double* colaux, double* bbar, const int* fexp, unsigned long long* absmax_slot,
                                    const int* siginv_diag, cudaStream_t st) {
+  BC_PREFER_MAX_SHARED(k_prepare_rows);
   k_prepare_rows<<<S, 128, (size_t)D * sizeof(double), st>>>(model, theta, S, D, ldt, siginv, siginvT, B, ldb, colaux, fexp, absmax_slot,
                                                              siginv_diag);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  BC_PREFER_MAX_SHARED(k_prepare_mean);
   k_prepare_mean<<<(ldb + 1 + kMeanCols - 1) / kMeanCols, kMeanThreads, 0, st>>>(B, S, ldb, model == MODEL_GAUSSIAN ? colaux : nullptr, bbar);
   return cudaGetLastError();
 }
@@ -239,6 +241,7 @@ __global__ void k_colsum_combine(const double* __restrict__ parts, int nparts, i
 }
 
 cudaError_t launch_colsum_combine(const double* parts, int nparts, int S, int Sld, double* out, cudaStream_t st) {
+  BC_PREFER_MAX_SHARED(k_colsum_combine);
   k_colsum_combine<<<(S + 127) / 128, 128, 0, st>>>(parts, nparts, S, Sld, out);
   return cudaGetLastError();
 }
@@ -364,6 +367,7 @@ __global__ void __launch_bounds__(1024) k_core_step(const double* __restrict__ c
 cudaError_t launch_core_step(const double* colsum, double scaling, const double* Vc, int M, int S, long long ldv, double* x, double* resid,
                              double* grad, double* m1, double* m2, double lr, double b1, double b2, double c1, double c2, double eps,
                              const unsigned char* nn_mask, const double* sched, int* step_counter, cudaStream_t st) {
+  BC_PREFER_MAX_SHARED(k_core_step);
   k_core_step<<<1, 1024, 0, st>>>(colsum, scaling, Vc, M, S, ldv, x, resid, grad, m1, m2, lr, b1, b2, c1, c2, eps, nn_mask, sched,
                                   step_counter);
   return cudaGetLastError();
