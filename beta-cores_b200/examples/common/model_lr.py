@@ -12,6 +12,7 @@ The functions below the potentials are the weighted-posterior Laplace approximat
 use as sampler (examples/zellner_logreg/main.py:86-111,139-144; bayesiancoresets/util/opt.py:10-33).
 They act on the M coreset points only (M x D, a few hundred rows at most) and stay on the host.
 """
+import os
 import numpy as np
 import scipy.linalg as sl
 from scipy.optimize import minimize
@@ -328,17 +329,33 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
         resident rows (`core`, a DeviceRows): mode (warm-started dual Newton steps), Cholesky factor and samples are formed by
         kernels (bc_laplace_logistic_factor, bc_sample_solve); nothing is read back, the host only queues work and draws the
         normals.  Rows with weight 0 do not contribute, exactly like `keep = wts > 0` on the host."""
+        prof = st.get('prof')                  # (tools/step_timeline.py: host seconds spent in each part of this call)
+        if prof is not None:
+            import time
+            tp = [time.perf_counter()]
         graph_prepare()
         eng = Engine.get()
         ctx = eng.ctx('sampler')
         theta = eng.empty(S, D)
+        if prof is not None:
+            tp.append(time.perf_counter())
         nv.call('bc_laplace_logistic_factor', ctx, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(st['mu']), ptr(st['L']), 200, 1e-13,
                 ptr(st['info']), stream_ptr())
+        if prof is not None:
+            tp.append(time.perf_counter())
         k, pin = normals(S, D, stage)          # after the factor kernel is queued: the GPU works while the host waits for the draw
+        if prof is not None:
+            tp.append(time.perf_counter())
+            prof.append(tuple(b - a for a, b in zip(tp[:-1], tp[1:])))
         # The 8 S D bytes of normals do not depend on anything the device computes: they go up on a copy stream of their own
         # the moment the host has them -- the host runs steps ahead of the device, so the copy overlaps an earlier data pass
         # instead of sitting between the factor kernel and the solve (45 us of every optimiser step at S = 1024, D = 128).
         # Four device buffers in turn; one is reused once the solve that read it has run.
+        if os.environ.get('BC_NORMALS_INLINE') == '1':    # (A/B switch: the upload in stream order, between the factor kernel and the solve)
+            Rd = pin.to(eng.device, non_blocking=True)
+            graph_launched(k)
+            nv.call('bc_sample_solve', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
+            return theta
         ring = st.get('ring')
         if ring is None or tuple(ring['buf'][0].shape) != (S, D):
             ring = st['ring'] = {'buf': [eng.empty(S, D) for _ in range(4)], 'free': [None]*4, 'i': 0, 'stream': torch.cuda.Stream(device=eng.device)}
