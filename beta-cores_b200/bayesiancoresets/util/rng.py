@@ -173,6 +173,15 @@ class StreamAhead(object):
     def randint(self, high, size):
         return self._request(('randint', (int(high), int(size)), None))
 
+    def peek_next(self):
+        """what the FIRST draw of the next cycle will return if the speculation holds (the very object the next cycle's
+        request hands out), or None without a speculation in flight.  Waits for the helper to have made the draw.  Nothing
+        is consumed: a caller may start moving the data (e.g. upload a pinned staging buffer) a cycle early and must be
+        ready for the next cycle to hand out something else."""
+        if self._nxt is None or not self._nxt.ops:
+            return None
+        return self._nxt.fut.result()[1][0]
+
     def drain(self):
         """stop speculating and leave the global stream exactly where the caller's own draws have left it"""
         if self._cur is not None:

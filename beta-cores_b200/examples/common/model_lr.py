@@ -229,12 +229,13 @@ def make_laplace_sampler(D, mu0=None, method='bfgs', prefetch=False):
             ahead.drain()
 
     if method in ('device', 'hybrid'):
-        sampler = _device_laplace_sampler(D, mu0, normals, host_factor=(method == 'hybrid'), new_call=new_call)
+        sampler = _device_laplace_sampler(D, mu0, normals, host_factor=(method == 'hybrid'), new_call=new_call,
+                                          peek=(lambda: ahead.peek_next()) if ahead is not None else (lambda: None))
     sampler.drain = drain
     return sampler
 
 
-def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None):
+def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None, peek=lambda: None):
     """method='device' / 'hybrid': the S x D samples are formed on the GPU and returned as a device tensor (the projector's
     fused path takes it without a host round trip).  The standard normals still come from numpy's global stream, so the
     sampler consumes it exactly like the host one.
@@ -339,17 +340,29 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
         theta = eng.empty(S, D)
         if prof is not None:
             tp.append(time.perf_counter())
+        ring = st.get('ring')
+        if ring is not None and ring.get('to_free') is not None:
+            # the ring buffer the previous call's solve read is released HERE, at the head of this call's kernels: the upload
+            # that waits for it (four uploads later, the host runs that far ahead) then runs beside the 140 us factor kernel.
+            # Released right behind the solve, it ran beside the sample-preparation kernels and stretched them.
+            jf, ring['to_free'] = ring['to_free'], None
+            ring['free'][jf] = torch.cuda.Event()
+            ring['free'][jf].record(torch.cuda.current_stream(eng.device))
         nv.call('bc_laplace_logistic_factor', ctx, ptr(core.t), core.ld, ptr(w_dev), core.n_local, D, ptr(st['mu']), ptr(st['L']), 200, 1e-13,
                 ptr(st['info']), stream_ptr())
         if prof is not None:
             tp.append(time.perf_counter())
-        k, pin = normals(S, D, stage)          # after the factor kernel is queued: the GPU works while the host waits for the draw
+        tok = normals(S, D, stage)             # after the factor kernel is queued: the GPU works while the host waits for the draw
+        k, pin = tok
         if prof is not None:
             tp.append(time.perf_counter())
             prof.append(tuple(b - a for a, b in zip(tp[:-1], tp[1:])))
-        # The 8 S D bytes of normals do not depend on anything the device computes: they go up on a copy stream of their own
-        # the moment the host has them -- the host runs steps ahead of the device, so the copy overlaps an earlier data pass
-        # instead of sitting between the factor kernel and the solve (45 us of every optimiser step at S = 1024, D = 128).
+        # The 8 S D bytes of normals do not depend on anything the device computes, and a single 1 MB pinned copy takes 90-150 us
+        # to cross PCIe on the B200 boxes (tools/step_timeline.py): it must not sit in the serial chain of the step.  It goes up
+        # on a copy stream of its own, and it goes up a STEP EARLY: the look-ahead generator (bayesiancoresets/util/rng.py) has
+        # already drawn the next call's normals into its other pinned staging buffer, so this call uploads them behind its own
+        # solve -- beside the data pass that follows -- and the next call finds them on the device.  Nothing is consumed from the
+        # random stream early; if the next call is handed another draw (the speculation was rewound) it uploads that one itself.
         # Four device buffers in turn; one is reused once the solve that read it has run.
         if os.environ.get('BC_NORMALS_INLINE') == '1':    # (A/B switch: the upload in stream order, between the factor kernel and the solve)
             Rd = pin.to(eng.device, non_blocking=True)
@@ -358,23 +371,38 @@ def _device_laplace_sampler(D, mu0, normals, host_factor, new_call=lambda: None)
             return theta
         ring = st.get('ring')
         if ring is None or tuple(ring['buf'][0].shape) != (S, D):
-            ring = st['ring'] = {'buf': [eng.empty(S, D) for _ in range(4)], 'free': [None]*4, 'i': 0, 'stream': torch.cuda.Stream(device=eng.device)}
-        j = ring['i'] % 4
-        ring['i'] += 1
+            ring = st['ring'] = {'buf': [eng.empty(S, D) for _ in range(4)], 'free': [None]*4, 'i': 0, 'stream': torch.cuda.Stream(device=eng.device),
+                                 'pre': None, 'to_free': None}
         cur = torch.cuda.current_stream(eng.device)
         side = ring['stream']
-        if ring['free'][j] is not None:
-            side.wait_event(ring['free'][j])
-        with torch.cuda.stream(side):
-            ring['buf'][j].copy_(pin, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(side)
-        st['ev'][k] = ready                    # the pinned staging buffer is free again once this copy has run
+
+        def upload(token):
+            """enqueue the copy of a pinned draw into the next ring buffer on the copy stream -> (ring slot, its completion event)"""
+            kk, src = token
+            jj = ring['i'] % 4
+            ring['i'] += 1
+            if ring['free'][jj] is not None:
+                side.wait_event(ring['free'][jj])
+            with torch.cuda.stream(side):
+                ring['buf'][jj].copy_(src, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
+            st['ev'][kk] = done                # the pinned staging buffer is free again once this copy has run
+            return jj, done
+
+        pre, ring['pre'] = ring['pre'], None
+        if pre is not None and pre[0] is tok:
+            j, ready = pre[1], pre[2]          # uploaded by the previous call
+        else:
+            j, ready = upload(tok)
         cur.wait_event(ready)
         Rd = ring['buf'][j]
         nv.call('bc_sample_solve', ctx, ptr(st['mu']), ptr(st['L']), ptr(Rd), S, D, ptr(theta), int(theta.stride(0)), stream_ptr())
-        ring['free'][j] = torch.cuda.Event()
-        ring['free'][j].record(cur)
+        ring['to_free'] = j                    # (recorded by the next call; a buffer never released is simply not reused)
+        if os.environ.get('BC_NORMALS_PREFETCH', '1') != '0':
+            nxt = peek()
+            if isinstance(nxt, tuple) and len(nxt) == 2 and isinstance(nxt[1], torch.Tensor) and tuple(nxt[1].shape) == (S, D):
+                ring['pre'] = (nxt,) + upload(nxt)
         return theta
 
     # The same call in parts, so that the device work of a step can be captured into a CUDA graph and replayed
