@@ -314,6 +314,42 @@ def test_native_legacy_stream_is_bit_identical_to_numpy():
         assert tuple(s2[2:]) == tuple(after[2:])
 
 
+def test_stream_ahead_peek_consumes_nothing():
+    """StreamAhead.peek_next(): the samplers look at the NEXT cycle's speculated draw to start its upload a step early
+    (examples/common/model_lr.py::device_step).  Peeking hands out the very object the next cycle's request returns when the
+    speculation holds, consumes nothing, and changes no number when the pattern changes and the speculation is rewound."""
+    from bayesiancoresets.util.rng import StreamAhead
+    S, D, N = 6, 4, 500
+    script = [[('randn', S, D)]]*5 + [[('randn', S, D), ('randint', N, 9)]]*4 + [[('randn', S+2, D)]]*3
+
+    def play(ahead, peek):
+        out, same = [], 0
+        pending = None
+        for cycle in script:
+            if ahead is not None:
+                ahead.begin_cycle()
+            for j, op in enumerate(cycle):
+                if op[0] == 'randn':
+                    r = ahead.randn(op[1], op[2]) if ahead is not None else np.random.randn(op[1], op[2])
+                    if j == 0 and pending is not None and pending is r:
+                        same += 1
+                else:
+                    r = ahead.randint(op[1], op[2]) if ahead is not None else np.random.randint(op[1], size=op[2])
+                out.append(r)
+            pending = ahead.peek_next() if (peek and ahead is not None) else None
+        if ahead is not None:
+            ahead.drain()
+        out.append(np.random.rand(2))
+        return out, same
+    np.random.seed(77)
+    ref, _ = play(None, False)
+    np.random.seed(77)
+    got, same = play(StreamAhead(), True)
+    for x, y in zip(ref, got):
+        np.testing.assert_array_equal(x, y)
+    assert same >= 6          # in the steady stretches the peeked object IS what the next cycle handed out
+
+
 def test_stream_ahead_consumes_the_global_stream_like_direct_draws():
     """util/rng.py: draws made one sampler call ahead on a helper thread, with pattern changes (selection vs optimiser
     sub-sample sizes, cycles that end early or run long) and a drain in between, return exactly the numbers direct
