@@ -29,6 +29,7 @@ struct bc_ctx {
   int tab_count = 0;
   const double* tab_cur = nullptr;   // slot of the current potential's tables (logistic beta-likelihood), or null
   bool tab_form = false;             // the tensor-core kernels run the current potential in its lane-table form
+  bool tab_off = false;              // more distinct betas than slots have come by: polynomial forms from here on
   int pot_form = 0;                  // bc_set_potential_form: 0 = fastest form available, 1 = polynomial forms only
   const double* d_siginv = nullptr;
   double* siginvT = nullptr;   // transposed copy of d_siginv (coalesced row walks in k_prepare_rows), refreshed after every bc_set_potential
@@ -309,21 +310,29 @@ int bc_set_potential(bc_ctx* c, int model, int kind, int D, const double* h_para
     }
     c->tab_cur = nullptr;
     double w[kPowTabDeg + 1], tabs[64];
-    if (c->pot_form == 0 && fit_pow_tab(beta, w, tabs, tabs + 32) < 5e-17) {   // under half an ulp of (1+t)^-beta in [1/2, 1]: beta up to about 1
+    if (c->pot_form == 0 && !c->tab_off && fit_pow_tab(beta, w, tabs, tabs + 32) < 5e-17) {   // under half an ulp of (1+t)^-beta in [1/2, 1]: beta up to about 1
       int slot = -1;
       for (int i = 0; i < c->tab_count; ++i)
         if (c->tab_beta[i] == beta) slot = i;
       if (slot < 0) {
-        if (c->tab_count == bc_ctx::kTabSlots) {   // every slot taken: wait for whatever still reads them, start over
-          BC_CUDA(cudaDeviceSynchronize());
-          c->tab_count = 0;
+        if (c->tab_count == bc_ctx::kTabSlots) {
+          // every slot taken: this workspace sees a new beta all the time (learn_beta = True moves it every optimiser step).
+          // Fitting and uploading tables per step, and waiting for the kernels that still read old slots, costs more than the
+          // tables save: from here on the workspace stays with the polynomial forms.
+          c->tab_off = true;
         }
+      }
+      if (c->tab_off) {
+        slot = -1;
+      } else if (slot < 0) {
         slot = c->tab_count++;
         c->tab_beta[slot] = beta;
         BC_CUDA(cudaMemcpy(c->tab_dev + (size_t)slot * 64, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
       }
-      for (int k = 0; k <= kPowTabDeg; ++k) c->mp.w[k] = w[k];
-      c->tab_cur = c->tab_dev + (size_t)slot * 64;
+      if (slot >= 0) {
+        for (int k = 0; k <= kPowTabDeg; ++k) c->mp.w[k] = w[k];
+        c->tab_cur = c->tab_dev + (size_t)slot * 64;
+      }
     }
     c->tab_form = c->tab_cur != nullptr;
   } else {

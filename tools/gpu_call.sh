@@ -1,3 +1,3 @@
 cd /root/repo
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r02_bench_n1_h.json 2> gpurun_out/r02_bench_n1_h.err; echo bench rc=$?
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_27.txt 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r02_pytest_27.txt
