@@ -113,3 +113,28 @@ def test_constant_rows_are_centred_like_numpy(geo):
             want = (V.dot(res)/np.sqrt((V**2).sum(axis=1))/S)[1]
         got = geo.np_score_const(x, S, float(res.sum()))
         assert (np.isnan(want) and np.isnan(got)) or np.isclose(got, want, rtol=1e-9, atol=0), (x, S, got, want)
+
+
+def test_recombination_forms_round_alike():
+    """q_combine_n (csrc/bc_umma.cuh): for up to 6 digits the diagonals are summed in ONE int64 and converted once; the 7-digit
+    split sums two halves and joins them with one FMA.  Both are a single rounding of the same integer -- restated here in
+    exact arithmetic over the diagonals' full range (|D_d| <= (d+1) 128 * 128 * 128) -- and the int64 never overflows."""
+    r = np.random.RandomState(11)
+    for NS in (5, 6):
+        for _ in range(4000):
+            big = r.rand() < 0.3
+            d = [int(r.randint(-(k+1)*2**21, (k+1)*2**21+1)) if not big else int(((k+1)*2**21)*r.choice([-1, 1])) for k in range(NS)]
+            exact = sum(dk*256**(NS-1-k) for k, dk in enumerate(d))
+            assert abs(exact) < 2**62
+            # the kernel's integer steps: four trailing digits by multiply-add, the leading ones into the high word
+            t = d[NS-1] + d[NS-2]*256 + d[NS-3]*65536 + d[NS-4]*16777216
+            hi = (t >> 32) + d[NS-5] + ((d[NS-6] << 8) if NS >= 6 else 0)
+            t = ((hi & 0xffffffff) << 32) | (t & 0xffffffff)
+            if t >= 2**63:
+                t -= 2**64
+            assert t == exact
+            one = float(np.float64(t))                                  # I2F.F64.S64, round to nearest
+            h = sum(dk*256**(NS-4-k) for k, dk in enumerate(d[:NS-3]))   # the two-half form of the same digits
+            lo = d[NS-3]*65536 + d[NS-2]*256 + d[NS-1]
+            two = float(Fraction(h)*16777216 + Fraction(lo))            # fma(h, 2^24, lo): one rounding of the exact sum
+            assert one == two == float(Fraction(exact))
